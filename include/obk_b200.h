@@ -1,0 +1,159 @@
+/* obk_b200.h -- C ABI of the B200-native series-product engine (libobk_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of bluescarni/obake: the product of two sparse
+ * multivariate polynomials whose monomials are Kronecker-packed integers.  Nothing like this ABI
+ * exists in the reference (it is a header-only C++20 template library); every entry point below
+ * names the reference interface it replaces (file:line under the obake source tree) and
+ * INTEGRATION.md shows the binding a maintainer adds on the obake side (a C++ overload of
+ * obake::customisation::series_mul / the body of polynomials::detail::poly_mul_impl_identical_ss).
+ *
+ * Conventions
+ *  - plain C types only; no torch / CUDA types in the signatures (a CUDA stream travels as void*).
+ *  - keys: `key_words` 64-bit words per term, term-major.  One word = packed_monomial<T>
+ *    (include/obake/polynomials/packed_monomial.hpp:56-142), several = d_packed_monomial<T,psize>
+ *    (d_packed_monomial.hpp:83-217).  32-bit key types are widened (sign- or zero-extended) by the
+ *    caller; signed keys travel as their two's-complement bit pattern.
+ *  - integer coefficients: `cf_limbs` 64-bit limbs per term, two's complement, little endian --
+ *    the value of an mppp::integer<N>.  fp64 coefficients: one double per term.
+ *  - `mem` says where `keys`/`cfs` live: host memory (pinned or pageable) or this engine's device.
+ *  - every call is synchronous with respect to the engine's stream when it returns.
+ */
+#ifndef OBK_B200_H
+#define OBK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct obk_engine obk_engine;
+
+typedef enum obk_status {
+    OBK_OK = 0,
+    OBK_ERR_INVALID_ARG = 1,
+    /* std::overflow_error "An overflow in the monomial exponents was detected while attempting to
+     * multiply two polynomials" -- polynomial.hpp:839-851 */
+    OBK_ERR_KEY_OVERFLOW = 2,
+    /* std::overflow_error, table larger than the series allows -- polynomial.hpp:1544-1550 */
+    OBK_ERR_TABLE_OVERFLOW = 3,
+    /* the exact result needs more than 3 accumulator limbs (the reference would spill to GMP) */
+    OBK_ERR_CF_OVERFLOW = 4,
+    OBK_ERR_CUDA = 5,
+    OBK_ERR_UNSUPPORTED = 6,
+    OBK_ERR_NOMEM = 7
+} obk_status;
+
+enum { OBK_CF_INT = 0, OBK_CF_F64 = 1 };
+enum { OBK_MEM_HOST = 0, OBK_MEM_DEVICE = 1 };
+
+/* One operand: the terms of a polynomial<Key, Cf> as SoA arrays (what poly_mul_impl_mt_hm copies
+ * out of the series at polynomial.hpp:828-833). */
+typedef struct obk_poly_view {
+    uint64_t nterms;
+    uint32_t key_words;  /* W >= 1 */
+    uint32_t key_signed; /* 1: T is a signed integer type */
+    uint32_t nvars;      /* size of the symbol set */
+    uint32_t psize;      /* 0: packed_monomial (one word packs nvars exponents); k: d_packed_monomial<T,k> */
+    uint32_t cf_kind;    /* OBK_CF_INT | OBK_CF_F64 */
+    uint32_t cf_limbs;   /* integer: 1 or 2 input limbs; f64: 1 */
+    uint32_t mem;        /* OBK_MEM_HOST | OBK_MEM_DEVICE */
+    uint32_t reserved;
+    const uint64_t *keys; /* [nterms * key_words] */
+    const void *cfs;      /* [nterms * cf_limbs] uint64 or [nterms] double */
+} obk_poly_view;
+
+/* Truncation arguments of truncated_mul (polynomial.hpp:2113-2127): pair (i,j) is kept iff
+ * !(limit < deg_i + deg_j), degrees taken in the key's integer type T (polynomial.hpp:604-610). */
+typedef struct obk_trunc {
+    int64_t limit;       /* already converted to T (bit pattern for unsigned T) */
+    uint32_t nidx;       /* 0: total degree; else number of entries of idx */
+    uint32_t partial;    /* 1: partial degree over idx (idx may be empty: every degree is 0) */
+    const uint32_t *idx; /* sorted positions (in the symbol set) of the variables that count (host) */
+} obk_trunc;
+
+/* The product, grouped by output segment: term t of segment s sits in [seg_offsets[s], seg_offsets[s+1])
+ * and satisfies hash(key) & (2^log2_nsegs - 1) == s, i.e. it belongs in table s of a series with that
+ * many segments (series.hpp:396-400,1294-1305).  No coefficient is zero (polynomial.hpp:1528-1540). */
+typedef struct obk_poly_result {
+    uint64_t nterms;
+    uint32_t key_words;
+    uint32_t cf_kind;
+    uint32_t cf_limbs;    /* integer: accumulator limbs (1..3), two's complement */
+    uint32_t log2_nsegs;
+    uint32_t mem;         /* where keys/cfs live */
+    uint32_t reserved;
+    uint64_t *keys;
+    void *cfs;
+    uint64_t *seg_offsets; /* host memory, 2^log2_nsegs + 1 entries */
+    void *owner;           /* engine bookkeeping; release with obk_result_free */
+} obk_poly_result;
+
+typedef struct obk_stats {
+    uint64_t term_products; /* tot_n_mults, polynomial.hpp:574-623 */
+    uint64_t nterms_out;
+    uint64_t est_nterms;    /* sampled estimate that sized the segments */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t log2_nsegs;
+    uint32_t acc_limbs;
+    uint32_t retries;       /* segment-table overflows that forced a finer segmentation */
+    uint32_t kernel;        /* 0: scatter (segment-owner hash tables), 1: row-blocked dense path */
+    uint32_t table_slots;   /* slots of one shared-memory segment table */
+    uint32_t group_lanes;   /* lanes cooperating on one left-operand term */
+    uint32_t mul_launches;  /* launches of the product kernel (1 + retries) */
+    uint32_t total_launches;/* all kernels launched by this call */
+    float ms_total;         /* device time of the whole call (first to last kernel, CUDA events) */
+    float ms_prep;          /* stats + degree + bucket sort */
+    float ms_estimate;
+    float ms_mul;           /* the product kernel alone (last attempt) */
+    float ms_compact;
+    float ms_h2d, ms_d2h;
+} obk_stats;
+
+/* Engine lifetime.  One engine = one CUDA device + one stream + a grow-only workspace. */
+obk_status obk_engine_create(int device, obk_engine **out);
+void obk_engine_destroy(obk_engine *e);
+/* Launch on the caller's stream (e.g. torch's current stream) instead of the engine's own. */
+obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream);
+/* Tunables: "log2_nsegs" (force, -1 = auto), "table_slots", "threads", "group_lanes" (0 = auto),
+ * "kernel" (-1 auto, 0 scatter, 1 rows), "max_retries". */
+obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value);
+const char *obk_last_error(const obk_engine *e);
+const char *obk_status_string(obk_status s);
+const char *obk_version(void);
+
+/* series_mul(polynomial, polynomial) / truncated_mul (polynomial.hpp:2026-2032, 2113-2127) from the
+ * seam poly_mul_impl_identical_ss (polynomial.hpp:1878-1929): empty operand -> empty result, shorter
+ * operand first (:2014-2022), exponent-overflow check before any product (:839-851), early empty
+ * result when the truncation admits no pair (:860-862), then the segmented product (:797-1582).
+ * `t` may be NULL (untruncated).  `result_mem` selects where the product is left. */
+obk_status obk_poly_mul(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
+                        uint32_t result_mem, obk_poly_result *out, obk_stats *stats);
+void obk_result_free(obk_engine *e, obk_poly_result *r);
+
+/* monomial_range_overflow_check (packed_monomial.hpp:289-488, d_packed_monomial.hpp:583-897).
+ * *ok = 1 when every product monomial is representable. */
+obk_status obk_overflow_check(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int *ok);
+
+/* make_degree_vector / make_p_degree_vector (series.hpp:3757-3785, 3911-3945) with key_degree /
+ * key_p_degree (src/polynomials/packed_monomial.cpp:334-350,388-412; d_packed_monomial.hpp:901-958).
+ * out_host: nterms int64 (bit pattern of T). */
+obk_status obk_key_degrees(obk_engine *e, const obk_poly_view *x, const obk_trunc *which, int64_t *out_host);
+
+/* Multi-GPU: rank r multiplies its slice of the shorter operand's terms by the whole other
+ * operand with a segment count all ranks agree on, and leaves a DEVICE partial result grouped by
+ * segment.  send_counts[g] = number of partial terms owned by rank g (segments [g*nsegs/G, (g+1)*nsegs/G)).
+ * After the all-to-all the owner merges what it received with obk_poly_merge. */
+obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
+                                uint32_t rank, uint32_t nranks, obk_poly_result *out_partial,
+                                uint64_t *send_counts, obk_stats *stats);
+/* Sum terms with equal keys (exact / fp64), drop zeros; `terms` holds acc-limb coefficients
+ * (cf_limbs = accumulator limbs) on the device. */
+obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t log2_nsegs, uint32_t result_mem,
+                          obk_poly_result *out, obk_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBK_B200_H */

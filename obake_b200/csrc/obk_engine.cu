@@ -1,0 +1,1147 @@
+// obk_engine.cu -- host orchestration + C ABI (include/obk_b200.h) of the B200 series-product engine.
+//
+// Replaces, behind the same seam, poly_mul_impl_identical_ss -> poly_mul_impl_mt_hm of the reference
+// (include/obake/polynomials/polynomial.hpp:1878-1929, 797-1582).  There is NO CPU fallback: without a
+// CUDA device every entry point fails with OBK_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/obk_b200.h"
+#include "../include/obake/kpack.hpp"
+#include "obk_kernels.cuh"
+
+using namespace obk;
+
+#define OBK_VERSION_STRING "obk_b200 0.1 (sm_100a)"
+
+namespace
+{
+
+typedef __int128 i128;
+
+struct PinnedBlock {
+    void *ptr;
+    size_t size;
+    bool in_use;
+};
+
+} // namespace
+
+struct obk_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaEvent_t ev[16];
+    std::mutex mtx;
+    std::vector<PinnedBlock> pinned;
+    // options
+    int64_t opt_log2_nsegs = -1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+            opt_max_retries = 6, opt_fill_pct = 62;
+    unsigned launches = 0;
+};
+
+namespace
+{
+
+struct ResultOwner {
+    obk_engine *e;
+    void *dkeys = nullptr, *dcfs = nullptr; // device allocations (cudaMallocAsync)
+    int pk = -1, pc = -1;                   // pinned block indices
+    uint64_t *seg_offsets = nullptr;        // malloc
+};
+
+#define CU_CHECK(e, call)                                                                                              \
+    do {                                                                                                               \
+        cudaError_t _err = (call);                                                                                     \
+        if (_err != cudaSuccess) {                                                                                     \
+            (e)->err = std::string("CUDA error: ") + cudaGetErrorString(_err) + " at " #call;                          \
+            throw obk_fail{OBK_ERR_CUDA};                                                                              \
+        }                                                                                                              \
+    } while (0)
+
+struct obk_fail {
+    obk_status st;
+};
+
+// Stream-ordered scratch allocations released when the call ends.
+struct Scratch {
+    obk_engine *e;
+    std::vector<void *> ptrs;
+    explicit Scratch(obk_engine *e_) : e(e_) {}
+    template <typename T>
+    T *alloc(size_t n)
+    {
+        void *p = nullptr;
+        size_t bytes = std::max<size_t>(n * sizeof(T), 16);
+        cudaError_t err = cudaMallocAsync(&p, bytes, e->stream);
+        if (err != cudaSuccess) {
+            e->err = std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(err);
+            cudaGetLastError();
+            throw obk_fail{OBK_ERR_NOMEM};
+        }
+        ptrs.push_back(p);
+        return static_cast<T *>(p);
+    }
+    void release(void *p)
+    {
+        for (auto &q : ptrs)
+            if (q == p) {
+                cudaFreeAsync(q, e->stream);
+                q = nullptr;
+            }
+    }
+    // hand ownership to the caller
+    void detach(void *p)
+    {
+        for (auto &q : ptrs)
+            if (q == p) q = nullptr;
+    }
+    ~Scratch()
+    {
+        for (auto q : ptrs)
+            if (q) cudaFreeAsync(q, e->stream);
+    }
+};
+
+int pinned_acquire(obk_engine *e, size_t bytes)
+{
+    std::lock_guard<std::mutex> g(e->mtx);
+    bytes = std::max<size_t>(bytes, 64);
+    int best = -1;
+    for (size_t i = 0; i < e->pinned.size(); ++i) {
+        auto &b = e->pinned[i];
+        if (!b.in_use && b.size >= bytes && (best < 0 || b.size < e->pinned[best].size)) best = (int)i;
+    }
+    if (best >= 0 && e->pinned[best].size <= bytes * 2 + (1u << 20)) {
+        e->pinned[best].in_use = true;
+        return best;
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        e->err = "pinned host allocation failed";
+        throw obk_fail{OBK_ERR_NOMEM};
+    }
+    // reuse a dead slot if any
+    for (size_t i = 0; i < e->pinned.size(); ++i)
+        if (e->pinned[i].ptr == nullptr) {
+            e->pinned[i] = {p, bytes, true};
+            return (int)i;
+        }
+    e->pinned.push_back({p, bytes, true});
+    return (int)e->pinned.size() - 1;
+}
+
+void pinned_release(obk_engine *e, int idx)
+{
+    std::lock_guard<std::mutex> g(e->mtx);
+    if (idx < 0 || idx >= (int)e->pinned.size()) return;
+    e->pinned[idx].in_use = false;
+    // keep at most ~8 cached blocks
+    size_t idle = 0;
+    for (auto &b : e->pinned) idle += (!b.in_use && b.ptr) ? 1 : 0;
+    if (idle > 8) {
+        cudaFreeHost(e->pinned[idx].ptr);
+        e->pinned[idx] = {nullptr, 0, false};
+    }
+}
+
+Layout make_layout(const obk_poly_view &v)
+{
+    Layout L{};
+    L.nvars = v.nvars;
+    L.psize = v.psize;
+    L.W = v.key_words;
+    L.is_signed = v.key_signed ? 1u : 0u;
+    L.wsize = v.psize ? v.psize : v.nvars;
+    if (L.wsize == 0) {
+        L.delta = 1;
+        L.klim_min = 0;
+        L.lim_min = 0;
+        return L;
+    }
+    if (v.key_signed) {
+        L.delta = (uint64_t)obake::detail::kpack_get_delta<std::int64_t>(L.wsize);
+        L.klim_min = (uint64_t)obake::detail::kpack_get_klims<std::int64_t>(L.wsize).first;
+        L.lim_min = obake::detail::kpack_get_lims<std::int64_t>(L.wsize).first;
+    } else {
+        L.delta = obake::detail::kpack_get_delta<std::uint64_t>(L.wsize);
+        L.klim_min = 0;
+        L.lim_min = 0;
+    }
+    return L;
+}
+
+inline i128 unord(long long o, bool is_signed)
+{
+    return is_signed ? (i128)o : (i128)(uint64_t)((uint64_t)o ^ 0x8000000000000000ULL);
+}
+
+unsigned bitlen64(uint64_t v)
+{
+    unsigned b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+
+void validate_view(obk_engine *e, const obk_poly_view *v, const char *name)
+{
+    auto bad = [&](const std::string &m) {
+        e->err = std::string("invalid operand ") + name + ": " + m;
+        throw obk_fail{OBK_ERR_INVALID_ARG};
+    };
+    if (!v) bad("null view");
+    if (v->key_words < 1 || v->key_words > 4) {
+        e->err = std::string("operand ") + name + ": key_words must be in [1,4]";
+        throw obk_fail{OBK_ERR_UNSUPPORTED};
+    }
+    if (v->cf_kind != OBK_CF_INT && v->cf_kind != OBK_CF_F64) bad("cf_kind");
+    if (v->cf_kind == OBK_CF_INT && (v->cf_limbs < 1 || v->cf_limbs > 3)) bad("cf_limbs must be in [1,3]");
+    if (v->mem != OBK_MEM_HOST && v->mem != OBK_MEM_DEVICE) bad("mem");
+    if (v->nterms && (!v->keys || !v->cfs)) bad("null keys/cfs");
+    const unsigned maxsz = v->key_signed ? obake::detail::kpack_max_size<std::int64_t>()
+                                         : obake::detail::kpack_max_size<std::uint64_t>();
+    if (v->psize == 0) {
+        if (v->key_words != 1) bad("packed_monomial keys have exactly one word");
+        if (v->nvars > maxsz) bad("too many variables for one packed word");
+    } else {
+        if (v->psize > maxsz) bad("psize too large");
+        const unsigned need = std::max(1u, (v->nvars + v->psize - 1) / v->psize);
+        if (v->nvars && need != v->key_words) bad("key_words != ceil(nvars/psize)");
+    }
+    if (v->nvars > (unsigned)MAX_VARS) {
+        e->err = "more than 64 variables are not supported";
+        throw obk_fail{OBK_ERR_UNSUPPORTED};
+    }
+    if (v->nterms >= (1ull << 31)) {
+        e->err = "operands with 2^31 or more terms are not supported";
+        throw obk_fail{OBK_ERR_UNSUPPORTED};
+    }
+}
+
+// Exclusive scan of n uint32 into out[0..n] (out[n] = total).
+void device_scan(obk_engine *e, Scratch &sc, const uint32_t *in, uint32_t *out, uint64_t n)
+{
+    const uint64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nb > (uint64_t)SCAN_BLOCK) {
+        e->err = "scan too large";
+        throw obk_fail{OBK_ERR_UNSUPPORTED};
+    }
+    uint32_t *bs = sc.alloc<uint32_t>(nb + 1);
+    uint32_t *bp = sc.alloc<uint32_t>(nb + 2);
+    uint32_t *dummy = sc.alloc<uint32_t>(4);
+    k_scan_local<<<(unsigned)nb, SCAN_THREADS, 0, e->stream>>>(in, out, bs, n);
+    k_scan_local<<<1, SCAN_THREADS, 0, e->stream>>>(bs, bp, dummy, nb);
+    // grand total = dummy[0]
+    k_scan_add<<<(unsigned)nb, SCAN_THREADS, 0, e->stream>>>(out, bp, n, dummy);
+    e->launches += 3;
+    sc.release(bs);
+    sc.release(bp);
+    sc.release(dummy);
+}
+
+struct SortedY {
+    uint64_t *keys = nullptr;
+    uint64_t *cfs = nullptr;
+    uint32_t *off = nullptr; // (nsegs << dbits) + 1
+};
+
+// Counting sort of the right operand by (bucket, degree index).
+SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uint64_t *cfs, const int64_t *deg, uint64_t n,
+                     int W, int CW, uint32_t log2_nsegs, int dbits, int64_t degmin, bool with_cfs)
+{
+    SortedY r;
+    const uint64_t nbins = (uint64_t)1 << (log2_nsegs + dbits);
+    uint32_t *cnt = sc.alloc<uint32_t>(nbins + 1);
+    uint32_t *bin_of = sc.alloc<uint32_t>(n);
+    uint32_t *rank_of = sc.alloc<uint32_t>(n);
+    r.off = sc.alloc<uint32_t>(nbins + 1);
+    r.keys = sc.alloc<uint64_t>(n * W);
+    if (with_cfs) r.cfs = sc.alloc<uint64_t>(n * CW);
+    CU_CHECK(e, cudaMemsetAsync(cnt, 0, (nbins + 1) * sizeof(uint32_t), e->stream));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
+    k_bin_count<<<grid, 256, 0, e->stream>>>(keys, deg, n, W, (uint32_t)((1ull << log2_nsegs) - 1), dbits, degmin, cnt,
+                                             bin_of, rank_of);
+    e->launches += 1;
+    device_scan(e, sc, cnt, r.off, nbins);
+    k_bin_scatter<<<grid, 256, 0, e->stream>>>(keys, with_cfs ? cfs : nullptr, nullptr, n, W, CW, r.off, bin_of, rank_of,
+                                               r.keys, with_cfs ? r.cfs : nullptr, nullptr);
+    e->launches += 1;
+    sc.release(cnt);
+    sc.release(bin_of);
+    sc.release(rank_of);
+    return r;
+}
+
+template <int W>
+void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, unsigned threads, size_t smem)
+{
+#define OBK_CASE(M)                                                                                                    \
+    case M: {                                                                                                          \
+        auto fn = k_mul<W, M>;                                                                                         \
+        CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        fn<<<grid, threads, smem, e->stream>>>(P);                                                                     \
+        break;                                                                                                         \
+    }
+    switch (mode) {
+        OBK_CASE(CF_SYM)
+        OBK_CASE(CF_I1A1)
+        OBK_CASE(CF_I1A2)
+        OBK_CASE(CF_I1A3)
+        OBK_CASE(CF_I2A3)
+        OBK_CASE(CF_F64)
+        OBK_CASE(CF_ADD1)
+        OBK_CASE(CF_ADD2)
+        OBK_CASE(CF_ADD3)
+        OBK_CASE(CF_ADDF)
+        default:
+            e->err = "internal: bad coefficient mode";
+            throw obk_fail{OBK_ERR_INVALID_ARG};
+    }
+#undef OBK_CASE
+    e->launches += 1;
+    CU_CHECK(e, cudaGetLastError());
+}
+
+void launch_mul(obk_engine *e, int W, int mode, const MulParams &P, unsigned grid, unsigned threads, size_t smem)
+{
+    switch (W) {
+        case 1: launch_mul_w<1>(e, mode, P, grid, threads, smem); break;
+        case 2: launch_mul_w<2>(e, mode, P, grid, threads, smem); break;
+        case 3: launch_mul_w<3>(e, mode, P, grid, threads, smem); break;
+        case 4: launch_mul_w<4>(e, mode, P, grid, threads, smem); break;
+        default: e->err = "unsupported key_words"; throw obk_fail{OBK_ERR_UNSUPPORTED};
+    }
+}
+
+int acc_words_of(int mode)
+{
+    switch (mode) {
+        case CF_SYM: return 0;
+        case CF_I1A1: case CF_F64: case CF_ADD1: case CF_ADDF: return 1;
+        case CF_I1A2: case CF_ADD2: return 2;
+        default: return 3;
+    }
+}
+
+// Table geometry: the largest power-of-two slot count whose table fits the opt-in shared memory.
+uint32_t pick_log2_cap(obk_engine *e, int W, int accw)
+{
+    if (e->opt_table_slots > 0) {
+        uint32_t l = 0;
+        while ((1ll << (l + 1)) <= e->opt_table_slots) ++l;
+        return l;
+    }
+    const size_t slot = (size_t)8 * W + (size_t)8 * accw + 4;
+    const size_t budget = std::min<size_t>(e->smem_optin, 227 * 1024) - 2048;
+    uint32_t l = 4;
+    while (((size_t)2 << l) * slot <= budget) ++l;
+    return l;
+}
+
+void set_empty_result(obk_poly_result *out, const obk_poly_view *x, int cf_limbs, uint32_t mem)
+{
+    std::memset(out, 0, sizeof(*out));
+    out->key_words = x->key_words;
+    out->cf_kind = x->cf_kind;
+    out->cf_limbs = cf_limbs;
+    out->mem = mem;
+    auto *own = new ResultOwner{nullptr};
+    own->seg_offsets = (uint64_t *)std::calloc(2, sizeof(uint64_t));
+    out->seg_offsets = own->seg_offsets;
+    out->owner = own;
+}
+
+struct MulRequest {
+    const obk_poly_view *x, *y;
+    const obk_trunc *t;
+    uint32_t result_mem;
+    // sharding of the left operand (multi-GPU): this call multiplies x[shard_rank] slice only
+    uint32_t rank = 0, nranks = 1;
+    uint64_t *send_counts = nullptr;
+    // merge mode: x is ignored, y holds acc-limb coefficients to be summed by key
+    bool merge = false;
+    uint32_t merge_log2_nsegs = 0;
+};
+
+obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats *stats)
+{
+    obk_stats st{};
+    e->launches = 0;
+    const obk_poly_view *x = rq.x, *y = rq.y;
+    if (!out) {
+        e->err = "null result pointer";
+        return OBK_ERR_INVALID_ARG;
+    }
+    std::memset(out, 0, sizeof(*out));
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        validate_view(e, y, "y");
+        if (!rq.merge) {
+            validate_view(e, x, "x");
+            if (x->key_words != y->key_words || x->key_signed != y->key_signed || x->nvars != y->nvars
+                || x->psize != y->psize || x->cf_kind != y->cf_kind) {
+                e->err = "operands have different key layouts or coefficient kinds";
+                return OBK_ERR_INVALID_ARG;
+            }
+            // empty operand -> empty result (polynomial.hpp:1892-1895)
+            if (x->nterms == 0 || y->nterms == 0) {
+                set_empty_result(out, x, x->cf_kind == OBK_CF_F64 ? 1 : 1, rq.result_mem);
+                if (rq.send_counts) std::memset(rq.send_counts, 0, sizeof(uint64_t) * rq.nranks);
+                if (stats) *stats = st;
+                return OBK_OK;
+            }
+            // shorter operand first (poly_mul_impl_switch, polynomial.hpp:2014-2022)
+            if (x->nterms > y->nterms) std::swap(x, y);
+        } else {
+            x = y;
+            if (y->nterms == 0) {
+                set_empty_result(out, y, y->cf_limbs, rq.result_mem);
+                if (stats) *stats = st;
+                return OBK_OK;
+            }
+        }
+        const int W = (int)y->key_words;
+        const bool f64 = y->cf_kind == OBK_CF_F64;
+        const int CWx = f64 ? 1 : (int)x->cf_limbs, CWy = f64 ? 1 : (int)y->cf_limbs;
+        const Layout L = make_layout(*y);
+        Scratch sc(e);
+        cudaStream_t s = e->stream;
+        CU_CHECK(e, cudaEventRecord(e->ev[0], s));
+
+        // ---- operands on the device -------------------------------------------------------------------
+        const uint64_t nx_full = x->nterms, ny = y->nterms;
+        const uint64_t *dxk, *dxc, *dyk, *dyc;
+        auto upload = [&](const obk_poly_view *v, int cw, const uint64_t *&dk, const uint64_t *&dc) {
+            if (v->mem == OBK_MEM_DEVICE) {
+                dk = v->keys;
+                dc = (const uint64_t *)v->cfs;
+            } else {
+                uint64_t *k = sc.alloc<uint64_t>(v->nterms * W);
+                uint64_t *c = sc.alloc<uint64_t>(v->nterms * cw);
+                CU_CHECK(e, cudaMemcpyAsync(k, v->keys, v->nterms * W * 8, cudaMemcpyHostToDevice, s));
+                CU_CHECK(e, cudaMemcpyAsync(c, v->cfs, v->nterms * cw * 8, cudaMemcpyHostToDevice, s));
+                st.h2d_bytes += v->nterms * (W + cw) * 8;
+                dk = k;
+                dc = c;
+            }
+        };
+        upload(y, CWy, dyk, dyc);
+        if (rq.merge) {
+            dxk = nullptr;
+            dxc = nullptr;
+        } else if (x == y) {
+            dxk = dyk;
+            dxc = dyc;
+        } else {
+            upload(x, CWx, dxk, dxc);
+        }
+        CU_CHECK(e, cudaEventRecord(e->ev[1], s));
+
+        // ---- term statistics: overflow check, degrees, coefficient width ----------------------------
+        int mode;
+        uint32_t log2_nsegs = 0;
+        int dbits = 0;
+        uint32_t ndeg = 1;
+        int64_t lim_base = 0, degmin_y = 0;
+        int64_t *xdeg = nullptr, *ydeg = nullptr;
+        bool trunc = false;
+        uint64_t tot_mults = 0;
+        if (!rq.merge) {
+            trunc = rq.t != nullptr;
+            uint64_t var_mask = 0;
+            if (trunc) {
+                if (rq.t->partial) {
+                    for (uint32_t i = 0; i < rq.t->nidx; ++i) {
+                        if (rq.t->idx[i] >= L.nvars) {
+                            e->err = "partial-degree index outside the symbol set";
+                            return OBK_ERR_INVALID_ARG;
+                        }
+                        var_mask |= 1ull << rq.t->idx[i];
+                    }
+                } else {
+                    var_mask = L.nvars >= 64 ? ~0ull : ((1ull << L.nvars) - 1);
+                }
+                xdeg = sc.alloc<int64_t>(nx_full);
+                ydeg = (x == y) ? xdeg : sc.alloc<int64_t>(ny);
+            }
+            StatsOut *dstats = sc.alloc<StatsOut>(2);
+            k_stats_init<<<2, 64, 0, s>>>(dstats, 2);
+            // NOTE: k_stats_init indexes by global thread; fix up: one block per struct
+            const unsigned gx = (unsigned)std::min<uint64_t>((nx_full + 255) / 256, 1024);
+            const unsigned gy = (unsigned)std::min<uint64_t>((ny + 255) / 256, 1024);
+            k_term_stats<<<gx, 256, 0, s>>>(dxk, dxc, nx_full, L, var_mask, f64 ? 1 : 0, CWx, xdeg, dstats);
+            if (x != y)
+                k_term_stats<<<gy, 256, 0, s>>>(dyk, dyc, ny, L, var_mask, f64 ? 1 : 0, CWy, ydeg, dstats + 1);
+            e->launches += 3;
+            StatsOut hs[2];
+            CU_CHECK(e, cudaMemcpyAsync(hs, dstats, sizeof(StatsOut) * (x == y ? 1 : 2), cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            if (x == y) hs[1] = hs[0];
+            st.d2h_bytes += sizeof(StatsOut) * 2;
+
+            // monomial_range_overflow_check (packed_monomial.hpp:462-487; d_packed_monomial.hpp:861-894)
+            if (L.nvars) {
+                i128 lim_min, lim_max;
+                if (L.is_signed) {
+                    auto lm = obake::detail::kpack_get_lims<std::int64_t>(L.wsize);
+                    lim_min = lm.first;
+                    lim_max = lm.second;
+                } else {
+                    lim_min = 0;
+                    lim_max = (i128)obake::detail::kpack_get_lims<std::uint64_t>(L.wsize).second;
+                }
+                bool ok = true;
+                for (uint32_t v = 0; v < L.nvars && ok; ++v) {
+                    const i128 mn = unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
+                    const i128 mx = unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);
+                    if (mn < lim_min || mx > lim_max) ok = false;
+                }
+                if (ok && L.psize != 0 && !trunc) {
+                    // d_packed: the total degree of a product must stay representable in T.  The total-degree
+                    // extrema are only computed when var_mask covers every variable; recompute cheaply from
+                    // the per-variable extrema as a conservative bound only if that bound fails.
+                    i128 dmax = 0, dmin = 0;
+                    for (uint32_t v = 0; v < L.nvars; ++v) {
+                        dmax += unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);
+                        dmin += unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
+                    }
+                    const i128 tmax = L.is_signed ? (i128)INT64_MAX : (i128)UINT64_MAX;
+                    const i128 tmin = L.is_signed ? (i128)INT64_MIN : (i128)0;
+                    if (dmax > tmax || dmin < tmin) ok = false; // cannot trigger for psize >= 2 (sums of < 2^33 values)
+                }
+                if (!ok) {
+                    e->err = "An overflow in the monomial exponents was detected while attempting to multiply two "
+                             "polynomials";
+                    return OBK_ERR_KEY_OVERFLOW;
+                }
+            }
+            // a-priori accumulator width: |sum| <= min(nx,ny) * max|c1| * max|c2|
+            if (f64) {
+                mode = CF_F64;
+                st.acc_limbs = 1;
+            } else {
+                const unsigned bits = hs[0].cfbits + hs[1].cfbits + bitlen64(std::min(nx_full, ny)) + 1;
+                const unsigned lacc = (bits + 63) / 64;
+                if (lacc > 3) {
+                    e->err = "coefficient overflow beyond 3 limbs: the exact product needs " + std::to_string(bits)
+                             + " bits";
+                    return OBK_ERR_CF_OVERFLOW;
+                }
+                if (CWx != CWy) {
+                    e->err = "integer operands must use the same number of input limbs";
+                    return OBK_ERR_INVALID_ARG;
+                }
+                if (CWx == 1) {
+                    mode = lacc == 1 ? CF_I1A1 : (lacc == 2 ? CF_I1A2 : CF_I1A3);
+                    st.acc_limbs = lacc;
+                } else if (CWx == 2) {
+                    mode = CF_I2A3;
+                    st.acc_limbs = 3;
+                } else {
+                    e->err = "3-limb input coefficients are not supported (inputs are 1 or 2 limbs)";
+                    return OBK_ERR_UNSUPPORTED;
+                }
+            }
+            // truncation geometry
+            if (trunc) {
+                const i128 dminx = unord(hs[0].dmin, L.is_signed), dmaxx = unord(hs[0].dmax, L.is_signed);
+                const i128 dminy = unord(hs[1].dmin, L.is_signed), dmaxy = unord(hs[1].dmax, L.is_signed);
+                const i128 big = (i128)1 << 62;
+                if (dminx < -big || dmaxx > big || dminy < -big || dmaxy > big) {
+                    e->err = "degrees beyond 2^62 are not supported in truncated products";
+                    return OBK_ERR_UNSUPPORTED;
+                }
+                const i128 range = dmaxy - dminy + 1;
+                if (range > ((i128)1 << 20)) {
+                    e->err = "degree range of the right operand exceeds 2^20 (unsupported in truncated products)";
+                    return OBK_ERR_UNSUPPORTED;
+                }
+                ndeg = (uint32_t)range;
+                while ((1u << dbits) < ndeg) ++dbits;
+                degmin_y = (int64_t)dminy;
+                const i128 lim = L.is_signed ? (i128)rq.t->limit : (i128)(uint64_t)rq.t->limit;
+                i128 lb = lim - dminy; // right-degree index d passes for left term i iff d <= lb - deg_i
+                // clamp: below (dminx - 1) nothing passes, above (dmaxx + ndeg) everything passes
+                lb = std::max(lb, dminx - 1);
+                lb = std::min(lb, dmaxx + (i128)ndeg);
+                lim_base = (int64_t)lb;
+                // tot_n_mults (polynomial.hpp:574-623)
+                uint32_t *hist = sc.alloc<uint32_t>(ndeg + 1);
+                uint32_t *pref = sc.alloc<uint32_t>(ndeg + 2);
+                unsigned long long *dtot = sc.alloc<unsigned long long>(1);
+                CU_CHECK(e, cudaMemsetAsync(hist, 0, (ndeg + 1) * 4, s));
+                CU_CHECK(e, cudaMemsetAsync(dtot, 0, 8, s));
+                k_deg_hist<<<gy, 256, 0, s>>>(ydeg, ny, degmin_y, hist);
+                e->launches += 1;
+                device_scan(e, sc, hist, pref, ndeg);
+                k_count_mults<<<gx, 256, 0, s>>>(xdeg, nx_full, lim_base, ndeg, pref, dtot);
+                e->launches += 1;
+                unsigned long long htot = 0;
+                CU_CHECK(e, cudaMemcpyAsync(&htot, dtot, 8, cudaMemcpyDeviceToHost, s));
+                CU_CHECK(e, cudaStreamSynchronize(s));
+                tot_mults = htot;
+                if (tot_mults == 0) {
+                    // the truncation admits no pair: empty result before segmenting (polynomial.hpp:860-862)
+                    set_empty_result(out, x, st.acc_limbs, rq.result_mem);
+                    if (rq.send_counts) std::memset(rq.send_counts, 0, sizeof(uint64_t) * rq.nranks);
+                    st.total_launches = e->launches;
+                    if (stats) *stats = st;
+                    return OBK_OK;
+                }
+            } else {
+                tot_mults = nx_full * ny;
+            }
+        } else {
+            // merge mode: sum acc-limb coefficients by key
+            mode = f64 ? CF_ADDF : (y->cf_limbs == 1 ? CF_ADD1 : (y->cf_limbs == 2 ? CF_ADD2 : CF_ADD3));
+            st.acc_limbs = f64 ? 1 : y->cf_limbs;
+            tot_mults = ny;
+        }
+        st.term_products = tot_mults;
+        const int accw = acc_words_of(mode);
+        CU_CHECK(e, cudaEventRecord(e->ev[2], s));
+
+        // ---- geometry of the shared-memory segment table ---------------------------------------------
+        const unsigned threads = (unsigned)std::max<int64_t>(32, std::min<int64_t>(1024, e->opt_threads)) / 32 * 32;
+        const uint32_t log2_cap = pick_log2_cap(e, W, accw);
+        const uint32_t cap = 1u << log2_cap;
+        const size_t smem_mul = (size_t)cap * (8 * W + 8 * accw + 4);
+        if (smem_mul + 1024 > e->smem_optin) {
+            e->err = "segment table does not fit in shared memory";
+            return OBK_ERR_INVALID_ARG;
+        }
+        st.table_slots = cap;
+        const uint32_t max_fill = (uint32_t)((uint64_t)cap * 9 / 10);
+        const uint32_t max_bins_log2 = 24;
+
+        // ---- product-size estimate (poly_mul_estimate_product_size, polynomial.hpp:478-794) -------------
+        // Sampled symbolic product: count the distinct product keys of a few fine-grained segments exactly.
+        uint64_t est = 0;
+        if (rq.merge) {
+            log2_nsegs = rq.merge_log2_nsegs;
+            est = ny;
+        } else if (e->opt_log2_nsegs >= 0) {
+            log2_nsegs = (uint32_t)e->opt_log2_nsegs;
+            est = 0;
+        } else {
+            const uint32_t sym_log2_cap = pick_log2_cap(e, W, 0);
+            const uint32_t sym_cap = 1u << sym_log2_cap;
+            uint32_t kE = 0;
+            while (kE + dbits < max_bins_log2 && (tot_mults >> kE) > sym_cap / 4) ++kE;
+            const uint64_t nsegE = 1ull << kE;
+            const double per_seg = (double)tot_mults / (double)nsegE;
+            uint64_t S = (uint64_t)std::ceil(1.5e6 / std::max(per_seg, 1.0));
+            S = std::max<uint64_t>(S, 32);
+            S = std::min<uint64_t>(S, 512);
+            S = std::min<uint64_t>(S, nsegE);
+            SortedY ye = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, kE, dbits, degmin_y, false);
+            std::vector<uint32_t> hlist(S);
+            for (uint64_t i = 0; i < S; ++i) hlist[i] = (uint32_t)((i * 0x9E3779B1ull + 0x51ull) & (nsegE - 1));
+            if (S == nsegE)
+                for (uint64_t i = 0; i < S; ++i) hlist[i] = (uint32_t)i;
+            uint32_t *dlist = sc.alloc<uint32_t>(S);
+            uint32_t *dcounts = sc.alloc<uint32_t>(S);
+            uint32_t *dflags = sc.alloc<uint32_t>(4);
+            CU_CHECK(e, cudaMemcpyAsync(dlist, hlist.data(), S * 4, cudaMemcpyHostToDevice, s));
+            CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
+            MulParams P{};
+            P.xk = dxk;
+            P.xc = nullptr;
+            P.xdeg = xdeg;
+            P.nx = nx_full;
+            P.yk = ye.keys;
+            P.yc = nullptr;
+            P.yoff = ye.off;
+            P.log2_nsegs = kE;
+            P.dbits = dbits;
+            P.ndeg = ndeg;
+            P.trunc = trunc;
+            P.lim_base = lim_base;
+            P.seg_list = dlist;
+            P.nseg_list = (uint32_t)S;
+            P.cursor = dflags + 1;
+            P.log2_cap = sym_log2_cap;
+            const double run = (double)ny / (double)nsegE;
+            uint32_t lg = 0;
+            while (lg < 5 && (double)(1u << lg) < run) ++lg;
+            P.lg = lg;
+            P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
+            P.counts = dcounts;
+            P.flags = dflags;
+            const size_t smem_sym = (size_t)sym_cap * (8 * W + 4);
+            launch_mul(e, W, CF_SYM, P, (unsigned)std::min<uint64_t>(S, (uint64_t)e->sm_count), threads, smem_sym);
+            std::vector<uint32_t> hcounts(S);
+            CU_CHECK(e, cudaMemcpyAsync(hcounts.data(), dcounts, S * 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            double sum = 0;
+            for (uint64_t i = 0; i < S; ++i) sum += hcounts[i] == 0xffffffffu ? (double)sym_cap : (double)hcounts[i];
+            est = (uint64_t)std::ceil(sum * (double)nsegE / (double)S);
+            est = std::max<uint64_t>(est, 1);
+            sc.release(ye.keys);
+            sc.release(ye.off);
+            // segment count: every table should end up at most ~opt_fill_pct % full
+            const double target = (double)cap * (double)e->opt_fill_pct / 100.0;
+            log2_nsegs = 0;
+            while (log2_nsegs < max_bins_log2 - (uint32_t)dbits && (double)est / (double)(1ull << log2_nsegs) > target)
+                ++log2_nsegs;
+        }
+        st.est_nterms = est;
+        CU_CHECK(e, cudaEventRecord(e->ev[3], s));
+
+        // ---- left-operand slice for multi-GPU sharding --------------------------------------
+        uint64_t x_begin = 0, x_end = nx_full;
+        if (rq.nranks > 1) {
+            x_begin = nx_full * rq.rank / rq.nranks;
+            x_end = nx_full * (rq.rank + 1) / rq.nranks;
+        }
+
+        // ---- sort the right operand, multiply, retry with a finer segmentation on table overflow --------
+        uint64_t *stage_k = nullptr, *stage_c = nullptr;
+        uint32_t *counts = nullptr, *offs = nullptr, *dflags = nullptr;
+        uint64_t total = 0;
+        float ms_prep_extra = 0;
+        for (unsigned attempt = 0;; ++attempt) {
+            if (log2_nsegs + dbits > max_bins_log2) {
+                e->err = "The homomorphic multiplication of two polynomials needs more than 2^"
+                         + std::to_string(max_bins_log2) + " segment bins; table size overflow";
+                return OBK_ERR_TABLE_OVERFLOW;
+            }
+            const uint64_t nsegs = 1ull << log2_nsegs;
+            CU_CHECK(e, cudaEventRecord(e->ev[4], s));
+            SortedY ys;
+            if (rq.merge)
+                ys = sort_operand(e, sc, dyk, dyc, nullptr, ny, W, accw, log2_nsegs, 0, 0, true);
+            else
+                ys = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, log2_nsegs, dbits, degmin_y, true);
+            stage_k = sc.alloc<uint64_t>(nsegs * cap * W);
+            stage_c = sc.alloc<uint64_t>(nsegs * cap * accw);
+            counts = sc.alloc<uint32_t>(nsegs + 1);
+            offs = sc.alloc<uint32_t>(nsegs + 2);
+            dflags = sc.alloc<uint32_t>(4);
+            CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
+            CU_CHECK(e, cudaMemsetAsync(counts, 0, (nsegs + 1) * 4, s));
+            MulParams P{};
+            uint64_t *zero_key = nullptr;
+            if (rq.merge) {
+                zero_key = sc.alloc<uint64_t>(W);
+                CU_CHECK(e, cudaMemsetAsync(zero_key, 0, W * 8, s));
+                P.xk = zero_key;
+                P.xc = nullptr;
+                P.nx = 1;
+            } else {
+                P.xk = dxk + x_begin * W;
+                P.xc = dxc + x_begin * CWx;
+                P.xdeg = xdeg ? xdeg + x_begin : nullptr;
+                P.nx = x_end - x_begin;
+            }
+            P.yk = ys.keys;
+            P.yc = ys.cfs;
+            P.yoff = ys.off;
+            P.log2_nsegs = log2_nsegs;
+            P.dbits = dbits;
+            P.ndeg = ndeg;
+            P.trunc = trunc;
+            P.lim_base = lim_base;
+            P.seg_list = nullptr;
+            P.nseg_list = (uint32_t)nsegs;
+            P.cursor = dflags + 1;
+            P.log2_cap = log2_cap;
+            uint32_t lg = 0;
+            if (rq.merge) {
+                while ((1u << (lg + 1)) <= threads) ++lg;
+            } else if (e->opt_group_lanes > 0) {
+                while ((1ll << (lg + 1)) <= e->opt_group_lanes && lg < 5) ++lg;
+            } else {
+                const double run = (double)tot_mults / (double)nx_full / (double)nsegs;
+                while (lg < 5 && (double)(1u << lg) < run) ++lg;
+            }
+            P.lg = lg;
+            st.group_lanes = 1u << lg;
+            P.max_fill = max_fill;
+            P.okeys = stage_k;
+            P.ocfs = stage_c;
+            P.counts = counts;
+            P.flags = dflags;
+            CU_CHECK(e, cudaEventRecord(e->ev[5], s));
+            launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(nsegs, (uint64_t)e->sm_count), threads, smem_mul);
+            CU_CHECK(e, cudaEventRecord(e->ev[6], s));
+            st.mul_launches += 1;
+            device_scan(e, sc, counts, offs, nsegs);
+            uint32_t hflag[4], htotal = 0;
+            CU_CHECK(e, cudaMemcpyAsync(hflag, dflags, 16, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaMemcpyAsync(&htotal, offs + nsegs, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
+            ms_prep_extra += ms;
+            if (zero_key) sc.release(zero_key);
+            sc.release(ys.keys);
+            sc.release(ys.cfs);
+            sc.release(ys.off);
+            if (hflag[0] == 0) {
+                total = htotal;
+                break;
+            }
+            // some segment's table filled up: finer segmentation (the HBM staging is re-made)
+            sc.release(stage_k);
+            sc.release(stage_c);
+            sc.release(counts);
+            sc.release(offs);
+            sc.release(dflags);
+            st.retries += 1;
+            if ((int64_t)st.retries > e->opt_max_retries || rq.merge || rq.nranks > 1) {
+                e->err = "The homomorphic multiplication of two polynomials resulted in a segment table whose size "
+                         "is larger than the maximum allowed value (shared-memory table overflow after "
+                         + std::to_string(st.retries) + " finer segmentations)";
+                return OBK_ERR_TABLE_OVERFLOW;
+            }
+            log2_nsegs += 1;
+        }
+        st.log2_nsegs = log2_nsegs;
+        st.nterms_out = total;
+        const uint64_t nsegs = 1ull << log2_nsegs;
+
+        // ---- segment-ordered dense result ---------------------------------------------------------------
+        uint64_t *rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * W);
+        uint64_t *rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
+        uint64_t *off64 = sc.alloc<uint64_t>(nsegs + 1);
+        k_compact<<<(unsigned)std::min<uint64_t>(nsegs, 4096), 256, 0, s>>>(stage_k, stage_c, counts, offs, cap, W, accw, rk, rc,
+                                                                        off64, (uint32_t)nsegs);
+        e->launches += 1;
+        CU_CHECK(e, cudaGetLastError());
+        CU_CHECK(e, cudaEventRecord(e->ev[7], s));
+
+        auto *own = new ResultOwner{e};
+        out->owner = own;
+        out->nterms = total;
+        out->key_words = W;
+        out->cf_kind = f64 ? OBK_CF_F64 : OBK_CF_INT;
+        out->cf_limbs = f64 ? 1 : accw;
+        out->log2_nsegs = log2_nsegs;
+        out->mem = rq.result_mem;
+        own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * (nsegs + 1));
+        out->seg_offsets = own->seg_offsets;
+        CU_CHECK(e, cudaMemcpyAsync(own->seg_offsets, off64, (nsegs + 1) * 8, cudaMemcpyDeviceToHost, s));
+        st.d2h_bytes += (nsegs + 1) * 8;
+        if (rq.result_mem == OBK_MEM_DEVICE) {
+            sc.detach(rk);
+            sc.detach(rc);
+            own->dkeys = rk;
+            own->dcfs = rc;
+            out->keys = rk;
+            out->cfs = rc;
+        } else {
+            own->pk = pinned_acquire(e, total * W * 8);
+            own->pc = pinned_acquire(e, total * accw * 8);
+            out->keys = (uint64_t *)e->pinned[own->pk].ptr;
+            out->cfs = e->pinned[own->pc].ptr;
+            if (total) {
+                CU_CHECK(e, cudaMemcpyAsync(out->keys, rk, total * W * 8, cudaMemcpyDeviceToHost, s));
+                CU_CHECK(e, cudaMemcpyAsync(out->cfs, rc, total * accw * 8, cudaMemcpyDeviceToHost, s));
+            }
+            st.d2h_bytes += total * (W + accw) * 8;
+        }
+        CU_CHECK(e, cudaEventRecord(e->ev[8], s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        if (rq.send_counts) {
+            for (uint32_t g = 0; g < rq.nranks; ++g) {
+                const uint64_t a = nsegs * g / rq.nranks, b = nsegs * (g + 1) / rq.nranks;
+                rq.send_counts[g] = own->seg_offsets[b] - own->seg_offsets[a];
+            }
+        }
+        float ms;
+        cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+        st.ms_h2d = ms;
+        cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]);
+        st.ms_prep = ms + ms_prep_extra;
+        cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]);
+        st.ms_estimate = ms;
+        cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]);
+        st.ms_mul = ms;
+        cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]);
+        st.ms_compact = ms;
+        cudaEventElapsedTime(&ms, e->ev[7], e->ev[8]);
+        st.ms_d2h = ms;
+        cudaEventElapsedTime(&ms, e->ev[0], e->ev[8]);
+        st.ms_total = ms;
+        st.total_launches = e->launches;
+        st.kernel = 0;
+        if (stats) *stats = st;
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        // strong-ish guarantee of the reference: the result is left empty (polynomial.hpp:1575-1580)
+        if (out->owner) {
+            obk_result_free(e, out);
+        }
+        std::memset(out, 0, sizeof(*out));
+        cudaStreamSynchronize(e->stream);
+        return f.st;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+const char *obk_version(void)
+{
+    return OBK_VERSION_STRING;
+}
+
+const char *obk_status_string(obk_status s)
+{
+    switch (s) {
+        case OBK_OK: return "ok";
+        case OBK_ERR_INVALID_ARG: return "invalid argument";
+        case OBK_ERR_KEY_OVERFLOW: return "monomial exponent overflow";
+        case OBK_ERR_TABLE_OVERFLOW: return "segment table overflow";
+        case OBK_ERR_CF_OVERFLOW: return "coefficient overflow beyond 3 limbs";
+        case OBK_ERR_CUDA: return "CUDA error";
+        case OBK_ERR_UNSUPPORTED: return "unsupported";
+        case OBK_ERR_NOMEM: return "out of memory";
+    }
+    return "unknown";
+}
+
+static thread_local std::string g_create_err;
+
+obk_status obk_engine_create(int device, obk_engine **out)
+{
+    if (!out) return OBK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        g_create_err = "no usable CUDA device (the engine has no CPU fallback)";
+        return OBK_ERR_CUDA;
+    }
+    auto *e = new obk_engine();
+    e->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete e;
+        return OBK_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) {
+        // built for sm_100a only: refuse anything else loudly
+        g_create_err = "device is not a Blackwell (sm_100) GPU";
+        delete e;
+        return OBK_ERR_CUDA;
+    }
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete e;
+        return OBK_ERR_CUDA;
+    }
+    for (auto &ev : e->ev) cudaEventCreate(&ev);
+    // keep freed scratch in the driver's stream-ordered pool (grow-only workspace)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = e;
+    return OBK_OK;
+}
+
+void obk_engine_destroy(obk_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto &b : e->pinned)
+        if (b.ptr) cudaFreeHost(b.ptr);
+    for (auto &ev : e->ev) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream)
+{
+    if (!e) return OBK_ERR_INVALID_ARG;
+    cudaStreamSynchronize(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    e->stream = (cudaStream_t)cuda_stream;
+    e->own_stream = false;
+    return OBK_OK;
+}
+
+obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
+{
+    if (!e || !name) return OBK_ERR_INVALID_ARG;
+    const std::string n(name);
+    if (n == "log2_nsegs") e->opt_log2_nsegs = value;
+    else if (n == "table_slots") e->opt_table_slots = value;
+    else if (n == "threads") e->opt_threads = value;
+    else if (n == "group_lanes") e->opt_group_lanes = value;
+    else if (n == "kernel") e->opt_kernel = value;
+    else if (n == "max_retries") e->opt_max_retries = value;
+    else if (n == "fill_pct") e->opt_fill_pct = value;
+    else {
+        e->err = "unknown option " + n;
+        return OBK_ERR_INVALID_ARG;
+    }
+    return OBK_OK;
+}
+
+const char *obk_last_error(const obk_engine *e)
+{
+    return e ? e->err.c_str() : g_create_err.c_str();
+}
+
+obk_status obk_poly_mul(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
+                        uint32_t result_mem, obk_poly_result *out, obk_stats *stats)
+{
+    if (!e) return OBK_ERR_INVALID_ARG;
+    MulRequest rq{x, y, t, result_mem};
+    return run_mul(e, rq, out, stats);
+}
+
+obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
+                                uint32_t rank, uint32_t nranks, obk_poly_result *out_partial, uint64_t *send_counts,
+                                obk_stats *stats)
+{
+    if (!e || nranks == 0 || rank >= nranks) return OBK_ERR_INVALID_ARG;
+    MulRequest rq{x, y, t, OBK_MEM_DEVICE};
+    rq.rank = rank;
+    rq.nranks = nranks;
+    rq.send_counts = send_counts;
+    return run_mul(e, rq, out_partial, stats);
+}
+
+obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t log2_nsegs, uint32_t result_mem,
+                          obk_poly_result *out, obk_stats *stats)
+{
+    if (!e || !terms) return OBK_ERR_INVALID_ARG;
+    MulRequest rq{nullptr, terms, nullptr, result_mem};
+    rq.merge = true;
+    rq.merge_log2_nsegs = log2_nsegs;
+    return run_mul(e, rq, out, stats);
+}
+
+void obk_result_free(obk_engine *e, obk_poly_result *r)
+{
+    if (!r || !r->owner) return;
+    auto *own = static_cast<ResultOwner *>(r->owner);
+    obk_engine *eng = own->e ? own->e : e;
+    if (eng) {
+        if (own->dkeys) cudaFreeAsync(own->dkeys, eng->stream);
+        if (own->dcfs) cudaFreeAsync(own->dcfs, eng->stream);
+        if (own->pk >= 0) pinned_release(eng, own->pk);
+        if (own->pc >= 0) pinned_release(eng, own->pc);
+    }
+    std::free(own->seg_offsets);
+    delete own;
+    std::memset(r, 0, sizeof(*r));
+}
+
+obk_status obk_overflow_check(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int *ok)
+{
+    if (!e || !x || !y || !ok) return OBK_ERR_INVALID_ARG;
+    // Same statistics pass as the product; report the verdict only.
+    *ok = 1;
+    if (x->nterms == 0 || y->nterms == 0 || x->nvars == 0) return OBK_OK;
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        validate_view(e, x, "x");
+        validate_view(e, y, "y");
+        const Layout L = make_layout(*x);
+        const int W = x->key_words;
+        Scratch sc(e);
+        cudaStream_t s = e->stream;
+        StatsOut *dstats = sc.alloc<StatsOut>(2);
+        k_stats_init<<<2, 64, 0, s>>>(dstats, 2);
+        const obk_poly_view *vs[2] = {x, y};
+        for (int i = 0; i < 2; ++i) {
+            const obk_poly_view *v = vs[i];
+            const uint64_t *dk = v->keys;
+            if (v->mem == OBK_MEM_HOST) {
+                uint64_t *k = sc.alloc<uint64_t>(v->nterms * W);
+                CU_CHECK(e, cudaMemcpyAsync(k, v->keys, v->nterms * W * 8, cudaMemcpyHostToDevice, s));
+                dk = k;
+            }
+            const unsigned g = (unsigned)std::min<uint64_t>((v->nterms + 255) / 256, 1024);
+            k_term_stats<<<g, 256, 0, s>>>(dk, dk, v->nterms, L, 0, 2 /* no coefficient pass */, 1, nullptr, dstats + i);
+        }
+        StatsOut hs[2];
+        CU_CHECK(e, cudaMemcpyAsync(hs, dstats, sizeof(hs), cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        i128 lim_min = 0, lim_max;
+        if (L.is_signed) {
+            auto lm = obake::detail::kpack_get_lims<std::int64_t>(L.wsize);
+            lim_min = lm.first;
+            lim_max = lm.second;
+        } else {
+            lim_max = (i128)obake::detail::kpack_get_lims<std::uint64_t>(L.wsize).second;
+        }
+        for (uint32_t v = 0; v < L.nvars; ++v) {
+            const i128 mn = unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
+            const i128 mx = unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);
+            if (mn < lim_min || mx > lim_max) *ok = 0;
+        }
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        return f.st;
+    }
+}
+
+obk_status obk_key_degrees(obk_engine *e, const obk_poly_view *x, const obk_trunc *which, int64_t *out_host)
+{
+    if (!e || !x || !out_host) return OBK_ERR_INVALID_ARG;
+    if (x->nterms == 0) return OBK_OK;
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        validate_view(e, x, "x");
+        const Layout L = make_layout(*x);
+        const int W = x->key_words;
+        uint64_t var_mask = L.nvars >= 64 ? ~0ull : ((1ull << L.nvars) - 1);
+        if (which && which->partial) {
+            var_mask = 0;
+            for (uint32_t i = 0; i < which->nidx; ++i) {
+                if (which->idx[i] >= L.nvars) {
+                    e->err = "partial-degree index outside the symbol set";
+                    return OBK_ERR_INVALID_ARG;
+                }
+                var_mask |= 1ull << which->idx[i];
+            }
+        }
+        Scratch sc(e);
+        cudaStream_t s = e->stream;
+        StatsOut *dstats = sc.alloc<StatsOut>(1);
+        k_stats_init<<<1, 64, 0, s>>>(dstats, 1);
+        const uint64_t *dk = x->keys;
+        if (x->mem == OBK_MEM_HOST) {
+            uint64_t *k = sc.alloc<uint64_t>(x->nterms * W);
+            CU_CHECK(e, cudaMemcpyAsync(k, x->keys, x->nterms * W * 8, cudaMemcpyHostToDevice, s));
+            dk = k;
+        }
+        int64_t *dd = sc.alloc<int64_t>(x->nterms);
+        const unsigned g = (unsigned)std::min<uint64_t>((x->nterms + 255) / 256, 1024);
+        k_term_stats<<<g, 256, 0, s>>>(dk, dk, x->nterms, L, var_mask, 2, 1, dd, dstats);
+        CU_CHECK(e, cudaMemcpyAsync(out_host, dd, x->nterms * 8, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        return f.st;
+    }
+}
+
+} // extern "C"

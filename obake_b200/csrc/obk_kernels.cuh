@@ -1,0 +1,639 @@
+// obk_kernels.cuh -- device code of the B200 series-product engine (sm_100a).
+//
+// What the reference does on CPU threads (include/obake/polynomials/polynomial.hpp:797-1582,
+// poly_mul_impl_mt_hm) is re-designed here around one idea it shares with the reference: the hash of a
+// Kronecker-packed monomial is the key itself (packed_monomial.hpp:172-176), monomial multiplication
+// is integer addition (:249-262), hence bucket(a*b) = (bucket(a)+bucket(b)) mod nsegs
+// (polynomial.hpp:1441-1450) and every output segment can be owned by exactly one CTA.
+//
+// Kernels in this file
+//   k_term_stats   per-variable exponent min/max (overflow check), (partial) degrees, coefficient width
+//   k_bin_count / k_scan_* / k_bin_scatter   counting sort of the right operand by (bucket, degree)
+//   k_deg_hist / k_count_mults               tot_n_mults of a truncated product
+//   k_mul          the product: one CTA owns one output segment's open-addressing table in shared memory
+//   k_compact      segment-ordered dense output
+//   k_merge        multi-GPU owner-side merge of partial segments
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace obk
+{
+
+// ------------------------------------------------------------------------------------------------
+// Key layout (Kronecker packing; kpack.hpp:219-375, tables src/kpack.cpp)
+// ------------------------------------------------------------------------------------------------
+struct Layout {
+    uint32_t nvars, psize, W, is_signed;
+    uint32_t wsize; // exponents per word: psize, or nvars for packed_monomial
+    uint32_t pad;
+    uint64_t delta;    // kpack delta for wsize components
+    uint64_t klim_min; // two's-complement bit pattern of the smallest coded value (0 if unsigned)
+    int64_t lim_min;   // smallest component value (0 if unsigned)
+};
+
+constexpr int MAX_VARS = 64;
+
+struct StatsOut {
+    // exponent extrema, stored order-preserving as signed 64-bit (unsigned values are biased by 2^63)
+    long long emin[MAX_VARS], emax[MAX_VARS];
+    long long dmin, dmax; // (partial) degree extrema, same encoding
+    unsigned cfbits;      // max bit length of |coefficient| (integers)
+    unsigned nonfinite;   // fp64: number of non-finite coefficients
+};
+
+__device__ __forceinline__ long long ord64(int64_t v, uint32_t is_signed)
+{
+    return is_signed ? (long long)v : (long long)((uint64_t)v ^ 0x8000000000000000ULL);
+}
+
+__device__ __forceinline__ long long shfl_min_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+__device__ __forceinline__ long long shfl_max_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// Unpack every exponent of every term once: feeds monomial_range_overflow_check
+// (packed_monomial.hpp:289-488 / d_packed_monomial.hpp:583-897), key_degree / key_p_degree
+// (src/polynomials/packed_monomial.cpp:334-412, d_packed_monomial.hpp:901-958) and the a-priori
+// coefficient bound.  var_mask selects the variables that count towards the degree.
+__global__ void __launch_bounds__(256) k_term_stats(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ cfs,
+                                                    uint64_t n, Layout L, uint64_t var_mask, int cf_kind, int cf_limbs,
+                                                    int64_t *__restrict__ deg_out, StatsOut *__restrict__ out)
+{
+    __shared__ long long s_min[MAX_VARS], s_max[MAX_VARS];
+    __shared__ long long s_dmin, s_dmax;
+    __shared__ unsigned s_bits, s_nonf;
+    const int tid = threadIdx.x;
+    if (tid < MAX_VARS) {
+        s_min[tid] = 0x7fffffffffffffffLL;
+        s_max[tid] = (long long)0x8000000000000000ULL;
+    }
+    if (tid == 0) {
+        s_dmin = 0x7fffffffffffffffLL;
+        s_dmax = (long long)0x8000000000000000ULL;
+        s_bits = 0;
+        s_nonf = 0;
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t nround = (n + 31) / 32 * 32; // keep warps converged for the shuffles
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < nround; i += stride) {
+        const bool live = i < n;
+        int64_t deg = 0;
+        uint32_t vi = 0;
+        for (uint32_t w = 0; w < L.W; ++w) {
+            uint64_t v = live ? keys[i * L.W + w] - L.klim_min : 0;
+            for (uint32_t j = 0; j < L.wsize && vi < L.nvars; ++j, ++vi) {
+                const uint64_t q = v / L.delta;
+                const int64_t e = (int64_t)(v - q * L.delta) + L.lim_min;
+                v = q;
+                if ((var_mask >> vi) & 1) deg += e;
+                long long o = ord64(e, L.is_signed);
+                long long mn = shfl_min_ll(live ? o : 0x7fffffffffffffffLL);
+                long long mx = shfl_max_ll(live ? o : (long long)0x8000000000000000ULL);
+                if ((tid & 31) == 0) {
+                    atomicMin(&s_min[vi], mn);
+                    atomicMax(&s_max[vi], mx);
+                }
+            }
+        }
+        if (live && deg_out) deg_out[i] = deg;
+        {
+            long long o = ord64(deg, L.is_signed);
+            long long mn = shfl_min_ll(live ? o : 0x7fffffffffffffffLL);
+            long long mx = shfl_max_ll(live ? o : (long long)0x8000000000000000ULL);
+            if ((tid & 31) == 0) {
+                atomicMin(&s_dmin, mn);
+                atomicMax(&s_dmax, mx);
+            }
+        }
+        unsigned bits = 0, nonf = 0;
+        if (live) {
+            if (cf_kind == 0) {
+                // bit length of |c| for a two's-complement cf_limbs-limb integer
+                const uint64_t *c = cfs + i * cf_limbs;
+                const bool neg = (int64_t)c[cf_limbs - 1] < 0;
+                for (int l = cf_limbs - 1; l >= 0; --l) {
+                    uint64_t m = neg ? ~c[l] : c[l];
+                    if (m) {
+                        bits = 64u * l + (64u - __clzll((long long)m));
+                        break;
+                    }
+                }
+                if (neg) bits += 1; // |-(2^k)| needs k+1 bits; cheap upper bound for every negative value
+            } else if (cf_kind == 1) {
+                const double d = __longlong_as_double((long long)cfs[i]);
+                nonf = !isfinite(d);
+            }
+        }
+        bits = __reduce_max_sync(0xffffffffu, bits);
+        nonf = __reduce_add_sync(0xffffffffu, nonf);
+        if ((tid & 31) == 0) {
+            atomicMax(&s_bits, bits);
+            if (nonf) atomicAdd(&s_nonf, nonf);
+        }
+    }
+    __syncthreads();
+    if (tid < (int)L.nvars) {
+        atomicMin(&out->emin[tid], s_min[tid]);
+        atomicMax(&out->emax[tid], s_max[tid]);
+    }
+    if (tid == 0) {
+        atomicMin(&out->dmin, s_dmin);
+        atomicMax(&out->dmax, s_dmax);
+        atomicMax(&out->cfbits, s_bits);
+        if (s_nonf) atomicAdd(&out->nonfinite, s_nonf);
+    }
+}
+
+__global__ void k_stats_init(StatsOut *s, int n)
+{
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    for (int v = threadIdx.x; v < MAX_VARS; v += blockDim.x) {
+        s[i].emin[v] = 0x7fffffffffffffffLL;
+        s[i].emax[v] = (long long)0x8000000000000000ULL;
+    }
+    if (threadIdx.x == 0) {
+        s[i].dmin = 0x7fffffffffffffffLL;
+        s[i].dmax = (long long)0x8000000000000000ULL;
+        s[i].cfbits = 0;
+        s[i].nonfinite = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hash / bucket: packed_monomial.hpp:172-176 (hash = value), d_packed_monomial.hpp:274-284 (sum of words)
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ uint64_t key_hash(const uint64_t (&k)[W])
+{
+    uint64_t h = k[0];
+#pragma unroll
+    for (int w = 1; w < W; ++w) h += k[w];
+    return h;
+}
+
+// Counting sort of the right operand by bin = (hash & mask) << dbits | (deg - degmin)
+// (replaces tbb::parallel_sort by bucket + compute_vseg + seg_sorter, polynomial.hpp:914-1105).
+// Pass 1: histogram; the value returned by the atomic is the term's rank inside its bin, so pass 3
+// scatters without a second round of atomics.
+__global__ void __launch_bounds__(256) k_bin_count(const uint64_t *__restrict__ keys, const int64_t *__restrict__ deg,
+                                                   uint64_t n, int W, uint32_t mask, int dbits, int64_t degmin,
+                                                   uint32_t *__restrict__ cnt, uint32_t *__restrict__ bin_of,
+                                                   uint32_t *__restrict__ rank_of)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t h = 0;
+        for (int w = 0; w < W; ++w) h += keys[i * W + w];
+        uint32_t bin = (uint32_t)(h & mask);
+        if (dbits) bin = (bin << dbits) | (uint32_t)(deg[i] - degmin);
+        bin_of[i] = bin;
+        rank_of[i] = atomicAdd(&cnt[bin], 1u);
+    }
+}
+
+// Exclusive scan, three passes (block-local scan, scan of block sums, add back); 4096 items per block.
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_BLOCK = SCAN_ITEMS * SCAN_THREADS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+        uint32_t si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        warp_sums[lane] = si - s; // exclusive prefix of warp sums
+        if (lane == 31) *total = si;
+    }
+    __syncthreads();
+    const uint32_t r = inc - v + warp_sums[wid];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                             uint32_t *__restrict__ block_sums, uint64_t n)
+{
+    __shared__ uint32_t total;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        v[j] = base + j < n ? in[base + j] : 0;
+        s += v[j];
+    }
+    uint32_t ex = block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        if (base + j < n) out[base + j] = ex;
+        ex += v[j];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// out has n+1 entries: out[n] = grand total.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict__ out,
+                                                           const uint32_t *__restrict__ block_prefix, uint64_t n,
+                                                           const uint32_t *__restrict__ grand_total)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    const uint32_t add = block_prefix[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j)
+        if (base + j < n) out[base + j] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *grand_total;
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ cfs,
+                                                     const int64_t *__restrict__ deg, uint64_t n, int W, int CW,
+                                                     const uint32_t *__restrict__ off, const uint32_t *__restrict__ bin_of,
+                                                     const uint32_t *__restrict__ rank_of, uint64_t *__restrict__ okeys,
+                                                     uint64_t *__restrict__ ocfs, int64_t *__restrict__ odeg)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t dst = (uint64_t)off[bin_of[i]] + rank_of[i];
+        for (int w = 0; w < W; ++w) okeys[dst * W + w] = keys[i * W + w];
+        if (ocfs)
+            for (int c = 0; c < CW; ++c) ocfs[dst * CW + c] = cfs[i * CW + c];
+        if (odeg) odeg[dst] = deg[i];
+    }
+}
+
+// tot_n_mults of a truncated product (polynomial.hpp:574-623): for each left term the number of right
+// terms whose degree passes the limit, via the degree histogram's prefix sums.
+__global__ void __launch_bounds__(256) k_deg_hist(const int64_t *__restrict__ deg, uint64_t n, int64_t degmin,
+                                                  uint32_t *__restrict__ hist)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&hist[(uint32_t)(deg[i] - degmin)], 1u);
+}
+
+// lim_base = limit - degmin_y expressed so that right-degree index d passes for left term i iff
+// d <= lim_base - xdeg[i]  (all in int64; the host has already ruled out wrap-around).
+__global__ void __launch_bounds__(256) k_count_mults(const int64_t *__restrict__ xdeg, uint64_t nx, int64_t lim_base,
+                                                     uint32_t ndeg, const uint32_t *__restrict__ prefix /* ndeg+1 */,
+                                                     unsigned long long *__restrict__ tot)
+{
+    unsigned long long local = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += stride) {
+        const int64_t r = lim_base - xdeg[i];
+        if (r < 0) continue;
+        const uint32_t d = r >= (int64_t)ndeg ? ndeg - 1 : (uint32_t)r;
+        local += prefix[d + 1];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(tot, local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Coefficient arithmetic (polynomial.hpp:1368-1384; fma3.hpp:84-88 mppp::addmul; :65-72 double)
+// ------------------------------------------------------------------------------------------------
+enum CfMode { CF_SYM = 0, CF_I1A1 = 1, CF_I1A2 = 2, CF_I1A3 = 3, CF_F64 = 4, CF_I2A3 = 5, CF_ADD1 = 6, CF_ADD2 = 7,
+              CF_ADD3 = 8, CF_ADDF = 9 };
+
+template <int MODE>
+struct CfTraits;
+// LIN: limbs of one right-operand coefficient; LACC: accumulator limbs; ADD: merge mode (the "product" is the
+// right coefficient itself, there is no left coefficient).
+#define OBK_TRAITS(M, LIN_, LACC_, F64_, SYM_, ADD_)                                                                   \
+    template <>                                                                                                        \
+    struct CfTraits<M> {                                                                                               \
+        static constexpr int LIN = LIN_, LACC = LACC_;                                                                 \
+        static constexpr bool F64 = F64_, SYM = SYM_, ADD = ADD_;                                                      \
+    };
+OBK_TRAITS(CF_SYM, 0, 0, false, true, false)
+OBK_TRAITS(CF_I1A1, 1, 1, false, false, false)
+OBK_TRAITS(CF_I1A2, 1, 2, false, false, false)
+OBK_TRAITS(CF_I1A3, 1, 3, false, false, false)
+OBK_TRAITS(CF_I2A3, 2, 3, false, false, false)
+OBK_TRAITS(CF_F64, 1, 1, true, false, false)
+OBK_TRAITS(CF_ADD1, 1, 1, false, false, true)
+OBK_TRAITS(CF_ADD2, 2, 2, false, false, true)
+OBK_TRAITS(CF_ADD3, 3, 3, false, false, true)
+OBK_TRAITS(CF_ADDF, 1, 1, true, false, true)
+#undef OBK_TRAITS
+
+// p (LACC limbs, two's complement) = a * b for LIN-limb two's-complement inputs.
+template <int LIN, int LACC>
+__device__ __forceinline__ void cf_mul(const uint64_t *a, const uint64_t *b, uint64_t *p)
+{
+    if constexpr (LIN == 1) {
+        const long long x = (long long)a[0], y = (long long)b[0];
+        p[0] = (uint64_t)(x * y);
+        if constexpr (LACC >= 2) {
+            const long long hi = __mul64hi(x, y);
+            p[1] = (uint64_t)hi;
+            if constexpr (LACC >= 3) p[2] = (uint64_t)(hi >> 63);
+        }
+    } else {
+        // 128 x 128 -> low 192 bits of the signed product (the a-priori bound guarantees it fits).
+        // Signed product mod 2^192 = unsigned schoolbook on the sign-extended operands, truncated.
+        const uint64_t a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+        const uint64_t a2 = (uint64_t)((long long)a1 >> 63), b2 = (uint64_t)((long long)b1 >> 63);
+        uint64_t r0 = a0 * b0;
+        uint64_t c = __umul64hi(a0, b0);
+        // column 1: a0*b1 + a1*b0 + c
+        uint64_t t0 = a0 * b1, t1 = a1 * b0;
+        uint64_t r1 = c + t0;
+        uint64_t cy = r1 < t0;
+        r1 += t1;
+        cy += r1 < t1;
+        // column 2 (low parts only matter mod 2^192)
+        uint64_t r2 = __umul64hi(a0, b1) + __umul64hi(a1, b0) + a1 * b1 + a0 * b2 + a2 * b0 + cy;
+        p[0] = r0;
+        p[1] = r1;
+        if constexpr (LACC >= 3) p[2] = r2;
+    }
+}
+
+template <int LACC>
+__device__ __forceinline__ void limbs_add(uint64_t *acc, const uint64_t *p)
+{
+    if constexpr (LACC == 1) {
+        acc[0] += p[0];
+    } else if constexpr (LACC == 2) {
+        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(acc[0]), "+l"(acc[1]) : "l"(p[0]), "l"(p[1]));
+    } else {
+        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, %5;"
+            : "+l"(acc[0]), "+l"(acc[1]), "+l"(acc[2])
+            : "l"(p[0]), "l"(p[1]), "l"(p[2]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The product kernel
+// ------------------------------------------------------------------------------------------------
+struct MulParams {
+    // left operand, original order (streamed by every CTA)
+    const uint64_t *xk;
+    const uint64_t *xc;
+    const int64_t *xdeg;
+    uint64_t nx;
+    // right operand, sorted by (bucket, degree); yoff has (nsegs << dbits) + 1 entries
+    const uint64_t *yk;
+    const uint64_t *yc;
+    const uint32_t *yoff;
+    uint32_t log2_nsegs;
+    uint32_t dbits;
+    uint32_t ndeg;
+    uint32_t trunc;
+    int64_t lim_base;
+    // work list: segment ids to process (NULL = all 2^log2_nsegs) and the dynamic cursor
+    const uint32_t *seg_list;
+    uint32_t nseg_list;
+    uint32_t *cursor;
+    // shared-memory table geometry
+    uint32_t log2_cap;
+    uint32_t lg; // log2(lanes per left term)
+    uint32_t max_fill;
+    // staging output: [segment][cap] slots, counts per segment
+    uint64_t *okeys;
+    uint64_t *ocfs;
+    uint32_t *counts;
+    uint32_t *flags; // [0] = number of segments whose table overflowed
+};
+
+enum : uint32_t { ST_EMPTY = 0, ST_INIT = 1, ST_FULL = 2, ST_BUSY = 3 };
+
+template <int W>
+__device__ __forceinline__ uint32_t slot_hash(const uint64_t (&k)[W], uint32_t log2_nsegs, uint32_t log2_cap)
+{
+    // All keys of a segment share their low log2_nsegs bits: mix the rest (multiply-shift).
+    uint64_t h = k[0];
+#pragma unroll
+    for (int w = 1; w < W; ++w) h = h * 0x9E3779B97F4A7C15ULL + k[w];
+    h = (h >> log2_nsegs) * 0x9E3779B97F4A7C15ULL;
+    return (uint32_t)(h >> (64 - log2_cap));
+}
+
+// One CTA owns one output segment (polynomial.hpp:1421-1553, dense_par_functor): its open-addressing
+// table lives in shared memory; every left term x_i pairs with the right bucket (seg - bucket(x_i))
+// mod nsegs (:1449-1456); truncation keeps the prefix of that bucket with deg_j <= limit - deg_i
+// (compute_end_idx2, :1187-1238 -- the bucket is degree-sorted, so the prefix is one table lookup).
+template <int W, int MODE>
+__global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
+{
+    using T = CfTraits<MODE>;
+    constexpr int ACCW = T::SYM ? 0 : T::LACC;
+    constexpr int CW = T::SYM ? 0 : T::LIN;         // limbs of a right-operand coefficient
+    constexpr int XCW = (T::SYM || T::ADD) ? 0 : CW;  // limbs of a left-operand coefficient
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t cap = 1u << P.log2_cap;
+    uint64_t *tkeys = reinterpret_cast<uint64_t *>(smem_raw);           // [W][cap]
+    uint64_t *tacc = tkeys + (size_t)W * cap;                          // [ACCW][cap]
+    uint32_t *tstate = reinterpret_cast<uint32_t *>(tacc + (size_t)ACCW * cap); // [cap]
+    __shared__ uint32_t s_seg, s_count, s_out, s_over;
+
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const uint32_t G = 1u << P.lg;
+    const uint32_t gid = tid >> P.lg, lg_lane = tid & (G - 1), ngroups = nthr >> P.lg;
+    const uint32_t smask = (1u << P.log2_nsegs) - 1u;
+    const uint32_t cmask = cap - 1u;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s_seg = atomicAdd(P.cursor, 1u);
+            s_count = 0;
+            s_out = 0;
+            s_over = 0;
+        }
+        for (uint32_t h = tid; h < cap; h += nthr) tstate[h] = ST_EMPTY;
+        __syncthreads();
+        const uint32_t work = s_seg;
+        if (work >= P.nseg_list) break;
+        const uint32_t seg = P.seg_list ? P.seg_list[work] : work;
+
+        for (uint64_t i = gid; i < P.nx; i += ngroups) {
+            if (*(volatile uint32_t *)&s_over) break;
+            uint64_t kx[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) kx[w] = __ldg(P.xk + i * W + w);
+            const uint32_t bx = (uint32_t)key_hash<W>(kx) & smask;
+            const uint32_t by = (seg - bx) & smask;
+            uint32_t y0, y1;
+            if (P.trunc) {
+                const int64_t r = P.lim_base - __ldg(P.xdeg + i);
+                if (r < 0) continue;
+                const uint32_t d = r >= (int64_t)P.ndeg ? P.ndeg - 1u : (uint32_t)r;
+                y0 = __ldg(P.yoff + ((size_t)by << P.dbits));
+                y1 = __ldg(P.yoff + ((size_t)by << P.dbits) + d + 1u);
+            } else {
+                y0 = __ldg(P.yoff + by);
+                y1 = __ldg(P.yoff + by + 1u);
+            }
+            if (y0 == y1) continue;
+            uint64_t cx[XCW > 0 ? XCW : 1];
+#pragma unroll
+            for (int c = 0; c < XCW; ++c) cx[c] = __ldg(P.xc + i * XCW + c);
+
+            for (uint32_t t = y0 + lg_lane; t < y1; t += G) {
+                uint64_t k[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg(P.yk + (size_t)t * W + w); // monomial_mul
+                uint64_t p[ACCW > 0 ? ACCW : 1];
+                if constexpr (!T::SYM) {
+                    uint64_t cy[CW];
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) cy[c] = __ldg(P.yc + (size_t)t * CW + c);
+                    if constexpr (T::ADD) {
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) p[c] = cy[c];
+                    } else if constexpr (T::F64) {
+                        // cf += c1*c2 with two roundings (no FP_FAST_FMA in the reference build, fma3.hpp:65-72)
+                        p[0] = (uint64_t)__double_as_longlong(
+                            __dmul_rn(__longlong_as_double((long long)cx[0]), __longlong_as_double((long long)cy[0])));
+                    } else {
+                        cf_mul<T::LIN, T::LACC>(cx, cy, p);
+                    }
+                }
+                // ---- find-or-insert + accumulate ---------------------------------------------
+                uint32_t h = slot_hash<W>(k, P.log2_nsegs, P.log2_cap);
+                uint32_t probes = 0;
+                for (;;) {
+                    const uint32_t st = *(volatile uint32_t *)&tstate[h];
+                    if (st >= ST_FULL) {
+                        bool eq = true;
+#pragma unroll
+                        for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
+                        if (eq) {
+                            if constexpr (T::SYM) {
+                                break;
+                            } else {
+                                if (st == ST_BUSY) continue;
+                                if (atomicExch(&tstate[h], ST_BUSY) != ST_FULL) continue;
+                                __threadfence_block();
+                                if constexpr (T::F64) {
+                                    double a = __longlong_as_double((long long)*(volatile uint64_t *)&tacc[h]);
+                                    a = __dadd_rn(a, __longlong_as_double((long long)p[0]));
+                                    *(volatile uint64_t *)&tacc[h] = (uint64_t)__double_as_longlong(a);
+                                } else {
+                                    uint64_t a[ACCW];
+#pragma unroll
+                                    for (int l = 0; l < ACCW; ++l) a[l] = *(volatile uint64_t *)&tacc[(size_t)l * cap + h];
+                                    limbs_add<ACCW>(a, p);
+#pragma unroll
+                                    for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = a[l];
+                                }
+                                __threadfence_block();
+                                *(volatile uint32_t *)&tstate[h] = ST_FULL;
+                                break;
+                            }
+                        }
+                        h = (h + 1u) & cmask;
+                        if (++probes > cap) {
+                            s_over = 1;
+                            break;
+                        }
+                        continue;
+                    }
+                    if (st == ST_EMPTY) {
+                        if (atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) != ST_EMPTY) continue;
+#pragma unroll
+                        for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
+#pragma unroll
+                        for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = p[l];
+                        __threadfence_block();
+                        *(volatile uint32_t *)&tstate[h] = ST_FULL;
+                        if (atomicAdd(&s_count, 1u) + 1u > P.max_fill) s_over = 1;
+                        break;
+                    }
+                    // ST_INIT: another thread is writing this slot's key; look again
+                }
+                if (*(volatile uint32_t *)&s_over) break;
+            }
+        }
+        __syncthreads();
+        // ---- flush: erase zeros (polynomial.hpp:1528-1540) and stage the segment -------------------
+        const bool over = s_over != 0;
+        if constexpr (T::SYM) {
+            if (tid == 0) {
+                P.counts[work] = over ? 0xffffffffu : s_count;
+                if (over) atomicAdd(&P.flags[0], 1u);
+            }
+        } else {
+            if (!over) {
+                uint64_t *ok = P.okeys + (size_t)seg * cap * W;
+                uint64_t *oc = P.ocfs + (size_t)seg * cap * ACCW;
+                for (uint32_t h = tid; h < cap; h += nthr) {
+                    if (tstate[h] != ST_FULL) continue;
+                    uint64_t a[ACCW];
+                    bool nz = false;
+#pragma unroll
+                    for (int l = 0; l < ACCW; ++l) {
+                        a[l] = tacc[(size_t)l * cap + h];
+                        nz |= a[l] != 0;
+                    }
+                    if constexpr (T::F64) nz = __longlong_as_double((long long)a[0]) != 0.0;
+                    if (!nz) continue;
+                    const uint32_t pos = atomicAdd(&s_out, 1u);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) ok[(size_t)pos * W + w] = tkeys[(size_t)w * cap + h];
+#pragma unroll
+                    for (int l = 0; l < ACCW; ++l) oc[(size_t)pos * ACCW + l] = a[l];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                P.counts[seg] = over ? 0u : s_out;
+                if (over) atomicAdd(&P.flags[0], 1u);
+            }
+        }
+    }
+}
+
+// Segment-ordered dense output: one CTA copies one segment's staged terms to its final offset.
+__global__ void __launch_bounds__(256) k_compact(const uint64_t *__restrict__ skeys, const uint64_t *__restrict__ scfs,
+                                                 const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offs,
+                                                 uint32_t cap, int W, int ACCW, uint64_t *__restrict__ okeys,
+                                                 uint64_t *__restrict__ ocfs, uint64_t *__restrict__ off64, uint32_t nsegs)
+{
+    for (uint32_t seg = blockIdx.x; seg < nsegs; seg += gridDim.x) {
+        const uint32_t n = counts[seg], o = offs[seg];
+        const uint64_t *sk = skeys + (size_t)seg * cap * W;
+        const uint64_t *sc = scfs + (size_t)seg * cap * ACCW;
+        for (uint32_t i = threadIdx.x; i < n * W; i += blockDim.x) okeys[(size_t)o * W + i] = sk[i];
+        for (uint32_t i = threadIdx.x; i < n * ACCW; i += blockDim.x) ocfs[(size_t)o * ACCW + i] = sc[i];
+        if (threadIdx.x == 0) {
+            off64[seg] = o;
+            if (seg == nsegs - 1) off64[nsegs] = (uint64_t)o + n;
+        }
+    }
+}
+
+} // namespace obk

@@ -199,6 +199,8 @@ def random_poly(rng: np.random.Generator, nterms: int, nvars: int, max_expo: int
     """Random sparse polynomial with distinct monomials (seeded by the caller's Generator)."""
     seen = {}
     lo = -max_expo if signed_expos else 0
+    if nterms > (max_expo - lo + 1) ** nvars:
+        raise ValueError("more terms requested than distinct monomials exist")
     while len(seen) < nterms:
         need = nterms - len(seen)
         e = rng.integers(lo, max_expo + 1, size=(need * 2 + 4, nvars))

@@ -1,0 +1,346 @@
+"""Parity tests proper: the CUDA engine (through the C ABI) against the CPU oracle on the same inputs,
+the reference's known answers, and size-independent properties at the benchmark sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+from obake_b200 import kpack, workloads as wl
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+KA = json.load(open(os.path.join(HERE, "golden", "known_answers.json")))
+NT = os.cpu_count() or 1
+
+
+def as_key_dict(keys, cfs):
+    if keys.shape[1] == 1:
+        return dict(zip(keys[:, 0].tolist(), cfs if isinstance(cfs, list) else cfs.tolist()))
+    return {tuple(r): c for r, c in zip(keys.tolist(), cfs if isinstance(cfs, list) else cfs.tolist())}
+
+
+def check_exact(engine, x, y, limit=None, idx=None, nthreads=NT):
+    p = engine.mul(x, y, limit=limit, idx=idx)
+    r = orc.poly_mul(x, y, limit=limit, idx=idx, nthreads=nthreads)
+    assert r["status"] == 0
+    got = p.as_dict()
+    ref = as_key_dict(r["keys"], r["cfs"])
+    assert len(got) == p.nterms, "duplicate keys in the engine's result"
+    assert got == ref
+    assert p.stats["term_products"] == r["n_mults"]
+    check_segments(p)
+    return p
+
+
+def check_segments(p):
+    """series invariants (series.hpp:866-909): term in table hash & (2^k-1); no zero coefficient."""
+    n = p.nterms
+    so = p.seg_offsets
+    assert so[0] == 0 and so[-1] == n and (np.diff(so.astype(np.int64)) >= 0).all()
+    if n == 0:
+        return
+    keys = p.keys
+    h = keys.sum(axis=1, dtype=np.uint64)
+    seg = np.searchsorted(so, np.arange(n), side="right") - 1
+    assert ((h & np.uint64((1 << p.log2_nsegs) - 1)) == seg.astype(np.uint64)).all()
+    if p.is_f64:
+        assert (p.cfs != 0).all()
+    else:
+        assert (p.cf_limb_array != 0).any(axis=1).all()
+
+
+def check_f64(engine, x, y, limit=None, idx=None, rtol=1e-12):
+    """fp64 parity: same key set; |got - ref| <= rtol * sum|c1*c2| bound (BASELINE.json: relative 1e-12)."""
+    p = engine.mul(x, y, limit=limit, idx=idx)
+    r = orc.poly_mul(x, y, limit=limit, idx=idx, nthreads=NT)
+    got, ref = p.as_dict(), as_key_dict(r["keys"], r["cfs"])
+    scale = float(np.abs(x.cfs).max() * np.abs(y.cfs).max()) * min(x.nterms, y.nterms)
+    for k in set(got) | set(ref):
+        a, b = got.get(k, 0.0), ref.get(k, 0.0)
+        if k in got and k in ref:
+            assert abs(a - b) <= rtol * max(abs(b), abs(a)) + 1e-15 * scale, (k, a, b)
+        else:
+            # exact cancellation in one summation order may leave a tiny residue in the other (Appendix A.5)
+            assert abs(a - b) <= 1e-13 * scale, (k, a, b)
+    check_segments(p)
+    return p
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_small_identities(engine):
+    # test/polynomials_polynomial_00.cpp:198-214
+    sy = ("a", "b")
+    three = wl.from_dict(sy, {(0, 0): 3}, "i64")
+    four = wl.from_dict(sy, {(0, 0): 4}, "i64")
+    p = engine.mul(three, four)
+    assert p.as_dict() == {0: 12}
+    apb = wl.from_dict(sy, {(1, 0): 1, (0, 1): 1}, "i64")
+    amb = wl.from_dict(sy, {(1, 0): 1, (0, 1): -1}, "i64")
+    p = check_exact(engine, apb, amb)
+    assert p.nterms == 2  # a^2 - b^2: the cancelled cross term is erased
+    a2b2 = wl.from_dict(sy, {(2, 0): 1, (0, 2): 1}, "i64")
+    a2mb2 = wl.from_dict(sy, {(2, 0): 1, (0, 2): -1}, "i64")
+    p = check_exact(engine, a2b2, a2mb2)
+    assert sorted(p.cfs) == [-1, 1]
+
+
+def test_empty_operands(engine):
+    sy = ("a", "b")
+    x = wl.from_dict(sy, {(1, 0): 1}, "i64")
+    e = wl.Operand(sy, np.zeros((0, 2), dtype=np.int64), np.zeros(0, dtype=object), "i64")
+    for a, b in ((x, e), (e, x), (e, e)):
+        p = engine.mul(a, b)
+        assert p.nterms == 0 and p.seg_offsets.tolist() == [0, 0]
+
+
+def test_zero_variables(engine):
+    x = wl.Operand((), np.zeros((1, 0), dtype=np.int64), np.array([7], dtype=object), "u64")
+    y = wl.Operand((), np.zeros((1, 0), dtype=np.int64), np.array([-6], dtype=object), "u64")
+    assert engine.mul(x, y).as_dict() == {0: -42}
+
+
+@pytest.mark.parametrize("tn", ["i64", "u64"])
+def test_random_vs_oracle(engine, tn):
+    rng = np.random.default_rng(11)
+    for nv, n1, n2, mx, bits in ((3, 40, 60, 6, 30), (6, 300, 100, 3, 20), (1, 50, 50, 1000, 40), (5, 2000, 1500, 9, 31),
+                                 (21, 500, 400, 1, 10)):
+        x = wl.random_poly(rng, n1, nv, mx, bits, tn, signed_expos=(tn == "i64" and mx <= 3))
+        y = wl.random_poly(rng, n2, nv, mx, bits, tn, signed_expos=(tn == "i64" and mx <= 3))
+        check_exact(engine, x, y)
+        check_exact(engine, y, x)  # operand order (Appendix A.7)
+
+
+def test_squaring_same_operand(engine):
+    rng = np.random.default_rng(12)
+    x = wl.random_poly(rng, 500, 4, 7, 25, "u64")
+    check_exact(engine, x, x)
+
+
+def test_accumulator_widths(engine):
+    rng = np.random.default_rng(13)
+    for bits, want in ((8, 1), (30, 2), (45, 2), (61, 3), (63, 3)):
+        x = wl.random_poly(rng, 300, 2, 20, bits, "u64")
+        y = wl.random_poly(rng, 300, 2, 20, bits, "u64")
+        p = check_exact(engine, x, y)
+        assert p.cf_limbs == want, (bits, p.cf_limbs)
+    # all-positive 61-bit dense product: sums really exceed 128 bits
+    x = wl.random_poly(rng, 400, 2, 19, 61, "u64", signed_cfs=False)
+    p = check_exact(engine, x, x)
+    assert max(abs(c) for c in p.cfs) >= 1 << 127
+
+
+def test_two_limb_inputs(engine):
+    rng = np.random.default_rng(14)
+    x = wl.random_poly(rng, 200, 3, 6, 90, "u64")
+    y = wl.random_poly(rng, 200, 3, 6, 80, "u64")
+    p = check_exact(engine, x, y)
+    assert p.cf_limbs == 3
+
+
+def test_coefficient_overflow_is_detected(engine):
+    rng = np.random.default_rng(15)
+    x = wl.random_poly(rng, 50, 2, 9, 120, "u64")
+    y = wl.random_poly(rng, 50, 2, 9, 120, "u64")
+    with pytest.raises(OverflowError, match="coefficient overflow beyond 3 limbs"):
+        engine.mul(x, y)
+
+
+def test_exponent_overflow_throws(engine):
+    # test/polynomials_polynomial_00.cpp:216-238
+    msg = KA["overflow_message"]["value"]
+    for tn in ("i64", "u64"):
+        lo, hi = kpack.lims(tn, 2)
+        sy = ("a", "b")
+        big = wl.from_dict(sy, {(hi, 0): 1, (0, 1): 1}, tn)
+        one = wl.from_dict(sy, {(1, 0): 1}, tn)
+        with pytest.raises(OverflowError, match=msg):
+            engine.mul(big, one)
+        assert not engine.overflow_check(big, one)
+        assert engine.overflow_check(one, one)
+        ok = wl.from_dict(sy, {(hi - 1, 0): 1, (0, 1): 1}, tn)
+        check_exact(engine, ok, one)
+    lo, hi = kpack.lims("i64", 2)
+    small = wl.from_dict(("a", "b"), {(lo, 0): 1}, "i64")
+    neg = wl.from_dict(("a", "b"), {(-1, 0): 1}, "i64")
+    with pytest.raises(OverflowError, match=msg):
+        engine.mul(small, neg)
+
+
+def test_degrees_and_overflow_entry_points(engine):
+    rng = np.random.default_rng(16)
+    for tn, psize in (("u64", 0), ("i64", 0), ("u64", 4), ("i64", 3)):
+        x = wl.random_poly(rng, 3000, 10, 5, 10, tn, psize, signed_expos=tn == "i64")
+        assert (engine.degrees(x) == x.expos.sum(axis=1)).all()
+        assert (engine.degrees(x, [1, 4, 9]) == x.expos[:, [1, 4, 9]].sum(axis=1)).all()
+        assert (engine.degrees(x, []) == 0).all()
+
+
+def test_fateman_closed_form(engine):
+    for n, tn in ((6, "u64"), (10, "i64"), (12, "u64")):
+        f, g = wl.fateman(n, 4, tn)
+        p = engine.mul(f, g)
+        exp = wl.fateman_expected(n)
+        expk = {kpack.pack(k, tn) & ((1 << 64) - 1): v for k, v in exp.items()}
+        assert p.as_dict() == expk
+        assert p.stats["term_products"] == f.nterms * g.nterms
+
+
+def test_sparse_n10_known_answer(engine):
+    # test/polynomials_polynomial_00.cpp:398-424: 2 096 600 terms, integer<1> and double
+    f, g = wl.sparse_mp(10, "i64")
+    p = check_exact(engine, f, g)
+    assert p.nterms == KA["sparse_n10_terms"]["value"]
+    pd = engine.mul(f.as_f64(), g.as_f64())
+    assert pd.nterms == KA["sparse_n10_terms"]["value"]
+    check_segments(pd)
+
+
+def test_rect_pow20_known_answer(engine):
+    # test/polynomials_polynomial_04.cpp:264-285
+    base = wl.mp_base("i64")
+    cur = base
+    for _ in range(19):
+        p = engine.mul(base, cur)
+        keys = p.keys
+        cur = wl.Operand(base.symbols, np.zeros((p.nterms, 5), dtype=np.int64), np.array(p.cfs, dtype=object), "i64", 0,
+                         keys)
+    assert cur.nterms == KA["rect_pow20_terms"]["value"]
+
+
+def test_truncated_small(engine):
+    # test/polynomials_polynomial_01.cpp:131-183: (x+y)(x-y) and (zx+y)(x-y-1) with limits 100/2/1/0/-1
+    sy = ("x", "y", "z")
+    a = wl.from_dict(sy, {(1, 0, 0): 1, (0, 1, 0): 1}, "i64")
+    b = wl.from_dict(sy, {(1, 0, 0): 1, (0, 1, 0): -1}, "i64")
+    c = wl.from_dict(sy, {(1, 0, 1): 1, (0, 1, 0): 1}, "i64")
+    d = wl.from_dict(sy, {(1, 0, 0): 1, (0, 1, 0): -1, (0, 0, 0): -1}, "i64")
+    for lim in (100, 2, 1, 0, -1):
+        check_exact(engine, a, b, limit=lim)
+        check_exact(engine, c, d, limit=lim)
+        for idx in ([0], [1, 2], []):
+            if idx == []:
+                # partial degree over no symbol: every degree is 0, nothing is cut unless limit < 0
+                p = engine.mul(c, d, limit=lim, idx=idx)
+                full = engine.mul(c, d)
+                assert p.as_dict() == (full.as_dict() if lim >= 0 else {})
+            else:
+                check_exact(engine, c, d, limit=lim, idx=idx)
+
+
+def test_truncated_n8_reference_cases(engine):
+    # test/polynomials_polynomial_01.cpp:185-236, _04.cpp:239-262
+    f, g = wl.sparse_mp(8, "i64")
+    full = check_exact(engine, f, g)
+    assert full.nterms == 591235
+    fd = full.as_dict()
+    for lim in (1000, 80):
+        assert engine.mul(f, g, limit=lim).as_dict() == fd
+    for lim in (50, 40, 5, 0):
+        p = check_exact(engine, f, g, limit=lim)
+        deg = engine.degrees(wl.Operand(f.symbols, np.zeros((p.nterms, 5), dtype=np.int64), np.zeros(p.nterms), "i64", 0,
+                                        p.keys))
+        assert deg.max() == (lim if lim else 0)
+    assert engine.mul(f, g, limit=0).as_dict() == {0: 1}
+    p = engine.mul(f, g, limit=-1)
+    assert p.nterms == 0 and p.stats["term_products"] == 0
+
+
+def test_partial_degree_truncation(engine):
+    # test/polynomials_polynomial_02.cpp:182-327, _05.cpp:105-126
+    f, g = wl.sparse_mp(5, "i64")
+    for idx in ([0], [1, 3], [0, 1, 2, 3, 4]):
+        for lim in (0, 3, 9, 100):
+            check_exact(engine, f, g, limit=lim, idx=idx)
+
+
+def test_unsigned_limit_conversion(engine):
+    # limit is passed as the bit pattern of T: a huge unsigned limit never cuts
+    f, g = wl.sparse_mp(3, "u64")
+    full = engine.mul(f, g).as_dict()
+    assert engine.mul(f, g, limit=-1).as_dict() == full  # (uint64)-1
+    check_exact(engine, f, g, limit=7)
+
+
+def test_d_packed_vs_packed(engine):
+    rng = np.random.default_rng(17)
+    x = wl.random_poly(rng, 800, 10, 4, 20, "u64", 0)
+    y = wl.random_poly(rng, 600, 10, 4, 20, "u64", 0)
+    ref = orc.result_to_dict(orc.poly_mul(x, y, nthreads=NT), x)
+    for tn, psize in (("u64", 8), ("u64", 4), ("i64", 3), ("u64", 10)):
+        xd, yd = x.with_layout(tn, psize), y.with_layout(tn, psize)
+        p = check_exact(engine, xd, yd)
+        r = {"keys": p.keys, "cfs": p.cfs}
+        assert orc.result_to_dict(r, xd) == ref
+        check_exact(engine, xd, yd, limit=12)
+        check_exact(engine, xd, yd, limit=9, idx=[0, 5, 9])
+
+
+def test_f64_random_and_audi_small(engine):
+    rng = np.random.default_rng(18)
+    x = wl.random_poly(rng, 1500, 4, 8, f64=True)
+    y = wl.random_poly(rng, 1200, 4, 8, f64=True)
+    check_f64(engine, x, y)
+    f, g = wl.audi("u64", 0, nvars=6, n=6)
+    check_f64(engine, f, g, limit=6)
+    fd, gd = wl.audi("u64", 4, nvars=6, n=6)
+    check_f64(engine, fd, gd, limit=6)
+
+
+def test_f64_first_contribution_and_signed_zero(engine):
+    sy = ("a",)
+    x = wl.from_dict(sy, {(0,): 1.5, (1,): -1.5}, "u64", f64=True)
+    y = wl.from_dict(sy, {(0,): 2.0, (1,): 2.0}, "u64", f64=True)
+    p = engine.mul(x, y)
+    assert p.as_dict() == {0: 3.0, 2: -3.0}  # the middle term cancels exactly and is erased
+
+
+def test_skewed_buckets_force_retry(engine):
+    # every key is a multiple of 1024: all terms hash to segment 0 until the segmentation is fine enough
+    n = 1500
+    e = (np.arange(n, dtype=np.int64) * 1024).reshape(-1, 1)
+    x = wl.Operand(("a",), e, np.array([i + 1 for i in range(n)], dtype=object), "u64")
+    p = check_exact(engine, x, x)
+    assert p.nterms == 2 * n - 1
+
+
+def test_forced_geometry_options(engine):
+    rng = np.random.default_rng(19)
+    x = wl.random_poly(rng, 1000, 4, 7, 25, "u64")
+    y = wl.random_poly(rng, 900, 4, 7, 25, "u64")
+    ref = check_exact(engine, x, y).as_dict()
+    try:
+        for opts in ({"log2_nsegs": 0}, {"log2_nsegs": 7}, {"group_lanes": 1}, {"group_lanes": 32},
+                     {"table_slots": 1024, "threads": 256}, {"threads": 64}):
+            for k, v in opts.items():
+                engine.set_option(k, v)
+            assert engine.mul(x, y).as_dict() == ref, opts
+            for k in opts:
+                engine.set_option(k, {"log2_nsegs": -1, "group_lanes": 0, "table_slots": 0, "threads": 1024}[k])
+    finally:
+        for k, v in {"log2_nsegs": -1, "group_lanes": 0, "table_slots": 0, "threads": 1024}.items():
+            engine.set_option(k, v)
+
+
+def test_benchmark_size_properties(engine):
+    """F20 at full size: closed form on every coefficient; S12: term count + checksum identity
+    sum(cf) == f(1)*g(1) (evaluate at all-ones) and linearity in the left operand."""
+    f, g = wl.fateman(20, 4, "u64")
+    p = engine.mul(f, g)
+    assert p.nterms == 135751
+    exp = wl.fateman_expected(20)
+    expk = {kpack.pack(k, "u64"): v for k, v in exp.items()}
+    assert p.as_dict() == expk
+    f, g = wl.sparse_mp(12, "u64")
+    p = engine.mul(f, g)
+    assert p.nterms == 5821335
+    assert sum(p.cfs) == 13 ** 24
+    check_segments(p)
+    half = f.nterms // 2
+    a = engine.mul(f.take(slice(0, half)), g)
+    b = engine.mul(f.take(slice(half, None)), g)
+    da, db = a.as_dict(), b.as_dict()
+    for k, v in db.items():
+        da[k] = da.get(k, 0) + v
+    assert {k: v for k, v in da.items() if v} == p.as_dict()
