@@ -1,0 +1,405 @@
+#!/usr/bin/env python3
+"""bench.py -- term-products/s of the series product on B200 (driver contract, see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload F30|F20|S12|S16T|D5|AUDI] [--impl reference]
+
+A "step" is one full product of the named workload through the C ABI (statistics/overflow check,
+size estimate, bucket sort, product kernel, compaction).  `value` times it with the operands already
+resident in HBM and the result left in HBM; `e2e` times the same call with HOST (pinned) operands and a
+HOST result, copies included.  `roofline` is the product kernel alone against the measured HBM peak using
+the algorithmic bytes per term-product of SURVEY 8(d).  `cpu_baseline` times the CPU restatement of obake's
+poly_mul_impl_mt_hm (oracle/) on this box's host cores (the obake binary itself cannot be built here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "term_products_per_s"
+UNIT = "term-products/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="F30")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--also", default="", help="comma list of extra workloads to report in 'also' (N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(key_words: int, f64: bool, lin: int, lacc: int) -> int:
+    """B = K_in + C_in + K_slot + 2*A  per term-product."""
+    K = 8 * key_words
+    C_in = 8 if f64 else 8 * lin
+    A = 8 if f64 else 8 * lacc
+    return K + C_in + K + 2 * A
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median of the upper half: samples taken while a kernel was resident
+        sm.sort()
+        load = sm[len(sm) // 2:]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------
+def operand_arrays(op, lin):
+    from obake_b200.engine import int_to_limbs
+
+    keys = np.ascontiguousarray(op.keys, dtype=np.uint64)
+    if op.is_f64:
+        cfs = np.ascontiguousarray(op.cfs, dtype=np.float64).view(np.uint64).reshape(-1, 1)
+    else:
+        cfs = int_to_limbs(op.cfs, lin)
+    return keys, cfs
+
+
+def cpu_reference_run(f, g, limit, threads, budget_products=3.0e9):
+    """Time the oracle (CPU restatement of obake's algorithm) on a bounded sample of the workload: the first
+    rows of the left operand so that at most `budget_products` term products are formed."""
+    import orc
+
+    nx = f.nterms
+    full = nx * g.nterms
+    take = nx if full <= budget_products else max(1, int(nx * budget_products / full))
+    fs = f if take == nx else f.take(slice(0, take))
+    lacc = orc.acc_limbs_bound(f, g)
+    r = orc.poly_mul(fs, g, limit=limit, nthreads=threads, lacc=None if f.is_f64 else lacc)
+    assert r["status"] == 0
+    sample = "full workload" if take == nx else f"first {take} of {nx} left-operand terms x whole right operand"
+    return r["n_mults"] / max(r["seconds"], 1e-9), r["seconds"], r["n_mults"], sample
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU restatement on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import orc
+    from obake_b200 import workloads as wl
+
+    f, g, limit, desc = wl.named(args.workload)
+    cores = orc.lib().orc_hardware_concurrency()
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_run(f, g, limit, cores, budget_products=2.0e8)
+    vals, secs, sample, prods = [], [], "", 0
+    for _ in range(max(1, args.steps)):
+        v, s, prods, sample = cpu_reference_run(f, g, limit, cores, budget_products=1.5e9)
+        vals.append(v)
+        secs.append(s)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(secs) * 1e3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64" if f.is_f64 else "int64 limbs (exact)",
+        "data": "synthetic (closed-form operands)",
+        "config": {"workload": args.workload, "description": desc, "truncation": limit,
+                   "note": "CPU restatement of obake poly_mul_impl_mt_hm (oracle/), not the obake binary: mp++/Boost/"
+                           "TBB are not installable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "products_per_step": prods},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------
+def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with_e2e=True):
+    from obake_b200 import _capi, workloads as wl
+    from obake_b200.engine import needed_limbs, raw_view
+
+    f, g, limit, desc = wl.named(name)
+    lin = 1 if f.is_f64 else max(needed_limbs(f.cfs), needed_limbs(g.cfs))
+    kind = _capi.OBK_CF_F64 if f.is_f64 else _capi.OBK_CF_INT
+    signed = 1 if f.tname.startswith("i") else 0
+    hk, hc = {}, {}
+    dk, dc = {}, {}
+    for tag, op in (("f", f), ("g", g)):
+        k, c = operand_arrays(op, lin)
+        hk[tag] = torch.from_numpy(k.view(np.int64)).pin_memory()
+        hc[tag] = torch.from_numpy(c.view(np.int64)).pin_memory()
+        dk[tag] = hk[tag].to(dev)
+        dc[tag] = hc[tag].to(dev)
+
+    def view(tag, op, mem):
+        kk, cc = (dk, dc) if mem == _capi.OBK_MEM_DEVICE else (hk, hc)
+        return raw_view(op.nterms, op.key_words, signed, op.nvars, op.psize, kind, lin, mem, kk[tag].data_ptr(),
+                        cc[tag].data_ptr())
+
+    vfd, vgd = view("f", f, _capi.OBK_MEM_DEVICE), view("g", g, _capi.OBK_MEM_DEVICE)
+    vfh, vgh = view("f", f, _capi.OBK_MEM_HOST), view("g", g, _capi.OBK_MEM_HOST)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    if world > 1:
+        import torch.distributed as dist
+        from obake_b200 import dist as obd
+
+    def step_device():
+        if world == 1:
+            p = eng.mul_views(vfd, vgd, limit=limit, result_mem=_capi.OBK_MEM_DEVICE)
+            return p, {}
+        return obd.sharded_mul(eng, vfd, vgd, limit=limit)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        p, _info = step_device()
+        p.free()
+    sampler = ClockSampler(dev.index if dev.index is not None else 0)
+    barrier()
+    sampler.start()
+    times, kernel_ms, launches = [], [], 0
+    stats_last, nterms_out, products, info_last = None, 0, 0, {}
+    t_wall0 = time.perf_counter()
+    for _ in range(steps):
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        p, info = step_device()
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+        st = info.get("partial_stats", p.stats)
+        kernel_ms.append(st["ms_mul"])
+        launches += st["total_launches"] + (info["merge_stats"]["total_launches"] if info else 0)
+        stats_last, info_last = st, info
+        products = st["term_products"]
+        nterms_out = p.nterms
+        p.free()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms = float(np.mean(times))
+    if world > 1:
+        t = torch.tensor([ms, float(nterms_out), float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0].item())
+        nterms_out = int(tsum[1].item())
+        kernel_mean = float(tmax[2].item())
+    else:
+        kernel_mean = float(np.mean(kernel_ms))
+
+    # full-job products: every rank reports the products of the WHOLE job (the partial kernel did 1/world of them)
+    f64 = f.is_f64
+    lacc = stats_last["acc_limbs"]
+    B = algorithmic_bytes(f.key_words, f64, lin, lacc)
+    peak, peak_src = measured_peak()
+    per_launch_products = products / world
+    achieved = B * per_launch_products / (kernel_mean * 1e-3) / 1e9
+    out = {
+        "workload": name, "description": desc, "products": int(products), "terms_out": int(nterms_out),
+        "ms_per_step": ms, "value": products / (ms * 1e-3), "kernel_ms": kernel_mean,
+        "stats": {k: (float(v) if isinstance(v, float) else int(v)) for k, v in stats_last.items()},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_mul", "algorithmic_bytes_per_product": B,
+                     "peak_source": peak_src, "kernel_ms": kernel_mean,
+                     "kernel_share_of_step": kernel_mean / ms},
+        "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
+        "lin": lin, "lacc": int(lacc), "f64": f64, "limit": limit,
+    }
+    if info_last:
+        out["exchange"] = {k: info_last[k] for k in ("partial_terms", "sent_rows", "recv_rows", "bytes_sent", "log2_nsegs")}
+    # ---- end to end: host (pinned) operands in, host result out, through the same public call ---------------
+    if with_e2e and world == 1:
+        for _ in range(min(warmup, 2)):
+            eng.mul_views(vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST).free()
+        et, h2d, d2h = [], 0, 0
+        for _ in range(max(3, steps // 2)):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            p = eng.mul_views(vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
+            checksum = int(p.nterms)  # the result is on the host when the call returns
+            et.append(time.perf_counter() - t0)
+            h2d, d2h = p.stats["h2d_bytes"], p.stats["d2h_bytes"]
+            p.free()
+        out["e2e"] = {"value": products / float(np.mean(et)), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(d2h), "ms_per_step": float(np.mean(et) * 1e3),
+                      "timing": "host wall-clock around the synchronous C-ABI call (H2D + product + D2H)",
+                      "result_terms": checksum}
+    elif with_e2e:
+        # N > 1: host operands on every rank, distributed result left on the owners' hosts
+        et = []
+        for _ in range(max(3, steps // 2)):
+            barrier()
+            t0 = time.perf_counter()
+            p, info = obd.sharded_mul(eng, vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
+            torch.cuda.synchronize(dev)
+            et.append(time.perf_counter() - t0)
+            h2d = info["partial_stats"]["h2d_bytes"]
+            d2h = p.stats["d2h_bytes"]
+            p.free()
+        t = torch.tensor([float(np.mean(et))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": products / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t.item() * 1e3),
+                      "timing": "max over ranks of host wall-clock (H2D + partial + all-to-all + merge + D2H)"}
+    out["_operands"] = (f, g, limit)
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+
+    from obake_b200 import build, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the engine has no CPU fallback"}))
+        return 2
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    build.build_native()
+    eng = engine.Engine(local_rank)
+    # launch on a torch stream so that torch.cuda.Event brackets the engine's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    for o in args.opt:
+        k, v = o.split("=")
+        eng.set_option(k, int(v))
+    res = bench_workload(args.workload, args, eng, torch, dev, rank, world, args.steps, args.warmup)
+    f, g, limit = res.pop("_operands")
+    also = {}
+    if world == 1 and args.also:
+        for nm in [s for s in args.also.split(",") if s]:
+            r = bench_workload(nm, args, eng, torch, dev, rank, world, max(3, args.steps // 2), 3, with_e2e=True)
+            r.pop("_operands")
+            also[nm] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"],
+                        "roofline_frac": r["roofline"]["frac"], "e2e": r.get("e2e", {}).get("value"),
+                        "terms_out": r["terms_out"], "products": r["products"], "stats": r["stats"]}
+    line = {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64" if res["f64"] else f"int64 limbs (exact, {res['lin']} in / {res['lacc']} acc)",
+        "data": "synthetic (closed-form operands, random-free)",
+        "config": {"workload": args.workload, "description": res["description"], "truncation": res["limit"],
+                   "term_products": res["products"], "terms_out": res["terms_out"],
+                   "l2": "256 MB buffer written between timed steps (L2 flush)",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"left operand sharded over {world} GPUs, NCCL all-to-all of partial segments, owner merge",
+                   "engine": res["stats"]},
+        "roofline": res["roofline"], "clocks": res["clocks"], "gpu_launches": res["gpu_launches"],
+    }
+    if "e2e" in res:
+        line["e2e"] = res["e2e"]
+    if "exchange" in res:
+        line["config"]["exchange"] = res["exchange"]
+    if also:
+        line["also"] = also
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import orc
+
+        cores = orc.lib().orc_hardware_concurrency()
+        v, s, prods, sample = cpu_reference_run(f, g, limit, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "seconds": s, "products": prods,
+                                "note": "CPU restatement of obake's poly_mul_impl_mt_hm (oracle/), not the obake binary"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -804,7 +804,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             sc.release(offs);
             sc.release(dflags);
             st.retries += 1;
-            if ((int64_t)st.retries > e->opt_max_retries || rq.merge || rq.nranks > 1) {
+            if ((int64_t)st.retries > e->opt_max_retries || rq.merge) {
                 e->err = "The homomorphic multiplication of two polynomials resulted in a segment table whose size "
                          "is larger than the maximum allowed value (shared-memory table overflow after "
                          + std::to_string(st.retries) + " finer segmentations)";

@@ -1,0 +1,92 @@
+"""Multi-GPU series product: one process per GPU, torch.distributed for the plumbing.
+
+The left (shorter) operand's terms are split into `world` contiguous slices; rank r multiplies slice r
+by the whole right operand with a segment count every rank derives identically (same inputs, same
+deterministic estimate), which leaves a partial product grouped by output segment.  Segment s is owned
+by rank s * world // nsegs (contiguous ranges), so the rows a rank must send to each peer are contiguous:
+one all-to-all of counts, one of keys, one of coefficient limbs (NCCL over NVLink on the GPU box; gloo in
+the CPU tests), then the owner sums what it received by key.  No other collective is on the data path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from .engine import Engine, Product, raw_view
+
+
+class _DevArray:
+    """Zero-copy torch view of engine-owned device memory (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def device_tensor(ptr: int, shape, device) -> torch.Tensor:
+    if int(np.prod(shape)) == 0:
+        return torch.empty(tuple(shape), dtype=torch.int64, device=device)
+    return torch.as_tensor(_DevArray(ptr, shape), device=device)
+
+
+def owner_ranges(log2_nsegs: int, world: int):
+    nsegs = 1 << log2_nsegs
+    return [(nsegs * g // world, nsegs * (g + 1) // world) for g in range(world)]
+
+
+def exchange_partials(keys: torch.Tensor, cfs: torch.Tensor, send_counts, group=None):
+    """All-to-all of the rows of `keys` [n, W] and `cfs` [n, L] (int64 bit patterns); rows are already ordered
+    by destination rank with `send_counts[g]` rows for rank g.  Returns (recv_keys, recv_cfs, recv_counts)."""
+    world = dist.get_world_size(group)
+    dev = keys.device
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(v) for v in rc.tolist()]
+    nrecv = sum(recv_counts)
+    W, L = keys.shape[1], cfs.shape[1]
+    rkeys = torch.empty((nrecv, W), dtype=keys.dtype, device=dev)
+    rcfs = torch.empty((nrecv, L), dtype=cfs.dtype, device=dev)
+    dist.all_to_all_single(rkeys, keys.contiguous(), output_split_sizes=recv_counts,
+                           input_split_sizes=list(send_counts), group=group)
+    dist.all_to_all_single(rcfs, cfs.contiguous(), output_split_sizes=recv_counts,
+                           input_split_sizes=list(send_counts), group=group)
+    return rkeys, rcfs, recv_counts
+
+
+def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result_mem=_capi.OBK_MEM_DEVICE):
+    """This rank's share of x*y: partial product -> all-to-all by owner -> merge.  Returns (Product holding the
+    segments this rank owns, info dict)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", engine.device)
+    part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
+    # Every rank derives the segmentation from the same full operands, but a rank whose slice overflowed a
+    # shared-memory table refined it locally: agree on the finest one and redo coarser partials with it.
+    k = torch.tensor([part.log2_nsegs], dtype=torch.int64, device=dev)
+    dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+    log2_nsegs = int(k.item())
+    if part.log2_nsegs != log2_nsegs and part.stats["term_products"] > 0:
+        part.free()
+        engine.set_option("log2_nsegs", log2_nsegs)
+        try:
+            part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
+        finally:
+            engine.set_option("log2_nsegs", -1)
+    W, L = part.key_words, part.cf_limbs
+    pk = device_tensor(part.keys_ptr, (part.nterms, W), dev)
+    pc = device_tensor(part.cfs_ptr, (part.nterms, L), dev)
+    rkeys, rcfs, recv_counts = exchange_partials(pk, pc, counts, group)
+    info = {"partial_terms": part.nterms, "sent_rows": sum(counts) - counts[rank], "recv_rows": sum(recv_counts),
+            "bytes_sent": (sum(counts) - counts[rank]) * 8 * (W + L), "partial_stats": part.stats,
+            "log2_nsegs": log2_nsegs}
+    is_f64 = part.is_f64
+    torch.cuda.current_stream(dev).synchronize()
+    view = raw_view(rkeys.shape[0], W, vx.key_signed, vx.nvars, vx.psize,
+                    _capi.OBK_CF_F64 if is_f64 else _capi.OBK_CF_INT, L, _capi.OBK_MEM_DEVICE,
+                    rkeys.data_ptr() if rkeys.numel() else 0, rcfs.data_ptr() if rcfs.numel() else 0)
+    merged = engine.merge_view(view, log2_nsegs, result_mem)
+    info["merge_stats"] = merged.stats
+    part.free()
+    return merged, info
