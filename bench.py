@@ -284,7 +284,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         "lin": lin, "lacc": int(lacc), "f64": f64, "limit": limit,
     }
     if info_last:
-        out["exchange"] = {k: info_last[k] for k in ("partial_terms", "sent_rows", "recv_rows", "bytes_sent", "log2_nsegs")}
+        out["exchange"] = {k: info_last[k] for k in ("partial_terms", "sent_rows", "recv_rows", "bytes_sent", "nsegs")}
     # ---- end to end: host (pinned) operands in, host result out, through the same public call ---------------
     if with_e2e and world == 1:
         for _ in range(min(warmup, 2)):

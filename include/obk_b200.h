@@ -73,9 +73,15 @@ typedef struct obk_trunc {
     const uint32_t *idx; /* sorted positions (in the symbol set) of the variables that count (host) */
 } obk_trunc;
 
-/* The product, grouped by output segment: term t of segment s sits in [seg_offsets[s], seg_offsets[s+1])
- * and satisfies hash(key) & (2^log2_nsegs - 1) == s, i.e. it belongs in table s of a series with that
- * many segments (series.hpp:396-400,1294-1305).  No coefficient is zero (polynomial.hpp:1528-1540). */
+enum { OBK_SEG_HASH_POW2 = 0, OBK_SEG_KEY_MOD = 1 };
+
+/* The product, grouped by segment: the terms of group s sit in [seg_offsets[s], seg_offsets[s+1]).
+ * seg_kind == OBK_SEG_HASH_POW2 (every complete product): nsegs = 2^log2_nsegs and a term of group s
+ * satisfies hash(key) & (nsegs - 1) == s, i.e. it belongs in table s of a series with that many segments
+ * (series.hpp:396-400,1294-1305), so a host series can be rebuilt table-parallel.
+ * seg_kind == OBK_SEG_KEY_MOD (partial products of the multi-GPU path): group s holds the keys with
+ * sum_w(word_w mod nsegs) mod nsegs == s, the engine's internal prime segmentation.
+ * No coefficient is zero (polynomial.hpp:1528-1540). */
 typedef struct obk_poly_result {
     uint64_t nterms;
     uint32_t key_words;
@@ -83,10 +89,12 @@ typedef struct obk_poly_result {
     uint32_t cf_limbs;    /* integer: accumulator limbs (1..3), two's complement */
     uint32_t log2_nsegs;
     uint32_t mem;         /* where keys/cfs live */
+    uint32_t nsegs;       /* number of groups */
+    uint32_t seg_kind;
     uint32_t reserved;
     uint64_t *keys;
     void *cfs;
-    uint64_t *seg_offsets; /* host memory, 2^log2_nsegs + 1 entries */
+    uint64_t *seg_offsets; /* host memory, nsegs + 1 entries */
     void *owner;           /* engine bookkeeping; release with obk_result_free */
 } obk_poly_result;
 
@@ -95,7 +103,8 @@ typedef struct obk_stats {
     uint64_t nterms_out;
     uint64_t est_nterms;    /* sampled estimate that sized the segments */
     uint64_t h2d_bytes, d2h_bytes;
-    uint32_t log2_nsegs;
+    uint32_t log2_nsegs;    /* grouping of the returned terms (hash & (2^k - 1)) */
+    uint32_t nsegs;         /* the engine's segment count: a prime modulus m, one CTA-owned table per segment */
     uint32_t acc_limbs;
     uint32_t retries;       /* segment-table overflows that forced a finer segmentation */
     uint32_t kernel;        /* 0: scatter (segment-owner hash tables), 1: row-blocked dense path */
@@ -103,6 +112,7 @@ typedef struct obk_stats {
     uint32_t group_lanes;   /* lanes cooperating on one left-operand term */
     uint32_t mul_launches;  /* launches of the product kernel (1 + retries) */
     uint32_t total_launches;/* all kernels launched by this call */
+    uint32_t reserved;
     float ms_total;         /* device time of the whole call (first to last kernel, CUDA events) */
     float ms_prep;          /* stats + degree + bucket sort */
     float ms_estimate;
@@ -116,8 +126,9 @@ obk_status obk_engine_create(int device, obk_engine **out);
 void obk_engine_destroy(obk_engine *e);
 /* Launch on the caller's stream (e.g. torch's current stream) instead of the engine's own. */
 obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream);
-/* Tunables: "log2_nsegs" (force, -1 = auto), "table_slots", "threads", "group_lanes" (0 = auto),
- * "kernel" (-1 auto, 0 scatter, 1 rows), "max_retries". */
+/* Tunables: "nsegs" (force the segment modulus, -1 = auto), "table_slots", "threads", "group_lanes" (0 = auto),
+ * "fill_pct", "fence" (1: fence.acq_rel.cta around the slot lock), "regroup" (0: leave the result in the
+ * engine's own segmentation), "kernel" (-1 auto, 0 scatter, 1 rows), "max_retries". */
 obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value);
 const char *obk_last_error(const obk_engine *e);
 const char *obk_status_string(obk_status s);
@@ -144,13 +155,14 @@ obk_status obk_key_degrees(obk_engine *e, const obk_poly_view *x, const obk_trun
 /* Multi-GPU: rank r multiplies its slice of the shorter operand's terms by the whole other
  * operand with a segment count all ranks agree on, and leaves a DEVICE partial result grouped by
  * segment.  send_counts[g] = number of partial terms owned by rank g (segments [g*nsegs/G, (g+1)*nsegs/G)).
- * After the all-to-all the owner merges what it received with obk_poly_merge. */
+ * After the all-to-all the owner merges what it received with obk_poly_merge (same nsegs = the partial
+ * result's nsegs). */
 obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
                                 uint32_t rank, uint32_t nranks, obk_poly_result *out_partial,
                                 uint64_t *send_counts, obk_stats *stats);
 /* Sum terms with equal keys (exact / fp64), drop zeros; `terms` holds acc-limb coefficients
  * (cf_limbs = accumulator limbs) on the device. */
-obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t log2_nsegs, uint32_t result_mem,
+obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t nsegs, uint32_t result_mem,
                           obk_poly_result *out, obk_stats *stats);
 
 #ifdef __cplusplus

@@ -32,16 +32,17 @@ class Trunc(C.Structure):
 
 class PolyResult(C.Structure):
     _fields_ = [("nterms", C.c_uint64), ("key_words", C.c_uint32), ("cf_kind", C.c_uint32),
-                ("cf_limbs", C.c_uint32), ("log2_nsegs", C.c_uint32), ("mem", C.c_uint32), ("reserved", C.c_uint32),
+                ("cf_limbs", C.c_uint32), ("log2_nsegs", C.c_uint32), ("mem", C.c_uint32), ("nsegs", C.c_uint32),
+                ("seg_kind", C.c_uint32), ("reserved", C.c_uint32),
                 ("keys", C.c_void_p), ("cfs", C.c_void_p), ("seg_offsets", C.c_void_p), ("owner", C.c_void_p)]
 
 
 class Stats(C.Structure):
     _fields_ = [("term_products", C.c_uint64), ("nterms_out", C.c_uint64), ("est_nterms", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("log2_nsegs", C.c_uint32), ("acc_limbs", C.c_uint32), ("retries", C.c_uint32),
+                ("log2_nsegs", C.c_uint32), ("nsegs", C.c_uint32), ("acc_limbs", C.c_uint32), ("retries", C.c_uint32),
                 ("kernel", C.c_uint32), ("table_slots", C.c_uint32), ("group_lanes", C.c_uint32),
-                ("mul_launches", C.c_uint32), ("total_launches", C.c_uint32),
+                ("mul_launches", C.c_uint32), ("total_launches", C.c_uint32), ("reserved", C.c_uint32),
                 ("ms_total", C.c_float), ("ms_prep", C.c_float), ("ms_estimate", C.c_float), ("ms_mul", C.c_float),
                 ("ms_compact", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float)]
 

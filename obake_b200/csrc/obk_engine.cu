@@ -46,7 +46,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_log2_nsegs = -1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
 };
@@ -260,12 +260,13 @@ struct SortedY {
     uint32_t *off = nullptr; // (nsegs << dbits) + 1
 };
 
-// Counting sort of the right operand by (bucket, degree index).
+// Counting sort of an operand by (segment, degree index).  pow2: segment = hash & (m-1) (m a power of two,
+// used to regroup the result the way a series stores it); otherwise segment = key mod m.
 SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uint64_t *cfs, const int64_t *deg, uint64_t n,
-                     int W, int CW, uint32_t log2_nsegs, int dbits, int64_t degmin, bool with_cfs)
+                     int W, int CW, uint32_t m, uint32_t is_signed, bool pow2, int dbits, int64_t degmin, bool with_cfs)
 {
     SortedY r;
-    const uint64_t nbins = (uint64_t)1 << (log2_nsegs + dbits);
+    const uint64_t nbins = (uint64_t)m << dbits;
     uint32_t *cnt = sc.alloc<uint32_t>(nbins + 1);
     uint32_t *bin_of = sc.alloc<uint32_t>(n);
     uint32_t *rank_of = sc.alloc<uint32_t>(n);
@@ -274,8 +275,8 @@ SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uin
     if (with_cfs) r.cfs = sc.alloc<uint64_t>(n * CW);
     CU_CHECK(e, cudaMemsetAsync(cnt, 0, (nbins + 1) * sizeof(uint32_t), e->stream));
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
-    k_bin_count<<<grid, 256, 0, e->stream>>>(keys, deg, n, W, (uint32_t)((1ull << log2_nsegs) - 1), dbits, degmin, cnt,
-                                             bin_of, rank_of);
+    k_bin_count<<<grid, 256, 0, e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0, dbits, degmin, cnt, bin_of,
+                                             rank_of);
     e->launches += 1;
     device_scan(e, sc, cnt, r.off, nbins);
     k_bin_scatter<<<grid, 256, 0, e->stream>>>(keys, with_cfs ? cfs : nullptr, nullptr, n, W, CW, r.off, bin_of, rank_of,
@@ -285,6 +286,19 @@ SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uin
     sc.release(bin_of);
     sc.release(rank_of);
     return r;
+}
+
+uint32_t prev_prime(uint64_t n)
+{
+    if (n < 2) return 1;
+    while (n > 2 && !obake::detail::kp_is_prime(n)) --n;
+    return (uint32_t)n;
+}
+uint32_t next_prime(uint64_t n)
+{
+    if (n < 2) return 1;
+    while (!obake::detail::kp_is_prime(n)) ++n;
+    return (uint32_t)n;
 }
 
 template <int W>
@@ -360,6 +374,8 @@ void set_empty_result(obk_poly_result *out, const obk_poly_view *x, int cf_limbs
     out->cf_kind = x->cf_kind;
     out->cf_limbs = cf_limbs;
     out->mem = mem;
+    out->nsegs = 1;
+    out->seg_kind = 0;
     auto *own = new ResultOwner{nullptr};
     own->seg_offsets = (uint64_t *)std::calloc(2, sizeof(uint64_t));
     out->seg_offsets = own->seg_offsets;
@@ -375,7 +391,7 @@ struct MulRequest {
     uint64_t *send_counts = nullptr;
     // merge mode: x is ignored, y holds acc-limb coefficients to be summed by key
     bool merge = false;
-    uint32_t merge_log2_nsegs = 0;
+    uint32_t merge_nsegs = 1;
 };
 
 obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats *stats)
@@ -627,33 +643,37 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         }
         st.table_slots = cap;
         const uint32_t max_fill = (uint32_t)((uint64_t)cap * 9 / 10);
-        const uint32_t max_bins_log2 = 24;
+        const uint64_t max_bins = 1ull << 25;
+        const uint32_t wave = (uint32_t)e->sm_count; // resident CTAs: one per SM (the table takes the whole SM)
 
         // ---- product-size estimate (poly_mul_estimate_product_size, polynomial.hpp:478-794) -------------
         // Sampled symbolic product: count the distinct product keys of a few fine-grained segments exactly.
         uint64_t est = 0;
+        uint32_t nsegs = 1;
         if (rq.merge) {
-            log2_nsegs = rq.merge_log2_nsegs;
+            nsegs = rq.merge_nsegs;
             est = ny;
-        } else if (e->opt_log2_nsegs >= 0) {
-            log2_nsegs = (uint32_t)e->opt_log2_nsegs;
-            est = 0;
+        } else if (e->opt_nsegs > 0) {
+            nsegs = (uint32_t)e->opt_nsegs;
         } else {
             const uint32_t sym_log2_cap = pick_log2_cap(e, W, 0);
             const uint32_t sym_cap = 1u << sym_log2_cap;
-            uint32_t kE = 0;
-            while (kE + dbits < max_bins_log2 && (tot_mults >> kE) > sym_cap / 4) ++kE;
-            const uint64_t nsegE = 1ull << kE;
-            const double per_seg = (double)tot_mults / (double)nsegE;
+            // fine modulus: about sym_cap/4 products per segment, so a sampled table can never fill up
+            uint64_t want = (tot_mults + sym_cap / 4 - 1) / (sym_cap / 4);
+            want = std::min<uint64_t>(want, max_bins >> dbits);
+            const uint32_t mE = want <= 1 ? 1u : prev_prime(want);
+            const double per_seg = (double)tot_mults / (double)mE;
             uint64_t S = (uint64_t)std::ceil(1.5e6 / std::max(per_seg, 1.0));
-            S = std::max<uint64_t>(S, 32);
-            S = std::min<uint64_t>(S, 512);
-            S = std::min<uint64_t>(S, nsegE);
-            SortedY ye = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, kE, dbits, degmin_y, false);
+            S = std::max<uint64_t>(S, 64);
+            S = std::min<uint64_t>(S, 1024);
+            S = std::min<uint64_t>(S, mE);
+            SortedY ye = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, mE, L.is_signed, false, dbits, degmin_y, false);
+            uint32_t *xsegE = sc.alloc<uint32_t>(nx_full);
+            k_segments<<<(unsigned)std::min<uint64_t>((nx_full + 255) / 256, 4096), 256, 0, s>>>(dxk, nx_full, W, mE,
+                                                                                                 L.is_signed, xsegE);
+            e->launches += 1;
             std::vector<uint32_t> hlist(S);
-            for (uint64_t i = 0; i < S; ++i) hlist[i] = (uint32_t)((i * 0x9E3779B1ull + 0x51ull) & (nsegE - 1));
-            if (S == nsegE)
-                for (uint64_t i = 0; i < S; ++i) hlist[i] = (uint32_t)i;
+            for (uint64_t i = 0; i < S; ++i) hlist[i] = (uint32_t)((i * (uint64_t)mE) / S); // evenly spread, distinct
             uint32_t *dlist = sc.alloc<uint32_t>(S);
             uint32_t *dcounts = sc.alloc<uint32_t>(S);
             uint32_t *dflags = sc.alloc<uint32_t>(4);
@@ -663,11 +683,12 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             P.xk = dxk;
             P.xc = nullptr;
             P.xdeg = xdeg;
+            P.xseg = xsegE;
             P.nx = nx_full;
             P.yk = ye.keys;
             P.yc = nullptr;
             P.yoff = ye.off;
-            P.log2_nsegs = kE;
+            P.nsegs = mE;
             P.dbits = dbits;
             P.ndeg = ndeg;
             P.trunc = trunc;
@@ -676,11 +697,12 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             P.nseg_list = (uint32_t)S;
             P.cursor = dflags + 1;
             P.log2_cap = sym_log2_cap;
-            const double run = (double)ny / (double)nsegE;
+            const double run = (double)tot_mults / (double)nx_full / (double)mE;
             uint32_t lg = 0;
             while (lg < 5 && (double)(1u << lg) < run) ++lg;
             P.lg = lg;
             P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
+            P.fence = 0;
             P.counts = dcounts;
             P.flags = dflags;
             const size_t smem_sym = (size_t)sym_cap * (8 * W + 4);
@@ -690,15 +712,27 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             CU_CHECK(e, cudaStreamSynchronize(s));
             double sum = 0;
             for (uint64_t i = 0; i < S; ++i) sum += hcounts[i] == 0xffffffffu ? (double)sym_cap : (double)hcounts[i];
-            est = (uint64_t)std::ceil(sum * (double)nsegE / (double)S);
+            est = (uint64_t)std::ceil(sum * (double)mE / (double)S);
             est = std::max<uint64_t>(est, 1);
             sc.release(ye.keys);
             sc.release(ye.off);
-            // segment count: every table should end up at most ~opt_fill_pct % full
+            sc.release(xsegE);
+            // Segment count: a prime modulus (flat residues) just below a whole number of waves of resident CTAs,
+            // large enough that every table ends up about opt_fill_pct % full.
             const double target = (double)cap * (double)e->opt_fill_pct / 100.0;
-            log2_nsegs = 0;
-            while (log2_nsegs < max_bins_log2 - (uint32_t)dbits && (double)est / (double)(1ull << log2_nsegs) > target)
-                ++log2_nsegs;
+            uint64_t needed = (uint64_t)std::ceil((double)est / target);
+            // enough segments to occupy the machine when there is enough work to share
+            const uint64_t by_work = std::min<uint64_t>(wave, (tot_mults + 65535) / 65536);
+            needed = std::max<uint64_t>(needed, by_work);
+            needed = std::max<uint64_t>(needed, 1);
+            if (needed == 1) {
+                nsegs = 1;
+            } else {
+                const uint64_t waves = (needed + wave - 1) / wave;
+                uint32_t m = prev_prime(waves * wave);
+                if (m < needed) m = next_prime(needed);
+                nsegs = m;
+            }
         }
         st.est_nterms = est;
         CU_CHECK(e, cudaEventRecord(e->ev[3], s));
@@ -716,49 +750,56 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         uint64_t total = 0;
         float ms_prep_extra = 0;
         for (unsigned attempt = 0;; ++attempt) {
-            if (log2_nsegs + dbits > max_bins_log2) {
-                e->err = "The homomorphic multiplication of two polynomials needs more than 2^"
-                         + std::to_string(max_bins_log2) + " segment bins; table size overflow";
+            if (((uint64_t)nsegs << dbits) > max_bins) {
+                e->err = "The homomorphic multiplication of two polynomials needs more segment bins than the maximum "
+                         "allowed value (table size overflow)";
                 return OBK_ERR_TABLE_OVERFLOW;
             }
-            const uint64_t nsegs = 1ull << log2_nsegs;
             CU_CHECK(e, cudaEventRecord(e->ev[4], s));
             SortedY ys;
-            if (rq.merge)
-                ys = sort_operand(e, sc, dyk, dyc, nullptr, ny, W, accw, log2_nsegs, 0, 0, true);
-            else
-                ys = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, log2_nsegs, dbits, degmin_y, true);
-            stage_k = sc.alloc<uint64_t>(nsegs * cap * W);
-            stage_c = sc.alloc<uint64_t>(nsegs * cap * accw);
-            counts = sc.alloc<uint32_t>(nsegs + 1);
-            offs = sc.alloc<uint32_t>(nsegs + 2);
+            uint32_t *xseg = nullptr;
+            if (rq.merge) {
+                ys = sort_operand(e, sc, dyk, dyc, nullptr, ny, W, accw, nsegs, L.is_signed, false, 0, 0, true);
+            } else {
+                ys = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, nsegs, L.is_signed, false, dbits, degmin_y, true);
+                xseg = sc.alloc<uint32_t>(x_end - x_begin);
+                k_segments<<<(unsigned)std::min<uint64_t>((x_end - x_begin + 255) / 256, 4096), 256, 0, s>>>(
+                    dxk + x_begin * W, x_end - x_begin, W, nsegs, L.is_signed, xseg);
+                e->launches += 1;
+            }
+            stage_k = sc.alloc<uint64_t>((uint64_t)nsegs * cap * W);
+            stage_c = sc.alloc<uint64_t>((uint64_t)nsegs * cap * accw);
+            counts = sc.alloc<uint32_t>((uint64_t)nsegs + 1);
+            offs = sc.alloc<uint32_t>((uint64_t)nsegs + 2);
             dflags = sc.alloc<uint32_t>(4);
             CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
-            CU_CHECK(e, cudaMemsetAsync(counts, 0, (nsegs + 1) * 4, s));
+            CU_CHECK(e, cudaMemsetAsync(counts, 0, ((uint64_t)nsegs + 1) * 4, s));
             MulParams P{};
             uint64_t *zero_key = nullptr;
             if (rq.merge) {
-                zero_key = sc.alloc<uint64_t>(W);
-                CU_CHECK(e, cudaMemsetAsync(zero_key, 0, W * 8, s));
+                zero_key = sc.alloc<uint64_t>(W + 1);
+                CU_CHECK(e, cudaMemsetAsync(zero_key, 0, (W + 1) * 8, s));
                 P.xk = zero_key;
+                P.xseg = (const uint32_t *)(zero_key + W);
                 P.xc = nullptr;
                 P.nx = 1;
             } else {
                 P.xk = dxk + x_begin * W;
                 P.xc = dxc + x_begin * CWx;
                 P.xdeg = xdeg ? xdeg + x_begin : nullptr;
+                P.xseg = xseg;
                 P.nx = x_end - x_begin;
             }
             P.yk = ys.keys;
             P.yc = ys.cfs;
             P.yoff = ys.off;
-            P.log2_nsegs = log2_nsegs;
+            P.nsegs = nsegs;
             P.dbits = dbits;
             P.ndeg = ndeg;
             P.trunc = trunc;
             P.lim_base = lim_base;
             P.seg_list = nullptr;
-            P.nseg_list = (uint32_t)nsegs;
+            P.nseg_list = nsegs;
             P.cursor = dflags + 1;
             P.log2_cap = log2_cap;
             uint32_t lg = 0;
@@ -773,6 +814,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             P.lg = lg;
             st.group_lanes = 1u << lg;
             P.max_fill = max_fill;
+            P.fence = e->opt_fence ? 1u : 0u;
             P.okeys = stage_k;
             P.ocfs = stage_c;
             P.counts = counts;
@@ -790,6 +832,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
             ms_prep_extra += ms;
             if (zero_key) sc.release(zero_key);
+            if (xseg) sc.release(xseg);
             sc.release(ys.keys);
             sc.release(ys.cfs);
             sc.release(ys.off);
@@ -810,34 +853,82 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                          + std::to_string(st.retries) + " finer segmentations)";
                 return OBK_ERR_TABLE_OVERFLOW;
             }
-            log2_nsegs += 1;
+            nsegs = prev_prime(((uint64_t)nsegs * 2 + wave - 1) / wave * wave);
+            if (nsegs < 2) nsegs = 2;
         }
-        st.log2_nsegs = log2_nsegs;
+        st.nsegs = nsegs;
         st.nterms_out = total;
-        const uint64_t nsegs = 1ull << log2_nsegs;
 
         // ---- segment-ordered dense result ---------------------------------------------------------------
         uint64_t *rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * W);
         uint64_t *rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
-        uint64_t *off64 = sc.alloc<uint64_t>(nsegs + 1);
+        uint64_t *off64 = sc.alloc<uint64_t>((uint64_t)nsegs + 1);
         k_compact<<<(unsigned)std::min<uint64_t>(nsegs, 4096), 256, 0, s>>>(stage_k, stage_c, counts, offs, cap, W, accw, rk, rc,
-                                                                        off64, (uint32_t)nsegs);
+                                                                        off64, nsegs);
         e->launches += 1;
         CU_CHECK(e, cudaGetLastError());
+        sc.release(stage_k);
+        sc.release(stage_c);
+
+        // ---- regroup the way a series stores its terms: table hash & (2^k - 1) (series.hpp:396-400) ---------
+        // k follows the reference's sizing rule (polynomial.hpp:870-902).  Partial products of the multi-GPU
+        // path keep the engine's own segmentation (key mod nsegs): the all-to-all needs owner ranges contiguous.
+        uint32_t out_groups = nsegs, out_log2 = 0, seg_kind = 1;
+        const bool regroup = rq.nranks <= 1 && e->opt_regroup != 0;
+        if (regroup) {
+            const double term_bytes = 8.0 * W + 8.0 * accw;
+            const double est_sp = tot_mults ? (double)total / (double)tot_mults : 1.0;
+            const double seg_kb = est_sp >= 1e-3 ? 200.0 : 20.0;
+            const uint64_t est_nsegs = (uint64_t)((double)total * term_bytes / (seg_kb * 1024.0));
+            while ((est_nsegs >> out_log2) != 0 && out_log2 < 22) ++out_log2; // nbits()
+            if (total > 0 && out_log2 > 0) {
+                SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, 1u << out_log2, 0, true, 0, 0, true);
+                sc.release(rk);
+                sc.release(rc);
+                rk = g.keys;
+                rc = g.cfs;
+                // widen the 32-bit offsets
+                std::vector<uint32_t> h32((1u << out_log2) + 1);
+                CU_CHECK(e, cudaMemcpyAsync(h32.data(), g.off, h32.size() * 4, cudaMemcpyDeviceToHost, s));
+                CU_CHECK(e, cudaStreamSynchronize(s));
+                sc.release(g.off);
+                out_groups = 1u << out_log2;
+                seg_kind = 0;
+                auto *own = new ResultOwner{e};
+                out->owner = own;
+                own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * ((size_t)out_groups + 1));
+                for (size_t i = 0; i <= out_groups; ++i) own->seg_offsets[i] = h32[i];
+            } else {
+                out_groups = 1;
+                out_log2 = 0;
+                seg_kind = 0;
+                auto *own = new ResultOwner{e};
+                out->owner = own;
+                own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * 2);
+                own->seg_offsets[0] = 0;
+                own->seg_offsets[1] = total;
+            }
+        }
         CU_CHECK(e, cudaEventRecord(e->ev[7], s));
 
-        auto *own = new ResultOwner{e};
-        out->owner = own;
+        ResultOwner *own = static_cast<ResultOwner *>(out->owner);
+        if (!own) {
+            own = new ResultOwner{e};
+            out->owner = own;
+            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * ((size_t)nsegs + 1));
+            CU_CHECK(e, cudaMemcpyAsync(own->seg_offsets, off64, ((size_t)nsegs + 1) * 8, cudaMemcpyDeviceToHost, s));
+        }
+        st.d2h_bytes += ((uint64_t)out_groups + 1) * 8;
         out->nterms = total;
         out->key_words = W;
         out->cf_kind = f64 ? OBK_CF_F64 : OBK_CF_INT;
         out->cf_limbs = f64 ? 1 : accw;
-        out->log2_nsegs = log2_nsegs;
+        out->log2_nsegs = out_log2;
+        out->nsegs = out_groups;
+        out->seg_kind = seg_kind;
         out->mem = rq.result_mem;
-        own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * (nsegs + 1));
         out->seg_offsets = own->seg_offsets;
-        CU_CHECK(e, cudaMemcpyAsync(own->seg_offsets, off64, (nsegs + 1) * 8, cudaMemcpyDeviceToHost, s));
-        st.d2h_bytes += (nsegs + 1) * 8;
+        st.log2_nsegs = out_log2;
         if (rq.result_mem == OBK_MEM_DEVICE) {
             sc.detach(rk);
             sc.detach(rc);
@@ -860,7 +951,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         CU_CHECK(e, cudaStreamSynchronize(s));
         if (rq.send_counts) {
             for (uint32_t g = 0; g < rq.nranks; ++g) {
-                const uint64_t a = nsegs * g / rq.nranks, b = nsegs * (g + 1) / rq.nranks;
+                const uint64_t a = (uint64_t)nsegs * g / rq.nranks, b = (uint64_t)nsegs * (g + 1) / rq.nranks;
                 rq.send_counts[g] = own->seg_offsets[b] - own->seg_offsets[a];
             }
         }
@@ -988,7 +1079,9 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
 {
     if (!e || !name) return OBK_ERR_INVALID_ARG;
     const std::string n(name);
-    if (n == "log2_nsegs") e->opt_log2_nsegs = value;
+    if (n == "nsegs") e->opt_nsegs = value;
+    else if (n == "fence") e->opt_fence = value;
+    else if (n == "regroup") e->opt_regroup = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
     else if (n == "group_lanes") e->opt_group_lanes = value;
@@ -1027,13 +1120,13 @@ obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk
     return run_mul(e, rq, out_partial, stats);
 }
 
-obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t log2_nsegs, uint32_t result_mem,
+obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t nsegs, uint32_t result_mem,
                           obk_poly_result *out, obk_stats *stats)
 {
     if (!e || !terms) return OBK_ERR_INVALID_ARG;
     MulRequest rq{nullptr, terms, nullptr, result_mem};
     rq.merge = true;
-    rq.merge_log2_nsegs = log2_nsegs;
+    rq.merge_nsegs = nsegs ? nsegs : 1;
     return run_mul(e, rq, out, stats);
 }
 

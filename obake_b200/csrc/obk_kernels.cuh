@@ -177,31 +177,62 @@ __global__ void k_stats_init(StatsOut *s, int n)
 }
 
 // ------------------------------------------------------------------------------------------------
-// hash / bucket: packed_monomial.hpp:172-176 (hash = value), d_packed_monomial.hpp:274-284 (sum of words)
+// hash / segment of a monomial.
+//   hash = value (packed_monomial.hpp:172-176) or the sum of the words (d_packed_monomial.hpp:274-284);
+//   the reference routes a product to table hash & (2^k - 1) because hash(a*b) = hash(a) + hash(b)
+//   (polynomial.hpp:1441-1450).  The same homomorphism holds modulo ANY m as long as the key addition
+//   does not wrap -- which the exponent-overflow check guarantees (the product key stays within the
+//   kpack limits) -- so the engine segments by  seg(key) = sum_w (word_w mod m) mod m  with m a prime:
+//   the low bits of Kronecker keys are badly clumped (Fateman n=30: fullest 2^8-segment is 1.53x the
+//   mean), residues modulo a prime are flat to ~1 %.
 // ------------------------------------------------------------------------------------------------
-template <int W>
-__device__ __forceinline__ uint64_t key_hash(const uint64_t (&k)[W])
+__device__ __forceinline__ uint32_t word_mod(uint64_t w, uint32_t m, uint32_t is_signed)
 {
-    uint64_t h = k[0];
-#pragma unroll
-    for (int w = 1; w < W; ++w) h += k[w];
-    return h;
+    if (is_signed) {
+        const long long r = (long long)w % (long long)m;
+        return (uint32_t)(r < 0 ? r + (long long)m : r);
+    }
+    return (uint32_t)(w % m);
 }
 
-// Counting sort of the right operand by bin = (hash & mask) << dbits | (deg - degmin)
+__device__ __forceinline__ uint32_t key_segment(const uint64_t *k, int W, uint32_t m, uint32_t is_signed)
+{
+    uint32_t s = 0;
+    for (int w = 0; w < W; ++w) {
+        s += word_mod(k[w], m, is_signed);
+        if (s >= m) s -= m;
+    }
+    return s;
+}
+
+// Segment index of every term of the left operand (read once per visit by the product kernel).
+__global__ void __launch_bounds__(256) k_segments(const uint64_t *__restrict__ keys, uint64_t n, int W, uint32_t m,
+                                                  uint32_t is_signed, uint32_t *__restrict__ seg_of)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        seg_of[i] = key_segment(keys + i * W, W, m, is_signed);
+}
+
+// Counting sort of the right operand by bin = seg(key) << dbits | (deg - degmin)
 // (replaces tbb::parallel_sort by bucket + compute_vseg + seg_sorter, polynomial.hpp:914-1105).
 // Pass 1: histogram; the value returned by the atomic is the term's rank inside its bin, so pass 3
-// scatters without a second round of atomics.
+// scatters without a second round of atomics.  pow2 != 0: bin = hash & (m-1) (output regrouping).
 __global__ void __launch_bounds__(256) k_bin_count(const uint64_t *__restrict__ keys, const int64_t *__restrict__ deg,
-                                                   uint64_t n, int W, uint32_t mask, int dbits, int64_t degmin,
-                                                   uint32_t *__restrict__ cnt, uint32_t *__restrict__ bin_of,
-                                                   uint32_t *__restrict__ rank_of)
+                                                   uint64_t n, int W, uint32_t m, uint32_t is_signed, int pow2, int dbits,
+                                                   int64_t degmin, uint32_t *__restrict__ cnt,
+                                                   uint32_t *__restrict__ bin_of, uint32_t *__restrict__ rank_of)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t h = 0;
-        for (int w = 0; w < W; ++w) h += keys[i * W + w];
-        uint32_t bin = (uint32_t)(h & mask);
+        uint32_t bin;
+        if (pow2) {
+            uint64_t h = 0;
+            for (int w = 0; w < W; ++w) h += keys[i * W + w];
+            bin = (uint32_t)(h & (uint64_t)(m - 1));
+        } else {
+            bin = key_segment(keys + i * W, W, m, is_signed);
+        }
         if (dbits) bin = (bin << dbits) | (uint32_t)(deg[i] - degmin);
         bin_of[i] = bin;
         rank_of[i] = atomicAdd(&cnt[bin], 1u);
@@ -403,17 +434,18 @@ struct MulParams {
     const uint64_t *xk;
     const uint64_t *xc;
     const int64_t *xdeg;
+    const uint32_t *xseg; // segment of each left term
     uint64_t nx;
-    // right operand, sorted by (bucket, degree); yoff has (nsegs << dbits) + 1 entries
+    // right operand, sorted by (segment, degree); yoff has (nsegs << dbits) + 1 entries
     const uint64_t *yk;
     const uint64_t *yc;
     const uint32_t *yoff;
-    uint32_t log2_nsegs;
+    uint32_t nsegs; // the modulus m
     uint32_t dbits;
     uint32_t ndeg;
     uint32_t trunc;
     int64_t lim_base;
-    // work list: segment ids to process (NULL = all 2^log2_nsegs) and the dynamic cursor
+    // work list: segment ids to process (NULL = all nsegs) and the dynamic cursor
     const uint32_t *seg_list;
     uint32_t nseg_list;
     uint32_t *cursor;
@@ -421,6 +453,7 @@ struct MulParams {
     uint32_t log2_cap;
     uint32_t lg; // log2(lanes per left term)
     uint32_t max_fill;
+    uint32_t fence; // 1: fence.acq_rel.cta around the slot lock (validation build of the protocol)
     // staging output: [segment][cap] slots, counts per segment
     uint64_t *okeys;
     uint64_t *ocfs;
@@ -431,14 +464,28 @@ struct MulParams {
 enum : uint32_t { ST_EMPTY = 0, ST_INIT = 1, ST_FULL = 2, ST_BUSY = 3 };
 
 template <int W>
-__device__ __forceinline__ uint32_t slot_hash(const uint64_t (&k)[W], uint32_t log2_nsegs, uint32_t log2_cap)
+__device__ __forceinline__ uint32_t slot_hash(const uint64_t (&k)[W], uint32_t log2_cap)
 {
-    // All keys of a segment share their low log2_nsegs bits: mix the rest (multiply-shift).
-    uint64_t h = k[0];
+    // multiply-shift over the whole key: the top bits of the product depend on every key bit
+    uint64_t h = k[0] * 0x9E3779B97F4A7C15ULL;
 #pragma unroll
-    for (int w = 1; w < W; ++w) h = h * 0x9E3779B97F4A7C15ULL + k[w];
-    h = (h >> log2_nsegs) * 0x9E3779B97F4A7C15ULL;
+    for (int w = 1; w < W; ++w) h = (h ^ (h >> 29)) * 0xBF58476D1CE4E5B9ULL + k[w] * 0x94D049BB133111EBULL;
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ULL;
     return (uint32_t)(h >> (64 - log2_cap));
+}
+
+// Slot lock protocol.  A slot's state word goes EMPTY -> INIT -> FULL and then FULL <-> BUSY; key and
+// accumulator limbs are only written by the thread that moved the state to INIT or BUSY.  All of it is
+// shared-memory traffic of ONE SM, which the LSU / shared-memory pipeline performs in issue order, so a
+// store to the limbs followed by the store that releases the state cannot be observed out of order by
+// another warp of the CTA; the acquiring side only touches the limbs after the atomic exchange returned
+// FULL (a control dependency).  That is why the default build uses compiler barriers only; fence != 0
+// adds fence.acq_rel.cta on both sides (the PTX-memory-model form of the same protocol), used by the tests
+// to cross-check the fence-free path.
+__device__ __forceinline__ void slot_fence(uint32_t fence)
+{
+    if (fence) asm volatile("fence.acq_rel.cta;" ::: "memory"); else asm volatile("" ::: "memory");
 }
 
 // One CTA owns one output segment (polynomial.hpp:1421-1553, dense_par_functor): its open-addressing
@@ -462,7 +509,6 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t G = 1u << P.lg;
     const uint32_t gid = tid >> P.lg, lg_lane = tid & (G - 1), ngroups = nthr >> P.lg;
-    const uint32_t smask = (1u << P.log2_nsegs) - 1u;
     const uint32_t cmask = cap - 1u;
 
     for (;;) {
@@ -484,8 +530,8 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
             uint64_t kx[W];
 #pragma unroll
             for (int w = 0; w < W; ++w) kx[w] = __ldg(P.xk + i * W + w);
-            const uint32_t bx = (uint32_t)key_hash<W>(kx) & smask;
-            const uint32_t by = (seg - bx) & smask;
+            const uint32_t bx = __ldg(P.xseg + i);
+            const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
             uint32_t y0, y1;
             if (P.trunc) {
                 const int64_t r = P.lim_base - __ldg(P.xdeg + i);
@@ -523,7 +569,7 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
                     }
                 }
                 // ---- find-or-insert + accumulate ---------------------------------------------
-                uint32_t h = slot_hash<W>(k, P.log2_nsegs, P.log2_cap);
+                uint32_t h = slot_hash<W>(k, P.log2_cap);
                 uint32_t probes = 0;
                 for (;;) {
                     const uint32_t st = *(volatile uint32_t *)&tstate[h];
@@ -537,7 +583,7 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
                             } else {
                                 if (st == ST_BUSY) continue;
                                 if (atomicExch(&tstate[h], ST_BUSY) != ST_FULL) continue;
-                                __threadfence_block();
+                                slot_fence(P.fence);
                                 if constexpr (T::F64) {
                                     double a = __longlong_as_double((long long)*(volatile uint64_t *)&tacc[h]);
                                     a = __dadd_rn(a, __longlong_as_double((long long)p[0]));
@@ -550,7 +596,7 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
 #pragma unroll
                                     for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = a[l];
                                 }
-                                __threadfence_block();
+                                slot_fence(P.fence);
                                 *(volatile uint32_t *)&tstate[h] = ST_FULL;
                                 break;
                             }
@@ -568,7 +614,7 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
                         for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
 #pragma unroll
                         for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = p[l];
-                        __threadfence_block();
+                        slot_fence(P.fence);
                         *(volatile uint32_t *)&tstate[h] = ST_FULL;
                         if (atomicAdd(&s_count, 1u) + 1u > P.max_fill) s_over = 1;
                         break;

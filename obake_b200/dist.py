@@ -31,8 +31,7 @@ def device_tensor(ptr: int, shape, device) -> torch.Tensor:
     return torch.as_tensor(_DevArray(ptr, shape), device=device)
 
 
-def owner_ranges(log2_nsegs: int, world: int):
-    nsegs = 1 << log2_nsegs
+def owner_ranges(nsegs: int, world: int):
     return [(nsegs * g // world, nsegs * (g + 1) // world) for g in range(world)]
 
 
@@ -64,29 +63,29 @@ def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result
     part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
     # Every rank derives the segmentation from the same full operands, but a rank whose slice overflowed a
     # shared-memory table refined it locally: agree on the finest one and redo coarser partials with it.
-    k = torch.tensor([part.log2_nsegs], dtype=torch.int64, device=dev)
+    k = torch.tensor([part.nsegs], dtype=torch.int64, device=dev)
     dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
-    log2_nsegs = int(k.item())
-    if part.log2_nsegs != log2_nsegs and part.stats["term_products"] > 0:
+    nsegs = int(k.item())
+    if part.nsegs != nsegs and part.stats["term_products"] > 0:
         part.free()
-        engine.set_option("log2_nsegs", log2_nsegs)
+        engine.set_option("nsegs", nsegs)
         try:
             part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
         finally:
-            engine.set_option("log2_nsegs", -1)
+            engine.set_option("nsegs", -1)
     W, L = part.key_words, part.cf_limbs
     pk = device_tensor(part.keys_ptr, (part.nterms, W), dev)
     pc = device_tensor(part.cfs_ptr, (part.nterms, L), dev)
     rkeys, rcfs, recv_counts = exchange_partials(pk, pc, counts, group)
     info = {"partial_terms": part.nterms, "sent_rows": sum(counts) - counts[rank], "recv_rows": sum(recv_counts),
             "bytes_sent": (sum(counts) - counts[rank]) * 8 * (W + L), "partial_stats": part.stats,
-            "log2_nsegs": log2_nsegs}
+            "nsegs": nsegs}
     is_f64 = part.is_f64
     torch.cuda.current_stream(dev).synchronize()
     view = raw_view(rkeys.shape[0], W, vx.key_signed, vx.nvars, vx.psize,
                     _capi.OBK_CF_F64 if is_f64 else _capi.OBK_CF_INT, L, _capi.OBK_MEM_DEVICE,
                     rkeys.data_ptr() if rkeys.numel() else 0, rcfs.data_ptr() if rcfs.numel() else 0)
-    merged = engine.merge_view(view, log2_nsegs, result_mem)
+    merged = engine.merge_view(view, nsegs, result_mem)
     info["merge_stats"] = merged.stats
     part.free()
     return merged, info

@@ -130,6 +130,16 @@ class Product:
         return int(self._res.log2_nsegs)
 
     @property
+    def nsegs(self) -> int:
+        """Number of groups of seg_offsets."""
+        return int(self._res.nsegs)
+
+    @property
+    def seg_kind(self) -> int:
+        """0: group = hash & (nsegs-1) (series tables); 1: group = key mod nsegs (multi-GPU partials)."""
+        return int(self._res.seg_kind)
+
+    @property
     def on_device(self) -> bool:
         return self._res.mem == OBK_MEM_DEVICE
 
@@ -143,7 +153,7 @@ class Product:
 
     @property
     def seg_offsets(self) -> np.ndarray:
-        n = (1 << self.log2_nsegs) + 1 if self._res.seg_offsets else 0
+        n = self.nsegs + 1 if self._res.seg_offsets else 0
         if n == 0:
             return np.zeros(2, dtype=np.uint64)
         return np.ctypeslib.as_array(C.cast(self._res.seg_offsets, C.POINTER(C.c_uint64)), (n,)).copy()
@@ -284,9 +294,9 @@ class Engine:
             _raise(rc, self.last_error())
         return Product(self, res, st), [int(c) for c in counts]
 
-    def merge_view(self, vterms: PolyView, log2_nsegs: int, result_mem=OBK_MEM_HOST) -> Product:
+    def merge_view(self, vterms: PolyView, nsegs: int, result_mem=OBK_MEM_HOST) -> Product:
         res, st = PolyResult(), Stats()
-        rc = _capi.lib().obk_poly_merge(self._h, C.byref(vterms), int(log2_nsegs), int(result_mem), C.byref(res),
+        rc = _capi.lib().obk_poly_merge(self._h, C.byref(vterms), int(nsegs), int(result_mem), C.byref(res),
                                         C.byref(st))
         if rc != 0:
             _raise(rc, self.last_error())

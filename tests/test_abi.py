@@ -30,8 +30,8 @@ def test_struct_sizes_match_header_layout():
     # fixed-width fields only: the ctypes mirrors must have the C sizes
     assert C.sizeof(_capi.PolyView) == 8 + 8 * 4 + 16
     assert C.sizeof(_capi.Trunc) == 24
-    assert C.sizeof(_capi.PolyResult) == 8 + 6 * 4 + 4 * 8
-    assert C.sizeof(_capi.Stats) == 5 * 8 + 8 * 4 + 7 * 4 + 4  # padded to 8
+    assert C.sizeof(_capi.PolyResult) == 8 + 8 * 4 + 4 * 8
+    assert C.sizeof(_capi.Stats) == 5 * 8 + 10 * 4 + 7 * 4 + 4  # padded to 8
 
 
 def test_version_and_status_strings():

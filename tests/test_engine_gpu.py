@@ -44,7 +44,8 @@ def check_segments(p):
     keys = p.keys
     h = keys.sum(axis=1, dtype=np.uint64)
     seg = np.searchsorted(so, np.arange(n), side="right") - 1
-    assert ((h & np.uint64((1 << p.log2_nsegs) - 1)) == seg.astype(np.uint64)).all()
+    assert p.seg_kind == 0 and p.nsegs == 1 << p.log2_nsegs
+    assert ((h & np.uint64(p.nsegs - 1)) == seg.astype(np.uint64)).all()
     if p.is_f64:
         assert (p.cfs != 0).all()
     else:
@@ -297,12 +298,15 @@ def test_f64_first_contribution_and_signed_zero(engine):
 
 
 def test_skewed_buckets_force_retry(engine):
-    # every key is a multiple of 1024: all terms hash to segment 0 until the segmentation is fine enough
+    # keys that are all multiples of 1024 (one power-of-two bucket); the prime segmentation does not care
     n = 1500
     e = (np.arange(n, dtype=np.int64) * 1024).reshape(-1, 1)
     x = wl.Operand(("a",), e, np.array([i + 1 for i in range(n)], dtype=object), "u64")
     p = check_exact(engine, x, x)
     assert p.nterms == 2 * n - 1
+
+
+DEFAULTS = {"nsegs": -1, "group_lanes": 0, "table_slots": 0, "threads": 1024, "fence": 0, "fill_pct": 62}
 
 
 def test_forced_geometry_options(engine):
@@ -311,15 +315,15 @@ def test_forced_geometry_options(engine):
     y = wl.random_poly(rng, 900, 4, 7, 25, "u64")
     ref = check_exact(engine, x, y).as_dict()
     try:
-        for opts in ({"log2_nsegs": 0}, {"log2_nsegs": 7}, {"group_lanes": 1}, {"group_lanes": 32},
-                     {"table_slots": 1024, "threads": 256}, {"threads": 64}):
+        for opts in ({"nsegs": 1}, {"nsegs": 128}, {"nsegs": 1000}, {"group_lanes": 1}, {"group_lanes": 32},
+                     {"table_slots": 1024, "threads": 256}, {"threads": 64}, {"fence": 1}, {"fill_pct": 85}):
             for k, v in opts.items():
                 engine.set_option(k, v)
             assert engine.mul(x, y).as_dict() == ref, opts
             for k in opts:
-                engine.set_option(k, {"log2_nsegs": -1, "group_lanes": 0, "table_slots": 0, "threads": 1024}[k])
+                engine.set_option(k, DEFAULTS[k])
     finally:
-        for k, v in {"log2_nsegs": -1, "group_lanes": 0, "table_slots": 0, "threads": 1024}.items():
+        for k, v in DEFAULTS.items():
             engine.set_option(k, v)
 
 
