@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity check (run under torchrun): sharded product -> NCCL all-to-all -> owner merge, gathered on
+rank 0 and compared with the CPU oracle.  Used by tests/test_dist_gpu.py."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    import orc
+    from obake_b200 import _capi, dist as obd, engine, workloads as wl
+
+    eng = engine.Engine(local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    cases = []
+    f, g = wl.fateman(10, 4, "u64")
+    cases.append(("fateman10", f, g, None, None))
+    f, g = wl.sparse_mp(7, "i64")
+    cases.append(("sparse7", f, g, None, None))
+    cases.append(("sparse7 trunc 30", f, g, 30, None))
+    cases.append(("sparse7 ptrunc", f, g, 9, [0, 3]))
+    fa, ga = wl.audi("u64", 4, nvars=6, n=6)
+    cases.append(("audi66 d_packed f64", fa, ga, 6, None))
+    ok_all = True
+    for name, f, g, limit, idx in cases:
+        lin = None if f.is_f64 else max(engine.needed_limbs(f.cfs), engine.needed_limbs(g.cfs))
+        hx, hy = engine.HostOperand(f, lin), engine.HostOperand(g, lin)
+        p, info = obd.sharded_mul(eng, hx.view, hy.view, limit=limit, idx=idx, result_mem=_capi.OBK_MEM_HOST)
+        mine = p.as_dict()
+        nsegs = info["nsegs"]
+        a, b = obd.owner_ranges(nsegs, world)[rank]
+        keys = p.keys
+        if len(keys):
+            seg = (keys % np.uint64(nsegs)).sum(axis=1) % nsegs if keys.shape[1] > 1 or f.tname == "u64" else None
+            if seg is not None:
+                assert ((seg >= a) & (seg < b)).all(), "rank holds a segment it does not own"
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            full = {}
+            for d in gathered:
+                assert not (set(full) & set(d))
+                full.update(d)
+            r = orc.poly_mul(f, g, limit=limit, idx=idx, nthreads=os.cpu_count() or 1)
+            if r["keys"].shape[1] == 1:
+                ref = dict(zip(r["keys"][:, 0].tolist(), r["cfs"] if isinstance(r["cfs"], list) else r["cfs"].tolist()))
+            else:
+                ref = {tuple(k): c for k, c in zip(r["keys"].tolist(), r["cfs"] if isinstance(r["cfs"], list) else r["cfs"].tolist())}
+            if f.is_f64:
+                ok = set(full) == set(ref) and all(abs(full[k] - ref[k]) <= 1e-12 * max(abs(ref[k]), 1e-300) + 1e-3 for k in ref)
+            else:
+                ok = full == ref
+            print(f"[dist_check] {name}: world={world} terms={len(full)} nsegs={nsegs} sent_rows(rank0)={info['sent_rows']} ok={ok}",
+                  flush=True)
+            ok_all &= ok
+        p.free()
+    flag = torch.tensor([1 if ok_all else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    eng.close()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
