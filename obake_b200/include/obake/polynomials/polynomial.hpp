@@ -1,0 +1,674 @@
+// obake/polynomials/polynomial.hpp -- polynomial<Key, Cf> whose product runs on the B200 engine.
+//
+// Drop-in for the series-product path of the reference (include/obake/polynomials/polynomial.hpp):
+//   operator* / series_mul(polynomial, polynomial)                      :2026-2032
+//   truncated_mul(x, y, max_degree[, symbol_set])                       :2113-2127
+//   poly_mul_impl_switch (shorter operand first)                        :2014-2022
+//   poly_mul_impl (merge the symbol sets, re-pack the keys)             :1955-2010
+//   poly_mul_impl_identical_ss (empty operand -> empty result)          :1878-1929   <- the seam
+// Everything below the seam (overflow check, size estimate, segmentation, the multiply itself,
+// :797-1582) is the CUDA engine behind include/obk_b200.h; there is NO CPU multiplication here
+// (the reference's poly_mul_impl_simple small-input path, :1602-1874, is routed to the engine too).
+// The container is a plain hash map: the reference's segmented series table (series.hpp:637-639) is host
+// bookkeeping outside the path; the engine returns terms already grouped by hash & (2^k-1) for it.
+#ifndef OBAKE_B200_POLYNOMIAL_HPP
+#define OBAKE_B200_POLYNOMIAL_HPP
+
+#include <array>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../b200/engine.hpp"
+#include "../integer.hpp"
+#include "../symbols.hpp"
+#include "d_packed_monomial.hpp"
+#include "packed_monomial.hpp"
+
+namespace obake
+{
+
+// is_zero (math/is_zero.hpp): x == T(0)
+template <typename C>
+inline bool is_zero(const C &c)
+{
+    return c == C(0);
+}
+
+// mixed coefficient products (polynomial_mul_general_test: integer<1> x double -> double)
+inline double operator*(const integer &a, double b)
+{
+    return static_cast<double>(a) * b;
+}
+inline double operator*(double a, const integer &b)
+{
+    return a * static_cast<double>(b);
+}
+
+namespace detail
+{
+template <typename K>
+struct key_hasher {
+    std::size_t operator()(const K &k) const
+    {
+        return ::obake::hash(k);
+    }
+};
+template <typename T, typename = void>
+struct is_poly : std::false_type {
+};
+} // namespace detail
+
+template <typename K, typename C>
+class polynomial
+{
+public:
+    using key_type = K;
+    using cf_type = C;
+    using table_type = std::unordered_map<K, C, detail::key_hasher<K>>;
+
+private:
+    symbol_set m_ss;
+    table_type m_terms;
+
+public:
+    polynomial() = default;
+    template <typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+    explicit polynomial(const S &c)
+    {
+        C cc = [&] {
+            if constexpr (std::is_same_v<S, integer> && std::is_same_v<C, double>) {
+                return static_cast<double>(c);
+            } else {
+                return C(c);
+            }
+        }();
+        if (!is_zero(cc)) {
+            m_terms.emplace(K(m_ss), std::move(cc));
+        }
+    }
+    const symbol_set &get_symbol_set() const
+    {
+        return m_ss;
+    }
+    void set_symbol_set(const symbol_set &s)
+    {
+        if (!m_terms.empty()) {
+            throw std::invalid_argument("A symbol set can be set only in an empty series");
+        }
+        m_ss = s;
+    }
+    std::size_t size() const
+    {
+        return m_terms.size();
+    }
+    bool empty() const
+    {
+        return m_terms.empty();
+    }
+    auto begin() const
+    {
+        return m_terms.begin();
+    }
+    auto end() const
+    {
+        return m_terms.end();
+    }
+    void clear()
+    {
+        m_terms.clear();
+    }
+    void reserve(std::size_t n)
+    {
+        m_terms.reserve(n);
+    }
+    const table_type &_terms() const
+    {
+        return m_terms;
+    }
+    auto find(const K &k) const
+    {
+        return m_terms.find(k);
+    }
+    // add_term<Sign>: accumulate, erase on zero (series.hpp add_term semantics)
+    template <bool Sign = true>
+    void add_term(const K &k, const C &c)
+    {
+        if (!key_is_compatible(k, m_ss)) {
+            throw std::invalid_argument("Cannot add a term to a series: the term's key is not compatible with the "
+                                        "series' symbol set");
+        }
+        auto [it, inserted] = m_terms.try_emplace(k, c);
+        if (inserted) {
+            if constexpr (!Sign) {
+                it->second = C(0) - it->second;
+            }
+        } else {
+            if constexpr (Sign) {
+                it->second = it->second + c;
+            } else {
+                it->second = it->second - c;
+            }
+        }
+        if (is_zero(it->second)) {
+            m_terms.erase(it);
+        }
+    }
+    // unchecked insertion of a term known to be new and non-zero (engine results)
+    void _insert_unique(K k, C c)
+    {
+        m_terms.emplace(std::move(k), std::move(c));
+    }
+};
+
+namespace detail
+{
+template <typename K, typename C>
+struct is_poly<polynomial<K, C>> : std::true_type {
+};
+
+// Re-express p over the larger symbol set `u` (series_sym_extender, series.hpp:539-625): zero exponents
+// are inserted for the new symbols and every key is re-packed.
+template <typename K, typename C>
+inline polynomial<K, C> extend_symbols(const polynomial<K, C> &p, const symbol_set &u, const std::vector<std::size_t> &pos)
+{
+    using T = typename K::value_type;
+    polynomial<K, C> r;
+    r.set_symbol_set(u);
+    r.reserve(p.size());
+    const auto n_old = p.get_symbol_set().size();
+    std::vector<T> e(u.size());
+    for (const auto &[k, c] : p) {
+        std::fill(e.begin(), e.end(), T(0));
+        const auto old = k.unpack(n_old);
+        for (std::size_t i = 0; i < n_old; ++i) {
+            e[pos[i]] = old[i];
+        }
+        r._insert_unique(K(e.begin(), e.size()), c);
+    }
+    return r;
+}
+
+template <typename P>
+inline void unify(const P &x, const P &y, P &xs, P &ys, const P *&px, const P *&py)
+{
+    if (x.get_symbol_set() == y.get_symbol_set()) {
+        px = &x;
+        py = &y;
+        return;
+    }
+    std::vector<std::size_t> pa, pb;
+    const auto u = merge_symbol_sets(x.get_symbol_set(), y.get_symbol_set(), pa, pb);
+    if (u == x.get_symbol_set()) {
+        px = &x;
+    } else {
+        xs = extend_symbols(x, u, pa);
+        px = &xs;
+    }
+    if (u == y.get_symbol_set()) {
+        py = &y;
+    } else {
+        ys = extend_symbols(y, u, pb);
+        py = &ys;
+    }
+}
+
+struct trunc_args {
+    bool on = false;
+    bool reject_all = false;
+    std::int64_t limit = 0;
+    bool partial = false;
+    std::vector<unsigned> idx;
+};
+
+// Reduce the truncation limit V to the key's integer type T with the conversions the reference's comparison
+// `max_deg < d_i + d_j` performs (polynomial.hpp:604-610): built-in integers follow the usual arithmetic
+// conversions (a negative int against an unsigned T wraps), multiprecision integers compare by value.
+template <typename T, typename V>
+inline void reduce_limit(trunc_args &ta, const V &lim)
+{
+    ta.on = true;
+    if constexpr (std::is_same_v<V, integer>) {
+        if constexpr (std::is_signed_v<T>) {
+            if (lim < integer(std::numeric_limits<std::int64_t>::min())) {
+                ta.reject_all = true;
+            } else if (lim > integer(std::numeric_limits<std::int64_t>::max())) {
+                ta.limit = std::numeric_limits<std::int64_t>::max();
+            } else {
+                ta.limit = static_cast<std::int64_t>(lim);
+            }
+        } else {
+            if (lim.sgn() < 0) {
+                ta.reject_all = true;
+            } else if (lim.nbits() > 64u) {
+                ta.limit = -1; // UINT64_MAX
+            } else {
+                std::uint64_t l[2] = {0, 0};
+                lim.to_limbs(l, 2);
+                ta.limit = static_cast<std::int64_t>(l[0]);
+            }
+        }
+    } else {
+        static_assert(std::is_integral_v<V>, "the truncation limit must be an integer");
+        if constexpr (std::is_signed_v<T>) {
+            if constexpr (std::is_unsigned_v<V> && sizeof(V) >= sizeof(std::int64_t)) {
+                ta.limit = lim > static_cast<V>(std::numeric_limits<std::int64_t>::max())
+                               ? std::numeric_limits<std::int64_t>::max()
+                               : static_cast<std::int64_t>(lim);
+            } else {
+                ta.limit = static_cast<std::int64_t>(lim);
+            }
+        } else {
+            // T unsigned: int -> unsigned conversion (wraps for negative values), 64-bit bit pattern
+            if constexpr (std::is_signed_v<V>) {
+                if constexpr (sizeof(T) < 8) {
+                    // 32-bit unsigned T: int converts to uint32 when ranks are equal
+                    ta.limit = static_cast<std::int64_t>(static_cast<std::uint64_t>(static_cast<std::uint32_t>(lim)));
+                    if (sizeof(V) > sizeof(T)) {
+                        // wider signed V: the comparison happens in V; a negative limit rejects everything
+                        if (lim < 0) {
+                            ta.reject_all = true;
+                        } else {
+                            ta.limit = static_cast<std::int64_t>(lim);
+                        }
+                    }
+                } else {
+                    ta.limit = static_cast<std::int64_t>(static_cast<std::uint64_t>(static_cast<std::int64_t>(lim)));
+                }
+            } else {
+                ta.limit = static_cast<std::int64_t>(static_cast<std::uint64_t>(lim));
+            }
+        }
+    }
+}
+
+// poly_mul_impl_identical_ss: both operands share the symbol set.
+template <typename K, typename C0, typename C1, typename R = decltype(std::declval<C0>() * std::declval<C1>())>
+inline polynomial<K, R> poly_mul_impl_identical_ss(const polynomial<K, C0> &x, const polynomial<K, C1> &y,
+                                                   const trunc_args &ta)
+{
+    using T = typename K::value_type;
+    polynomial<K, R> ret;
+    ret.set_symbol_set(x.get_symbol_set());
+    // empty operand -> empty result (polynomial.hpp:1892-1895)
+    if (x.empty() || y.empty() || ta.reject_all) {
+        return ret;
+    }
+    const auto &ss = x.get_symbol_set();
+    const std::size_t nvars = ss.size();
+    const unsigned W = K::n_words(nvars);
+    using RT = b200::cf_traits<R>;
+
+    // Marshal the terms to SoA (what the reference copies into vectors at :828-833).
+    unsigned lin = 1;
+    if constexpr (RT::kind == OBK_CF_INT) {
+        for (const auto &[k, c] : x) lin = std::max(lin, b200::cf_traits<C0>::limbs_needed(c));
+        for (const auto &[k, c] : y) lin = std::max(lin, b200::cf_traits<C1>::limbs_needed(c));
+    }
+    auto marshal = [&](const auto &p, std::vector<std::uint64_t> &keys, std::vector<std::uint64_t> &cfs) {
+        using CP = typename std::decay_t<decltype(p)>::cf_type;
+        keys.resize(p.size() * W);
+        cfs.resize(p.size() * lin);
+        std::size_t i = 0;
+        for (const auto &[k, c] : p) {
+            k.to_words(&keys[i * W], nvars);
+            if constexpr (std::is_same_v<CP, R>) {
+                RT::store(c, &cfs[i * lin], lin);
+            } else {
+                // mixed coefficient types: convert to the result type once on the host
+                RT::store(static_cast<R>(c), &cfs[i * lin], lin);
+            }
+            ++i;
+        }
+    };
+    std::vector<std::uint64_t> kx, cx, ky, cy;
+    marshal(x, kx, cx);
+    marshal(y, ky, cy);
+    auto view = [&](std::size_t n, const std::vector<std::uint64_t> &k, const std::vector<std::uint64_t> &c) {
+        obk_poly_view v{};
+        v.nterms = n;
+        v.key_words = W;
+        v.key_signed = std::is_signed_v<T> ? 1u : 0u;
+        v.nvars = static_cast<std::uint32_t>(nvars);
+        v.psize = K::psize;
+        v.cf_kind = RT::kind;
+        v.cf_limbs = lin;
+        v.mem = OBK_MEM_HOST;
+        v.keys = k.data();
+        v.cfs = c.data();
+        return v;
+    };
+    const obk_poly_view vx = view(x.size(), kx, cx), vy = view(y.size(), ky, cy);
+    obk_trunc tr{};
+    if (ta.on) {
+        tr.limit = ta.limit;
+        tr.partial = ta.partial ? 1u : 0u;
+        tr.nidx = static_cast<std::uint32_t>(ta.idx.size());
+        tr.idx = ta.idx.data();
+    }
+    auto &eng = b200::engine::instance();
+    obk_poly_result res{};
+    {
+        std::lock_guard<std::mutex> g(eng.mutex());
+        eng.check(::obk_poly_mul(eng.handle(), &vx, &vy, ta.on ? &tr : nullptr, OBK_MEM_HOST, &res, nullptr));
+    }
+    // Rebuild the host container (terms arrive grouped by table, without zeros or duplicates).
+    try {
+        ret.reserve(res.nterms);
+        const auto *rc = static_cast<const std::uint64_t *>(res.cfs);
+        for (std::uint64_t i = 0; i < res.nterms; ++i) {
+            ret._insert_unique(K::from_words(res.keys + i * W, nvars), RT::load(rc + i * res.cf_limbs, res.cf_limbs));
+        }
+    } catch (...) {
+        ::obk_result_free(eng.handle(), &res);
+        ret.clear(); // polynomial.hpp:1575-1580
+        throw;
+    }
+    ::obk_result_free(eng.handle(), &res);
+    return ret;
+}
+
+// poly_mul_impl + poly_mul_impl_switch
+template <typename K, typename C0, typename C1>
+inline auto poly_mul_impl_switch(const polynomial<K, C0> &x, const polynomial<K, C1> &y, const trunc_args &ta)
+{
+    if constexpr (std::is_same_v<C0, C1>) {
+        polynomial<K, C0> xs, ys;
+        const polynomial<K, C0> *px, *py;
+        unify(x, y, xs, ys, px, py);
+        return poly_mul_impl_identical_ss(*px, *py, ta);
+    } else {
+        if (x.get_symbol_set() == y.get_symbol_set()) {
+            return poly_mul_impl_identical_ss(x, y, ta);
+        }
+        std::vector<std::size_t> pa, pb;
+        const auto u = merge_symbol_sets(x.get_symbol_set(), y.get_symbol_set(), pa, pb);
+        return poly_mul_impl_identical_ss(extend_symbols(x, u, pa), extend_symbols(y, u, pb), ta);
+    }
+}
+
+} // namespace detail
+
+// ---- the public product entry points ---------------------------------------------------------------------
+namespace polynomials
+{
+template <typename K, typename C0, typename C1>
+inline auto series_mul(const polynomial<K, C0> &x, const polynomial<K, C1> &y)
+{
+    return detail::poly_mul_impl_switch(x, y, detail::trunc_args{});
+}
+
+template <typename K, typename C0, typename C1, typename V>
+inline auto truncated_mul(const polynomial<K, C0> &x, const polynomial<K, C1> &y, const V &max_degree)
+{
+    detail::trunc_args ta;
+    detail::reduce_limit<typename K::value_type>(ta, max_degree);
+    return detail::poly_mul_impl_switch(x, y, ta);
+}
+
+template <typename K, typename C0, typename C1, typename V>
+inline auto truncated_mul(const polynomial<K, C0> &x, const polynomial<K, C1> &y, const V &max_degree, const symbol_set &s)
+{
+    detail::trunc_args ta;
+    detail::reduce_limit<typename K::value_type>(ta, max_degree);
+    ta.partial = true;
+    // positions in the MERGED symbol set of the symbols of s that are present
+    std::vector<std::size_t> pa, pb;
+    const auto u = merge_symbol_sets(x.get_symbol_set(), y.get_symbol_set(), pa, pb);
+    ta.idx = ss_intersect_idx(s, u);
+    return detail::poly_mul_impl_switch(x, y, ta);
+}
+} // namespace polynomials
+
+using polynomials::series_mul;
+using polynomials::truncated_mul;
+
+template <typename K, typename C0, typename C1>
+inline auto operator*(const polynomial<K, C0> &x, const polynomial<K, C1> &y)
+{
+    return polynomials::series_mul(x, y);
+}
+
+// series x scalar (series_default_mul_impl, series.hpp:3098-3182) -- host arithmetic, outside the path
+template <typename K, typename C, typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+inline polynomial<K, C> operator*(const polynomial<K, C> &x, const S &s)
+{
+    polynomial<K, C> r;
+    r.set_symbol_set(x.get_symbol_set());
+    const C sc = [&] {
+        if constexpr (std::is_same_v<S, integer> && std::is_same_v<C, double>) {
+            return static_cast<double>(s);
+        } else {
+            return C(s);
+        }
+    }();
+    if (is_zero(sc)) {
+        return r;
+    }
+    r.reserve(x.size());
+    for (const auto &[k, c] : x) {
+        C v = c * sc;
+        if (!is_zero(v)) {
+            r._insert_unique(k, std::move(v));
+        }
+    }
+    return r;
+}
+template <typename K, typename C, typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+inline polynomial<K, C> operator*(const S &s, const polynomial<K, C> &x)
+{
+    return x * s;
+}
+template <typename K, typename C, typename U>
+inline polynomial<K, C> &operator*=(polynomial<K, C> &x, const U &y)
+{
+    x = x * y; // series.hpp:3200-3207
+    return x;
+}
+
+// ---- addition / subtraction (series.hpp:2195-2991; host bookkeeping used to build operands) ---------------
+namespace detail
+{
+template <bool Sign, typename K, typename C>
+inline polynomial<K, C> poly_addsub(const polynomial<K, C> &x, const polynomial<K, C> &y)
+{
+    polynomial<K, C> xs, ys;
+    const polynomial<K, C> *px, *py;
+    unify(x, y, xs, ys, px, py);
+    polynomial<K, C> r(*px);
+    for (const auto &[k, c] : *py) {
+        r.template add_term<Sign>(k, c);
+    }
+    return r;
+}
+} // namespace detail
+
+template <typename K, typename C>
+inline polynomial<K, C> operator+(const polynomial<K, C> &x, const polynomial<K, C> &y)
+{
+    return detail::poly_addsub<true>(x, y);
+}
+template <typename K, typename C>
+inline polynomial<K, C> operator-(const polynomial<K, C> &x, const polynomial<K, C> &y)
+{
+    return detail::poly_addsub<false>(x, y);
+}
+template <typename K, typename C, typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+inline polynomial<K, C> operator+(const polynomial<K, C> &x, const S &s)
+{
+    polynomial<K, C> c(s);
+    return x + c;
+}
+template <typename K, typename C, typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+inline polynomial<K, C> operator+(const S &s, const polynomial<K, C> &x)
+{
+    return x + s;
+}
+template <typename K, typename C, typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+inline polynomial<K, C> operator-(const polynomial<K, C> &x, const S &s)
+{
+    polynomial<K, C> c(s);
+    return x - c;
+}
+template <typename K, typename C, typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+inline polynomial<K, C> operator-(const S &s, const polynomial<K, C> &x)
+{
+    polynomial<K, C> c(s);
+    return c - x;
+}
+template <typename K, typename C>
+inline polynomial<K, C> operator-(const polynomial<K, C> &x)
+{
+    return polynomial<K, C>() - x;
+}
+template <typename K, typename C, typename U>
+inline polynomial<K, C> &operator+=(polynomial<K, C> &x, const U &y)
+{
+    x = x + y;
+    return x;
+}
+template <typename K, typename C, typename U>
+inline polynomial<K, C> &operator-=(polynomial<K, C> &x, const U &y)
+{
+    x = x - y;
+    return x;
+}
+
+template <typename K, typename C>
+inline bool operator==(const polynomial<K, C> &x, const polynomial<K, C> &y)
+{
+    polynomial<K, C> xs, ys;
+    const polynomial<K, C> *px, *py;
+    detail::unify(x, y, xs, ys, px, py);
+    if (px->size() != py->size()) {
+        return false;
+    }
+    for (const auto &[k, c] : *px) {
+        const auto it = py->find(k);
+        if (it == py->end() || !(it->second == c)) {
+            return false;
+        }
+    }
+    return true;
+}
+template <typename K, typename C>
+inline bool operator!=(const polynomial<K, C> &x, const polynomial<K, C> &y)
+{
+    return !(x == y);
+}
+template <typename K, typename C, typename S, std::enable_if_t<std::is_arithmetic_v<S> || std::is_same_v<S, integer>, int> = 0>
+inline bool operator==(const polynomial<K, C> &x, const S &s)
+{
+    return x == polynomial<K, C>(s);
+}
+
+// ---- degrees and truncation as test oracles (polynomial.hpp:2364-2445; series.hpp degree) -------------------
+template <typename K, typename C>
+inline typename K::value_type degree(const polynomial<K, C> &p)
+{
+    using T = typename K::value_type;
+    bool first = true;
+    T best(0);
+    for (const auto &[k, c] : p) {
+        const T d = key_degree(k, p.get_symbol_set());
+        if (first || d > best) {
+            best = d;
+            first = false;
+        }
+    }
+    return best;
+}
+template <typename K, typename C>
+inline typename K::value_type p_degree(const polynomial<K, C> &p, const symbol_set &s)
+{
+    using T = typename K::value_type;
+    const auto idx = ss_intersect_idx(s, p.get_symbol_set());
+    bool first = true;
+    T best(0);
+    for (const auto &[k, c] : p) {
+        const T d = key_p_degree(k, idx, p.get_symbol_set());
+        if (first || d > best) {
+            best = d;
+            first = false;
+        }
+    }
+    return best;
+}
+template <typename K, typename C, typename V>
+inline polynomial<K, C> truncate_degree(const polynomial<K, C> &p, const V &lim)
+{
+    polynomial<K, C> r;
+    r.set_symbol_set(p.get_symbol_set());
+    for (const auto &[k, c] : p) {
+        if (!(lim < key_degree(k, p.get_symbol_set()))) {
+            r._insert_unique(k, c);
+        }
+    }
+    return r;
+}
+template <typename K, typename C, typename V>
+inline polynomial<K, C> truncate_p_degree(const polynomial<K, C> &p, const V &lim, const symbol_set &s)
+{
+    const auto idx = ss_intersect_idx(s, p.get_symbol_set());
+    polynomial<K, C> r;
+    r.set_symbol_set(p.get_symbol_set());
+    for (const auto &[k, c] : p) {
+        if (!(lim < key_p_degree(k, idx, p.get_symbol_set()))) {
+            r._insert_unique(k, c);
+        }
+    }
+    return r;
+}
+
+// obake::pow by repeated multiplication (series pow, series.hpp:1628-1712: v.back() * b)
+template <typename K, typename C>
+inline polynomial<K, C> pow(const polynomial<K, C> &b, unsigned n)
+{
+    polynomial<K, C> r(1);
+    for (unsigned i = 0; i < n; ++i) {
+        r = r * b;
+    }
+    return r;
+}
+
+// ---- make_polynomials (polynomial.hpp:97-227) --------------------------------------------------------------
+namespace detail
+{
+template <typename P>
+inline P make_generator(const symbol_set &ss, const std::string &name)
+{
+    using K = typename P::key_type;
+    using T = typename K::value_type;
+    const auto pos = ss.index_of(name);
+    if (pos == ss.size()) {
+        throw std::invalid_argument("Cannot create a polynomial with symbol set " + std::string("{...}") + " from the generator '"
+                                    + name + "': the generator is not in the symbol set");
+    }
+    std::vector<T> e(ss.size(), T(0));
+    e[pos] = T(1);
+    P p;
+    p.set_symbol_set(ss);
+    p.add_term(K(e.begin(), e.size()), typename P::cf_type(1));
+    return p;
+}
+} // namespace detail
+
+template <typename P, typename... Names>
+inline std::array<P, sizeof...(Names)> make_polynomials(const symbol_set &ss, const Names &...names)
+{
+    return {{detail::make_generator<P>(ss, std::string(names))...}};
+}
+template <typename P, typename... Names, std::enable_if_t<(std::is_convertible_v<Names, std::string> && ...), int> = 0>
+inline std::array<P, sizeof...(Names)> make_polynomials(const Names &...names)
+{
+    return {{detail::make_generator<P>(symbol_set{std::string(names)}, std::string(names))...}};
+}
+
+} // namespace obake
+
+#endif

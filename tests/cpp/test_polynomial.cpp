@@ -1,0 +1,324 @@
+// C++ parity tests for the drop-in boundary, written after the reference's own Catch2 tests for the
+// series-product path (file:line cited per case).  Everything that multiplies goes through
+// obake::polynomial::operator* / truncated_mul -> C ABI -> CUDA engine.
+//   ./test_polynomial          all tests (needs a B200)
+//   ./test_polynomial --cpu    host-only tests (kpack, monomials, integer, symbol sets)
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+
+#include <obake/polynomials/polynomial.hpp>
+
+using namespace obake;
+
+static int g_fail = 0, g_checks = 0;
+#define REQUIRE(...)                                                                                                   \
+    do {                                                                                                               \
+        ++g_checks;                                                                                                    \
+        if (!(__VA_ARGS__)) {                                                                                          \
+            ++g_fail;                                                                                                  \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #__VA_ARGS__);                                       \
+        }                                                                                                              \
+    } while (0)
+// test/test_utils.hpp:36-47 -- exception type AND message substring are part of the contract
+#define REQUIRES_THROWS_CONTAINS(expr, exc, msg)                                                                       \
+    do {                                                                                                               \
+        ++g_checks;                                                                                                    \
+        bool ok_ = false;                                                                                              \
+        try {                                                                                                          \
+            (void)(expr);                                                                                              \
+        } catch (const exc &e_) {                                                                                      \
+            ok_ = std::string(e_.what()).find(msg) != std::string::npos;                                               \
+            if (!ok_) std::printf("  wrong message: %s\n", e_.what());                                                 \
+        } catch (...) {                                                                                                \
+        }                                                                                                              \
+        if (!ok_) {                                                                                                    \
+            ++g_fail;                                                                                                  \
+            std::printf("FAILED %s:%d: %s should throw %s containing '%s'\n", __FILE__, __LINE__, #expr, #exc, msg);   \
+        }                                                                                                              \
+    } while (0)
+
+template <typename T>
+static void kpack_tests()
+{
+    // test/kpack.cpp:101-219 (round trips, extrema, range errors)
+    std::mt19937 rng;
+    for (unsigned size = 1; size <= detail::kpack_max_size<T>(); ++size) {
+        const auto [lo, hi] = detail::kpack_get_lims<T>(size);
+        const long double hi_ld = static_cast<long double>(hi);
+        std::uniform_int_distribution<long long> dist(static_cast<long long>(lo),
+                                                      hi_ld > 4.0e18L ? 4000000000000000000ll : static_cast<long long>(hi));
+        for (int t = 0; t < 200; ++t) {
+            std::vector<T> v(size), w(size);
+            kpacker<T> kp(size);
+            for (auto &e : v) {
+                e = static_cast<T>(dist(rng));
+                kp << e;
+            }
+            kunpacker<T> ku(kp.get(), size);
+            for (auto &e : w) ku >> e;
+            REQUIRE(v == w);
+        }
+        kpacker<T> kmin(size), kmax(size);
+        for (unsigned i = 0; i < size; ++i) {
+            kmin << lo;
+            kmax << hi;
+        }
+        REQUIRE(kmin.get() == detail::kpack_get_klims<T>(size).first);
+        REQUIRE(kmax.get() == detail::kpack_get_klims<T>(size).second);
+        if (size > 1u) {
+            kpacker<T> kp(size);
+            REQUIRES_THROWS_CONTAINS(kp << static_cast<T>(hi + 1), std::overflow_error, "the value is outside the allowed range");
+        }
+    }
+    REQUIRES_THROWS_CONTAINS(kpacker<T>(detail::kpack_max_size<T>() + 1u), std::overflow_error, "the maximum possible size is");
+    {
+        kpacker<T> kp(2);
+        kp << T(1) << T(2);
+        REQUIRES_THROWS_CONTAINS(kp << T(3), std::out_of_range, "Cannot push any more values to this Kronecker packer");
+    }
+    REQUIRES_THROWS_CONTAINS(kunpacker<T>(T(1), 0), std::invalid_argument, "Only a value of zero can be used in a Kronecker unpacker");
+}
+
+template <typename T>
+static void monomial_tests()
+{
+    using pm_t = packed_monomial<T>;
+    symbol_set ss{"x", "y", "z"};
+    // test/polynomials_packed_monomial_00.cpp:472-494: {1,2,3}*{4,5,6} == {5,7,9}
+    pm_t a{1, 2, 3}, b{4, 5, 6}, c;
+    monomial_mul(c, a, b, ss);
+    REQUIRE(c == pm_t{5, 7, 9});
+    // :198-210 hash == value
+    REQUIRE(hash(a) == static_cast<std::size_t>(a.get_value()));
+    // :574-618 homomorphic hash
+    std::mt19937 rng;
+    std::uniform_int_distribution<int> d(0, 5);
+    for (int t = 0; t < 500; ++t) {
+        std::vector<T> v1(6), v2(6), v3(6);
+        for (int i = 0; i < 6; ++i) {
+            v1[i] = static_cast<T>(d(rng));
+            v2[i] = static_cast<T>(d(rng));
+            v3[i] = static_cast<T>(v1[i] + v2[i]);
+        }
+        REQUIRE(hash(pm_t(v1)) + hash(pm_t(v2)) == hash(pm_t(v3)));
+        using dpm_t = d_packed_monomial<T, 4>;
+        REQUIRE(hash(dpm_t(v1)) + hash(dpm_t(v2)) == hash(dpm_t(v3)));
+        dpm_t out;
+        monomial_mul(out, dpm_t(v1), dpm_t(v2), symbol_set{"a", "b", "c", "d", "e", "f"});
+        REQUIRE(out == dpm_t(v3));
+        REQUIRE(dpm_t(v1).unpack(6) == v1);
+        REQUIRE(key_degree(dpm_t(v1), symbol_set{"a", "b", "c", "d", "e", "f"}) == static_cast<T>(v1[0] + v1[1] + v1[2] + v1[3] + v1[4] + v1[5]));
+    }
+    REQUIRE(key_degree(a, ss) == T(6));
+    REQUIRE(key_p_degree(a, std::vector<unsigned>{0, 2}, ss) == T(4));
+    REQUIRE(key_is_compatible(a, ss));
+    // overflow check (polynomials_packed_monomial_00.cpp:496-552)
+    const auto [lo, hi] = detail::kpack_get_lims<T>(3);
+    std::vector<pm_t> r1{pm_t{1, 2, 3}, pm_t{hi, 0, 0}}, r2{pm_t{1, 0, 0}}, r3{pm_t{0, 1, 1}};
+    REQUIRE(!monomial_range_overflow_check(r1, r2, ss));
+    REQUIRE(monomial_range_overflow_check(r1, r3, ss));
+    REQUIRE(monomial_range_overflow_check(std::vector<pm_t>{}, r3, ss));
+}
+
+static void integer_tests()
+{
+    integer a(std::string("123456789012345678901234567890")), b(-42);
+    REQUIRE((a * b).to_string() == "-5185185138518518513851851851380");
+    REQUIRE((a + b - a) == b);
+    REQUIRE(pow(integer(13), 24).to_string() == "542800770374370512771595361");
+    std::uint64_t l[3];
+    (a * b).to_limbs(l, 3);
+    REQUIRE(integer::from_limbs(l, 3) == a * b);
+    REQUIRE(integer(-1).limbs_needed() == 1u);
+    REQUIRE((integer(1) * integer(std::string("18446744073709551616"))).limbs_needed() == 2u);
+    REQUIRE(integer(5) < integer(7) && integer(-7) < integer(-5) && integer(-1) < integer(1));
+    REQUIRES_THROWS_CONTAINS(a.to_limbs(l, 1), std::overflow_error, "does not fit");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename K, typename C>
+static void mul_mt_hm_test()
+{
+    // test/polynomials_polynomial_00.cpp:189-240 (polynomial_mul_mt_hm_test)
+    using poly_t = polynomial<K, C>;
+    auto [a, b] = make_polynomials<poly_t>(symbol_set{"a", "b"}, "a", "b");
+    REQUIRE(poly_t(3) * poly_t(4) == poly_t(12));
+    REQUIRE((a + b) * (a - b) == a * a - b * b);
+    REQUIRE((a * a + b * b) * (a + b) * (a - b) == a * a * a * a - b * b * b * b);
+    REQUIRE(((a + b) * (a - b)).size() == 2u);
+    // empty operands (:1892-1895)
+    REQUIRE((poly_t() * a).empty());
+    REQUIRE((a * poly_t()).empty());
+    // exponent overflow (:216-238)
+    using T = typename K::value_type;
+    const unsigned sz = K::psize ? K::psize : 2u;
+    const auto [lo, hi] = detail::kpack_get_lims<T>(sz);
+    poly_t big;
+    big.set_symbol_set(symbol_set{"a", "b"});
+    big.add_term(K{hi, T(0)}, C(1));
+    big.add_term(K{T(0), T(1)}, C(1));
+    REQUIRES_THROWS_CONTAINS(big * a, std::overflow_error,
+                             "An overflow in the monomial exponents was detected while attempting to multiply two polynomials");
+    if constexpr (std::is_signed_v<T>) {
+        poly_t small;
+        small.set_symbol_set(symbol_set{"a", "b"});
+        small.add_term(K{lo, T(0)}, C(1));
+        poly_t inv;
+        inv.set_symbol_set(symbol_set{"a", "b"});
+        inv.add_term(K{T(-1), T(0)}, C(1));
+        REQUIRES_THROWS_CONTAINS(small * inv, std::overflow_error,
+                                 "An overflow in the monomial exponents was detected while attempting to multiply two polynomials");
+    }
+}
+
+template <typename K>
+static void mul_general_test()
+{
+    // test/polynomials_polynomial_00.cpp:244-394: symbol-set merging in all three cases, *=, mixed coefficients
+    using p_int = polynomial<K, integer>;
+    using p_dbl = polynomial<K, double>;
+    auto [x] = make_polynomials<p_int>("x");
+    auto [y] = make_polynomials<p_int>("y");
+    auto [xx, yy, zz] = make_polynomials<p_int>(symbol_set{"x", "y", "z"}, "x", "y", "z");
+    auto r = x * y; // both extended
+    REQUIRE(r.get_symbol_set() == symbol_set{"x", "y"});
+    REQUIRE(r.size() == 1u);
+    auto r2 = xx * y; // only the second extended
+    REQUIRE(r2.get_symbol_set() == symbol_set{"x", "y", "z"});
+    REQUIRE(r2 == xx * yy);
+    auto r3 = y * zz; // only the first extended
+    REQUIRE(r3 == yy * zz);
+    auto acc = x + 1;
+    acc *= x - 1;
+    REQUIRE(acc == x * x - 1);
+    // integer x double -> double
+    auto [xd] = make_polynomials<p_dbl>("x");
+    auto m = (x * 3 + 1) * (xd * 0.5 + 2.);
+    static_assert(std::is_same_v<decltype(m), p_dbl>);
+    REQUIRE(m == xd * xd * 1.5 + xd * 6.5 + 2.);
+}
+
+template <typename K, typename C>
+static void truncated_tests()
+{
+    // test/polynomials_polynomial_01.cpp:131-183
+    using poly_t = polynomial<K, C>;
+    auto [x, y, z] = make_polynomials<poly_t>(symbol_set{"x", "y", "z"}, "x", "y", "z");
+    REQUIRE(truncated_mul(x + y, x - y, 100) == x * x - y * y);
+    REQUIRE(truncated_mul(x + y, x - y, 2) == x * x - y * y);
+    REQUIRE(truncated_mul(x + y, x - y, 1).empty());
+    REQUIRE(truncated_mul(x + y, x - y, 0).empty());
+    REQUIRE(truncated_mul(x + y, x - y, -1).empty() || !std::is_signed_v<typename K::value_type>);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 100) == z * x * x - z * x * y - z * x + y * x - y * y - y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 2) == -z * x + y * x - y * y - y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, integer(2)) == -z * x + y * x - y * y - y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 1) == -y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, integer(1)) == -y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 0).empty());
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, integer(-1)).empty());
+    // partial degree (test/polynomials_polynomial_02.cpp:182-252)
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 100, symbol_set{"x"}) == z * x * x - z * x * y - z * x + y * x - y * y - y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 1, symbol_set{"x"}) == -z * x * y - z * x + y * x - y * y - y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 0, symbol_set{"x"}) == -y * y - y);
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 0, symbol_set{"x", "y"}).empty());
+    REQUIRE(truncated_mul(z * x + y, x - y - 1, 1, symbol_set{"y", "zzz"}) == z * x * x - z * x * y - z * x + y * x - y);
+}
+
+template <typename K, typename C>
+static void large_tests()
+{
+    using poly_t = polynomial<K, C>;
+    auto [t, u, x, y, z] = make_polynomials<poly_t>(symbol_set{"t", "u", "x", "y", "z"}, "t", "u", "x", "y", "z");
+    auto f = x + y + z * z * 2 + t * t * t * 3 + u * u * u * u * u * 5 + 1;
+    auto g = u + t + z * z * 2 + y * y * y * 3 + x * x * x * x * x * 5 + 1;
+    const auto tf = f, tg = g;
+    // n = 8: truncation cases of test/polynomials_polynomial_01.cpp:185-236 and _04.cpp:239-262
+    for (int i = 1; i < 8; ++i) {
+        f *= tf;
+        g *= tg;
+    }
+    const auto full = f * g;
+    REQUIRE(full.size() == 591235u);
+    REQUIRE(truncated_mul(f, g, 1000) == full);
+    REQUIRE(truncated_mul(f, g, 80) == full);
+    REQUIRE(degree(truncated_mul(f, g, 40)) == 40);
+    REQUIRE(degree(truncated_mul(f, g, 5)) == 5);
+    REQUIRE(truncated_mul(f, g, 0) == poly_t(1));
+    if constexpr (std::is_signed_v<typename K::value_type>) {
+        REQUIRE(truncated_mul(f, g, -1).empty());
+    }
+    REQUIRE(truncated_mul(f, g, 50) == truncate_degree(full, 50));
+    REQUIRE(truncated_mul(f, g, 20, symbol_set{"x", "z"}) == truncate_p_degree(full, 20, symbol_set{"x", "z"}));
+    // n = 10: 2 096 600 terms (test/polynomials_polynomial_00.cpp:398-424)
+    for (int i = 8; i < 10; ++i) {
+        f *= tf;
+        g *= tg;
+    }
+    REQUIRE(f.size() == 3003u);
+    REQUIRE((f * g).size() == 2096600u);
+    // (..)^20 by 19 rectangular products: 53 130 terms (test/polynomials_polynomial_04.cpp:264-285)
+    auto h = tf;
+    for (int i = 0; i < 19; ++i) {
+        h *= tf;
+    }
+    REQUIRE(h.size() == 53130u);
+}
+
+static void fateman_test()
+{
+    // benchmark/dense.hpp:21-44 at n = 12, checked against (1+..)^(2n) + (1+..)^n coefficient by coefficient
+    using poly_t = polynomial<packed_monomial<std::uint64_t>, integer>;
+    auto [t, x, y, z] = make_polynomials<poly_t>(symbol_set{"t", "x", "y", "z"}, "t", "x", "y", "z");
+    auto f = x + y + z + t + 1;
+    const auto tmp = f;
+    for (int i = 1; i < 12; ++i) {
+        f *= tmp;
+    }
+    auto g = f + 1;
+    const auto ret = f * g;
+    REQUIRE(ret.size() == 20475u); // C(28,4)
+    auto f24 = f * f;              // (1+..)^24
+    REQUIRE(ret == f24 + f);
+    // sum of the coefficients = 5^24 + 5^12
+    integer sum(0);
+    for (const auto &[k, c] : ret) {
+        sum += c;
+    }
+    REQUIRE(sum == pow(integer(5), 24) + pow(integer(5), 12));
+}
+
+int main(int argc, char **argv)
+{
+    const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
+    kpack_tests<std::int32_t>();
+    kpack_tests<std::uint32_t>();
+    kpack_tests<std::int64_t>();
+    kpack_tests<std::uint64_t>();
+    monomial_tests<std::int64_t>();
+    monomial_tests<std::uint64_t>();
+    monomial_tests<std::int32_t>();
+    integer_tests();
+    if (!cpu_only) {
+        mul_mt_hm_test<packed_monomial<std::int64_t>, integer>();
+        mul_mt_hm_test<packed_monomial<std::int64_t>, double>();
+        mul_mt_hm_test<packed_monomial<std::uint64_t>, integer>();
+        mul_mt_hm_test<packed_monomial<std::int32_t>, integer>();
+        mul_mt_hm_test<d_packed_monomial<std::int64_t, 8>, integer>();
+        mul_mt_hm_test<d_packed_monomial<std::uint64_t, 1>, double>();
+        mul_general_test<packed_monomial<std::int64_t>>();
+        mul_general_test<d_packed_monomial<std::int64_t, 2>>();
+        truncated_tests<packed_monomial<std::int64_t>, integer>();
+        truncated_tests<packed_monomial<std::int64_t>, double>();
+        truncated_tests<d_packed_monomial<std::int64_t, 2>, integer>();
+        large_tests<packed_monomial<std::int64_t>, integer>();
+        large_tests<d_packed_monomial<std::int64_t, 3>, double>();
+        fateman_test();
+    }
+    std::printf("%s: %d checks, %d failures%s\n", g_fail ? "FAILED" : "OK", g_checks, g_fail, cpu_only ? " (host-only subset)" : "");
+    return g_fail ? 1 : 0;
+}

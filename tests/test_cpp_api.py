@@ -1,0 +1,41 @@
+"""Builds tests/cpp/test_polynomial.cpp (the obake-shaped C++ host API over the C ABI) and runs it: the
+host-only subset on CPU, everything (operator*, truncated_mul, known answers) on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "_build", "test_polynomial")
+SRC = os.path.join(ROOT, "tests", "cpp", "test_polynomial.cpp")
+
+
+def build_exe():
+    from obake_b200 import build
+
+    build.build_native()
+    inc = os.path.join(ROOT, "obake_b200", "include")
+    newest = max(os.path.getmtime(os.path.join(dp, f)) for dp, _, fs in os.walk(inc) for f in fs)
+    newest = max(newest, os.path.getmtime(SRC), os.path.getmtime(os.path.join(ROOT, "include", "obk_b200.h")))
+    if os.path.exists(EXE) and os.path.getmtime(EXE) >= newest:
+        return EXE
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    cmd = ["g++", "-std=c++20", "-O2", "-Wall", "-I", inc, "-o", EXE, SRC, "-L", os.path.join(ROOT, "obake_b200", "lib"),
+           "-lobk_b200", "-Wl,-rpath,$ORIGIN/../../obake_b200/lib"]
+    subprocess.check_call(cmd)
+    return EXE
+
+
+def test_cpp_host_only_subset():
+    exe = build_exe()
+    r = subprocess.run([exe, "--cpu"], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "OK:" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_full_suite_on_gpu():
+    exe = build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=580)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "OK:" in r.stdout
