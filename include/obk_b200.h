@@ -59,7 +59,8 @@ typedef struct obk_poly_view {
     uint32_t cf_kind;    /* OBK_CF_INT | OBK_CF_F64 */
     uint32_t cf_limbs;   /* integer: 1 or 2 input limbs; f64: 1 */
     uint32_t mem;        /* OBK_MEM_HOST | OBK_MEM_DEVICE */
-    uint32_t reserved;
+    uint32_t key_bits;   /* width of T: 64 (or 0) | 32.  Selects the Kronecker tables (delta, limits); 32-bit
+                          * keys still travel widened to 64-bit words */
     const uint64_t *keys; /* [nterms * key_words] */
     const void *cfs;      /* [nterms * cf_limbs] uint64 or [nterms] double */
 } obk_poly_view;

@@ -23,7 +23,7 @@ OBK_MEM_HOST, OBK_MEM_DEVICE = 0, 1
 class PolyView(C.Structure):
     _fields_ = [("nterms", C.c_uint64), ("key_words", C.c_uint32), ("key_signed", C.c_uint32),
                 ("nvars", C.c_uint32), ("psize", C.c_uint32), ("cf_kind", C.c_uint32), ("cf_limbs", C.c_uint32),
-                ("mem", C.c_uint32), ("reserved", C.c_uint32), ("keys", C.c_void_p), ("cfs", C.c_void_p)]
+                ("mem", C.c_uint32), ("key_bits", C.c_uint32), ("keys", C.c_void_p), ("cfs", C.c_void_p)]
 
 
 class Trunc(C.Structure):

@@ -171,16 +171,52 @@ Layout make_layout(const obk_poly_view &v)
         L.lim_min = 0;
         return L;
     }
+    const bool b32 = v.key_bits == 32;
     if (v.key_signed) {
-        L.delta = (uint64_t)obake::detail::kpack_get_delta<std::int64_t>(L.wsize);
-        L.klim_min = (uint64_t)obake::detail::kpack_get_klims<std::int64_t>(L.wsize).first;
-        L.lim_min = obake::detail::kpack_get_lims<std::int64_t>(L.wsize).first;
+        if (b32) {
+            L.delta = (uint64_t)obake::detail::kpack_get_delta<std::int32_t>(L.wsize);
+            L.klim_min = (uint64_t)(int64_t)obake::detail::kpack_get_klims<std::int32_t>(L.wsize).first;
+            L.lim_min = obake::detail::kpack_get_lims<std::int32_t>(L.wsize).first;
+        } else {
+            L.delta = (uint64_t)obake::detail::kpack_get_delta<std::int64_t>(L.wsize);
+            L.klim_min = (uint64_t)obake::detail::kpack_get_klims<std::int64_t>(L.wsize).first;
+            L.lim_min = obake::detail::kpack_get_lims<std::int64_t>(L.wsize).first;
+        }
     } else {
-        L.delta = obake::detail::kpack_get_delta<std::uint64_t>(L.wsize);
+        L.delta = b32 ? (uint64_t)obake::detail::kpack_get_delta<std::uint32_t>(L.wsize)
+                      : obake::detail::kpack_get_delta<std::uint64_t>(L.wsize);
         L.klim_min = 0;
         L.lim_min = 0;
     }
     return L;
+}
+
+// (lim_min, lim_max) of one packed component for the view's key type
+void component_lims(const obk_poly_view &v, unsigned wsize, i128 &lim_min, i128 &lim_max)
+{
+    const bool b32 = v.key_bits == 32;
+    if (v.key_signed) {
+        if (b32) {
+            auto lm = obake::detail::kpack_get_lims<std::int32_t>(wsize);
+            lim_min = lm.first;
+            lim_max = lm.second;
+        } else {
+            auto lm = obake::detail::kpack_get_lims<std::int64_t>(wsize);
+            lim_min = lm.first;
+            lim_max = lm.second;
+        }
+    } else {
+        lim_min = 0;
+        lim_max = b32 ? (i128)obake::detail::kpack_get_lims<std::uint32_t>(wsize).second
+                      : (i128)obake::detail::kpack_get_lims<std::uint64_t>(wsize).second;
+    }
+}
+
+unsigned key_max_size(const obk_poly_view &v)
+{
+    const bool b32 = v.key_bits == 32;
+    if (v.key_signed) return b32 ? obake::detail::kpack_max_size<std::int32_t>() : obake::detail::kpack_max_size<std::int64_t>();
+    return b32 ? obake::detail::kpack_max_size<std::uint32_t>() : obake::detail::kpack_max_size<std::uint64_t>();
 }
 
 inline i128 unord(long long o, bool is_signed)
@@ -213,8 +249,8 @@ void validate_view(obk_engine *e, const obk_poly_view *v, const char *name)
     if (v->cf_kind == OBK_CF_INT && (v->cf_limbs < 1 || v->cf_limbs > 3)) bad("cf_limbs must be in [1,3]");
     if (v->mem != OBK_MEM_HOST && v->mem != OBK_MEM_DEVICE) bad("mem");
     if (v->nterms && (!v->keys || !v->cfs)) bad("null keys/cfs");
-    const unsigned maxsz = v->key_signed ? obake::detail::kpack_max_size<std::int64_t>()
-                                         : obake::detail::kpack_max_size<std::uint64_t>();
+    if (v->key_bits != 0 && v->key_bits != 32 && v->key_bits != 64) bad("key_bits must be 32 or 64");
+    const unsigned maxsz = key_max_size(*v);
     if (v->psize == 0) {
         if (v->key_words != 1) bad("packed_monomial keys have exactly one word");
         if (v->nvars > maxsz) bad("too many variables for one packed word");
@@ -410,7 +446,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         if (!rq.merge) {
             validate_view(e, x, "x");
             if (x->key_words != y->key_words || x->key_signed != y->key_signed || x->nvars != y->nvars
-                || x->psize != y->psize || x->cf_kind != y->cf_kind) {
+                || x->psize != y->psize || x->cf_kind != y->cf_kind || (x->key_bits == 32) != (y->key_bits == 32)) {
                 e->err = "operands have different key layouts or coefficient kinds";
                 return OBK_ERR_INVALID_ARG;
             }
@@ -513,14 +549,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             // monomial_range_overflow_check (packed_monomial.hpp:462-487; d_packed_monomial.hpp:861-894)
             if (L.nvars) {
                 i128 lim_min, lim_max;
-                if (L.is_signed) {
-                    auto lm = obake::detail::kpack_get_lims<std::int64_t>(L.wsize);
-                    lim_min = lm.first;
-                    lim_max = lm.second;
-                } else {
-                    lim_min = 0;
-                    lim_max = (i128)obake::detail::kpack_get_lims<std::uint64_t>(L.wsize).second;
-                }
+                component_lims(*y, L.wsize, lim_min, lim_max);
                 bool ok = true;
                 for (uint32_t v = 0; v < L.nvars && ok; ++v) {
                     const i128 mn = unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
@@ -536,8 +565,10 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                         dmax += unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);
                         dmin += unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
                     }
-                    const i128 tmax = L.is_signed ? (i128)INT64_MAX : (i128)UINT64_MAX;
-                    const i128 tmin = L.is_signed ? (i128)INT64_MIN : (i128)0;
+                    const bool b32 = y->key_bits == 32;
+                    const i128 tmax = L.is_signed ? (b32 ? (i128)INT32_MAX : (i128)INT64_MAX)
+                                                  : (b32 ? (i128)UINT32_MAX : (i128)UINT64_MAX);
+                    const i128 tmin = L.is_signed ? (b32 ? (i128)INT32_MIN : (i128)INT64_MIN) : (i128)0;
                     if (dmax > tmax || dmin < tmin) ok = false; // cannot trigger for psize >= 2 (sums of < 2^33 values)
                 }
                 if (!ok) {
@@ -1182,13 +1213,7 @@ obk_status obk_overflow_check(obk_engine *e, const obk_poly_view *x, const obk_p
         CU_CHECK(e, cudaMemcpyAsync(hs, dstats, sizeof(hs), cudaMemcpyDeviceToHost, s));
         CU_CHECK(e, cudaStreamSynchronize(s));
         i128 lim_min = 0, lim_max;
-        if (L.is_signed) {
-            auto lm = obake::detail::kpack_get_lims<std::int64_t>(L.wsize);
-            lim_min = lm.first;
-            lim_max = lm.second;
-        } else {
-            lim_max = (i128)obake::detail::kpack_get_lims<std::uint64_t>(L.wsize).second;
-        }
+        component_lims(*x, L.wsize, lim_min, lim_max);
         for (uint32_t v = 0; v < L.nvars; ++v) {
             const i128 mn = unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
             const i128 mx = unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);

@@ -84,7 +84,8 @@ def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result
     torch.cuda.current_stream(dev).synchronize()
     view = raw_view(rkeys.shape[0], W, vx.key_signed, vx.nvars, vx.psize,
                     _capi.OBK_CF_F64 if is_f64 else _capi.OBK_CF_INT, L, _capi.OBK_MEM_DEVICE,
-                    rkeys.data_ptr() if rkeys.numel() else 0, rcfs.data_ptr() if rcfs.numel() else 0)
+                    rkeys.data_ptr() if rkeys.numel() else 0, rcfs.data_ptr() if rcfs.numel() else 0,
+                    vx.key_bits or 64)
     merged = engine.merge_view(view, nsegs, result_mem)
     info["merge_stats"] = merged.stats
     part.free()

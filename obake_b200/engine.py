@@ -95,10 +95,11 @@ class HostOperand:
                              op.psize, kind, limbs, OBK_MEM_HOST, 0, self.keys.ctypes.data, self.cfs.ctypes.data)
 
 
-def raw_view(nterms, key_words, key_signed, nvars, psize, cf_kind, cf_limbs, mem, keys_ptr, cfs_ptr) -> PolyView:
+def raw_view(nterms, key_words, key_signed, nvars, psize, cf_kind, cf_limbs, mem, keys_ptr, cfs_ptr,
+             key_bits=64) -> PolyView:
     """View over caller-owned buffers (torch tensors: pass ``t.data_ptr()``), host-pinned or device."""
     return PolyView(int(nterms), int(key_words), int(key_signed), int(nvars), int(psize), int(cf_kind),
-                    int(cf_limbs), int(mem), 0, int(keys_ptr), int(cfs_ptr))
+                    int(cf_limbs), int(mem), int(key_bits), int(keys_ptr), int(cfs_ptr))
 
 
 class Product:

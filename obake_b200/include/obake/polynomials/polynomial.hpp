@@ -339,6 +339,7 @@ inline polynomial<K, R> poly_mul_impl_identical_ss(const polynomial<K, C0> &x, c
         v.cf_kind = RT::kind;
         v.cf_limbs = lin;
         v.mem = OBK_MEM_HOST;
+        v.key_bits = sizeof(T) * 8u;
         v.keys = k.data();
         v.cfs = c.data();
         return v;
