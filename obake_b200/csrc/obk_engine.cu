@@ -403,6 +403,371 @@ uint32_t pick_log2_cap(obk_engine *e, int W, int accw)
     return l;
 }
 
+struct EstimateIn {
+    const uint64_t *xk;
+    const int64_t *xdeg;
+    uint64_t nx;
+    const uint64_t *yk;
+    const int64_t *ydeg;
+    uint64_t ny;
+    int W;
+    uint32_t is_signed;
+    int dbits;
+    int64_t degmin_y;
+    uint32_t ndeg;
+    bool trunc;
+    int64_t lim_base;
+    uint64_t tot_mults;
+    unsigned threads;
+};
+
+// Product-size estimate (stands in for poly_mul_estimate_product_size, polynomial.hpp:478-794): a sampled
+// SYMBOLIC product.  The operands are segmented by a fine prime modulus mE (about sym_cap/4 pairs per
+// segment, so a sampled table can never fill up), S evenly spread segments are multiplied key-only and
+// their distinct keys counted exactly; the total is the sample mean times mE.  Deterministic.
+uint64_t estimate_terms(obk_engine *e, Scratch &sc, const EstimateIn &in)
+{
+    cudaStream_t s = e->stream;
+    const int W = in.W;
+    const uint64_t max_bins = 1ull << 25;
+    const uint32_t sym_log2_cap = pick_log2_cap(e, W, 0);
+    const uint32_t sym_cap = 1u << sym_log2_cap;
+    uint64_t want = (in.tot_mults + sym_cap / 4 - 1) / (sym_cap / 4);
+    want = std::min<uint64_t>(want, max_bins >> in.dbits);
+    const uint32_t mE = want <= 1 ? 1u : prev_prime(want);
+    const double per_seg = (double)in.tot_mults / (double)mE;
+    uint64_t S = (uint64_t)std::ceil(1.5e6 / std::max(per_seg, 1.0));
+    S = std::max<uint64_t>(S, 64);
+    S = std::min<uint64_t>(S, 1024);
+    S = std::min<uint64_t>(S, mE);
+    SortedY ye = sort_operand(e, sc, in.yk, nullptr, in.ydeg, in.ny, W, 0, mE, in.is_signed, false, in.dbits, in.degmin_y,
+                              false);
+    uint32_t *xsegE = sc.alloc<uint32_t>(in.nx);
+    k_segments<<<(unsigned)std::min<uint64_t>((in.nx + 255) / 256, 4096), 256, 0, s>>>(in.xk, in.nx, W, mE, in.is_signed,
+                                                                                     xsegE);
+    e->launches += 1;
+    std::vector<uint32_t> hlist(S);
+    for (uint64_t i = 0; i < S; ++i) hlist[i] = (uint32_t)((i * (uint64_t)mE) / S); // evenly spread, distinct
+    uint32_t *dlist = sc.alloc<uint32_t>(S);
+    uint32_t *dcounts = sc.alloc<uint32_t>(S);
+    uint32_t *dflags = sc.alloc<uint32_t>(4);
+    CU_CHECK(e, cudaMemcpyAsync(dlist, hlist.data(), S * 4, cudaMemcpyHostToDevice, s));
+    CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
+    MulParams P{};
+    P.xk = in.xk;
+    P.xdeg = in.xdeg;
+    P.xseg = xsegE;
+    P.nx = in.nx;
+    P.yk = ye.keys;
+    P.yoff = ye.off;
+    P.nsegs = mE;
+    P.dbits = in.dbits;
+    P.ndeg = in.ndeg;
+    P.trunc = in.trunc;
+    P.lim_base = in.lim_base;
+    P.seg_list = dlist;
+    P.nseg_list = (uint32_t)S;
+    P.cursor = dflags + 1;
+    P.log2_cap = sym_log2_cap;
+    const double run = (double)in.tot_mults / (double)in.nx / (double)mE;
+    P.lg = run >= 24.0 ? 5 : 0;
+    P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
+    P.counts = dcounts;
+    P.flags = dflags;
+    const size_t smem_sym = (size_t)sym_cap * (8 * W + 4);
+    launch_mul(e, W, CF_SYM, P, (unsigned)std::min<uint64_t>(S, (uint64_t)e->sm_count), in.threads, smem_sym);
+    std::vector<uint32_t> hcounts(S);
+    CU_CHECK(e, cudaMemcpyAsync(hcounts.data(), dcounts, S * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    double sum = 0;
+    for (uint64_t i = 0; i < S; ++i) sum += hcounts[i] == 0xffffffffu ? (double)sym_cap : (double)hcounts[i];
+    uint64_t est = (uint64_t)std::ceil(sum * (double)mE / (double)S);
+    sc.release(ye.keys);
+    sc.release(ye.off);
+    sc.release(xsegE);
+    sc.release(dlist);
+    sc.release(dcounts);
+    sc.release(dflags);
+    return std::max<uint64_t>(est, 1);
+}
+
+// Segment count for a product with `est` distinct terms whose tables hold `slots_target` terms each: a prime
+// modulus (flat residues) just below a whole number of waves of resident CTAs; small products get fewer.
+uint32_t pick_nsegs(uint64_t est, double slots_target, uint64_t tot_mults, uint32_t wave)
+{
+    uint64_t needed = (uint64_t)std::ceil((double)est / slots_target);
+    needed = std::max<uint64_t>(needed, 1);
+    const uint64_t by_work = std::max<uint64_t>(1, std::min<uint64_t>(wave, tot_mults / 65536));
+    if (needed <= 1 && by_work <= 1) return 1;
+    if (needed <= wave && by_work < wave) {
+        uint32_t n = next_prime(std::max<uint64_t>(needed, by_work));
+        if (n > wave) n = prev_prime(wave) >= needed ? prev_prime(wave) : n;
+        return n;
+    }
+    const uint64_t waves = (needed + wave - 1) / wave;
+    uint32_t m = prev_prime(waves * wave);
+    if (m < needed) m = prev_prime((waves + 1) * wave);
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-blocked dense path (obk_kernels.cuh, "kernel 1")
+// ------------------------------------------------------------------------------------------------
+struct RowSide {
+    uint64_t *tab = nullptr;
+    uint32_t log2_cap = 0;
+    uint32_t *rank = nullptr;
+    uint64_t *row_hi = nullptr;
+    uint64_t *mat = nullptr;
+    uint32_t *row_len = nullptr;
+    uint32_t nrows = 0;
+    uint64_t sum_len = 0;
+};
+
+void rows_phase_a(obk_engine *e, Scratch &sc, const uint64_t *keys, uint64_t n, uint64_t delta, RowSide &r)
+{
+    cudaStream_t s = e->stream;
+    r.log2_cap = 4;
+    while ((1ull << r.log2_cap) < 2 * n) ++r.log2_cap;
+    const uint32_t cap = 1u << r.log2_cap;
+    r.tab = sc.alloc<uint64_t>(cap);
+    CU_CHECK(e, cudaMemsetAsync(r.tab, 0xFF, (size_t)cap * 8, s));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
+    k_row_insert<<<grid, 256, 0, s>>>(keys, n, delta, r.tab, r.log2_cap);
+    uint32_t *flags = sc.alloc<uint32_t>((size_t)cap + 1);
+    k_row_flags<<<(cap + 255) / 256, 256, 0, s>>>(r.tab, cap, flags);
+    e->launches += 2;
+    r.rank = sc.alloc<uint32_t>((size_t)cap + 2);
+    device_scan(e, sc, flags, r.rank, cap);
+    sc.release(flags);
+}
+
+void rows_phase_b(obk_engine *e, Scratch &sc, const uint64_t *keys, const uint64_t *cfs, uint64_t n, uint64_t delta,
+                  RowSide &r)
+{
+    cudaStream_t s = e->stream;
+    const uint32_t cap = 1u << r.log2_cap;
+    r.row_hi = sc.alloc<uint64_t>(r.nrows);
+    r.mat = sc.alloc<uint64_t>((size_t)r.nrows * 32);
+    r.row_len = sc.alloc<uint32_t>(r.nrows);
+    CU_CHECK(e, cudaMemsetAsync(r.mat, 0, (size_t)r.nrows * 32 * 8, s));
+    CU_CHECK(e, cudaMemsetAsync(r.row_len, 0, (size_t)r.nrows * 4, s));
+    k_row_keys<<<(cap + 255) / 256, 256, 0, s>>>(r.tab, cap, r.rank, r.row_hi);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
+    k_row_fill<<<grid, 256, 0, s>>>(keys, cfs, n, delta, r.tab, r.log2_cap, r.rank, r.mat, r.row_len);
+    e->launches += 2;
+}
+
+__global__ void k_iota64(uint64_t *p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+template <int LACC, bool F64>
+void launch_rows_t(obk_engine *e, const RowParams &P, unsigned grid, size_t smem, const uint32_t *offs, uint64_t delta,
+                   uint64_t *rk, uint64_t *rc, bool expand)
+{
+    if (!expand) {
+        auto fn = k_rowconv<LACC, F64>;
+        CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        fn<<<grid, 1024, smem, e->stream>>>(P);
+    } else {
+        k_row_expand<LACC, F64><<<(unsigned)std::min<uint32_t>((P.nro + 7) / 8, 8192), 256, 0, e->stream>>>(
+            P.or_hi, P.omat, offs, P.nro, delta, rk, rc);
+    }
+    e->launches += 1;
+    CU_CHECK(e, cudaGetLastError());
+}
+
+void launch_rows(obk_engine *e, int mode, const RowParams &P, unsigned grid, size_t smem, const uint32_t *offs,
+                 uint64_t delta, uint64_t *rk, uint64_t *rc, bool expand)
+{
+    switch (mode) {
+        case CF_I1A1: launch_rows_t<1, false>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
+        case CF_I1A2: launch_rows_t<2, false>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
+        case CF_I1A3: launch_rows_t<3, false>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
+        case CF_F64: launch_rows_t<1, true>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
+        default: e->err = "internal: coefficient mode not supported by the row path"; throw obk_fail{OBK_ERR_INVALID_ARG};
+    }
+}
+
+struct RowsResult {
+    bool done = false;
+    uint64_t *rk = nullptr, *rc = nullptr;
+    uint64_t total = 0;
+    uint64_t est_rows = 0;
+    uint32_t nro = 0, m = 0;
+    float ms_rowconv = 0;
+};
+
+// Returns done=false when the operands are not dense enough (the caller then runs the scatter kernel).
+RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx, const uint64_t *dyk,
+                    const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, uint64_t tot_mults,
+                    unsigned threads, bool forced, obk_stats &st)
+{
+    RowsResult R;
+    cudaStream_t s = e->stream;
+    const uint64_t delta = L.delta;
+    RowSide X, Y;
+    const bool same = dxk == dyk && nx == ny;
+    rows_phase_a(e, sc, dxk, nx, delta, X);
+    if (!same) rows_phase_a(e, sc, dyk, ny, delta, Y);
+    uint32_t hx = 0, hy = 0;
+    CU_CHECK(e, cudaMemcpyAsync(&hx, X.rank + (1u << X.log2_cap), 4, cudaMemcpyDeviceToHost, s));
+    if (!same) CU_CHECK(e, cudaMemcpyAsync(&hy, Y.rank + (1u << Y.log2_cap), 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    X.nrows = hx;
+    rows_phase_b(e, sc, dxk, dxc, nx, delta, X);
+    if (same) {
+        Y = X;
+    } else {
+        Y.nrows = hy;
+        rows_phase_b(e, sc, dyk, dyc, ny, delta, Y);
+    }
+    // density test on the host: the convolution loops over the shorter row of every pair
+    std::vector<uint32_t> lx(X.nrows), ly(Y.nrows);
+    CU_CHECK(e, cudaMemcpyAsync(lx.data(), X.row_len, (size_t)X.nrows * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaMemcpyAsync(ly.data(), Y.row_len, (size_t)Y.nrows * 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    for (auto v : lx) X.sum_len += v;
+    for (auto v : ly) Y.sum_len += v;
+    const double iters = std::min((double)X.sum_len * (double)Y.nrows, (double)Y.sum_len * (double)X.nrows);
+    // measured costs: ~40 warp instructions per convolution step vs ~22 per product in the scatter kernel
+    if (!forced && iters * 40.0 > (double)tot_mults * 22.0 * 0.7) return R;
+
+    const uint32_t wave = (uint32_t)e->sm_count;
+    // ---- symbolic row product: the set of output rows ------------------------------------------------------
+    const uint64_t row_pairs = (uint64_t)X.nrows * Y.nrows;
+    EstimateIn ein{X.row_hi, nullptr, X.nrows, Y.row_hi, nullptr, Y.nrows, 1, 0, 0, 0, 1, false, 0, row_pairs, threads};
+    R.est_rows = estimate_terms(e, sc, ein);
+    const uint32_t sym_log2_cap = pick_log2_cap(e, 1, 0);
+    const uint32_t sym_cap = 1u << sym_log2_cap;
+    uint32_t mR = pick_nsegs(R.est_rows, 0.5 * sym_cap, row_pairs, wave);
+    uint32_t *counts = nullptr, *offs = nullptr;
+    uint64_t *stage = nullptr;
+    uint32_t nro = 0;
+    for (int attempt = 0;; ++attempt) {
+        SortedY ys = sort_operand(e, sc, Y.row_hi, nullptr, nullptr, Y.nrows, 1, 0, mR, 0, false, 0, 0, false);
+        uint32_t *xseg = sc.alloc<uint32_t>(X.nrows);
+        k_segments<<<(X.nrows + 255) / 256, 256, 0, s>>>(X.row_hi, X.nrows, 1, mR, 0, xseg);
+        e->launches += 1;
+        stage = sc.alloc<uint64_t>((size_t)mR * sym_cap);
+        counts = sc.alloc<uint32_t>((size_t)mR + 1);
+        offs = sc.alloc<uint32_t>((size_t)mR + 2);
+        uint32_t *dflags = sc.alloc<uint32_t>(4);
+        CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
+        CU_CHECK(e, cudaMemsetAsync(counts, 0, ((size_t)mR + 1) * 4, s));
+        MulParams P{};
+        P.xk = X.row_hi;
+        P.xseg = xseg;
+        P.nx = X.nrows;
+        P.yk = ys.keys;
+        P.yoff = ys.off;
+        P.nsegs = mR;
+        P.ndeg = 1;
+        P.nseg_list = mR;
+        P.cursor = dflags + 1;
+        P.log2_cap = sym_log2_cap;
+        P.lg = ((double)Y.nrows / (double)mR) >= 24.0 ? 5 : 0;
+        P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
+        P.okeys = stage;
+        P.counts = counts;
+        P.flags = dflags;
+        launch_mul(e, 1, CF_SYM, P, std::min<uint32_t>(mR, wave), threads, (size_t)sym_cap * 12);
+        device_scan(e, sc, counts, offs, mR);
+        uint32_t hflag[4], htot = 0;
+        CU_CHECK(e, cudaMemcpyAsync(hflag, dflags, 16, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaMemcpyAsync(&htot, offs + mR, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        sc.release(ys.keys);
+        sc.release(ys.off);
+        sc.release(xseg);
+        sc.release(dflags);
+        if (hflag[0] == 0) {
+            nro = htot;
+            break;
+        }
+        sc.release(stage);
+        sc.release(counts);
+        sc.release(offs);
+        if (attempt > 6) {
+            e->err = "row path: symbolic row product overflowed its tables";
+            throw obk_fail{OBK_ERR_TABLE_OVERFLOW};
+        }
+        mR = prev_prime((uint64_t)mR * 2 + wave);
+    }
+    uint64_t *or_hi = sc.alloc<uint64_t>(std::max<uint32_t>(nro, 1));
+    uint64_t *off64 = sc.alloc<uint64_t>((size_t)mR + 1);
+    k_compact<<<std::min<uint32_t>(mR, 4096), 256, 0, s>>>(stage, nullptr, counts, offs, sym_cap, 1, 0, or_hi, nullptr, off64, mR);
+    e->launches += 1;
+    sc.release(stage);
+    sc.release(counts);
+    sc.release(offs);
+    sc.release(off64);
+
+    // ---- gather directory: right rows sorted by a fine prime modulus (2-3 rows per run) ------------------------
+    const uint32_t mG = next_prime(std::max<uint32_t>(Y.nrows / 2, 3));
+    uint64_t *iota = sc.alloc<uint64_t>(Y.nrows);
+    k_iota64<<<(Y.nrows + 255) / 256, 256, 0, s>>>(iota, Y.nrows);
+    SortedY yg = sort_operand(e, sc, Y.row_hi, iota, nullptr, Y.nrows, 1, 1, mG, 0, false, 0, 0, true);
+    uint32_t *xsegG = sc.alloc<uint32_t>(X.nrows);
+    k_segments<<<(X.nrows + 255) / 256, 256, 0, s>>>(X.row_hi, X.nrows, 1, mG, 0, xsegG);
+    uint32_t *or_seg = sc.alloc<uint32_t>(std::max<uint32_t>(nro, 1));
+    if (nro) k_segments<<<(nro + 255) / 256, 256, 0, s>>>(or_hi, nro, 1, mG, 0, or_seg);
+    e->launches += 3;
+
+    // ---- one warp per output row ------------------------------------------------------------------------------
+    uint64_t *omat = sc.alloc<uint64_t>((size_t)std::max<uint32_t>(nro, 1) * 64 * accw);
+    uint32_t *or_cnt = sc.alloc<uint32_t>((size_t)nro + 1);
+    uint32_t *roffs = sc.alloc<uint32_t>((size_t)nro + 2);
+    uint32_t *cursor = sc.alloc<uint32_t>(4);
+    CU_CHECK(e, cudaMemsetAsync(cursor, 0, 16, s));
+    RowParams P{};
+    P.xr_hi = X.row_hi;
+    P.xr_seg = xsegG;
+    P.xr_len = X.row_len;
+    P.xmat = X.mat;
+    P.nrx = X.nrows;
+    P.yr_hi = yg.keys;
+    P.yr_idx = yg.cfs;
+    P.yr_off = yg.off;
+    P.yr_len = Y.row_len;
+    P.ymat = Y.mat;
+    P.nry = Y.nrows;
+    P.m = mG;
+    P.or_hi = or_hi;
+    P.or_seg = or_seg;
+    P.nro = nro;
+    P.cursor = cursor;
+    P.omat = omat;
+    P.or_cnt = or_cnt;
+    const size_t dir_bytes = (size_t)X.nrows * 12 + (size_t)Y.nrows * 12 + ((size_t)mG + 1) * 4 + 64;
+    P.dir_in_smem = dir_bytes + 2048 <= e->smem_optin ? 1u : 0u;
+    CU_CHECK(e, cudaEventRecord(e->ev[5], s));
+    if (nro) launch_rows(e, mode, P, wave, P.dir_in_smem ? dir_bytes : 0, nullptr, delta, nullptr, nullptr, false);
+    CU_CHECK(e, cudaEventRecord(e->ev[6], s));
+    st.mul_launches += 1;
+    uint64_t total = 0;
+    if (nro) {
+        device_scan(e, sc, or_cnt, roffs, nro);
+        uint32_t htot = 0;
+        CU_CHECK(e, cudaMemcpyAsync(&htot, roffs + nro, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        total = htot;
+    }
+    R.rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1));
+    R.rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
+    if (total) launch_rows(e, mode, P, 0, 0, roffs, delta, R.rk, R.rc, true);
+    R.total = total;
+    R.nro = nro;
+    R.m = mG;
+    R.done = true;
+    st.table_slots = 64;
+    st.group_lanes = 32;
+    return R;
+}
+
 void set_empty_result(obk_poly_result *out, const obk_poly_view *x, int cf_limbs, uint32_t mem)
 {
     std::memset(out, 0, sizeof(*out));
@@ -512,6 +877,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         int64_t lim_base = 0, degmin_y = 0;
         int64_t *xdeg = nullptr, *ydeg = nullptr;
         bool trunc = false;
+        bool rows_ok = false; // every exponent >= 0 and the first symbol's exponents < 32 in both operands
         uint64_t tot_mults = 0;
         if (!rq.merge) {
             trunc = rq.t != nullptr;
@@ -576,6 +942,12 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                              "polynomials";
                     return OBK_ERR_KEY_OVERFLOW;
                 }
+            }
+            if (L.nvars) {
+                rows_ok = unord(hs[0].emax[0], L.is_signed) < 32 && unord(hs[1].emax[0], L.is_signed) < 32
+                          && hs[0].nonfinite == 0 && hs[1].nonfinite == 0;
+                for (uint32_t v = 0; v < L.nvars; ++v)
+                    if (unord(hs[0].emin[v], L.is_signed) < 0 || unord(hs[1].emin[v], L.is_signed) < 0) rows_ok = false;
             }
             // a-priori accumulator width: |sum| <= min(nx,ny) * max|c1| * max|c2|
             if (f64) {
@@ -677,233 +1049,183 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         const uint64_t max_bins = 1ull << 25;
         const uint32_t wave = (uint32_t)e->sm_count; // resident CTAs: one per SM (the table takes the whole SM)
 
-        // ---- product-size estimate (poly_mul_estimate_product_size, polynomial.hpp:478-794) -------------
-        // Sampled symbolic product: count the distinct product keys of a few fine-grained segments exactly.
-        uint64_t est = 0;
-        uint32_t nsegs = 1;
-        if (rq.merge) {
-            nsegs = rq.merge_nsegs;
-            est = ny;
-        } else if (e->opt_nsegs > 0) {
-            nsegs = (uint32_t)e->opt_nsegs;
-        } else {
-            const uint32_t sym_log2_cap = pick_log2_cap(e, W, 0);
-            const uint32_t sym_cap = 1u << sym_log2_cap;
-            // fine modulus: about sym_cap/4 products per segment, so a sampled table can never fill up
-            uint64_t want = (tot_mults + sym_cap / 4 - 1) / (sym_cap / 4);
-            want = std::min<uint64_t>(want, max_bins >> dbits);
-            const uint32_t mE = want <= 1 ? 1u : prev_prime(want);
-            const double per_seg = (double)tot_mults / (double)mE;
-            uint64_t S = (uint64_t)std::ceil(1.5e6 / std::max(per_seg, 1.0));
-            S = std::max<uint64_t>(S, 64);
-            S = std::min<uint64_t>(S, 1024);
-            S = std::min<uint64_t>(S, mE);
-            SortedY ye = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, mE, L.is_signed, false, dbits, degmin_y, false);
-            uint32_t *xsegE = sc.alloc<uint32_t>(nx_full);
-            k_segments<<<(unsigned)std::min<uint64_t>((nx_full + 255) / 256, 4096), 256, 0, s>>>(dxk, nx_full, W, mE,
-                                                                                                 L.is_signed, xsegE);
-            e->launches += 1;
-            std::vector<uint32_t> hlist(S);
-            for (uint64_t i = 0; i < S; ++i) hlist[i] = (uint32_t)((i * (uint64_t)mE) / S); // evenly spread, distinct
-            uint32_t *dlist = sc.alloc<uint32_t>(S);
-            uint32_t *dcounts = sc.alloc<uint32_t>(S);
-            uint32_t *dflags = sc.alloc<uint32_t>(4);
-            CU_CHECK(e, cudaMemcpyAsync(dlist, hlist.data(), S * 4, cudaMemcpyHostToDevice, s));
-            CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
-            MulParams P{};
-            P.xk = dxk;
-            P.xc = nullptr;
-            P.xdeg = xdeg;
-            P.xseg = xsegE;
-            P.nx = nx_full;
-            P.yk = ye.keys;
-            P.yc = nullptr;
-            P.yoff = ye.off;
-            P.nsegs = mE;
-            P.dbits = dbits;
-            P.ndeg = ndeg;
-            P.trunc = trunc;
-            P.lim_base = lim_base;
-            P.seg_list = dlist;
-            P.nseg_list = (uint32_t)S;
-            P.cursor = dflags + 1;
-            P.log2_cap = sym_log2_cap;
-            const double run = (double)tot_mults / (double)nx_full / (double)mE;
-            uint32_t lg = 0;
-            while (lg < 5 && (double)(1u << lg) < run) ++lg;
-            P.lg = lg;
-            P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
-            P.fence = 0;
-            P.counts = dcounts;
-            P.flags = dflags;
-            const size_t smem_sym = (size_t)sym_cap * (8 * W + 4);
-            launch_mul(e, W, CF_SYM, P, (unsigned)std::min<uint64_t>(S, (uint64_t)e->sm_count), threads, smem_sym);
-            std::vector<uint32_t> hcounts(S);
-            CU_CHECK(e, cudaMemcpyAsync(hcounts.data(), dcounts, S * 4, cudaMemcpyDeviceToHost, s));
-            CU_CHECK(e, cudaStreamSynchronize(s));
-            double sum = 0;
-            for (uint64_t i = 0; i < S; ++i) sum += hcounts[i] == 0xffffffffu ? (double)sym_cap : (double)hcounts[i];
-            est = (uint64_t)std::ceil(sum * (double)mE / (double)S);
-            est = std::max<uint64_t>(est, 1);
-            sc.release(ye.keys);
-            sc.release(ye.off);
-            sc.release(xsegE);
-            // Segment count: a prime modulus (flat residues) just below a whole number of waves of resident CTAs,
-            // large enough that every table ends up about opt_fill_pct % full.
-            const double target = (double)cap * (double)e->opt_fill_pct / 100.0;
-            uint64_t needed = (uint64_t)std::ceil((double)est / target);
-            needed = std::max<uint64_t>(needed, 1);
-            // a whole number of waves of resident CTAs (prime just below it); small products get fewer segments
-            const uint64_t by_work = std::max<uint64_t>(1, std::min<uint64_t>(wave, tot_mults / 65536));
-            if (needed <= 1 && by_work <= 1) {
-                nsegs = 1;
-            } else if (needed <= wave && by_work < wave) {
-                nsegs = next_prime(std::max<uint64_t>(needed, by_work));
-                if (nsegs > wave) nsegs = prev_prime(wave) >= needed ? prev_prime(wave) : nsegs;
-            } else {
-                uint64_t waves = (needed + wave - 1) / wave;
-                uint32_t m = prev_prime(waves * wave);
-                if (m < needed) m = prev_prime((waves + 1) * wave);
-                nsegs = m;
-            }
-        }
-        st.est_nterms = est;
-        CU_CHECK(e, cudaEventRecord(e->ev[3], s));
-
-        // ---- left-operand slice for multi-GPU sharding --------------------------------------
-        uint64_t x_begin = 0, x_end = nx_full;
-        if (rq.nranks > 1) {
-            x_begin = nx_full * rq.rank / rq.nranks;
-            x_end = nx_full * (rq.rank + 1) / rq.nranks;
+        // ---- dense operands: row-blocked path (register accumulation, no table) --------------------------------
+        RowsResult rows;
+        if (!rq.merge && !trunc && rq.nranks <= 1 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
+            && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok
+            && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
+            rows = run_rows(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, tot_mults, threads, e->opt_kernel == 1, st);
         }
 
-        // ---- sort the right operand, multiply, retry with a finer segmentation on table overflow --------
-        uint64_t *stage_k = nullptr, *stage_c = nullptr;
-        uint32_t *counts = nullptr, *offs = nullptr, *dflags = nullptr;
+        uint64_t *rk = nullptr, *rc = nullptr, *off64 = nullptr;
         uint64_t total = 0;
+        uint32_t nsegs = 1;
         float ms_prep_extra = 0;
-        for (unsigned attempt = 0;; ++attempt) {
-            if (((uint64_t)nsegs << dbits) > max_bins) {
-                e->err = "The homomorphic multiplication of two polynomials needs more segment bins than the maximum "
-                         "allowed value (table size overflow)";
-                return OBK_ERR_TABLE_OVERFLOW;
-            }
-            CU_CHECK(e, cudaEventRecord(e->ev[4], s));
-            SortedY ys;
-            uint32_t *xseg = nullptr;
-            if (rq.merge) {
-                ys = sort_operand(e, sc, dyk, dyc, nullptr, ny, W, accw, nsegs, L.is_signed, false, 0, 0, true);
-            } else {
-                ys = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, nsegs, L.is_signed, false, dbits, degmin_y, true);
-                xseg = sc.alloc<uint32_t>(x_end - x_begin);
-                k_segments<<<(unsigned)std::min<uint64_t>((x_end - x_begin + 255) / 256, 4096), 256, 0, s>>>(
-                    dxk + x_begin * W, x_end - x_begin, W, nsegs, L.is_signed, xseg);
-                e->launches += 1;
-            }
-            stage_k = sc.alloc<uint64_t>((uint64_t)nsegs * cap * W);
-            stage_c = sc.alloc<uint64_t>((uint64_t)nsegs * cap * accw);
-            counts = sc.alloc<uint32_t>((uint64_t)nsegs + 1);
-            offs = sc.alloc<uint32_t>((uint64_t)nsegs + 2);
-            dflags = sc.alloc<uint32_t>(4);
-            CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
-            CU_CHECK(e, cudaMemsetAsync(counts, 0, ((uint64_t)nsegs + 1) * 4, s));
-            MulParams P{};
-            uint64_t *zero_key = nullptr;
-            if (rq.merge) {
-                zero_key = sc.alloc<uint64_t>(W + 1);
-                CU_CHECK(e, cudaMemsetAsync(zero_key, 0, (W + 1) * 8, s));
-                P.xk = zero_key;
-                P.xseg = (const uint32_t *)(zero_key + W);
-                P.xc = nullptr;
-                P.nx = 1;
-            } else {
-                P.xk = dxk + x_begin * W;
-                P.xc = dxc + x_begin * CWx;
-                P.xdeg = xdeg ? xdeg + x_begin : nullptr;
-                P.xseg = xseg;
-                P.nx = x_end - x_begin;
-            }
-            P.yk = ys.keys;
-            P.yc = ys.cfs;
-            P.yoff = ys.off;
-            P.nsegs = nsegs;
-            P.dbits = dbits;
-            P.ndeg = ndeg;
-            P.trunc = trunc;
-            P.lim_base = lim_base;
-            P.seg_list = nullptr;
-            P.nseg_list = nsegs;
-            P.cursor = dflags + 1;
-            P.log2_cap = log2_cap;
-            uint32_t lg = 0;
-            if (rq.merge) {
-                while ((1u << (lg + 1)) <= threads) ++lg;
-            } else if (e->opt_group_lanes > 0) {
-                while ((1ll << (lg + 1)) <= e->opt_group_lanes && lg < 5) ++lg;
-            } else {
-                // long right-operand runs: a warp shares one left term (distinct keys, no intra-warp slot clash);
-                // short runs: one lane per left term (measured on S12: 1 lane 31 G/s vs 8 lanes 22 G/s)
-                const double run = (double)tot_mults / (double)nx_full / (double)nsegs;
-                lg = run >= 24.0 ? 5 : 0;
-            }
-            P.lg = lg;
-            st.group_lanes = 1u << lg;
-            P.max_fill = max_fill;
-            P.fence = e->opt_fence ? 1u : 0u;
-            P.okeys = stage_k;
-            P.ocfs = stage_c;
-            P.counts = counts;
-            P.flags = dflags;
-            CU_CHECK(e, cudaEventRecord(e->ev[5], s));
-            launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(nsegs, (uint64_t)e->sm_count), threads, smem_mul);
-            CU_CHECK(e, cudaEventRecord(e->ev[6], s));
-            st.mul_launches += 1;
-            device_scan(e, sc, counts, offs, nsegs);
-            uint32_t hflag[4], htotal = 0;
-            CU_CHECK(e, cudaMemcpyAsync(hflag, dflags, 16, cudaMemcpyDeviceToHost, s));
-            CU_CHECK(e, cudaMemcpyAsync(&htotal, offs + nsegs, 4, cudaMemcpyDeviceToHost, s));
+        if (rows.done) {
+            rk = rows.rk;
+            rc = rows.rc;
+            total = rows.total;
+            st.est_nterms = rows.est_rows;
+            st.nsegs = rows.m;
+            st.nterms_out = total;
+            st.kernel = 1;
+            off64 = sc.alloc<uint64_t>(2);
+            const uint64_t h2[2] = {0, total};
+            CU_CHECK(e, cudaMemcpyAsync(off64, h2, 16, cudaMemcpyHostToDevice, s));
             CU_CHECK(e, cudaStreamSynchronize(s));
-            float ms = 0;
-            cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
-            ms_prep_extra += ms;
-            if (zero_key) sc.release(zero_key);
-            if (xseg) sc.release(xseg);
-            sc.release(ys.keys);
-            sc.release(ys.cfs);
-            sc.release(ys.off);
-            if (hflag[0] == 0) {
-                total = htotal;
-                break;
+            CU_CHECK(e, cudaEventRecord(e->ev[3], s));
+        } else {
+            // ---- product-size estimate (poly_mul_estimate_product_size, polynomial.hpp:478-794) -------------
+            // Sampled symbolic product: count the distinct product keys of a few fine-grained segments exactly.
+            uint64_t est = 0;
+            if (rq.merge) {
+                nsegs = rq.merge_nsegs;
+                est = ny;
+            } else if (e->opt_nsegs > 0) {
+                nsegs = (uint32_t)e->opt_nsegs;
+            } else {
+                EstimateIn ein{dxk, xdeg, nx_full, dyk, ydeg, ny, W, L.is_signed, dbits, degmin_y, ndeg, trunc, lim_base,
+                               tot_mults, threads};
+                est = estimate_terms(e, sc, ein);
+                nsegs = pick_nsegs(est, (double)cap * (double)e->opt_fill_pct / 100.0, tot_mults, wave);
             }
-            // some segment's table filled up: finer segmentation (the HBM staging is re-made)
+            st.est_nterms = est;
+            CU_CHECK(e, cudaEventRecord(e->ev[3], s));
+
+            // ---- left-operand slice for multi-GPU sharding --------------------------------------
+            uint64_t x_begin = 0, x_end = nx_full;
+            if (rq.nranks > 1) {
+                x_begin = nx_full * rq.rank / rq.nranks;
+                x_end = nx_full * (rq.rank + 1) / rq.nranks;
+            }
+
+            // ---- sort the right operand, multiply, retry with a finer segmentation on table overflow --------
+            uint64_t *stage_k = nullptr, *stage_c = nullptr;
+            uint32_t *counts = nullptr, *offs = nullptr, *dflags = nullptr;
+            for (unsigned attempt = 0;; ++attempt) {
+                if (((uint64_t)nsegs << dbits) > max_bins) {
+                    e->err = "The homomorphic multiplication of two polynomials needs more segment bins than the maximum "
+                             "allowed value (table size overflow)";
+                    return OBK_ERR_TABLE_OVERFLOW;
+                }
+                CU_CHECK(e, cudaEventRecord(e->ev[4], s));
+                SortedY ys;
+                uint32_t *xseg = nullptr;
+                if (rq.merge) {
+                    ys = sort_operand(e, sc, dyk, dyc, nullptr, ny, W, accw, nsegs, L.is_signed, false, 0, 0, true);
+                } else {
+                    ys = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, nsegs, L.is_signed, false, dbits, degmin_y, true);
+                    xseg = sc.alloc<uint32_t>(x_end - x_begin);
+                    k_segments<<<(unsigned)std::min<uint64_t>((x_end - x_begin + 255) / 256, 4096), 256, 0, s>>>(
+                        dxk + x_begin * W, x_end - x_begin, W, nsegs, L.is_signed, xseg);
+                    e->launches += 1;
+                }
+                stage_k = sc.alloc<uint64_t>((uint64_t)nsegs * cap * W);
+                stage_c = sc.alloc<uint64_t>((uint64_t)nsegs * cap * accw);
+                counts = sc.alloc<uint32_t>((uint64_t)nsegs + 1);
+                offs = sc.alloc<uint32_t>((uint64_t)nsegs + 2);
+                dflags = sc.alloc<uint32_t>(4);
+                CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
+                CU_CHECK(e, cudaMemsetAsync(counts, 0, ((uint64_t)nsegs + 1) * 4, s));
+                MulParams P{};
+                uint64_t *zero_key = nullptr;
+                if (rq.merge) {
+                    zero_key = sc.alloc<uint64_t>(W + 1);
+                    CU_CHECK(e, cudaMemsetAsync(zero_key, 0, (W + 1) * 8, s));
+                    P.xk = zero_key;
+                    P.xseg = (const uint32_t *)(zero_key + W);
+                    P.xc = nullptr;
+                    P.nx = 1;
+                } else {
+                    P.xk = dxk + x_begin * W;
+                    P.xc = dxc + x_begin * CWx;
+                    P.xdeg = xdeg ? xdeg + x_begin : nullptr;
+                    P.xseg = xseg;
+                    P.nx = x_end - x_begin;
+                }
+                P.yk = ys.keys;
+                P.yc = ys.cfs;
+                P.yoff = ys.off;
+                P.nsegs = nsegs;
+                P.dbits = dbits;
+                P.ndeg = ndeg;
+                P.trunc = trunc;
+                P.lim_base = lim_base;
+                P.seg_list = nullptr;
+                P.nseg_list = nsegs;
+                P.cursor = dflags + 1;
+                P.log2_cap = log2_cap;
+                uint32_t lg = 0;
+                if (rq.merge) {
+                    while ((1u << (lg + 1)) <= threads) ++lg;
+                } else if (e->opt_group_lanes > 0) {
+                    while ((1ll << (lg + 1)) <= e->opt_group_lanes && lg < 5) ++lg;
+                } else {
+                    // long right-operand runs: a warp shares one left term (distinct keys, no intra-warp slot clash);
+                    // short runs: one lane per left term (measured on S12: 1 lane 31 G/s vs 8 lanes 22 G/s)
+                    const double run = (double)tot_mults / (double)nx_full / (double)nsegs;
+                    lg = run >= 24.0 ? 5 : 0;
+                }
+                P.lg = lg;
+                st.group_lanes = 1u << lg;
+                P.max_fill = max_fill;
+                P.fence = e->opt_fence ? 1u : 0u;
+                P.okeys = stage_k;
+                P.ocfs = stage_c;
+                P.counts = counts;
+                P.flags = dflags;
+                CU_CHECK(e, cudaEventRecord(e->ev[5], s));
+                launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(nsegs, (uint64_t)e->sm_count), threads, smem_mul);
+                CU_CHECK(e, cudaEventRecord(e->ev[6], s));
+                st.mul_launches += 1;
+                device_scan(e, sc, counts, offs, nsegs);
+                uint32_t hflag[4], htotal = 0;
+                CU_CHECK(e, cudaMemcpyAsync(hflag, dflags, 16, cudaMemcpyDeviceToHost, s));
+                CU_CHECK(e, cudaMemcpyAsync(&htotal, offs + nsegs, 4, cudaMemcpyDeviceToHost, s));
+                CU_CHECK(e, cudaStreamSynchronize(s));
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
+                ms_prep_extra += ms;
+                if (zero_key) sc.release(zero_key);
+                if (xseg) sc.release(xseg);
+                sc.release(ys.keys);
+                sc.release(ys.cfs);
+                sc.release(ys.off);
+                if (hflag[0] == 0) {
+                    total = htotal;
+                    break;
+                }
+                // some segment's table filled up: finer segmentation (the HBM staging is re-made)
+                sc.release(stage_k);
+                sc.release(stage_c);
+                sc.release(counts);
+                sc.release(offs);
+                sc.release(dflags);
+                st.retries += 1;
+                if ((int64_t)st.retries > e->opt_max_retries || rq.merge) {
+                    e->err = "The homomorphic multiplication of two polynomials resulted in a segment table whose size "
+                             "is larger than the maximum allowed value (shared-memory table overflow after "
+                             + std::to_string(st.retries) + " finer segmentations)";
+                    return OBK_ERR_TABLE_OVERFLOW;
+                }
+                nsegs = prev_prime(((uint64_t)nsegs * 2 + wave - 1) / wave * wave);
+                if (nsegs < 2) nsegs = 2;
+            }
+            st.nsegs = nsegs;
+            st.nterms_out = total;
+
+            // ---- segment-ordered dense result ---------------------------------------------------------------
+            rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * W);
+            rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
+            off64 = sc.alloc<uint64_t>((uint64_t)nsegs + 1);
+            k_compact<<<(unsigned)std::min<uint64_t>(nsegs, 4096), 256, 0, s>>>(stage_k, stage_c, counts, offs, cap, W, accw, rk, rc,
+                                                                            off64, nsegs);
+            e->launches += 1;
+            CU_CHECK(e, cudaGetLastError());
             sc.release(stage_k);
             sc.release(stage_c);
-            sc.release(counts);
-            sc.release(offs);
-            sc.release(dflags);
-            st.retries += 1;
-            if ((int64_t)st.retries > e->opt_max_retries || rq.merge) {
-                e->err = "The homomorphic multiplication of two polynomials resulted in a segment table whose size "
-                         "is larger than the maximum allowed value (shared-memory table overflow after "
-                         + std::to_string(st.retries) + " finer segmentations)";
-                return OBK_ERR_TABLE_OVERFLOW;
-            }
-            nsegs = prev_prime(((uint64_t)nsegs * 2 + wave - 1) / wave * wave);
-            if (nsegs < 2) nsegs = 2;
-        }
-        st.nsegs = nsegs;
-        st.nterms_out = total;
 
-        // ---- segment-ordered dense result ---------------------------------------------------------------
-        uint64_t *rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * W);
-        uint64_t *rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
-        uint64_t *off64 = sc.alloc<uint64_t>((uint64_t)nsegs + 1);
-        k_compact<<<(unsigned)std::min<uint64_t>(nsegs, 4096), 256, 0, s>>>(stage_k, stage_c, counts, offs, cap, W, accw, rk, rc,
-                                                                        off64, nsegs);
-        e->launches += 1;
-        CU_CHECK(e, cudaGetLastError());
-        sc.release(stage_k);
-        sc.release(stage_c);
+        }
 
         // ---- regroup the way a series stores its terms: table hash & (2^k - 1) (series.hpp:396-400) ---------
         // k follows the reference's sizing rule (polynomial.hpp:870-902).  Partial products of the multi-GPU
@@ -1006,7 +1328,6 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         cudaEventElapsedTime(&ms, e->ev[0], e->ev[8]);
         st.ms_total = ms;
         st.total_launches = e->launches;
-        st.kernel = 0;
         if (stats) *stats = st;
         return OBK_OK;
     } catch (const obk_fail &f) {

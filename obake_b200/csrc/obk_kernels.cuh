@@ -628,6 +628,16 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
         // ---- flush: erase zeros (polynomial.hpp:1528-1540) and stage the segment -------------------
         const bool over = s_over != 0;
         if constexpr (T::SYM) {
+            if (P.okeys != nullptr && !over) {
+                // symbolic product: stage the distinct keys of this segment (row-blocked path)
+                uint64_t *ok = P.okeys + (size_t)work * cap * W;
+                for (uint32_t h = tid; h < cap; h += nthr) {
+                    if (tstate[h] != ST_FULL) continue;
+                    const uint32_t pos = atomicAdd(&s_out, 1u);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) ok[(size_t)pos * W + w] = tkeys[(size_t)w * cap + h];
+                }
+            }
             if (tid == 0) {
                 P.counts[work] = over ? 0xffffffffu : s_count;
                 if (over) atomicAdd(&P.flags[0], 1u);
@@ -678,6 +688,276 @@ __global__ void __launch_bounds__(256) k_compact(const uint64_t *__restrict__ sk
         if (threadIdx.x == 0) {
             off64[seg] = o;
             if (seg == nsegs - 1) off64[nsegs] = (uint64_t)o + n;
+        }
+    }
+}
+
+
+// ================================================================================================
+// Row-blocked dense path ("kernel 1").
+//
+// A packed key is hi * delta + lo with lo = the exponent of the first symbol (kpack.hpp:262-267: the
+// first symbol is the lowest digit) and, because the exponent-overflow check guarantees digit-wise sums
+// stay below delta, (hi1, lo1) * (hi2, lo2) = (hi1 + hi2, lo1 + lo2): the product of two ROWS (all terms
+// sharing hi) is a 1-D convolution of their coefficient vectors that lands in the single output row
+// hi1 + hi2.  For dense operands (Fateman: ~8.5 terms per row, 31 wide) this turns ~10^3 hash-table
+// read-modify-writes into register accumulation: one warp owns one OUTPUT row, finds every contributing
+// row pair with the homomorphic segment trick on the row keys, convolves them with warp shuffles into
+// 64 exact accumulators held in registers, and writes the row once.  No atomics, no locks, no table.
+// ================================================================================================
+
+constexpr uint64_t ROW_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
+
+// Pass 1: insert hi = key / delta of every term into an open-addressing set (global memory).
+__global__ void __launch_bounds__(256) k_row_insert(const uint64_t *__restrict__ keys, uint64_t n, uint64_t delta,
+                                                    uint64_t *__restrict__ tab, uint32_t log2_cap)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mask = (1u << log2_cap) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t hi = keys[i] / delta;
+        uint32_t h = (uint32_t)((hi * 0x9E3779B97F4A7C15ULL) >> (64 - log2_cap));
+        for (;;) {
+            const unsigned long long old = atomicCAS((unsigned long long *)&tab[h], (unsigned long long)ROW_EMPTY, (unsigned long long)hi);
+            if (old == ROW_EMPTY || old == hi) break;
+            h = (h + 1u) & mask;
+        }
+    }
+}
+
+// Pass 2: occupancy flags of the set (scanned into row numbers by the host-side scan).
+__global__ void __launch_bounds__(256) k_row_flags(const uint64_t *__restrict__ tab, uint32_t cap, uint32_t *__restrict__ flag)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) flag[i] = tab[i] != ROW_EMPTY;
+}
+
+// Pass 3: row key per row number.
+__global__ void __launch_bounds__(256) k_row_keys(const uint64_t *__restrict__ tab, uint32_t cap, const uint32_t *__restrict__ rank,
+                                                  uint64_t *__restrict__ row_hi)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap && tab[i] != ROW_EMPTY) row_hi[rank[i]] = tab[i];
+}
+
+// Pass 4: scatter every term's coefficient into the dense row matrix [nrows][32] and record row lengths.
+__global__ void __launch_bounds__(256) k_row_fill(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ cfs, uint64_t n,
+                                                  uint64_t delta, const uint64_t *__restrict__ tab, uint32_t log2_cap,
+                                                  const uint32_t *__restrict__ rank, uint64_t *__restrict__ mat,
+                                                  uint32_t *__restrict__ row_len)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mask = (1u << log2_cap) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = keys[i];
+        const uint64_t hi = key / delta;
+        const uint32_t lo = (uint32_t)(key - hi * delta);
+        uint32_t h = (uint32_t)((hi * 0x9E3779B97F4A7C15ULL) >> (64 - log2_cap));
+        while (tab[h] != hi) h = (h + 1u) & mask;
+        const uint32_t r = rank[h];
+        mat[(size_t)r * 32 + lo] = cfs[i];
+        atomicMax(&row_len[r], lo + 1u);
+    }
+}
+
+struct RowParams {
+    // left rows (original order) and right rows (sorted by segment)
+    const uint64_t *xr_hi;
+    const uint32_t *xr_seg;
+    const uint32_t *xr_len;
+    const uint64_t *xmat; // [nrx][32]
+    uint32_t nrx;
+    const uint64_t *yr_hi;  // sorted by segment
+    const uint64_t *yr_idx; // original row number of each sorted right row (payload of the counting sort)
+    const uint32_t *yr_off; // [m + 1]
+    const uint32_t *yr_len; // by original row number
+    const uint64_t *ymat;   // [nry][32]
+    uint32_t nry;
+    uint32_t m; // segment modulus of the row keys
+    // output rows (from the symbolic row product): key and segment
+    const uint64_t *or_hi;
+    const uint32_t *or_seg;
+    uint32_t nro;
+    uint32_t *cursor;
+    // dense output [nro][64][LACC] and the number of non-zero entries per row
+    uint64_t *omat;
+    uint32_t *or_cnt;
+    uint32_t dir_in_smem; // 1: the row directories were staged in shared memory
+};
+
+template <int LACC, bool F64>
+struct RowAcc {
+    uint64_t l[LACC];
+};
+
+// z += (pred ? x*y : 0) for signed 64-bit x, y and an LACC-limb two's-complement accumulator
+template <int LACC>
+__device__ __forceinline__ void row_mac(uint64_t (&z)[LACC], long long x, long long y, bool pred)
+{
+    uint64_t lo = (uint64_t)(x * y);
+    uint64_t hi = (uint64_t)__mul64hi(x, y);
+    if (!pred) {
+        lo = 0;
+        hi = 0;
+    }
+    if constexpr (LACC == 1) {
+        z[0] += lo;
+    } else if constexpr (LACC == 2) {
+        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(z[0]), "+l"(z[1]) : "l"(lo), "l"(hi));
+    } else {
+        const uint64_t ext = (uint64_t)((long long)hi >> 63);
+        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, %5;"
+            : "+l"(z[0]), "+l"(z[1]), "+l"(z[2])
+            : "l"(lo), "l"(hi), "l"(ext));
+    }
+}
+
+// One warp = one output row.  The x-row and y-row directories (keys, segments, offsets) are staged in shared
+// memory once per CTA when they fit; coefficient rows stream from L2 (256 B per row, coalesced).
+template <int LACC, bool F64>
+__global__ void __launch_bounds__(1024, 1) k_rowconv(const RowParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t *xr_hi = P.xr_hi, *yr_hi = P.yr_hi;
+    const uint32_t *xr_seg = P.xr_seg, *yr_off = P.yr_off;
+    const uint32_t *yidx32 = nullptr;
+    if (P.dir_in_smem) {
+        // layout: xr_hi[nrx] | yr_hi[nry] | yr_idx[nry] (u32) | xr_seg[nrx] | yr_off[m+1]
+        uint64_t *s_xhi = reinterpret_cast<uint64_t *>(smem_raw);
+        uint64_t *s_yhi = s_xhi + P.nrx;
+        uint32_t *s_yidx = reinterpret_cast<uint32_t *>(s_yhi + P.nry);
+        uint32_t *s_xseg = s_yidx + P.nry;
+        uint32_t *s_yoff = s_xseg + P.nrx;
+        for (uint32_t i = threadIdx.x; i < P.nrx; i += blockDim.x) {
+            s_xhi[i] = P.xr_hi[i];
+            s_xseg[i] = P.xr_seg[i];
+        }
+        for (uint32_t i = threadIdx.x; i < P.nry; i += blockDim.x) {
+            s_yhi[i] = P.yr_hi[i];
+            s_yidx[i] = (uint32_t)P.yr_idx[i];
+        }
+        for (uint32_t i = threadIdx.x; i <= P.m; i += blockDim.x) s_yoff[i] = P.yr_off[i];
+        __syncthreads();
+        xr_hi = s_xhi;
+        yr_hi = s_yhi;
+        xr_seg = s_xseg;
+        yr_off = s_yoff;
+        yidx32 = s_yidx;
+    }
+    for (;;) {
+        uint32_t row = 0;
+        if (lane == 0) row = atomicAdd(P.cursor, 1u);
+        row = __shfl_sync(0xffffffffu, row, 0);
+        if (row >= P.nro) break;
+        const uint64_t H = __ldg(P.or_hi + row);
+        const uint32_t sg = __ldg(P.or_seg + row);
+        uint64_t z0[LACC], z1[LACC];
+#pragma unroll
+        for (int l = 0; l < LACC; ++l) z0[l] = z1[l] = 0;
+        double d0 = 0.0, d1 = 0.0;
+        for (uint32_t base = 0; base < P.nrx; base += 32u) {
+            const uint32_t r1 = base + lane;
+            int found = -1;
+            if (r1 < P.nrx) {
+                const uint64_t h1 = xr_hi[r1];
+                if (h1 <= H) {
+                    const uint64_t target = H - h1;
+                    const uint32_t s1 = xr_seg[r1];
+                    const uint32_t b = sg >= s1 ? sg - s1 : sg + P.m - s1;
+                    const uint32_t o1 = yr_off[b + 1];
+                    for (uint32_t o = yr_off[b]; o < o1; ++o) {
+                        if (yr_hi[o] == target) {
+                            found = (int)o;
+                            break;
+                        }
+                    }
+                }
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, found >= 0);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const uint32_t rr1 = base + (uint32_t)src;
+                const uint32_t oo = (uint32_t)__shfl_sync(0xffffffffu, found, src);
+                const uint32_t rr2 = yidx32 ? yidx32[oo] : (uint32_t)__ldg(P.yr_idx + oo);
+                uint32_t len1 = __ldg(P.xr_len + rr1);
+                const uint32_t len2 = __ldg(P.yr_len + rr2);
+                uint64_t X = __ldg(P.xmat + (size_t)rr1 * 32 + lane);
+                uint64_t Y = __ldg(P.ymat + (size_t)rr2 * 32 + lane);
+                if (len2 < len1) { // the convolution is symmetric: loop over the shorter row
+                    const uint64_t t = X;
+                    X = Y;
+                    Y = t;
+                    len1 = len2;
+                }
+                for (uint32_t i = 0; i < len1; ++i) {
+                    const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
+                    const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                    const bool lowhalf = lane >= i;
+                    if constexpr (F64) {
+                        const double p = __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv));
+                        if (lowhalf) d0 = __dadd_rn(d0, p); else d1 = __dadd_rn(d1, p);
+                    } else {
+                        row_mac<LACC>(z0, (long long)xi, (long long)yv, lowhalf);
+                        row_mac<LACC>(z1, (long long)xi, (long long)yv, !lowhalf);
+                    }
+                }
+            }
+        }
+        // write the row once; count its non-zero entries
+        uint64_t *o = P.omat + (size_t)row * 64 * LACC;
+        bool nz0, nz1;
+        if constexpr (F64) {
+            o[lane] = (uint64_t)__double_as_longlong(d0);
+            o[32 + lane] = (uint64_t)__double_as_longlong(d1);
+            nz0 = d0 != 0.0;
+            nz1 = d1 != 0.0;
+        } else {
+            nz0 = nz1 = false;
+#pragma unroll
+            for (int l = 0; l < LACC; ++l) {
+                o[(size_t)l * 64 + lane] = z0[l];
+                o[(size_t)l * 64 + 32 + lane] = z1[l];
+                nz0 |= z0[l] != 0;
+                nz1 |= z1[l] != 0;
+            }
+        }
+        const uint32_t c = __popc(__ballot_sync(0xffffffffu, nz0)) + __popc(__ballot_sync(0xffffffffu, nz1));
+        if (lane == 0) P.or_cnt[row] = c;
+    }
+}
+
+// Expand the dense output rows into terms: key = hi * delta + lo, zero coefficients dropped.
+template <int LACC, bool F64>
+__global__ void __launch_bounds__(256) k_row_expand(const uint64_t *__restrict__ or_hi, const uint64_t *__restrict__ omat,
+                                                    const uint32_t *__restrict__ off, uint32_t nro, uint64_t delta,
+                                                    uint64_t *__restrict__ okeys, uint64_t *__restrict__ ocfs)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < nro; row += gridDim.x * wpb) {
+        const uint64_t *o = omat + (size_t)row * 64 * LACC;
+        uint32_t base = off[row];
+        const uint64_t hi = or_hi[row];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint64_t v[LACC];
+            bool nz = false;
+#pragma unroll
+            for (int l = 0; l < LACC; ++l) {
+                v[l] = o[(size_t)l * 64 + half * 32 + lane];
+                nz |= v[l] != 0;
+            }
+            if constexpr (F64) nz = __longlong_as_double((long long)v[0]) != 0.0;
+            const uint32_t b = __ballot_sync(0xffffffffu, nz);
+            if (nz) {
+                const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+                okeys[pos] = hi * delta + (uint64_t)(half * 32 + lane);
+#pragma unroll
+                for (int l = 0; l < LACC; ++l) ocfs[(size_t)pos * LACC + l] = v[l];
+            }
+            base += __popc(b);
         }
     }
 }

