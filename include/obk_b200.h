@@ -154,15 +154,17 @@ obk_status obk_overflow_check(obk_engine *e, const obk_poly_view *x, const obk_p
 obk_status obk_key_degrees(obk_engine *e, const obk_poly_view *x, const obk_trunc *which, int64_t *out_host);
 
 /* Multi-GPU: rank r multiplies its slice of the shorter operand's terms by the whole other
- * operand with a segment count all ranks agree on, and leaves a DEVICE partial result grouped by
- * segment.  send_counts[g] = number of partial terms owned by rank g (segments [g*nsegs/G, (g+1)*nsegs/G)).
- * After the all-to-all the owner merges what it received with obk_poly_merge (same nsegs = the partial
- * result's nsegs). */
+ * operand and leaves a DEVICE partial result grouped by key mod 4093 (seg_kind OBK_SEG_KEY_MOD, a fixed
+ * prime every rank uses).  send_counts[g] = number of partial terms owned by rank g, i.e. those of groups
+ * [g*nsegs/G, (g+1)*nsegs/G) -- contiguous rows.  After the all-to-all the owner merges what it received
+ * with obk_poly_merge.  The exponent-overflow check and the accumulator width use the FULL operands, so
+ * every rank takes the same decisions and produces the same limb count. */
 obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
                                 uint32_t rank, uint32_t nranks, obk_poly_result *out_partial,
                                 uint64_t *send_counts, obk_stats *stats);
 /* Sum terms with equal keys (exact / fp64), drop zeros; `terms` holds acc-limb coefficients
- * (cf_limbs = accumulator limbs) on the device. */
+ * (cf_limbs = accumulator limbs).  `nsegs` is a hint (0 = auto): the merge sizes its own segment tables
+ * from the bound distinct <= nterms. */
 obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t nsegs, uint32_t result_mem,
                           obk_poly_result *out, obk_stats *stats);
 

@@ -18,6 +18,7 @@ OBK_ERR_UNSUPPORTED = 6
 OBK_ERR_NOMEM = 7
 OBK_CF_INT, OBK_CF_F64 = 0, 1
 OBK_MEM_HOST, OBK_MEM_DEVICE = 0, 1
+OBK_EXCHANGE_MOD = 4093  # partial products of the multi-GPU path are grouped by key mod this prime
 
 
 class PolyView(C.Structure):

@@ -21,6 +21,7 @@
 using namespace obk;
 
 #define OBK_VERSION_STRING "obk_b200 0.1 (sm_100a)"
+#define OBK_EXCHANGE_MOD 4093u
 
 namespace
 {
@@ -876,6 +877,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         uint32_t ndeg = 1;
         int64_t lim_base = 0, degmin_y = 0;
         int64_t *xdeg = nullptr, *ydeg = nullptr;
+        const uint64_t *sxk = nullptr, *sxc = nullptr; // this rank's slice of the left operand
+        const int64_t *sxdeg = nullptr;
+        uint64_t snx = 0, x_begin = 0;
         bool trunc = false;
         bool rows_ok = false; // every exponent >= 0 and the first symbol's exponents < 32 in both operands
         uint64_t tot_mults = 0;
@@ -911,6 +915,27 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             CU_CHECK(e, cudaStreamSynchronize(s));
             if (x == y) hs[1] = hs[0];
             st.d2h_bytes += sizeof(StatsOut) * 2;
+            // multi-GPU: from here on this rank only sees its slice of the left operand's terms;
+            // the checks above and the accumulator width below use the FULL operands so that every rank agrees.
+            if (rq.nranks > 1) {
+                x_begin = nx_full * rq.rank / rq.nranks;
+                snx = nx_full * (rq.rank + 1) / rq.nranks - x_begin;
+                sxk = dxk + x_begin * W;
+                sxc = dxc + x_begin * CWx;
+                if (xdeg) sxdeg = xdeg + x_begin;
+                if (snx == 0) {
+                    // more ranks than left-operand terms: this rank has nothing to multiply
+                    set_empty_result(out, x, f64 ? 1 : 1, rq.result_mem);
+                    if (rq.send_counts) std::memset(rq.send_counts, 0, sizeof(uint64_t) * rq.nranks);
+                    if (stats) *stats = st;
+                    return OBK_OK;
+                }
+            } else {
+                sxk = dxk;
+                sxc = dxc;
+                sxdeg = xdeg;
+                snx = nx_full;
+            }
 
             // monomial_range_overflow_check (packed_monomial.hpp:462-487; d_packed_monomial.hpp:861-894)
             if (L.nvars) {
@@ -1008,7 +1033,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 k_deg_hist<<<gy, 256, 0, s>>>(ydeg, ny, degmin_y, hist);
                 e->launches += 1;
                 device_scan(e, sc, hist, pref, ndeg);
-                k_count_mults<<<gx, 256, 0, s>>>(xdeg, nx_full, lim_base, ndeg, pref, dtot);
+                k_count_mults<<<gx, 256, 0, s>>>(sxdeg, snx, lim_base, ndeg, pref, dtot);
                 e->launches += 1;
                 unsigned long long htot = 0;
                 CU_CHECK(e, cudaMemcpyAsync(&htot, dtot, 8, cudaMemcpyDeviceToHost, s));
@@ -1023,7 +1048,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     return OBK_OK;
                 }
             } else {
-                tot_mults = nx_full * ny;
+                tot_mults = snx * ny;
             }
         } else {
             // merge mode: sum acc-limb coefficients by key
@@ -1051,10 +1076,10 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
 
         // ---- dense operands: row-blocked path (register accumulation, no table) --------------------------------
         RowsResult rows;
-        if (!rq.merge && !trunc && rq.nranks <= 1 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
+        if (!rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok
             && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
-            rows = run_rows(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, tot_mults, threads, e->opt_kernel == 1, st);
+            rows = run_rows(e, sc, sxk, sxc, snx, dyk, dyc, ny, L, mode, accw, tot_mults, threads, e->opt_kernel == 1, st);
         }
 
         uint64_t *rk = nullptr, *rc = nullptr, *off64 = nullptr;
@@ -1079,25 +1104,19 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             // Sampled symbolic product: count the distinct product keys of a few fine-grained segments exactly.
             uint64_t est = 0;
             if (rq.merge) {
-                nsegs = rq.merge_nsegs;
+                // distinct keys <= input terms: a segmentation sized for that bound can never overflow
                 est = ny;
+                nsegs = pick_nsegs(ny, (double)cap * 0.85, ny * 64, wave);
             } else if (e->opt_nsegs > 0) {
                 nsegs = (uint32_t)e->opt_nsegs;
             } else {
-                EstimateIn ein{dxk, xdeg, nx_full, dyk, ydeg, ny, W, L.is_signed, dbits, degmin_y, ndeg, trunc, lim_base,
+                EstimateIn ein{sxk, sxdeg, snx, dyk, ydeg, ny, W, L.is_signed, dbits, degmin_y, ndeg, trunc, lim_base,
                                tot_mults, threads};
                 est = estimate_terms(e, sc, ein);
                 nsegs = pick_nsegs(est, (double)cap * (double)e->opt_fill_pct / 100.0, tot_mults, wave);
             }
             st.est_nterms = est;
             CU_CHECK(e, cudaEventRecord(e->ev[3], s));
-
-            // ---- left-operand slice for multi-GPU sharding --------------------------------------
-            uint64_t x_begin = 0, x_end = nx_full;
-            if (rq.nranks > 1) {
-                x_begin = nx_full * rq.rank / rq.nranks;
-                x_end = nx_full * (rq.rank + 1) / rq.nranks;
-            }
 
             // ---- sort the right operand, multiply, retry with a finer segmentation on table overflow --------
             uint64_t *stage_k = nullptr, *stage_c = nullptr;
@@ -1115,9 +1134,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     ys = sort_operand(e, sc, dyk, dyc, nullptr, ny, W, accw, nsegs, L.is_signed, false, 0, 0, true);
                 } else {
                     ys = sort_operand(e, sc, dyk, dyc, ydeg, ny, W, CWy, nsegs, L.is_signed, false, dbits, degmin_y, true);
-                    xseg = sc.alloc<uint32_t>(x_end - x_begin);
-                    k_segments<<<(unsigned)std::min<uint64_t>((x_end - x_begin + 255) / 256, 4096), 256, 0, s>>>(
-                        dxk + x_begin * W, x_end - x_begin, W, nsegs, L.is_signed, xseg);
+                    xseg = sc.alloc<uint32_t>(std::max<uint64_t>(snx, 1));
+                    k_segments<<<(unsigned)std::min<uint64_t>((snx + 255) / 256 + 1, 4096), 256, 0, s>>>(sxk, snx, W, nsegs,
+                                                                                                       L.is_signed, xseg);
                     e->launches += 1;
                 }
                 stage_k = sc.alloc<uint64_t>((uint64_t)nsegs * cap * W);
@@ -1137,11 +1156,11 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     P.xc = nullptr;
                     P.nx = 1;
                 } else {
-                    P.xk = dxk + x_begin * W;
-                    P.xc = dxc + x_begin * CWx;
-                    P.xdeg = xdeg ? xdeg + x_begin : nullptr;
+                    P.xk = sxk;
+                    P.xc = sxc;
+                    P.xdeg = sxdeg;
                     P.xseg = xseg;
-                    P.nx = x_end - x_begin;
+                    P.nx = snx;
                 }
                 P.yk = ys.keys;
                 P.yc = ys.cfs;
@@ -1163,7 +1182,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 } else {
                     // long right-operand runs: a warp shares one left term (distinct keys, no intra-warp slot clash);
                     // short runs: one lane per left term (measured on S12: 1 lane 31 G/s vs 8 lanes 22 G/s)
-                    const double run = (double)tot_mults / (double)nx_full / (double)nsegs;
+                    const double run = (double)tot_mults / (double)std::max<uint64_t>(snx, 1) / (double)nsegs;
                     lg = run >= 24.0 ? 5 : 0;
                 }
                 P.lg = lg;
@@ -1232,6 +1251,29 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         // path keep the engine's own segmentation (key mod nsegs): the all-to-all needs owner ranges contiguous.
         uint32_t out_groups = nsegs, out_log2 = 0, seg_kind = 1;
         const bool regroup = rq.nranks <= 1 && e->opt_regroup != 0;
+        if (rq.nranks > 1) {
+            // multi-GPU partial product: group by key mod OBK_EXCHANGE_MOD, a fixed prime every rank uses, so the
+            // rows destined to one owner are contiguous whatever kernel and segmentation produced them
+            const uint32_t mx = OBK_EXCHANGE_MOD;
+            auto *own = new ResultOwner{e};
+            out->owner = own;
+            own->seg_offsets = (uint64_t *)std::calloc((size_t)mx + 1, sizeof(uint64_t));
+            if (total > 0) {
+                SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, mx, L.is_signed, false, 0, 0, true);
+                sc.release(rk);
+                sc.release(rc);
+                rk = g.keys;
+                rc = g.cfs;
+                std::vector<uint32_t> h32((size_t)mx + 1);
+                CU_CHECK(e, cudaMemcpyAsync(h32.data(), g.off, h32.size() * 4, cudaMemcpyDeviceToHost, s));
+                CU_CHECK(e, cudaStreamSynchronize(s));
+                sc.release(g.off);
+                for (size_t i = 0; i <= mx; ++i) own->seg_offsets[i] = h32[i];
+            }
+            out_groups = mx;
+            nsegs = mx;
+            seg_kind = 1;
+        }
         if (regroup) {
             const double term_bytes = 8.0 * W + 8.0 * accw;
             const double est_sp = tot_mults ? (double)total / (double)tot_mults : 1.0;
@@ -1272,8 +1314,10 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         if (!own) {
             own = new ResultOwner{e};
             out->owner = own;
-            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * ((size_t)nsegs + 1));
-            CU_CHECK(e, cudaMemcpyAsync(own->seg_offsets, off64, ((size_t)nsegs + 1) * 8, cudaMemcpyDeviceToHost, s));
+            const size_t ngr = rows.done ? 1 : (size_t)nsegs;
+            out_groups = (uint32_t)ngr;
+            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * (ngr + 1));
+            CU_CHECK(e, cudaMemcpyAsync(own->seg_offsets, off64, (ngr + 1) * 8, cudaMemcpyDeviceToHost, s));
         }
         st.d2h_bytes += ((uint64_t)out_groups + 1) * 8;
         out->nterms = total;

@@ -1,9 +1,9 @@
 """Multi-GPU series product: one process per GPU, torch.distributed for the plumbing.
 
 The left (shorter) operand's terms are split into `world` contiguous slices; rank r multiplies slice r
-by the whole right operand with a segment count every rank derives identically (same inputs, same
-deterministic estimate), which leaves a partial product grouped by output segment.  Segment s is owned
-by rank s * world // nsegs (contiguous ranges), so the rows a rank must send to each peer are contiguous:
+by the whole right operand (dense row kernel or segment-owner scatter kernel, whichever the engine picks)
+and leaves a partial product grouped by key mod 4093, a fixed prime.  Group s is owned by rank
+s * world // 4093 (contiguous ranges), so the rows a rank must send to each peer are contiguous:
 one all-to-all of counts, one of keys, one of coefficient limbs (NCCL over NVLink on the GPU box; gloo in
 the CPU tests), then the owner sums what it received by key.  No other collective is on the data path.
 """
@@ -61,18 +61,7 @@ def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", engine.device)
     part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
-    # Every rank derives the segmentation from the same full operands, but a rank whose slice overflowed a
-    # shared-memory table refined it locally: agree on the finest one and redo coarser partials with it.
-    k = torch.tensor([part.nsegs], dtype=torch.int64, device=dev)
-    dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
-    nsegs = int(k.item())
-    if part.nsegs != nsegs and part.stats["term_products"] > 0:
-        part.free()
-        engine.set_option("nsegs", nsegs)
-        try:
-            part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
-        finally:
-            engine.set_option("nsegs", -1)
+    nsegs = _capi.OBK_EXCHANGE_MOD  # fixed modulus: owner ranges are the same on every rank
     W, L = part.key_words, part.cf_limbs
     pk = device_tensor(part.keys_ptr, (part.nterms, W), dev)
     pc = device_tensor(part.cfs_ptr, (part.nterms, L), dev)
