@@ -605,7 +605,7 @@ struct RowsResult {
 // Returns done=false when the operands are not dense enough (the caller then runs the scatter kernel).
 RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx, const uint64_t *dyk,
                     const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, uint64_t tot_mults,
-                    unsigned threads, bool forced, obk_stats &st)
+                    unsigned threads, bool forced, uint32_t rank, uint32_t nranks, obk_stats &st)
 {
     RowsResult R;
     cudaStream_t s = e->stream;
@@ -626,6 +626,22 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         Y.nrows = hy;
         rows_phase_b(e, sc, dyk, dyc, ny, delta, Y);
     }
+    if (nranks > 1) {
+        // multi-GPU: this rank multiplies a contiguous slice of the left ROWS (row numbers come out of a hash
+        // table, so a slice is a pseudo-random, balanced subset) by every right row
+        const uint32_t b = (uint32_t)((uint64_t)X.nrows * rank / nranks);
+        const uint32_t c = (uint32_t)((uint64_t)X.nrows * (rank + 1) / nranks) - b;
+        X.row_hi += b;
+        X.mat += (size_t)b * 32;
+        X.row_len += b;
+        X.nrows = c;
+        if (c == 0) {
+            R.done = true;
+            R.rk = sc.alloc<uint64_t>(1);
+            R.rc = sc.alloc<uint64_t>(accw);
+            return R;
+        }
+    }
     // density test on the host: the convolution loops over the shorter row of every pair
     std::vector<uint32_t> lx(X.nrows), ly(Y.nrows);
     CU_CHECK(e, cudaMemcpyAsync(lx.data(), X.row_len, (size_t)X.nrows * 4, cudaMemcpyDeviceToHost, s));
@@ -635,7 +651,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     for (auto v : ly) Y.sum_len += v;
     const double iters = std::min((double)X.sum_len * (double)Y.nrows, (double)Y.sum_len * (double)X.nrows);
     // measured costs: ~40 warp instructions per convolution step vs ~22 per product in the scatter kernel
-    if (!forced && iters * 40.0 > (double)tot_mults * 22.0 * 0.7) return R;
+    if (!forced && iters * 40.0 * (double)nranks > (double)tot_mults * 22.0 * 0.7) return R;
 
     const uint32_t wave = (uint32_t)e->sm_count;
     // ---- symbolic row product: the set of output rows ------------------------------------------------------
@@ -1079,7 +1095,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         if (!rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok
             && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
-            rows = run_rows(e, sc, sxk, sxc, snx, dyk, dyc, ny, L, mode, accw, tot_mults, threads, e->opt_kernel == 1, st);
+            rows = run_rows(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, nx_full * ny, threads, e->opt_kernel == 1,
+                            rq.rank, rq.nranks, st);
         }
 
         uint64_t *rk = nullptr, *rc = nullptr, *off64 = nullptr;
