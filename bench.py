@@ -253,8 +253,10 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     ms = float(np.mean(times))
+    rank_products = products
     if world > 1:
-        t = torch.tensor([ms, float(nterms_out), float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, float(nterms_out), float(np.mean(kernel_ms)), float(products)], dtype=torch.float64,
+                         device=dev)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
@@ -262,6 +264,8 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         ms = float(tmax[0].item())
         nterms_out = int(tsum[1].item())
         kernel_mean = float(tmax[2].item())
+        rank_products = int(tmax[3].item())
+        products = int(tsum[3].item())  # whole job: every rank multiplied its slice of the left operand
     else:
         kernel_mean = float(np.mean(kernel_ms))
 
@@ -270,7 +274,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     lacc = stats_last["acc_limbs"]
     B = algorithmic_bytes(f.key_words, f64, lin, lacc)
     peak, peak_src = measured_peak()
-    per_launch_products = products / world
+    per_launch_products = rank_products  # the slowest rank's kernel and the products it formed
     achieved = B * per_launch_products / (kernel_mean * 1e-3) / 1e9
     out = {
         "workload": name, "description": desc, "products": int(products), "terms_out": int(nterms_out),
