@@ -47,7 +47,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
 };
@@ -565,14 +565,20 @@ __global__ void k_iota64(uint64_t *p, uint32_t n)
     if (i < n) p[i] = i;
 }
 
-template <int LACC, bool F64>
+template <int LACC, bool F64, bool UNS = false>
 void launch_rows_t(obk_engine *e, const RowParams &P, unsigned grid, size_t smem, const uint32_t *offs, uint64_t delta,
                    uint64_t *rk, uint64_t *rc, bool expand)
 {
     if (!expand) {
-        auto fn = k_rowconv<LACC, F64>;
-        CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        fn<<<grid, 1024, smem, e->stream>>>(P);
+        if (e->opt_row_threads <= 512) {
+            auto fn = k_rowconv<LACC, F64, UNS, 512>;
+            CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            fn<<<grid, 512, smem, e->stream>>>(P);
+        } else {
+            auto fn = k_rowconv<LACC, F64, UNS, 1024>;
+            CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+            fn<<<grid, 1024, smem, e->stream>>>(P);
+        }
     } else {
         k_row_expand<LACC, F64><<<(unsigned)std::min<uint32_t>((P.nro + 7) / 8, 8192), 256, 0, e->stream>>>(
             P.or_hi, P.omat, offs, P.nro, delta, rk, rc);
@@ -581,9 +587,18 @@ void launch_rows_t(obk_engine *e, const RowParams &P, unsigned grid, size_t smem
     CU_CHECK(e, cudaGetLastError());
 }
 
-void launch_rows(obk_engine *e, int mode, const RowParams &P, unsigned grid, size_t smem, const uint32_t *offs,
+void launch_rows(obk_engine *e, int mode, bool uns, const RowParams &P, unsigned grid, size_t smem, const uint32_t *offs,
                  uint64_t delta, uint64_t *rk, uint64_t *rc, bool expand)
 {
+    if (uns && !expand) {
+        // no negative coefficient anywhere: unsigned multiply, no sign fix-ups, no sign extension limb
+        switch (mode) {
+            case CF_I1A1: launch_rows_t<1, false, true>(e, P, grid, smem, offs, delta, rk, rc, expand); return;
+            case CF_I1A2: launch_rows_t<2, false, true>(e, P, grid, smem, offs, delta, rk, rc, expand); return;
+            case CF_I1A3: launch_rows_t<3, false, true>(e, P, grid, smem, offs, delta, rk, rc, expand); return;
+            default: break;
+        }
+    }
     switch (mode) {
         case CF_I1A1: launch_rows_t<1, false>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
         case CF_I1A2: launch_rows_t<2, false>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
@@ -605,7 +620,7 @@ struct RowsResult {
 // Returns done=false when the operands are not dense enough (the caller then runs the scatter kernel).
 RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx, const uint64_t *dyk,
                     const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, uint64_t tot_mults,
-                    unsigned threads, bool forced, uint32_t rank, uint32_t nranks, obk_stats &st)
+                    unsigned threads, bool forced, bool uns, uint32_t rank, uint32_t nranks, obk_stats &st)
 {
     RowsResult R;
     cudaStream_t s = e->stream;
@@ -762,7 +777,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     const size_t dir_bytes = (size_t)X.nrows * 12 + (size_t)Y.nrows * 12 + ((size_t)mG + 1) * 4 + 64;
     P.dir_in_smem = dir_bytes + 2048 <= e->smem_optin ? 1u : 0u;
     CU_CHECK(e, cudaEventRecord(e->ev[5], s));
-    if (nro) launch_rows(e, mode, P, wave, P.dir_in_smem ? dir_bytes : 0, nullptr, delta, nullptr, nullptr, false);
+    if (nro) launch_rows(e, mode, uns, P, wave, P.dir_in_smem ? dir_bytes : 0, nullptr, delta, nullptr, nullptr, false);
     CU_CHECK(e, cudaEventRecord(e->ev[6], s));
     st.mul_launches += 1;
     uint64_t total = 0;
@@ -775,7 +790,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     }
     R.rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1));
     R.rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
-    if (total) launch_rows(e, mode, P, 0, 0, roffs, delta, R.rk, R.rc, true);
+    if (total) launch_rows(e, mode, uns, P, 0, 0, roffs, delta, R.rk, R.rc, true);
     R.total = total;
     R.nro = nro;
     R.m = mG;
@@ -897,6 +912,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         const int64_t *sxdeg = nullptr;
         uint64_t snx = 0, x_begin = 0;
         bool trunc = false;
+        unsigned hs_anyneg = 1;
         bool rows_ok = false; // every exponent >= 0 and the first symbol's exponents < 32 in both operands
         uint64_t tot_mults = 0;
         if (!rq.merge) {
@@ -984,6 +1000,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     return OBK_ERR_KEY_OVERFLOW;
                 }
             }
+            hs_anyneg = hs[0].anyneg | hs[1].anyneg;
             if (L.nvars) {
                 rows_ok = unord(hs[0].emax[0], L.is_signed) < 32 && unord(hs[1].emax[0], L.is_signed) < 32
                           && hs[0].nonfinite == 0 && hs[1].nonfinite == 0;
@@ -1096,7 +1113,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok
             && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
             rows = run_rows(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, nx_full * ny, threads, e->opt_kernel == 1,
-                            rq.rank, rq.nranks, st);
+                            !f64 && hs_anyneg == 0, rq.rank, rq.nranks, st);
         }
 
         uint64_t *rk = nullptr, *rc = nullptr, *off64 = nullptr;
@@ -1499,6 +1516,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     if (n == "nsegs") e->opt_nsegs = value;
     else if (n == "fence") e->opt_fence = value;
     else if (n == "regroup") e->opt_regroup = value;
+    else if (n == "row_threads") e->opt_row_threads = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
     else if (n == "group_lanes") e->opt_group_lanes = value;

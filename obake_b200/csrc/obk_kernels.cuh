@@ -40,6 +40,8 @@ struct StatsOut {
     long long dmin, dmax; // (partial) degree extrema, same encoding
     unsigned cfbits;      // max bit length of |coefficient| (integers)
     unsigned nonfinite;   // fp64: number of non-finite coefficients
+    unsigned anyneg;      // integers: 1 if some coefficient is negative
+    unsigned pad;
 };
 
 __device__ __forceinline__ long long ord64(int64_t v, uint32_t is_signed)
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) k_term_stats(const uint64_t *__restrict__
 {
     __shared__ long long s_min[MAX_VARS], s_max[MAX_VARS];
     __shared__ long long s_dmin, s_dmax;
-    __shared__ unsigned s_bits, s_nonf;
+    __shared__ unsigned s_bits, s_nonf, s_neg;
     const int tid = threadIdx.x;
     if (tid < MAX_VARS) {
         s_min[tid] = 0x7fffffffffffffffLL;
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) k_term_stats(const uint64_t *__restrict__
         s_dmax = (long long)0x8000000000000000ULL;
         s_bits = 0;
         s_nonf = 0;
+        s_neg = 0;
     }
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(256) k_term_stats(const uint64_t *__restrict__
                 atomicMax(&s_dmax, mx);
             }
         }
-        unsigned bits = 0, nonf = 0;
+        unsigned bits = 0, nonf = 0, isneg = 0;
         if (live) {
             if (cf_kind == 0) {
                 // bit length of |c| for a two's-complement cf_limbs-limb integer
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(256) k_term_stats(const uint64_t *__restrict__
                     }
                 }
                 if (neg) bits += 1; // |-(2^k)| needs k+1 bits; cheap upper bound for every negative value
+                isneg = neg;
             } else if (cf_kind == 1) {
                 const double d = __longlong_as_double((long long)cfs[i]);
                 nonf = !isfinite(d);
@@ -142,9 +146,11 @@ __global__ void __launch_bounds__(256) k_term_stats(const uint64_t *__restrict__
         }
         bits = __reduce_max_sync(0xffffffffu, bits);
         nonf = __reduce_add_sync(0xffffffffu, nonf);
+        isneg = __any_sync(0xffffffffu, isneg);
         if ((tid & 31) == 0) {
             atomicMax(&s_bits, bits);
             if (nonf) atomicAdd(&s_nonf, nonf);
+            if (isneg) s_neg = 1;
         }
     }
     __syncthreads();
@@ -157,6 +163,7 @@ __global__ void __launch_bounds__(256) k_term_stats(const uint64_t *__restrict__
         atomicMax(&out->dmax, s_dmax);
         atomicMax(&out->cfbits, s_bits);
         if (s_nonf) atomicAdd(&out->nonfinite, s_nonf);
+        if (s_neg) atomicOr(&out->anyneg, 1u);
     }
 }
 
@@ -173,6 +180,8 @@ __global__ void k_stats_init(StatsOut *s, int n)
         s[i].dmax = (long long)0x8000000000000000ULL;
         s[i].cfbits = 0;
         s[i].nonfinite = 0;
+        s[i].anyneg = 0;
+        s[i].pad = 0;
     }
 }
 
@@ -790,32 +799,30 @@ struct RowAcc {
     uint64_t l[LACC];
 };
 
-// z += (pred ? x*y : 0) for signed 64-bit x, y and an LACC-limb two's-complement accumulator
-template <int LACC>
-__device__ __forceinline__ void row_mac(uint64_t (&z)[LACC], long long x, long long y, bool pred)
+// z += x*y for 64-bit x, y (signed, or unsigned when no coefficient is negative) and an LACC-limb accumulator
+template <int LACC, bool UNS>
+__device__ __forceinline__ void row_mac(uint64_t (&z)[LACC], uint64_t x, uint64_t y)
 {
-    uint64_t lo = (uint64_t)(x * y);
-    uint64_t hi = (uint64_t)__mul64hi(x, y);
-    if (!pred) {
-        lo = 0;
-        hi = 0;
-    }
+    const uint64_t lo = x * y;
     if constexpr (LACC == 1) {
         z[0] += lo;
-    } else if constexpr (LACC == 2) {
-        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(z[0]), "+l"(z[1]) : "l"(lo), "l"(hi));
     } else {
-        const uint64_t ext = (uint64_t)((long long)hi >> 63);
-        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, %5;"
-            : "+l"(z[0]), "+l"(z[1]), "+l"(z[2])
-            : "l"(lo), "l"(hi), "l"(ext));
+        const uint64_t hi = UNS ? __umul64hi(x, y) : (uint64_t)__mul64hi((long long)x, (long long)y);
+        if constexpr (LACC == 2) {
+            asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(z[0]), "+l"(z[1]) : "l"(lo), "l"(hi));
+        } else {
+            const uint64_t ext = UNS ? 0ull : (uint64_t)((long long)hi >> 63);
+            asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, %5;"
+                : "+l"(z[0]), "+l"(z[1]), "+l"(z[2])
+                : "l"(lo), "l"(hi), "l"(ext));
+        }
     }
 }
 
 // One warp = one output row.  The x-row and y-row directories (keys, segments, offsets) are staged in shared
 // memory once per CTA when they fit; coefficient rows stream from L2 (256 B per row, coalesced).
-template <int LACC, bool F64>
-__global__ void __launch_bounds__(1024, 1) k_rowconv(const RowParams P)
+template <int LACC, bool F64, bool UNS, int BT>
+__global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u;
@@ -885,22 +892,41 @@ __global__ void __launch_bounds__(1024, 1) k_rowconv(const RowParams P)
                 const uint32_t len2 = __ldg(P.yr_len + rr2);
                 uint64_t X = __ldg(P.xmat + (size_t)rr1 * 32 + lane);
                 uint64_t Y = __ldg(P.ymat + (size_t)rr2 * 32 + lane);
+                uint32_t len2x = len2;
                 if (len2 < len1) { // the convolution is symmetric: loop over the shorter row
                     const uint64_t t = X;
                     X = Y;
                     Y = t;
+                    len2x = len1;
                     len1 = len2;
                 }
-                for (uint32_t i = 0; i < len1; ++i) {
-                    const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
-                    const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
-                    const bool lowhalf = lane >= i;
-                    if constexpr (F64) {
-                        const double p = __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv));
-                        if (lowhalf) d0 = __dadd_rn(d0, p); else d1 = __dadd_rn(d1, p);
-                    } else {
-                        row_mac<LACC>(z0, (long long)xi, (long long)yv, lowhalf);
-                        row_mac<LACC>(z1, (long long)xi, (long long)yv, !lowhalf);
+                if (len1 + len2x <= 33u) {
+                    // the output row fits 32 lanes: the wrapped-around lanes of the rotation read zeros of the
+                    // right row, so every lane accumulates unconditionally into its low output
+                    for (uint32_t i = 0; i < len1; ++i) {
+                        const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
+                        const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                        if constexpr (F64) {
+                            d0 = __dadd_rn(d0, __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv)));
+                        } else {
+                            row_mac<LACC, UNS>(z0, xi, yv);
+                        }
+                    }
+                } else {
+                    for (uint32_t i = 0; i < len1; ++i) {
+                        const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
+                        const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                        // lane >= i: the rotated value belongs to output lo = lane, else to output lo = lane + 32;
+                        // mask the INPUT so both accumulators run branch-free multiply-adds
+                        const bool lowhalf = lane >= i;
+                        const uint64_t y0 = lowhalf ? yv : 0ull, y1 = lowhalf ? 0ull : yv;
+                        if constexpr (F64) {
+                            const double p = __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv));
+                            if (lowhalf) d0 = __dadd_rn(d0, p); else d1 = __dadd_rn(d1, p);
+                        } else {
+                            row_mac<LACC, UNS>(z0, xi, y0);
+                            row_mac<LACC, UNS>(z1, xi, y1);
+                        }
                     }
                 }
             }
