@@ -84,7 +84,7 @@ struct Scratch {
     T *alloc(size_t n)
     {
         void *p = nullptr;
-        size_t bytes = std::max<size_t>(n * sizeof(T), 16);
+        size_t bytes = (std::max<size_t>(n * sizeof(T), 16) + 255) / 256 * 256;
         cudaError_t err = cudaMallocAsync(&p, bytes, e->stream);
         if (err != cudaSuccess) {
             e->err = std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(err);
@@ -755,16 +755,21 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     uint32_t *roffs = sc.alloc<uint32_t>((size_t)nro + 2);
     uint32_t *cursor = sc.alloc<uint32_t>(4);
     CU_CHECK(e, cudaMemsetAsync(cursor, 0, 16, s));
+    // packed directories, padded to the 16-byte granularity of the bulk copies
+    auto pad16 = [](size_t b) { return (uint32_t)((b + 15) / 16 * 16); };
+    uint32_t *xsl = sc.alloc<uint32_t>((size_t)X.nrows + 4);
+    uint32_t *yil = sc.alloc<uint32_t>((size_t)Y.nrows + 4);
+    k_row_pack<<<(std::max(X.nrows, Y.nrows) + 255) / 256, 256, 0, s>>>(xsegG, X.row_len, X.nrows, yg.cfs, Y.row_len, Y.nrows,
+                                                                      xsl, yil);
+    e->launches += 1;
     RowParams P{};
     P.xr_hi = X.row_hi;
-    P.xr_seg = xsegG;
-    P.xr_len = X.row_len;
+    P.xr_sl = xsl;
     P.xmat = X.mat;
     P.nrx = X.nrows;
     P.yr_hi = yg.keys;
-    P.yr_idx = yg.cfs;
+    P.yr_il = yil;
     P.yr_off = yg.off;
-    P.yr_len = Y.row_len;
     P.ymat = Y.mat;
     P.nry = Y.nrows;
     P.m = mG;
@@ -774,8 +779,15 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     P.cursor = cursor;
     P.omat = omat;
     P.or_cnt = or_cnt;
-    const size_t dir_bytes = (size_t)X.nrows * 12 + (size_t)Y.nrows * 12 + ((size_t)mG + 1) * 4 + 64;
-    P.dir_in_smem = dir_bytes + 2048 <= e->smem_optin ? 1u : 0u;
+    P.b_xhi = pad16((size_t)X.nrows * 8);
+    P.b_yhi = pad16((size_t)Y.nrows * 8);
+    P.b_yil = pad16((size_t)Y.nrows * 4);
+    P.b_xsl = pad16((size_t)X.nrows * 4);
+    P.b_yoff = pad16(((size_t)mG + 1) * 4);
+    const size_t dir_bytes = (size_t)P.b_xhi + P.b_yhi + P.b_yil + P.b_xsl + P.b_yoff + 128;
+    // a multi-GPU slice offsets X.row_hi by a row count: bulk copies need 16-byte aligned sources
+    const bool aligned = ((uintptr_t)X.row_hi % 16 == 0);
+    P.dir_in_smem = (dir_bytes + 2048 <= e->smem_optin && aligned) ? 1u : 0u;
     CU_CHECK(e, cudaEventRecord(e->ev[5], s));
     if (nro) launch_rows(e, mode, uns, P, wave, P.dir_in_smem ? dir_bytes : 0, nullptr, delta, nullptr, nullptr, false);
     CU_CHECK(e, cudaEventRecord(e->ev[6], s));

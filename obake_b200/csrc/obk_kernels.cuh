@@ -770,17 +770,16 @@ __global__ void __launch_bounds__(256) k_row_fill(const uint64_t *__restrict__ k
 }
 
 struct RowParams {
-    // left rows (original order) and right rows (sorted by segment)
+    // left rows (original order): key, and segment | (len-1) << 27
     const uint64_t *xr_hi;
-    const uint32_t *xr_seg;
-    const uint32_t *xr_len;
+    const uint32_t *xr_sl;
     const uint64_t *xmat; // [nrx][32]
     uint32_t nrx;
-    const uint64_t *yr_hi;  // sorted by segment
-    const uint64_t *yr_idx; // original row number of each sorted right row (payload of the counting sort)
-    const uint32_t *yr_off; // [m + 1]
-    const uint32_t *yr_len; // by original row number
-    const uint64_t *ymat;   // [nry][32]
+    // right rows sorted by segment: key, and original row number | (len-1) << 27; offsets [m + 1]
+    const uint64_t *yr_hi;
+    const uint32_t *yr_il;
+    const uint32_t *yr_off;
+    const uint64_t *ymat; // [nry][32], by original row number
     uint32_t nry;
     uint32_t m; // segment modulus of the row keys
     // output rows (from the symbolic row product): key and segment
@@ -788,15 +787,12 @@ struct RowParams {
     const uint32_t *or_seg;
     uint32_t nro;
     uint32_t *cursor;
-    // dense output [nro][64][LACC] and the number of non-zero entries per row
+    // dense output [nro][LACC][64] and the number of non-zero entries per row
     uint64_t *omat;
     uint32_t *or_cnt;
-    uint32_t dir_in_smem; // 1: the row directories were staged in shared memory
-};
-
-template <int LACC, bool F64>
-struct RowAcc {
-    uint64_t l[LACC];
+    uint32_t dir_in_smem; // 1: the row directories are staged in shared memory (TMA bulk copies)
+    // byte sizes of the five directory arrays, each padded to a multiple of 16 (bulk-copy granularity)
+    uint32_t b_xhi, b_yhi, b_yil, b_xsl, b_yoff;
 };
 
 // z += x*y for 64-bit x, y (signed, or unsigned when no coefficient is negative) and an LACC-limb accumulator
@@ -819,38 +815,73 @@ __device__ __forceinline__ void row_mac(uint64_t (&z)[LACC], uint64_t x, uint64_
     }
 }
 
-// One warp = one output row.  The x-row and y-row directories (keys, segments, offsets) are staged in shared
-// memory once per CTA when they fit; coefficient rows stream from L2 (256 B per row, coalesced).
+// ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(
+                     smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// One warp = one output row.  The x-row and y-row directories (keys, segments, lengths, offsets) are staged in
+// shared memory once per CTA by TMA bulk copies when they fit; coefficient rows stream from L2 (256 B per row,
+// coalesced) and the rows of the NEXT matching pair are requested before the current pair is convolved.
 template <int LACC, bool F64, bool UNS, int BT>
 __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t *xr_hi = P.xr_hi, *yr_hi = P.yr_hi;
-    const uint32_t *xr_seg = P.xr_seg, *yr_off = P.yr_off;
-    const uint32_t *yidx32 = nullptr;
+    const uint32_t *xr_sl = P.xr_sl, *yr_off = P.yr_off, *yr_il = P.yr_il;
     if (P.dir_in_smem) {
-        // layout: xr_hi[nrx] | yr_hi[nry] | yr_idx[nry] (u32) | xr_seg[nrx] | yr_off[m+1]
-        uint64_t *s_xhi = reinterpret_cast<uint64_t *>(smem_raw);
-        uint64_t *s_yhi = s_xhi + P.nrx;
-        uint32_t *s_yidx = reinterpret_cast<uint32_t *>(s_yhi + P.nry);
-        uint32_t *s_xseg = s_yidx + P.nry;
-        uint32_t *s_yoff = s_xseg + P.nrx;
-        for (uint32_t i = threadIdx.x; i < P.nrx; i += blockDim.x) {
-            s_xhi[i] = P.xr_hi[i];
-            s_xseg[i] = P.xr_seg[i];
-        }
-        for (uint32_t i = threadIdx.x; i < P.nry; i += blockDim.x) {
-            s_yhi[i] = P.yr_hi[i];
-            s_yidx[i] = (uint32_t)P.yr_idx[i];
-        }
-        for (uint32_t i = threadIdx.x; i <= P.m; i += blockDim.x) s_yoff[i] = P.yr_off[i];
+        unsigned char *p = smem_raw;
+        uint64_t *s_xhi = reinterpret_cast<uint64_t *>(p);
+        p += P.b_xhi;
+        uint64_t *s_yhi = reinterpret_cast<uint64_t *>(p);
+        p += P.b_yhi;
+        uint32_t *s_yil = reinterpret_cast<uint32_t *>(p);
+        p += P.b_yil;
+        uint32_t *s_xsl = reinterpret_cast<uint32_t *>(p);
+        p += P.b_xsl;
+        uint32_t *s_yoff = reinterpret_cast<uint32_t *>(p);
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
         __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, P.b_xhi + P.b_yhi + P.b_yil + P.b_xsl + P.b_yoff);
+            tma_bulk_g2s(s_xhi, P.xr_hi, P.b_xhi, &s_bar);
+            tma_bulk_g2s(s_yhi, P.yr_hi, P.b_yhi, &s_bar);
+            tma_bulk_g2s(s_yil, P.yr_il, P.b_yil, &s_bar);
+            tma_bulk_g2s(s_xsl, P.xr_sl, P.b_xsl, &s_bar);
+            tma_bulk_g2s(s_yoff, P.yr_off, P.b_yoff, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
         xr_hi = s_xhi;
         yr_hi = s_yhi;
-        xr_seg = s_xseg;
+        yr_il = s_yil;
+        xr_sl = s_xsl;
         yr_off = s_yoff;
-        yidx32 = s_yidx;
     }
     for (;;) {
         uint32_t row = 0;
@@ -865,44 +896,61 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
         double d0 = 0.0, d1 = 0.0;
         for (uint32_t base = 0; base < P.nrx; base += 32u) {
             const uint32_t r1 = base + lane;
-            int found = -1;
+            uint32_t found = 0xffffffffu, sl1 = 0;
             if (r1 < P.nrx) {
                 const uint64_t h1 = xr_hi[r1];
                 if (h1 <= H) {
                     const uint64_t target = H - h1;
-                    const uint32_t s1 = xr_seg[r1];
+                    sl1 = xr_sl[r1];
+                    const uint32_t s1 = sl1 & 0x07ffffffu;
                     const uint32_t b = sg >= s1 ? sg - s1 : sg + P.m - s1;
                     const uint32_t o1 = yr_off[b + 1];
                     for (uint32_t o = yr_off[b]; o < o1; ++o) {
                         if (yr_hi[o] == target) {
-                            found = (int)o;
+                            found = yr_il[o];
                             break;
                         }
                     }
                 }
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, found >= 0);
-            while (mask) {
+            uint32_t mask = __ballot_sync(0xffffffffu, found != 0xffffffffu);
+            // software pipeline over the hits of this chunk: request the next pair's rows, convolve the current
+            uint64_t Xn = 0, Yn = 0;
+            uint32_t l1n = 0, l2n = 0;
+            bool have = mask != 0;
+            if (have) {
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1u;
-                const uint32_t rr1 = base + (uint32_t)src;
-                const uint32_t oo = (uint32_t)__shfl_sync(0xffffffffu, found, src);
-                const uint32_t rr2 = yidx32 ? yidx32[oo] : (uint32_t)__ldg(P.yr_idx + oo);
-                uint32_t len1 = __ldg(P.xr_len + rr1);
-                const uint32_t len2 = __ldg(P.yr_len + rr2);
-                uint64_t X = __ldg(P.xmat + (size_t)rr1 * 32 + lane);
-                uint64_t Y = __ldg(P.ymat + (size_t)rr2 * 32 + lane);
-                uint32_t len2x = len2;
+                const uint32_t il = __shfl_sync(0xffffffffu, found, src);
+                l1n = (__shfl_sync(0xffffffffu, sl1, src) >> 27) + 1u;
+                l2n = (il >> 27) + 1u;
+                Xn = __ldg(P.xmat + (size_t)(base + (uint32_t)src) * 32 + lane);
+                Yn = __ldg(P.ymat + (size_t)(il & 0x07ffffffu) * 32 + lane);
+            }
+            while (have) {
+                uint64_t X = Xn, Y = Yn;
+                uint32_t len1 = l1n, len2 = l2n;
+                have = mask != 0;
+                if (have) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    const uint32_t il = __shfl_sync(0xffffffffu, found, src);
+                    l1n = (__shfl_sync(0xffffffffu, sl1, src) >> 27) + 1u;
+                    l2n = (il >> 27) + 1u;
+                    Xn = __ldg(P.xmat + (size_t)(base + (uint32_t)src) * 32 + lane);
+                    Yn = __ldg(P.ymat + (size_t)(il & 0x07ffffffu) * 32 + lane);
+                }
                 if (len2 < len1) { // the convolution is symmetric: loop over the shorter row
                     const uint64_t t = X;
                     X = Y;
                     Y = t;
-                    len2x = len1;
+                    const uint32_t tl = len1;
                     len1 = len2;
+                    len2 = tl;
                 }
-                if (len1 + len2x <= 33u) {
+                if (len1 + len2 <= 33u) {
                     // the output row fits 32 lanes: the wrapped-around lanes of the rotation read zeros of the
-                    // right row, so every lane accumulates unconditionally into its low output
+                    // longer row, so every lane accumulates unconditionally into its low output
                     for (uint32_t i = 0; i < len1; ++i) {
                         const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
                         const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
@@ -919,11 +967,11 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
                         // lane >= i: the rotated value belongs to output lo = lane, else to output lo = lane + 32;
                         // mask the INPUT so both accumulators run branch-free multiply-adds
                         const bool lowhalf = lane >= i;
-                        const uint64_t y0 = lowhalf ? yv : 0ull, y1 = lowhalf ? 0ull : yv;
                         if constexpr (F64) {
                             const double p = __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv));
                             if (lowhalf) d0 = __dadd_rn(d0, p); else d1 = __dadd_rn(d1, p);
                         } else {
+                            const uint64_t y0 = lowhalf ? yv : 0ull, y1 = lowhalf ? 0ull : yv;
                             row_mac<LACC, UNS>(z0, xi, y0);
                             row_mac<LACC, UNS>(z1, xi, y1);
                         }
@@ -951,6 +999,19 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
         }
         const uint32_t c = __popc(__ballot_sync(0xffffffffu, nz0)) + __popc(__ballot_sync(0xffffffffu, nz1));
         if (lane == 0) P.or_cnt[row] = c;
+    }
+}
+
+// Directory packing: segment | (len-1) << 27 for the left rows, row number | (len-1) << 27 for the sorted right rows.
+__global__ void __launch_bounds__(256) k_row_pack(const uint32_t *__restrict__ xseg, const uint32_t *__restrict__ xlen, uint32_t nrx,
+                                                  const uint64_t *__restrict__ yidx, const uint32_t *__restrict__ ylen, uint32_t nry,
+                                                  uint32_t *__restrict__ xsl, uint32_t *__restrict__ yil)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nrx) xsl[i] = xseg[i] | ((xlen[i] - 1u) << 27);
+    if (i < nry) {
+        const uint32_t r = (uint32_t)yidx[i];
+        yil[i] = r | ((ylen[r] - 1u) << 27);
     }
 }
 
