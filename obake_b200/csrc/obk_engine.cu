@@ -565,17 +565,17 @@ __global__ void k_iota64(uint64_t *p, uint32_t n)
     if (i < n) p[i] = i;
 }
 
-template <int LACC, bool F64>
+template <int LACC, bool F64, bool UNS = false>
 void launch_rows_t(obk_engine *e, const RowParams &P, unsigned grid, size_t smem, const uint32_t *offs, uint64_t delta,
                    uint64_t *rk, uint64_t *rc, bool expand)
 {
     if (!expand) {
         if (e->opt_row_threads <= 512) {
-            auto fn = k_rowconv<LACC, F64, false, 512>;
+            auto fn = k_rowconv<LACC, F64, UNS, 512>;
             CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             fn<<<grid, 512, smem, e->stream>>>(P);
         } else {
-            auto fn = k_rowconv<LACC, F64, false, 1024>;
+            auto fn = k_rowconv<LACC, F64, UNS, 1024>;
             CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
             fn<<<grid, 1024, smem, e->stream>>>(P);
         }
@@ -590,6 +590,15 @@ void launch_rows_t(obk_engine *e, const RowParams &P, unsigned grid, size_t smem
 void launch_rows(obk_engine *e, int mode, bool uns, const RowParams &P, unsigned grid, size_t smem, const uint32_t *offs,
                  uint64_t delta, uint64_t *rk, uint64_t *rc, bool expand)
 {
+    if (uns && !expand) {
+        // no negative coefficient anywhere: unsigned multiply, no sign fix-ups, no sign extension limb
+        switch (mode) {
+            case CF_I1A1: launch_rows_t<1, false, true>(e, P, grid, smem, offs, delta, rk, rc, expand); return;
+            case CF_I1A2: launch_rows_t<2, false, true>(e, P, grid, smem, offs, delta, rk, rc, expand); return;
+            case CF_I1A3: launch_rows_t<3, false, true>(e, P, grid, smem, offs, delta, rk, rc, expand); return;
+            default: break;
+        }
+    }
     switch (mode) {
         case CF_I1A1: launch_rows_t<1, false>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
         case CF_I1A2: launch_rows_t<2, false>(e, P, grid, smem, offs, delta, rk, rc, expand); break;
@@ -1114,7 +1123,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         RowsResult rows;
         if (!rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok
-            && std::min(nx_full, ny) <= (1ull << 18) && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
+            && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
             rows = run_rows(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, nx_full * ny, threads, e->opt_kernel == 1,
                             !f64 && hs_anyneg == 0, rq.rank, rq.nranks, st);
         }

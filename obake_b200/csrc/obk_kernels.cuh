@@ -795,76 +795,34 @@ struct RowParams {
     uint32_t b_xhi, b_yhi, b_yil, b_xsl, b_yoff;
 };
 
-// Carry-free exact accumulation.  A 64-bit two's-complement coefficient is split into three 21-bit digits
-// (the top one signed): c = d0 + d1*2^21 + d2*2^42.  A product of two coefficients is then nine 32x32->64
-// signed multiply-adds (IMAD.WIDE, FMA pipe) into five 64-bit COLUMN accumulators (weights 2^0, 2^21, ... 2^84)
-// with no carry propagation at all: every digit product is below 2^43 and a column receives at most three of
-// them per coefficient product, so 2^18 coefficient products fit before a column could wrap -- the host only
-// selects this kernel when min(|x|,|y|) <= 2^18, the largest number of products one output term can receive.
-// The columns are folded into the LACC-limb result once per output row.
-struct Dig3 {
-    int d0, d1, d2;
-};
-__device__ __forceinline__ Dig3 split21(uint64_t v)
+// z += x*y for 64-bit x, y (signed, or unsigned when no coefficient is negative) and an LACC-limb accumulator.
+// The 64x64->128 product is written as four 32x32->64 multiply-adds (IMAD.WIDE with a 64-bit addend) so that the
+// partial products are formed once: asking for x*y and __umul64hi(x,y) separately makes the compiler form them twice.
+template <int LACC, bool UNS>
+__device__ __forceinline__ void row_mac(uint64_t (&z)[LACC], uint64_t x, uint64_t y)
 {
-    Dig3 r;
-    r.d0 = (int)(v & 0x1fffffu);
-    r.d1 = (int)((v >> 21) & 0x1fffffu);
-    r.d2 = (int)((long long)v >> 42);
-    return r;
-}
-struct Col5 {
-    long long c0, c1, c2, c3, c4;
-};
-__device__ __forceinline__ void col_mac(Col5 &z, const Dig3 &x, const Dig3 &y)
-{
-    z.c0 += (long long)x.d0 * y.d0;
-    z.c1 += (long long)x.d0 * y.d1;
-    z.c1 += (long long)x.d1 * y.d0;
-    z.c2 += (long long)x.d0 * y.d2;
-    z.c2 += (long long)x.d1 * y.d1;
-    z.c2 += (long long)x.d2 * y.d0;
-    z.c3 += (long long)x.d1 * y.d2;
-    z.c3 += (long long)x.d2 * y.d1;
-    z.c4 += (long long)x.d2 * y.d2;
-}
-// z (LACC limbs, two's complement) += c << SH, c sign-extended
-template <int LACC, int SH>
-__device__ __forceinline__ void add_shl(uint64_t (&z)[LACC], long long c)
-{
-    uint64_t w[3];
-    w[0] = (uint64_t)c;
-    w[1] = (uint64_t)(c >> 63);
-    w[2] = w[1];
-    constexpr int WS = SH / 64, BS = SH % 64;
-    uint64_t v[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const int src = i - WS;
-        uint64_t lo = src >= 0 ? w[src] : 0ull;
-        uint64_t below = src - 1 >= 0 ? w[src - 1] : 0ull;
-        v[i] = BS ? ((lo << BS) | (below >> (64 - BS))) : lo;
-    }
     if constexpr (LACC == 1) {
-        z[0] += v[0];
-    } else if constexpr (LACC == 2) {
-        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(z[0]), "+l"(z[1]) : "l"(v[0]), "l"(v[1]));
+        z[0] += x * y;
     } else {
-        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, %5;"
-            : "+l"(z[0]), "+l"(z[1]), "+l"(z[2])
-            : "l"(v[0]), "l"(v[1]), "l"(v[2]));
+        const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32);
+        const uint64_t p00 = (uint64_t)x0 * y0;
+        const uint64_t t = (uint64_t)x0 * y1 + (p00 >> 32);
+        const uint64_t u = (uint64_t)x1 * y0 + (uint32_t)t;
+        const uint64_t lo = (u << 32) | (uint32_t)p00;
+        uint64_t hi = (uint64_t)x1 * y1 + (t >> 32) + (u >> 32);
+        if constexpr (!UNS) {
+            // signed correction of the high half: hi_s = hi_u - (x < 0 ? y : 0) - (y < 0 ? x : 0)
+            hi -= ((long long)x < 0 ? y : 0ull) + ((long long)y < 0 ? x : 0ull);
+        }
+        if constexpr (LACC == 2) {
+            asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(z[0]), "+l"(z[1]) : "l"(lo), "l"(hi));
+        } else {
+            const uint64_t ext = UNS ? 0ull : (uint64_t)((long long)hi >> 63);
+            asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, %5;"
+                : "+l"(z[0]), "+l"(z[1]), "+l"(z[2])
+                : "l"(lo), "l"(hi), "l"(ext));
+        }
     }
-}
-template <int LACC>
-__device__ __forceinline__ void col_fold(const Col5 &c, uint64_t (&z)[LACC])
-{
-#pragma unroll
-    for (int l = 0; l < LACC; ++l) z[l] = 0;
-    add_shl<LACC, 0>(z, c.c0);
-    add_shl<LACC, 21>(z, c.c1);
-    add_shl<LACC, 42>(z, c.c2);
-    add_shl<LACC, 63>(z, c.c3);
-    add_shl<LACC, 84>(z, c.c4);
 }
 
 // ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier --------------------------------
@@ -942,7 +900,9 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
         if (row >= P.nro) break;
         const uint64_t H = __ldg(P.or_hi + row);
         const uint32_t sg = __ldg(P.or_seg + row);
-        Col5 q0{0, 0, 0, 0, 0}, q1{0, 0, 0, 0, 0};
+        uint64_t z0[LACC], z1[LACC];
+#pragma unroll
+        for (int l = 0; l < LACC; ++l) z0[l] = z1[l] = 0;
         double d0 = 0.0, d1 = 0.0;
         for (uint32_t base = 0; base < P.nrx; base += 32u) {
             const uint32_t r1 = base + lane;
@@ -998,58 +958,32 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
                     len1 = len2;
                     len2 = tl;
                 }
-                if constexpr (F64) {
-                    if (len1 + len2 <= 33u) {
-                        // the output row fits 32 lanes: the wrapped-around lanes of the rotation read zeros of the
-                        // longer row, so every lane accumulates unconditionally into its low output
-                        for (uint32_t i = 0; i < len1; ++i) {
-                            const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
-                            const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                if (len1 + len2 <= 33u) {
+                    // the output row fits 32 lanes: the wrapped-around lanes of the rotation read zeros of the
+                    // longer row, so every lane accumulates unconditionally into its low output
+                    for (uint32_t i = 0; i < len1; ++i) {
+                        const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
+                        const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                        if constexpr (F64) {
                             d0 = __dadd_rn(d0, __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv)));
-                        }
-                    } else {
-                        for (uint32_t i = 0; i < len1; ++i) {
-                            const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
-                            const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
-                            const double p = __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv));
-                            if (lane >= i) d0 = __dadd_rn(d0, p); else d1 = __dadd_rn(d1, p);
+                        } else {
+                            row_mac<LACC, UNS>(z0, xi, yv);
                         }
                     }
                 } else {
-                    const Dig3 xd = split21(X), yd = split21(Y);
-                    if (len1 + len2 <= 33u) {
-                        for (uint32_t i = 0; i < len1; ++i) {
-                            Dig3 a, b;
-                            const int sy = (int)((lane - i) & 31u);
-                            a.d0 = __shfl_sync(0xffffffffu, xd.d0, (int)i);
-                            a.d1 = __shfl_sync(0xffffffffu, xd.d1, (int)i);
-                            a.d2 = __shfl_sync(0xffffffffu, xd.d2, (int)i);
-                            b.d0 = __shfl_sync(0xffffffffu, yd.d0, sy);
-                            b.d1 = __shfl_sync(0xffffffffu, yd.d1, sy);
-                            b.d2 = __shfl_sync(0xffffffffu, yd.d2, sy);
-                            col_mac(q0, a, b);
-                        }
-                    } else {
-                        for (uint32_t i = 0; i < len1; ++i) {
-                            Dig3 a, b, b0, b1;
-                            const int sy = (int)((lane - i) & 31u);
-                            a.d0 = __shfl_sync(0xffffffffu, xd.d0, (int)i);
-                            a.d1 = __shfl_sync(0xffffffffu, xd.d1, (int)i);
-                            a.d2 = __shfl_sync(0xffffffffu, xd.d2, (int)i);
-                            b.d0 = __shfl_sync(0xffffffffu, yd.d0, sy);
-                            b.d1 = __shfl_sync(0xffffffffu, yd.d1, sy);
-                            b.d2 = __shfl_sync(0xffffffffu, yd.d2, sy);
-                            // lane >= i: the rotated value belongs to output lo = lane, else to lo = lane + 32;
-                            // mask the INPUT digits so both accumulator sets run branch-free multiply-adds
-                            const bool lowhalf = lane >= i;
-                            b0.d0 = lowhalf ? b.d0 : 0;
-                            b0.d1 = lowhalf ? b.d1 : 0;
-                            b0.d2 = lowhalf ? b.d2 : 0;
-                            b1.d0 = lowhalf ? 0 : b.d0;
-                            b1.d1 = lowhalf ? 0 : b.d1;
-                            b1.d2 = lowhalf ? 0 : b.d2;
-                            col_mac(q0, a, b0);
-                            col_mac(q1, a, b1);
+                    for (uint32_t i = 0; i < len1; ++i) {
+                        const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
+                        const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                        // lane >= i: the rotated value belongs to output lo = lane, else to output lo = lane + 32;
+                        // mask the INPUT so both accumulators run branch-free multiply-adds
+                        const bool lowhalf = lane >= i;
+                        if constexpr (F64) {
+                            const double p = __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv));
+                            if (lowhalf) d0 = __dadd_rn(d0, p); else d1 = __dadd_rn(d1, p);
+                        } else {
+                            const uint64_t y0 = lowhalf ? yv : 0ull, y1 = lowhalf ? 0ull : yv;
+                            row_mac<LACC, UNS>(z0, xi, y0);
+                            row_mac<LACC, UNS>(z1, xi, y1);
                         }
                     }
                 }
@@ -1064,9 +998,6 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
             nz0 = d0 != 0.0;
             nz1 = d1 != 0.0;
         } else {
-            uint64_t z0[LACC], z1[LACC];
-            col_fold<LACC>(q0, z0);
-            col_fold<LACC>(q1, z1);
             nz0 = nz1 = false;
 #pragma unroll
             for (int l = 0; l < LACC; ++l) {
