@@ -312,8 +312,14 @@ SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uin
     if (with_cfs) r.cfs = sc.alloc<uint64_t>(n * CW);
     CU_CHECK(e, cudaMemsetAsync(cnt, 0, (nbins + 1) * sizeof(uint32_t), e->stream));
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
-    k_bin_count<<<grid, 256, 0, e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0, dbits, degmin, cnt, bin_of,
-                                             rank_of);
+    if (nbins <= 8192 && n >= 8192) {
+        const unsigned g2 = (unsigned)((n + 256 * BINC_ITEMS - 1) / (256 * BINC_ITEMS));
+        k_bin_count_smem<<<g2, 256, nbins * sizeof(uint32_t), e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0, dbits,
+                                                                          degmin, (uint32_t)nbins, cnt, bin_of, rank_of);
+    } else {
+        k_bin_count<<<grid, 256, 0, e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0, dbits, degmin, cnt, bin_of,
+                                                 rank_of);
+    }
     e->launches += 1;
     device_scan(e, sc, cnt, r.off, nbins);
     k_bin_scatter<<<grid, 256, 0, e->stream>>>(keys, with_cfs ? cfs : nullptr, nullptr, n, W, CW, r.off, bin_of, rank_of,

@@ -248,6 +248,55 @@ __global__ void __launch_bounds__(256) k_bin_count(const uint64_t *__restrict__ 
     }
 }
 
+// Same as k_bin_count for a small number of bins: per-block histogram in shared memory (the block's rank of a
+// term comes from the shared atomic), one global atomic per (block, non-empty bin) for the block's base.  Avoids the
+// same-address global atomics that dominate k_bin_count when millions of terms fall into ~1000 bins.
+constexpr int BINC_ITEMS = 16;
+__global__ void __launch_bounds__(256) k_bin_count_smem(const uint64_t *__restrict__ keys, const int64_t *__restrict__ deg,
+                                                        uint64_t n, int W, uint32_t m, uint32_t is_signed, int pow2,
+                                                        int dbits, int64_t degmin, uint32_t nbins,
+                                                        uint32_t *__restrict__ cnt, uint32_t *__restrict__ bin_of,
+                                                        uint32_t *__restrict__ rank_of)
+{
+    extern __shared__ uint32_t sh_hist[];
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) sh_hist[b] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * blockDim.x * BINC_ITEMS;
+    uint32_t mybin[BINC_ITEMS], myrank[BINC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < BINC_ITEMS; ++j) {
+        const uint64_t i = base + (uint64_t)j * blockDim.x + threadIdx.x;
+        mybin[j] = 0xffffffffu;
+        if (i < n) {
+            uint32_t bin;
+            if (pow2) {
+                uint64_t h = 0;
+                for (int w = 0; w < W; ++w) h += keys[i * W + w];
+                bin = (uint32_t)(h & (uint64_t)(m - 1));
+            } else {
+                bin = key_segment(keys + i * W, W, m, is_signed);
+            }
+            if (dbits) bin = (bin << dbits) | (uint32_t)(deg[i] - degmin);
+            mybin[j] = bin;
+            myrank[j] = atomicAdd(&sh_hist[bin], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) {
+        const uint32_t c = sh_hist[b];
+        sh_hist[b] = c ? atomicAdd(&cnt[b], c) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < BINC_ITEMS; ++j) {
+        const uint64_t i = base + (uint64_t)j * blockDim.x + threadIdx.x;
+        if (mybin[j] != 0xffffffffu) {
+            bin_of[i] = mybin[j];
+            rank_of[i] = sh_hist[mybin[j]] + myrank[j];
+        }
+    }
+}
+
 // Exclusive scan, three passes (block-local scan, scan of block sums, add back); 4096 items per block.
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_THREADS = 1024;
@@ -534,34 +583,54 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
         if (work >= P.nseg_list) break;
         const uint32_t seg = P.seg_list ? P.seg_list[work] : work;
 
-        for (uint64_t i = gid; i < P.nx; i += ngroups) {
+        // Per-lane state machine.  A lane walks its own sequence of (left term, right term) pairs and keeps at most
+        // one product in flight; every trip of the warp-converged loop below lets EVERY lane advance one step --
+        // fetch the next left term (LX), form the next product (LY), or make one probe attempt (LP).  A lane that
+        // finishes its probe early starts on its next pair in the following trip instead of idling until the slowest
+        // lane of a 32-product batch is done: the nested-loop form of this kernel ran with 7-8 of 32 lanes active
+        // (ncu, profiles/r01a_*), i.e. 18-22 warp instructions per product.
+        enum : uint32_t { LX = 0, LY = 1, LP = 2, LDONE = 3 };
+        uint32_t lst = LX;
+        uint64_t xi = (uint64_t)gid - (uint64_t)ngroups; // wraps; the first LX step adds ngroups back
+        uint32_t t = 0, y1 = 0, h = 0, probes = 0;
+        uint64_t kx[W], k[W];
+        uint64_t cx[XCW > 0 ? XCW : 1];
+        uint64_t p[ACCW > 0 ? ACCW : 1];
+        for (;;) {
             if (*(volatile uint32_t *)&s_over) break;
-            uint64_t kx[W];
+            if (!__any_sync(0xffffffffu, lst != LDONE)) break;
+            if (lst == LX) {
+                xi += ngroups;
+                if (xi >= P.nx) {
+                    lst = LDONE;
+                } else {
 #pragma unroll
-            for (int w = 0; w < W; ++w) kx[w] = __ldg(P.xk + i * W + w);
-            const uint32_t bx = __ldg(P.xseg + i);
-            const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
-            uint32_t y0, y1;
-            if (P.trunc) {
-                const int64_t r = P.lim_base - __ldg(P.xdeg + i);
-                if (r < 0) continue;
-                const uint32_t d = r >= (int64_t)P.ndeg ? P.ndeg - 1u : (uint32_t)r;
-                y0 = __ldg(P.yoff + ((size_t)by << P.dbits));
-                y1 = __ldg(P.yoff + ((size_t)by << P.dbits) + d + 1u);
-            } else {
-                y0 = __ldg(P.yoff + by);
-                y1 = __ldg(P.yoff + by + 1u);
+                    for (int w = 0; w < W; ++w) kx[w] = __ldg(P.xk + xi * W + w);
+                    const uint32_t bx = __ldg(P.xseg + xi);
+                    const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
+                    uint32_t y0;
+                    bool any = true;
+                    if (P.trunc) {
+                        const int64_t r = P.lim_base - __ldg(P.xdeg + xi);
+                        any = r >= 0;
+                        const uint32_t d = r >= (int64_t)P.ndeg ? P.ndeg - 1u : (uint32_t)(r < 0 ? 0 : r);
+                        y0 = __ldg(P.yoff + ((size_t)by << P.dbits));
+                        y1 = __ldg(P.yoff + ((size_t)by << P.dbits) + d + 1u);
+                    } else {
+                        y0 = __ldg(P.yoff + by);
+                        y1 = __ldg(P.yoff + by + 1u);
+                    }
+                    t = y0 + lg_lane;
+                    if (any && t < y1) {
+#pragma unroll
+                        for (int c = 0; c < XCW; ++c) cx[c] = __ldg(P.xc + xi * XCW + c);
+                        lst = LY;
+                    }
+                }
             }
-            if (y0 == y1) continue;
-            uint64_t cx[XCW > 0 ? XCW : 1];
-#pragma unroll
-            for (int c = 0; c < XCW; ++c) cx[c] = __ldg(P.xc + i * XCW + c);
-
-            for (uint32_t t = y0 + lg_lane; t < y1; t += G) {
-                uint64_t k[W];
+            if (lst == LY) {
 #pragma unroll
                 for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg(P.yk + (size_t)t * W + w); // monomial_mul
-                uint64_t p[ACCW > 0 ? ACCW : 1];
                 if constexpr (!T::SYM) {
                     uint64_t cy[CW];
 #pragma unroll
@@ -577,21 +646,24 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
                         cf_mul<T::LIN, T::LACC>(cx, cy, p);
                     }
                 }
-                // ---- find-or-insert + accumulate ---------------------------------------------
-                uint32_t h = slot_hash<W>(k, P.log2_cap);
-                uint32_t probes = 0;
-                for (;;) {
-                    const uint32_t st = *(volatile uint32_t *)&tstate[h];
-                    if (st >= ST_FULL) {
-                        bool eq = true;
+                h = slot_hash<W>(k, P.log2_cap);
+                probes = 0;
+                t += G;
+                lst = LP;
+            }
+            if (lst == LP) {
+                // ---- one find-or-insert attempt ------------------------------------------------------------
+                bool fin = false;
+                const uint32_t st = *(volatile uint32_t *)&tstate[h];
+                if (st >= ST_FULL) {
+                    bool eq = true;
 #pragma unroll
-                        for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
-                        if (eq) {
-                            if constexpr (T::SYM) {
-                                break;
-                            } else {
-                                if (st == ST_BUSY) continue;
-                                if (atomicExch(&tstate[h], ST_BUSY) != ST_FULL) continue;
+                    for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
+                    if (eq) {
+                        if constexpr (T::SYM) {
+                            fin = true;
+                        } else {
+                            if (st == ST_FULL && atomicExch(&tstate[h], ST_BUSY) == ST_FULL) {
                                 slot_fence(P.fence);
                                 if constexpr (T::F64) {
                                     double a = __longlong_as_double((long long)*(volatile uint64_t *)&tacc[h]);
@@ -607,18 +679,16 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
                                 }
                                 slot_fence(P.fence);
                                 *(volatile uint32_t *)&tstate[h] = ST_FULL;
-                                break;
+                                fin = true;
                             }
+                            // else: the slot is being updated by another thread; try again next trip
                         }
+                    } else {
                         h = (h + 1u) & cmask;
-                        if (++probes > cap) {
-                            s_over = 1;
-                            break;
-                        }
-                        continue;
+                        if (++probes > cap) s_over = 1;
                     }
-                    if (st == ST_EMPTY) {
-                        if (atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) != ST_EMPTY) continue;
+                } else if (st == ST_EMPTY) {
+                    if (atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
 #pragma unroll
                         for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
 #pragma unroll
@@ -626,11 +696,11 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
                         slot_fence(P.fence);
                         *(volatile uint32_t *)&tstate[h] = ST_FULL;
                         if (atomicAdd(&s_count, 1u) + 1u > P.max_fill) s_over = 1;
-                        break;
+                        fin = true;
                     }
-                    // ST_INIT: another thread is writing this slot's key; look again
                 }
-                if (*(volatile uint32_t *)&s_over) break;
+                // ST_INIT: another thread is writing this slot's key; look again next trip
+                if (fin) lst = t < y1 ? LY : LX;
             }
         }
         __syncthreads();
