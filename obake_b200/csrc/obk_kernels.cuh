@@ -590,56 +590,65 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
         // lane of a 32-product batch is done: the nested-loop form of this kernel ran with 7-8 of 32 lanes active
         // (ncu, profiles/r01a_*), i.e. 18-22 warp instructions per product.
         enum : uint32_t { LX = 0, LY = 1, LP = 2, LDONE = 3 };
-        // Order inside a trip: LY (form the product from PREFETCHED operands), LP (probe), LX (advance to the next
-        // left term and request the first right term of its run).  Every global load is issued one trip before its
-        // value is used, so the L2 latency is covered by the other warps instead of stalling the converged loop.
         uint32_t lst = LX;
-        uint64_t xi = (uint64_t)gid; // next left term of this lane
+        uint64_t xi = (uint64_t)gid - (uint64_t)ngroups; // wraps; the first LX step adds ngroups back
         uint32_t t = 0, y1 = 0, h = 0, probes = 0;
-        uint64_t kx[W], k[W], nky[W];
+        uint64_t kx[W], k[W];
         uint64_t cx[XCW > 0 ? XCW : 1];
-        uint64_t ncy[CW > 0 ? CW : 1];
         uint64_t p[ACCW > 0 ? ACCW : 1];
-        // prefetched left term
-        uint64_t nkx[W];
-        uint64_t ncx[XCW > 0 ? XCW : 1];
-        uint32_t nbx = 0;
-        int64_t nxd = 0;
-        if (xi < P.nx) {
-#pragma unroll
-            for (int w = 0; w < W; ++w) nkx[w] = __ldg(P.xk + xi * W + w);
-#pragma unroll
-            for (int c = 0; c < XCW; ++c) ncx[c] = __ldg(P.xc + xi * XCW + c);
-            nbx = __ldg(P.xseg + xi);
-            if (P.trunc) nxd = __ldg(P.xdeg + xi);
-        }
         for (;;) {
             if (*(volatile uint32_t *)&s_over) break;
             if (!__any_sync(0xffffffffu, lst != LDONE)) break;
+            if (lst == LX) {
+                xi += ngroups;
+                if (xi >= P.nx) {
+                    lst = LDONE;
+                } else {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) kx[w] = __ldg(P.xk + xi * W + w);
+                    const uint32_t bx = __ldg(P.xseg + xi);
+                    const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
+                    uint32_t y0;
+                    bool any = true;
+                    if (P.trunc) {
+                        const int64_t r = P.lim_base - __ldg(P.xdeg + xi);
+                        any = r >= 0;
+                        const uint32_t d = r >= (int64_t)P.ndeg ? P.ndeg - 1u : (uint32_t)(r < 0 ? 0 : r);
+                        y0 = __ldg(P.yoff + ((size_t)by << P.dbits));
+                        y1 = __ldg(P.yoff + ((size_t)by << P.dbits) + d + 1u);
+                    } else {
+                        y0 = __ldg(P.yoff + by);
+                        y1 = __ldg(P.yoff + by + 1u);
+                    }
+                    t = y0 + lg_lane;
+                    if (any && t < y1) {
+#pragma unroll
+                        for (int c = 0; c < XCW; ++c) cx[c] = __ldg(P.xc + xi * XCW + c);
+                        lst = LY;
+                    }
+                }
+            }
             if (lst == LY) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) k[w] = kx[w] + nky[w]; // monomial_mul
+                for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg(P.yk + (size_t)t * W + w); // monomial_mul
                 if constexpr (!T::SYM) {
+                    uint64_t cy[CW];
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) cy[c] = __ldg(P.yc + (size_t)t * CW + c);
                     if constexpr (T::ADD) {
 #pragma unroll
-                        for (int c = 0; c < CW; ++c) p[c] = ncy[c];
+                        for (int c = 0; c < CW; ++c) p[c] = cy[c];
                     } else if constexpr (T::F64) {
                         // cf += c1*c2 with two roundings (no FP_FAST_FMA in the reference build, fma3.hpp:65-72)
                         p[0] = (uint64_t)__double_as_longlong(
-                            __dmul_rn(__longlong_as_double((long long)cx[0]), __longlong_as_double((long long)ncy[0])));
+                            __dmul_rn(__longlong_as_double((long long)cx[0]), __longlong_as_double((long long)cy[0])));
                     } else {
-                        cf_mul<T::LIN, T::LACC>(cx, ncy, p);
+                        cf_mul<T::LIN, T::LACC>(cx, cy, p);
                     }
                 }
                 h = slot_hash<W>(k, P.log2_cap);
                 probes = 0;
                 t += G;
-                if (t < y1) { // request the next right term of this run
-#pragma unroll
-                    for (int w = 0; w < W; ++w) nky[w] = __ldg(P.yk + (size_t)t * W + w);
-#pragma unroll
-                    for (int c = 0; c < CW; ++c) ncy[c] = __ldg(P.yc + (size_t)t * CW + c);
-                }
                 lst = LP;
             }
             if (lst == LP) {
@@ -692,48 +701,6 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
                 }
                 // ST_INIT: another thread is writing this slot's key; look again next trip
                 if (fin) lst = t < y1 ? LY : LX;
-            }
-            if (lst == LX) {
-                if (xi >= P.nx) {
-                    lst = LDONE;
-                } else {
-#pragma unroll
-                    for (int w = 0; w < W; ++w) kx[w] = nkx[w];
-#pragma unroll
-                    for (int c = 0; c < XCW; ++c) cx[c] = ncx[c];
-                    const uint32_t bx = nbx;
-                    const int64_t xd = nxd;
-                    xi += ngroups;
-                    if (xi < P.nx) { // request the left term after this one
-#pragma unroll
-                        for (int w = 0; w < W; ++w) nkx[w] = __ldg(P.xk + xi * W + w);
-#pragma unroll
-                        for (int c = 0; c < XCW; ++c) ncx[c] = __ldg(P.xc + xi * XCW + c);
-                        nbx = __ldg(P.xseg + xi);
-                        if (P.trunc) nxd = __ldg(P.xdeg + xi);
-                    }
-                    const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
-                    uint32_t y0;
-                    bool any = true;
-                    if (P.trunc) {
-                        const int64_t r = P.lim_base - xd;
-                        any = r >= 0;
-                        const uint32_t d = r >= (int64_t)P.ndeg ? P.ndeg - 1u : (uint32_t)(r < 0 ? 0 : r);
-                        y0 = __ldg(P.yoff + ((size_t)by << P.dbits));
-                        y1 = __ldg(P.yoff + ((size_t)by << P.dbits) + d + 1u);
-                    } else {
-                        y0 = __ldg(P.yoff + by);
-                        y1 = __ldg(P.yoff + by + 1u);
-                    }
-                    t = y0 + lg_lane;
-                    if (any && t < y1) {
-#pragma unroll
-                        for (int w = 0; w < W; ++w) nky[w] = __ldg(P.yk + (size_t)t * W + w);
-#pragma unroll
-                        for (int c = 0; c < CW; ++c) ncy[c] = __ldg(P.yc + (size_t)t * CW + c);
-                        lst = LY;
-                    }
-                }
             }
         }
         __syncthreads();
