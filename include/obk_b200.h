@@ -77,11 +77,12 @@ typedef struct obk_trunc {
 enum { OBK_SEG_HASH_POW2 = 0, OBK_SEG_KEY_MOD = 1 };
 
 /* The product, grouped by segment: the terms of group s sit in [seg_offsets[s], seg_offsets[s+1]).
- * seg_kind == OBK_SEG_HASH_POW2 (every complete product): nsegs = 2^log2_nsegs and a term of group s
- * satisfies hash(key) & (nsegs - 1) == s, i.e. it belongs in table s of a series with that many segments
- * (series.hpp:396-400,1294-1305), so a host series can be rebuilt table-parallel.
- * seg_kind == OBK_SEG_KEY_MOD (partial products of the multi-GPU path): group s holds the keys with
- * sum_w(word_w mod nsegs) mod nsegs == s, the engine's internal prime segmentation.
+ * seg_kind == OBK_SEG_HASH_POW2 (every product returned in HOST memory, or option regroup = 2): nsegs =
+ * 2^log2_nsegs and a term of group s satisfies hash(key) & (nsegs - 1) == s, i.e. it belongs in table s of a
+ * series with that many segments (series.hpp:396-400,1294-1305), so a host series can be rebuilt table-parallel.
+ * seg_kind == OBK_SEG_KEY_MOD (products left in DEVICE memory, partial products of the multi-GPU path): group s
+ * holds the keys with sum_w(word_w mod nsegs) mod nsegs == s (the engine's prime segmentation; nsegs = 1 after
+ * the row kernel, 4093 for multi-GPU partials).
  * No coefficient is zero (polynomial.hpp:1528-1540). */
 typedef struct obk_poly_result {
     uint64_t nterms;
@@ -128,7 +129,7 @@ void obk_engine_destroy(obk_engine *e);
 /* Launch on the caller's stream (e.g. torch's current stream) instead of the engine's own. */
 obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream);
 /* Tunables: "nsegs" (force the segment modulus, -1 = auto), "table_slots", "threads", "group_lanes" (0 = auto),
- * "fill_pct", "fence" (1: fence.acq_rel.cta around the slot lock), "regroup" (0: leave the result in the
+ * "fill_pct", "fence" (1: fence.acq_rel.cta around the slot lock), "regroup" (1 = default: series-table grouping for HOST results only; 2: always; 0: leave the result in the
  * engine's own segmentation), "kernel" (-1 auto, 0 scatter, 1 rows), "max_retries". */
 obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value);
 const char *obk_last_error(const obk_engine *e);

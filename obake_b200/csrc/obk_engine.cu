@@ -477,7 +477,8 @@ uint64_t estimate_terms(obk_engine *e, Scratch &sc, const EstimateIn &in)
     P.cursor = dflags + 1;
     P.log2_cap = sym_log2_cap;
     const double run = (double)in.tot_mults / (double)in.nx / (double)mE;
-    P.lg = run >= 24.0 ? 5 : 0;
+    (void)run;
+    P.lg = 0;
     P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
     P.counts = dcounts;
     P.flags = dflags;
@@ -707,7 +708,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         P.nseg_list = mR;
         P.cursor = dflags + 1;
         P.log2_cap = sym_log2_cap;
-        P.lg = ((double)Y.nrows / (double)mR) >= 24.0 ? 5 : 0;
+        P.lg = 0;
         P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
         P.okeys = stage;
         P.counts = counts;
@@ -1232,10 +1233,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 } else if (e->opt_group_lanes > 0) {
                     while ((1ll << (lg + 1)) <= e->opt_group_lanes && lg < 5) ++lg;
                 } else {
-                    // long right-operand runs: a warp shares one left term (distinct keys, no intra-warp slot clash);
-                    // short runs: one lane per left term (measured on S12: 1 lane 31 G/s vs 8 lanes 22 G/s)
-                    const double run = (double)tot_mults / (double)std::max<uint64_t>(snx, 1) / (double)nsegs;
-                    lg = run >= 24.0 ? 5 : 0;
+                    // one lane per left term: with the per-lane state machine this is the fastest mapping on every
+                    // workload measured (S12 38.6 vs 30.2 G/s at 4 lanes; F20 58.8 vs 38.2 G/s at 32 lanes)
+                    lg = 0;
                 }
                 P.lg = lg;
                 st.group_lanes = 1u << lg;
@@ -1302,7 +1302,10 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         // k follows the reference's sizing rule (polynomial.hpp:870-902).  Partial products of the multi-GPU
         // path keep the engine's own segmentation (key mod nsegs): the all-to-all needs owner ranges contiguous.
         uint32_t out_groups = nsegs, out_log2 = 0, seg_kind = 1;
-        const bool regroup = rq.nranks <= 1 && e->opt_regroup != 0;
+        // A device-resident product keeps the engine's own segmentation (seg_kind OBK_SEG_KEY_MOD); the series-table
+        // grouping is produced when the result is handed to the host (the container rebuild needs it) or on request
+        // (option regroup = 2).  regroup = 0 never regroups.
+        const bool regroup = rq.nranks <= 1 && (e->opt_regroup == 2 || (e->opt_regroup == 1 && rq.result_mem == OBK_MEM_HOST));
         if (rq.nranks > 1) {
             // multi-GPU partial product: group by key mod OBK_EXCHANGE_MOD, a fixed prime every rank uses, so the
             // rows destined to one owner are contiguous whatever kernel and segmentation produced them
