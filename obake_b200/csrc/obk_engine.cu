@@ -47,7 +47,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
 };
@@ -410,6 +410,21 @@ uint32_t pick_log2_cap(obk_engine *e, int W, int accw)
     return l;
 }
 
+// Two-sided truncation plan (see obk_kernels.cuh, MulParams::PassB): pass A multiplies the left terms of degree <= H
+// by the degree-sorted right operand, pass B the right terms of degree <= L-H-1 by the degree-sorted left operand
+// restricted to degrees > H.  Every admissible pair is formed exactly once, from its lower-degree side.
+struct TwoSided {
+    bool on = false;
+    // left lists (compacted)
+    uint64_t *ak = nullptr, *ac = nullptr, *bk = nullptr, *bc = nullptr;
+    int64_t *adeg = nullptr, *bdeg = nullptr;
+    uint64_t na = 0, nb = 0;
+    // geometry of the degree-sorted left operand (right side of pass B)
+    int dbits_x = 0;
+    uint32_t ndeg_x = 1, dlo_b = 0;
+    int64_t degmin_x = 0, lim_base_b = 0;
+};
+
 struct EstimateIn {
     const uint64_t *xk;
     const int64_t *xdeg;
@@ -426,6 +441,8 @@ struct EstimateIn {
     int64_t lim_base;
     uint64_t tot_mults;
     unsigned threads;
+    const TwoSided *ts = nullptr; // optional: two-sided truncation (xk/xdeg/nx then describe the FULL left operand)
+    const uint64_t *xc = nullptr;
 };
 
 // Product-size estimate (stands in for poly_mul_estimate_product_size, polynomial.hpp:478-794): a sampled
@@ -467,6 +484,32 @@ uint64_t estimate_terms(obk_engine *e, Scratch &sc, const EstimateIn &in)
     P.nx = in.nx;
     P.yk = ye.keys;
     P.yoff = ye.off;
+    P.npass = 1;
+    SortedY xe{};
+    uint32_t *asegE = nullptr, *bsegE = nullptr;
+    if (in.ts && in.ts->on) {
+        const TwoSided &ts = *in.ts;
+        asegE = sc.alloc<uint32_t>(std::max<uint64_t>(ts.na, 1));
+        bsegE = sc.alloc<uint32_t>(std::max<uint64_t>(ts.nb, 1));
+        if (ts.na) k_segments<<<(unsigned)std::min<uint64_t>((ts.na + 255) / 256, 4096), 256, 0, s>>>(ts.ak, ts.na, W, mE, in.is_signed, asegE);
+        if (ts.nb) k_segments<<<(unsigned)std::min<uint64_t>((ts.nb + 255) / 256, 4096), 256, 0, s>>>(ts.bk, ts.nb, W, mE, in.is_signed, bsegE);
+        xe = sort_operand(e, sc, in.xk, nullptr, in.xdeg, in.nx, W, 0, mE, in.is_signed, false, ts.dbits_x, ts.degmin_x, false);
+        P.xk = ts.ak;
+        P.xdeg = ts.adeg;
+        P.xseg = asegE;
+        P.nx = ts.na;
+        P.npass = 2;
+        P.b.xk = ts.bk;
+        P.b.xdeg = ts.bdeg;
+        P.b.xseg = bsegE;
+        P.b.nx = ts.nb;
+        P.b.yk = xe.keys;
+        P.b.yoff = xe.off;
+        P.b.dbits = ts.dbits_x;
+        P.b.ndeg = ts.ndeg_x;
+        P.b.dlo = ts.dlo_b;
+        P.b.lim_base = ts.lim_base_b;
+    }
     P.nsegs = mE;
     P.dbits = in.dbits;
     P.ndeg = in.ndeg;
@@ -493,6 +536,12 @@ uint64_t estimate_terms(obk_engine *e, Scratch &sc, const EstimateIn &in)
     sc.release(ye.keys);
     sc.release(ye.off);
     sc.release(xsegE);
+    if (xe.keys) {
+        sc.release(xe.keys);
+        sc.release(xe.off);
+        sc.release(asegE);
+        sc.release(bsegE);
+    }
     sc.release(dlist);
     sc.release(dcounts);
     sc.release(dflags);
@@ -927,6 +976,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         uint32_t ndeg = 1;
         int64_t lim_base = 0, degmin_y = 0;
         int64_t *xdeg = nullptr, *ydeg = nullptr;
+        TwoSided ts;
         const uint64_t *sxk = nullptr, *sxc = nullptr; // this rank's slice of the left operand
         const int64_t *sxdeg = nullptr;
         uint64_t snx = 0, x_begin = 0;
@@ -1089,8 +1139,75 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 e->launches += 1;
                 unsigned long long htot = 0;
                 CU_CHECK(e, cudaMemcpyAsync(&htot, dtot, 8, cudaMemcpyDeviceToHost, s));
+                // two-sided plan: degree histograms of both operands on the host
+                const i128 rangex = dmaxx - dminx + 1;
+                std::vector<uint32_t> hpy, hpx;
+                uint32_t *prefx = nullptr;
+                if (e->opt_two_sided != 0 && rangex <= ((i128)1 << 20) && snx >= 4096) {
+                    const uint32_t ndx = (uint32_t)rangex;
+                    uint32_t *histx = sc.alloc<uint32_t>(ndx + 1);
+                    prefx = sc.alloc<uint32_t>(ndx + 2);
+                    CU_CHECK(e, cudaMemsetAsync(histx, 0, (ndx + 1) * 4, s));
+                    k_deg_hist<<<gx, 256, 0, s>>>(sxdeg, snx, (int64_t)dminx, histx);
+                    e->launches += 1;
+                    device_scan(e, sc, histx, prefx, ndx);
+                    hpx.resize((size_t)ndx + 1);
+                    hpy.resize((size_t)ndeg + 1);
+                    CU_CHECK(e, cudaMemcpyAsync(hpx.data(), prefx, hpx.size() * 4, cudaMemcpyDeviceToHost, s));
+                    CU_CHECK(e, cudaMemcpyAsync(hpy.data(), pref, hpy.size() * 4, cudaMemcpyDeviceToHost, s));
+                }
                 CU_CHECK(e, cudaStreamSynchronize(s));
                 tot_mults = htot;
+                if (!hpx.empty() && tot_mults > 0) {
+                    // choose the left-degree threshold H that minimises the number of left terms visited
+                    const uint32_t ndx = (uint32_t)rangex;
+                    uint64_t best = ~0ull;
+                    i128 bestH = dminx - 1;
+                    for (i128 H = dminx - 1; H <= dmaxx; ++H) {
+                        const uint64_t na = hpx[(size_t)(H - dminx + 1)];
+                        const i128 yl = lim - H - 1 - dminy; // right-degree index bound of pass B's left list
+                        const uint64_t nb = yl < 0 ? 0 : hpy[(size_t)std::min<i128>(yl, (i128)ndeg - 1) + 1];
+                        if (na + nb < best) {
+                            best = na + nb;
+                            bestH = H;
+                        }
+                    }
+                    if (best * 2 < snx || e->opt_two_sided == 2) {
+                        ts.on = true;
+                        const int64_t H = (int64_t)bestH;
+                        const i128 yl128 = lim - bestH - 1;
+                        const int64_t YL = (int64_t)std::max<i128>(std::min<i128>(yl128, dmaxy), dminy - 1);
+                        ts.na = hpx[(size_t)(bestH - dminx + 1)];
+                        ts.nb = YL < (int64_t)dminy ? 0 : hpy[(size_t)(YL - (int64_t)dminy) + 1];
+                        ts.degmin_x = (int64_t)dminx;
+                        ts.ndeg_x = ndx;
+                        while ((1u << ts.dbits_x) < ndx) ++ts.dbits_x;
+                        ts.dlo_b = (uint32_t)std::min<i128>(std::max<i128>(bestH + 1 - dminx, 0), (i128)ndx);
+                        i128 lbb = lim - dminx; // pass B: left-degree index d passes for right term j iff d <= lbb - deg_j
+                        lbb = std::max(lbb, dminy - 1);
+                        lbb = std::min(lbb, dmaxy + (i128)ndx);
+                        ts.lim_base_b = (int64_t)lbb;
+                        // compact the two left lists
+                        auto select = [&](const uint64_t *k, const uint64_t *c, const int64_t *d, uint64_t n, int cw, int64_t thr,
+                                          uint64_t cnt, uint64_t *&ok, uint64_t *&oc, int64_t *&od) {
+                            uint32_t *flag = sc.alloc<uint32_t>(n + 1);
+                            uint32_t *pos = sc.alloc<uint32_t>(n + 2);
+                            const unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
+                            k_flag_le<<<g, 256, 0, s>>>(d, n, thr, flag);
+                            device_scan(e, sc, flag, pos, n);
+                            ok = sc.alloc<uint64_t>(std::max<uint64_t>(cnt, 1) * W);
+                            oc = sc.alloc<uint64_t>(std::max<uint64_t>(cnt, 1) * cw);
+                            od = sc.alloc<int64_t>(std::max<uint64_t>(cnt, 1));
+                            k_select<<<g, 256, 0, s>>>(k, c, d, n, W, cw, pos, ok, oc, od);
+                            e->launches += 2;
+                            sc.release(flag);
+                            sc.release(pos);
+                        };
+                        select(sxk, sxc, sxdeg, snx, CWx, H, ts.na, ts.ak, ts.ac, ts.adeg);
+                        select(dyk, dyc, ydeg, ny, CWy, YL, ts.nb, ts.bk, ts.bc, ts.bdeg);
+                        if (ts.dlo_b >= ndx || ts.nb == 0) ts.nb = 0; // pass B has nothing to do
+                    }
+                }
                 if (tot_mults == 0) {
                     // the truncation admits no pair: empty result before segmenting (polynomial.hpp:860-862)
                     set_empty_result(out, x, st.acc_limbs, rq.result_mem);
@@ -1165,6 +1282,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             } else {
                 EstimateIn ein{sxk, sxdeg, snx, dyk, ydeg, ny, W, L.is_signed, dbits, degmin_y, ndeg, trunc, lim_base,
                                tot_mults, threads};
+                ein.ts = &ts;
                 est = estimate_terms(e, sc, ein);
                 nsegs = pick_nsegs(est, (double)cap * (double)e->opt_fill_pct / 100.0, tot_mults, wave);
             }
@@ -1181,8 +1299,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     return OBK_ERR_TABLE_OVERFLOW;
                 }
                 CU_CHECK(e, cudaEventRecord(e->ev[4], s));
-                SortedY ys;
-                uint32_t *xseg = nullptr;
+                SortedY ys, xs{};
+                uint32_t *xseg = nullptr, *aseg = nullptr, *bseg = nullptr;
                 if (rq.merge) {
                     ys = sort_operand(e, sc, dyk, dyc, nullptr, ny, W, accw, nsegs, L.is_signed, false, 0, 0, true);
                 } else {
@@ -1214,6 +1332,33 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     P.xdeg = sxdeg;
                     P.xseg = xseg;
                     P.nx = snx;
+                    P.npass = 1;
+                    if (ts.on) {
+                        aseg = sc.alloc<uint32_t>(std::max<uint64_t>(ts.na, 1));
+                        bseg = sc.alloc<uint32_t>(std::max<uint64_t>(ts.nb, 1));
+                        if (ts.na) k_segments<<<(unsigned)std::min<uint64_t>((ts.na + 255) / 256, 4096), 256, 0, s>>>(ts.ak, ts.na, W, nsegs, L.is_signed, aseg);
+                        if (ts.nb) k_segments<<<(unsigned)std::min<uint64_t>((ts.nb + 255) / 256, 4096), 256, 0, s>>>(ts.bk, ts.nb, W, nsegs, L.is_signed, bseg);
+                        xs = sort_operand(e, sc, sxk, sxc, sxdeg, snx, W, CWx, nsegs, L.is_signed, false, ts.dbits_x, ts.degmin_x, true);
+                        e->launches += 2;
+                        P.xk = ts.ak;
+                        P.xc = ts.ac;
+                        P.xdeg = ts.adeg;
+                        P.xseg = aseg;
+                        P.nx = ts.na;
+                        P.npass = 2;
+                        P.b.xk = ts.bk;
+                        P.b.xc = ts.bc;
+                        P.b.xdeg = ts.bdeg;
+                        P.b.xseg = bseg;
+                        P.b.nx = ts.nb;
+                        P.b.yk = xs.keys;
+                        P.b.yc = xs.cfs;
+                        P.b.yoff = xs.off;
+                        P.b.dbits = ts.dbits_x;
+                        P.b.ndeg = ts.ndeg_x;
+                        P.b.dlo = ts.dlo_b;
+                        P.b.lim_base = ts.lim_base_b;
+                    }
                 }
                 P.yk = ys.keys;
                 P.yc = ys.cfs;
@@ -1259,6 +1404,13 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 ms_prep_extra += ms;
                 if (zero_key) sc.release(zero_key);
                 if (xseg) sc.release(xseg);
+                if (xs.keys) {
+                    sc.release(xs.keys);
+                    sc.release(xs.cfs);
+                    sc.release(xs.off);
+                    sc.release(aseg);
+                    sc.release(bseg);
+                }
                 sc.release(ys.keys);
                 sc.release(ys.cfs);
                 sc.release(ys.off);
@@ -1538,6 +1690,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "fence") e->opt_fence = value;
     else if (n == "regroup") e->opt_regroup = value;
     else if (n == "row_threads") e->opt_row_threads = value;
+    else if (n == "two_sided") e->opt_two_sided = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
     else if (n == "group_lanes") e->opt_group_lanes = value;

@@ -380,6 +380,28 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const uint64_t *__restrict_
     }
 }
 
+// Two-sided truncation: flag the terms whose degree is <= thr, then (after a scan of the flags) copy them out.
+__global__ void __launch_bounds__(256) k_flag_le(const int64_t *__restrict__ deg, uint64_t n, int64_t thr, uint32_t *__restrict__ flag)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flag[i] = deg[i] <= thr;
+}
+__global__ void __launch_bounds__(256) k_select(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ cfs,
+                                                const int64_t *__restrict__ deg, uint64_t n, int W, int CW,
+                                                const uint32_t *__restrict__ pos /* n+1, exclusive scan of flags */,
+                                                uint64_t *__restrict__ okeys, uint64_t *__restrict__ ocfs, int64_t *__restrict__ odeg)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t d = pos[i];
+        if (pos[i + 1] == d) continue;
+        for (int w = 0; w < W; ++w) okeys[(size_t)d * W + w] = keys[i * W + w];
+        if (ocfs)
+            for (int c = 0; c < CW; ++c) ocfs[(size_t)d * CW + c] = cfs[i * CW + c];
+        odeg[d] = deg[i];
+    }
+}
+
 // tot_n_mults of a truncated product (polynomial.hpp:574-623): for each left term the number of right
 // terms whose degree passes the limit, via the degree histogram's prefix sums.
 __global__ void __launch_bounds__(256) k_deg_hist(const int64_t *__restrict__ deg, uint64_t n, int64_t degmin,
@@ -503,6 +525,23 @@ struct MulParams {
     uint32_t ndeg;
     uint32_t trunc;
     int64_t lim_base;
+    uint32_t dlo;   // lowest right-degree index a left term may pair with (0 unless two-sided truncation)
+    uint32_t npass; // 2: a second pass with the operands' roles swapped follows (two-sided truncation)
+    // Second pass of a heavily truncated product (every admissible pair has its LOWER-degree factor on the left):
+    // left = the low-degree terms of the right operand, right = the left operand sorted by (segment, degree),
+    // degree window [dlo, lim_base - deg].  Same fields as above.
+    struct PassB {
+        const uint64_t *xk;
+        const uint64_t *xc;
+        const int64_t *xdeg;
+        const uint32_t *xseg;
+        uint64_t nx;
+        const uint64_t *yk;
+        const uint64_t *yc;
+        const uint32_t *yoff;
+        uint32_t dbits, ndeg, dlo, pad;
+        int64_t lim_base;
+    } b;
     // work list: segment ids to process (NULL = all nsegs) and the dynamic cursor
     const uint32_t *seg_list;
     uint32_t nseg_list;
@@ -590,7 +629,7 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
         // lane of a 32-product batch is done: the nested-loop form of this kernel ran with 7-8 of 32 lanes active
         // (ncu, profiles/r01a_*), i.e. 18-22 warp instructions per product.
         enum : uint32_t { LX = 0, LY = 1, LP = 2, LDONE = 3 };
-        uint32_t lst = LX;
+        uint32_t lst = LX, lpass = 0;
         uint64_t xi = (uint64_t)gid - (uint64_t)ngroups; // wraps; the first LX step adds ngroups back
         uint32_t t = 0, y1 = 0, h = 0, probes = 0;
         uint64_t kx[W], k[W];
@@ -601,40 +640,51 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
             if (!__any_sync(0xffffffffu, lst != LDONE)) break;
             if (lst == LX) {
                 xi += ngroups;
-                if (xi >= P.nx) {
-                    lst = LDONE;
+                const bool pb = lpass != 0;
+                if (xi >= (pb ? P.b.nx : P.nx)) {
+                    if (!pb && P.npass > 1) {
+                        lpass = 1; // roles swapped: continue with the second pass's left list
+                        xi = (uint64_t)gid - (uint64_t)ngroups;
+                    } else {
+                        lst = LDONE;
+                    }
                 } else {
+                    const uint64_t *xkp = pb ? P.b.xk : P.xk;
+                    const uint32_t *yoffp = pb ? P.b.yoff : P.yoff;
 #pragma unroll
-                    for (int w = 0; w < W; ++w) kx[w] = __ldg(P.xk + xi * W + w);
-                    const uint32_t bx = __ldg(P.xseg + xi);
+                    for (int w = 0; w < W; ++w) kx[w] = __ldg(xkp + xi * W + w);
+                    const uint32_t bx = __ldg((pb ? P.b.xseg : P.xseg) + xi);
                     const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
                     uint32_t y0;
                     bool any = true;
                     if (P.trunc) {
-                        const int64_t r = P.lim_base - __ldg(P.xdeg + xi);
-                        any = r >= 0;
-                        const uint32_t d = r >= (int64_t)P.ndeg ? P.ndeg - 1u : (uint32_t)(r < 0 ? 0 : r);
-                        y0 = __ldg(P.yoff + ((size_t)by << P.dbits));
-                        y1 = __ldg(P.yoff + ((size_t)by << P.dbits) + d + 1u);
+                        const uint32_t dbits = pb ? P.b.dbits : P.dbits, ndeg = pb ? P.b.ndeg : P.ndeg;
+                        const uint32_t dlo = pb ? P.b.dlo : P.dlo;
+                        const int64_t r = (pb ? P.b.lim_base : P.lim_base) - __ldg((pb ? P.b.xdeg : P.xdeg) + xi);
+                        any = r >= (int64_t)dlo;
+                        const uint32_t d = r >= (int64_t)ndeg ? ndeg - 1u : (uint32_t)(r < 0 ? 0 : r);
+                        y0 = __ldg(yoffp + ((size_t)by << dbits) + dlo);
+                        y1 = __ldg(yoffp + ((size_t)by << dbits) + d + 1u);
                     } else {
-                        y0 = __ldg(P.yoff + by);
-                        y1 = __ldg(P.yoff + by + 1u);
+                        y0 = __ldg(yoffp + by);
+                        y1 = __ldg(yoffp + by + 1u);
                     }
                     t = y0 + lg_lane;
                     if (any && t < y1) {
+                        const uint64_t *xcp = pb ? P.b.xc : P.xc;
 #pragma unroll
-                        for (int c = 0; c < XCW; ++c) cx[c] = __ldg(P.xc + xi * XCW + c);
+                        for (int c = 0; c < XCW; ++c) cx[c] = __ldg(xcp + xi * XCW + c);
                         lst = LY;
                     }
                 }
             }
             if (lst == LY) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg(P.yk + (size_t)t * W + w); // monomial_mul
+                for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg((lpass ? P.b.yk : P.yk) + (size_t)t * W + w); // monomial_mul
                 if constexpr (!T::SYM) {
                     uint64_t cy[CW];
 #pragma unroll
-                    for (int c = 0; c < CW; ++c) cy[c] = __ldg(P.yc + (size_t)t * CW + c);
+                    for (int c = 0; c < CW; ++c) cy[c] = __ldg((lpass ? P.b.yc : P.yc) + (size_t)t * CW + c);
                     if constexpr (T::ADD) {
 #pragma unroll
                         for (int c = 0; c < CW; ++c) p[c] = cy[c];

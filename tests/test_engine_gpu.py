@@ -414,3 +414,27 @@ def test_row_path_auto_selection(engine):
         assert p0.as_dict() == engine.mul(f, g).as_dict()
     finally:
         engine.set_option("kernel", -1)
+
+
+def test_two_sided_truncation(engine):
+    """Heavily truncated products are formed from the lower-degree side of every pair (pass A + pass B);
+    forced on (two_sided=2) and compared with the oracle and with the one-sided kernel."""
+    rng = np.random.default_rng(29)
+    fa, ga = wl.audi("u64", 0, nvars=7, n=7)       # automatic-differentiation shape: most terms sit at the top degree
+    xi = wl.Operand(fa.symbols, fa.expos, np.array([int(c) % 1000003 - 500000 for c in fa.cfs], dtype=object), "u64")
+    yi = wl.Operand(ga.symbols, ga.expos, np.array([int(c) % 999983 - 400000 for c in ga.cfs], dtype=object), "u64")
+    x2 = wl.random_poly(rng, 6000, 6, 6, 20, "i64", signed_expos=True)
+    y2 = wl.random_poly(rng, 5000, 6, 6, 20, "i64", signed_expos=True)
+    try:
+        for mode in (2, 0):
+            engine.set_option("two_sided", mode)
+            for lim in (7, 5, 3, 0):
+                check_exact(engine, xi, yi, limit=lim)
+                check_exact(engine, yi, xi, limit=lim)
+                check_exact(engine, xi, yi, limit=lim, idx=[0, 2, 5])
+            for lim in (6, 0, -9, -30):
+                check_exact(engine, x2, y2, limit=lim)
+            check_exact(engine, xi.with_layout("u64", 3), yi.with_layout("u64", 3), limit=4)
+            check_f64(engine, fa, ga, limit=7)
+    finally:
+        engine.set_option("two_sided", 1)
