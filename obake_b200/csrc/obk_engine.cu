@@ -1379,8 +1379,14 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     while ((1ll << (lg + 1)) <= e->opt_group_lanes && lg < 5) ++lg;
                 } else {
                     // one lane per left term: with the per-lane state machine this is the fastest mapping on every
-                    // workload measured (S12 38.6 vs 30.2 G/s at 4 lanes; F20 58.8 vs 38.2 G/s at 32 lanes)
+                    // untruncated workload measured (S12 38.6 vs 30.2 G/s at 4 lanes; F20 58.8 vs 38.2 G/s at 32 lanes).
+                    // Two-sided truncation leaves few left terms with long, very uneven runs (a degree-0 term pairs
+                    // with a whole bucket): split each run over a warp so that no single lane owns it.
                     lg = 0;
+                    if (ts.on) {
+                        const double run = (double)tot_mults / (double)std::max<uint64_t>(ts.na + ts.nb, 1) / (double)nsegs;
+                        lg = run >= 16.0 ? 5 : (run >= 4.0 ? 3 : 0);
+                    }
                 }
                 P.lg = lg;
                 st.group_lanes = 1u << lg;
