@@ -313,9 +313,15 @@ SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uin
     CU_CHECK(e, cudaMemsetAsync(cnt, 0, (nbins + 1) * sizeof(uint32_t), e->stream));
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
     if (nbins <= 8192 && n >= 8192) {
-        const unsigned g2 = (unsigned)((n + 256 * BINC_ITEMS - 1) / (256 * BINC_ITEMS));
-        k_bin_count_smem<<<g2, 256, nbins * sizeof(uint32_t), e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0, dbits,
-                                                                          degmin, (uint32_t)nbins, cnt, bin_of, rank_of);
+        if (n >= (1u << 21)) {
+            const unsigned g2 = (unsigned)((n + 256 * 16 - 1) / (256 * 16));
+            k_bin_count_smem<16><<<g2, 256, nbins * sizeof(uint32_t), e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0,
+                                                                                  dbits, degmin, (uint32_t)nbins, cnt, bin_of, rank_of);
+        } else {
+            const unsigned g2 = (unsigned)((n + 256 * 2 - 1) / (256 * 2));
+            k_bin_count_smem<2><<<g2, 256, nbins * sizeof(uint32_t), e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0,
+                                                                                 dbits, degmin, (uint32_t)nbins, cnt, bin_of, rank_of);
+        }
     } else {
         k_bin_count<<<grid, 256, 0, e->stream>>>(keys, deg, n, W, m, is_signed, pow2 ? 1 : 0, dbits, degmin, cnt, bin_of,
                                                  rank_of);
@@ -1132,7 +1138,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 unsigned long long *dtot = sc.alloc<unsigned long long>(1);
                 CU_CHECK(e, cudaMemsetAsync(hist, 0, (ndeg + 1) * 4, s));
                 CU_CHECK(e, cudaMemsetAsync(dtot, 0, 8, s));
-                k_deg_hist<<<gy, 256, 0, s>>>(ydeg, ny, degmin_y, hist);
+                k_deg_hist<<<gy, 256, ndeg <= 8192 ? ndeg * 4 : 0, s>>>(ydeg, ny, degmin_y, hist, ndeg <= 8192 ? ndeg : 0);
                 e->launches += 1;
                 device_scan(e, sc, hist, pref, ndeg);
                 k_count_mults<<<gx, 256, 0, s>>>(sxdeg, snx, lim_base, ndeg, pref, dtot);
@@ -1148,7 +1154,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     uint32_t *histx = sc.alloc<uint32_t>(ndx + 1);
                     prefx = sc.alloc<uint32_t>(ndx + 2);
                     CU_CHECK(e, cudaMemsetAsync(histx, 0, (ndx + 1) * 4, s));
-                    k_deg_hist<<<gx, 256, 0, s>>>(sxdeg, snx, (int64_t)dminx, histx);
+                    k_deg_hist<<<gx, 256, ndx <= 8192 ? ndx * 4 : 0, s>>>(sxdeg, snx, (int64_t)dminx, histx, ndx <= 8192 ? ndx : 0);
                     e->launches += 1;
                     device_scan(e, sc, histx, prefx, ndx);
                     hpx.resize((size_t)ndx + 1);

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) k_bin_count(const uint64_t *__restrict__ 
 // Same as k_bin_count for a small number of bins: per-block histogram in shared memory (the block's rank of a
 // term comes from the shared atomic), one global atomic per (block, non-empty bin) for the block's base.  Avoids the
 // same-address global atomics that dominate k_bin_count when millions of terms fall into ~1000 bins.
-constexpr int BINC_ITEMS = 16;
+template <int BINC_ITEMS>
 __global__ void __launch_bounds__(256) k_bin_count_smem(const uint64_t *__restrict__ keys, const int64_t *__restrict__ deg,
                                                         uint64_t n, int W, uint32_t m, uint32_t is_signed, int pow2,
                                                         int dbits, int64_t degmin, uint32_t nbins,
@@ -405,11 +405,24 @@ __global__ void __launch_bounds__(256) k_select(const uint64_t *__restrict__ key
 // tot_n_mults of a truncated product (polynomial.hpp:574-623): for each left term the number of right
 // terms whose degree passes the limit, via the degree histogram's prefix sums.
 __global__ void __launch_bounds__(256) k_deg_hist(const int64_t *__restrict__ deg, uint64_t n, int64_t degmin,
-                                                  uint32_t *__restrict__ hist)
+                                                  uint32_t *__restrict__ hist, uint32_t ndeg_smem)
 {
+    // ndeg_smem != 0: the histogram has that many bins and fits in shared memory (the usual case: tens of degrees,
+    // hundreds of thousands of terms -- global atomics on a dozen addresses would serialise)
+    extern __shared__ uint32_t sh_dh[];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&hist[(uint32_t)(deg[i] - degmin)], 1u);
+    if (ndeg_smem) {
+        for (uint32_t b = threadIdx.x; b < ndeg_smem; b += blockDim.x) sh_dh[b] = 0;
+        __syncthreads();
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            atomicAdd(&sh_dh[(uint32_t)(deg[i] - degmin)], 1u);
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < ndeg_smem; b += blockDim.x)
+            if (sh_dh[b]) atomicAdd(&hist[b], sh_dh[b]);
+    } else {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            atomicAdd(&hist[(uint32_t)(deg[i] - degmin)], 1u);
+    }
 }
 
 // lim_base = limit - degmin_y expressed so that right-degree index d passes for left term i iff
