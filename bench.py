@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="F30")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--also", default="", help="comma list of extra workloads to report in 'also' (N=1)")
+    ap.add_argument("--also", default="S12", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
     return ap.parse_args()

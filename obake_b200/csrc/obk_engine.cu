@@ -47,7 +47,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
 };
@@ -355,9 +355,20 @@ void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, un
 {
 #define OBK_CASE(M)                                                                                                    \
     case M: {                                                                                                          \
-        auto fn = k_mul<W, M>;                                                                                         \
-        CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        fn<<<grid, threads, smem, e->stream>>>(P);                                                                     \
+        if (P.npass > 1) {                                                                                             \
+            if constexpr (M == CF_ADD1 || M == CF_ADD2 || M == CF_ADD3 || M == CF_ADDF) {                              \
+                e->err = "internal: two-sided pass in merge mode";                                                     \
+                throw obk_fail{OBK_ERR_INVALID_ARG};                                                                   \
+            } else {                                                                                                   \
+                auto fn = k_mul<W, M, true>;                                                                           \
+                CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+                fn<<<grid, threads, smem, e->stream>>>(P);                                                             \
+            }                                                                                                          \
+        } else {                                                                                                       \
+            auto fn = k_mul<W, M, false>;                                                                              \
+            CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+            fn<<<grid, threads, smem, e->stream>>>(P);                                                                 \
+        }                                                                                                              \
         break;                                                                                                         \
     }
     switch (mode) {
@@ -1247,7 +1258,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         st.table_slots = cap;
         const uint32_t max_fill = (uint32_t)((uint64_t)cap * 9 / 10);
         const uint64_t max_bins = 1ull << 25;
-        const uint32_t wave = (uint32_t)e->sm_count; // resident CTAs: one per SM (the table takes the whole SM)
+        const uint32_t wave = (uint32_t)e->sm_count * (uint32_t)std::max<int64_t>(1, e->opt_ctas_per_sm); // resident CTAs
 
         // ---- dense operands: row-blocked path (register accumulation, no table) --------------------------------
         RowsResult rows;
@@ -1403,7 +1414,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 P.counts = counts;
                 P.flags = dflags;
                 CU_CHECK(e, cudaEventRecord(e->ev[5], s));
-                launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(nsegs, (uint64_t)e->sm_count), threads, smem_mul);
+                launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(nsegs, (uint64_t)e->sm_count * (uint64_t)std::max<int64_t>(1, e->opt_ctas_per_sm)), threads, smem_mul);
                 CU_CHECK(e, cudaEventRecord(e->ev[6], s));
                 st.mul_launches += 1;
                 device_scan(e, sc, counts, offs, nsegs);
@@ -1703,6 +1714,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "regroup") e->opt_regroup = value;
     else if (n == "row_threads") e->opt_row_threads = value;
     else if (n == "two_sided") e->opt_two_sided = value;
+    else if (n == "ctas_per_sm") e->opt_ctas_per_sm = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
     else if (n == "group_lanes") e->opt_group_lanes = value;

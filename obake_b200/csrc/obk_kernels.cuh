@@ -602,8 +602,8 @@ __device__ __forceinline__ void slot_fence(uint32_t fence)
 // table lives in shared memory; every left term x_i pairs with the right bucket (seg - bucket(x_i))
 // mod nsegs (:1449-1456); truncation keeps the prefix of that bucket with deg_j <= limit - deg_i
 // (compute_end_idx2, :1187-1238 -- the bucket is degree-sorted, so the prefix is one table lookup).
-template <int W, int MODE>
-__global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
+template <int W, int MODE, bool TWO>
+__global__ void __launch_bounds__(1024) k_mul(const MulParams P)
 {
     using T = CfTraits<MODE>;
     constexpr int ACCW = T::SYM ? 0 : T::LACC;
@@ -653,9 +653,9 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
             if (!__any_sync(0xffffffffu, lst != LDONE)) break;
             if (lst == LX) {
                 xi += ngroups;
-                const bool pb = lpass != 0;
+                const bool pb = TWO && lpass != 0;
                 if (xi >= (pb ? P.b.nx : P.nx)) {
-                    if (!pb && P.npass > 1) {
+                    if (TWO && !pb && P.npass > 1) {
                         lpass = 1; // roles swapped: continue with the second pass's left list
                         xi = (uint64_t)gid - (uint64_t)ngroups;
                     } else {
@@ -693,11 +693,11 @@ __global__ void __launch_bounds__(1024, 1) k_mul(const MulParams P)
             }
             if (lst == LY) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg((lpass ? P.b.yk : P.yk) + (size_t)t * W + w); // monomial_mul
+                for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg(((TWO && lpass) ? P.b.yk : P.yk) + (size_t)t * W + w); // monomial_mul
                 if constexpr (!T::SYM) {
                     uint64_t cy[CW];
 #pragma unroll
-                    for (int c = 0; c < CW; ++c) cy[c] = __ldg((lpass ? P.b.yc : P.yc) + (size_t)t * CW + c);
+                    for (int c = 0; c < CW; ++c) cy[c] = __ldg(((TWO && lpass) ? P.b.yc : P.yc) + (size_t)t * CW + c);
                     if constexpr (T::ADD) {
 #pragma unroll
                         for (int c = 0; c < CW; ++c) p[c] = cy[c];
