@@ -276,12 +276,22 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     peak, peak_src = measured_peak()
     per_launch_products = rank_products  # the slowest rank's kernel and the products it formed
     achieved = B * per_launch_products / (kernel_mean * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as tf:
+            tj = json.load(tf).get(name.upper())
+            if tj and world == 1:
+                traffic = tj["traffic_bytes"]
+    except Exception:
+        traffic = None
     out = {
         "workload": name, "description": desc, "products": int(products), "terms_out": int(nterms_out),
         "ms_per_step": ms, "value": products / (ms * 1e-3), "kernel_ms": kernel_mean,
         "stats": {k: (float(v) if isinstance(v, float) else int(v)) for k, v in stats_last.items()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_mul", "algorithmic_bytes_per_product": B,
+                     "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/traffic.json)",
+                     "kernel": "k_rowconv" if stats_last.get("kernel") == 1 else "k_mul",
+                     "algorithmic_bytes_per_launch": B * per_launch_products, "algorithmic_bytes_per_product": B,
                      "peak_source": peak_src, "kernel_ms": kernel_mean,
                      "kernel_share_of_step": kernel_mean / ms},
         "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
