@@ -273,6 +273,11 @@ void validate_view(obk_engine *e, const obk_poly_view *v, const char *name)
 // Exclusive scan of n uint32 into out[0..n] (out[n] = total).
 void device_scan(obk_engine *e, Scratch &sc, const uint32_t *in, uint32_t *out, uint64_t n)
 {
+    if (n <= 8 * (uint64_t)SCAN_BLOCK) {
+        k_scan_small<<<1, SCAN_THREADS, 0, e->stream>>>(in, out, n);
+        e->launches += 1;
+        return;
+    }
     const uint64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     if (nb > (uint64_t)SCAN_BLOCK) {
         e->err = "scan too large";

@@ -351,6 +351,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const uint32_t *__r
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
+// Exclusive scan of a short array by ONE block (n up to a few hundred thousand): chunks of SCAN_BLOCK items with a
+// running carry.  Replaces the three launches of the general scan for the many small scans of a call (bucket
+// offsets, segment counts), which were launch-latency bound.  out[n] = grand total.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_small(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t n)
+{
+    __shared__ uint32_t total, carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base0 = 0; base0 < n; base0 += SCAN_BLOCK) {
+        const uint64_t base = base0 + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            v[j] = base + j < n ? in[base + j] : 0;
+            sum += v[j];
+        }
+        uint32_t ex = block_exclusive_scan(sum, &total) + carry;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            if (base + j < n) out[base + j] = ex;
+            ex += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
 // out has n+1 entries: out[n] = grand total.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *__restrict__ out,
                                                            const uint32_t *__restrict__ block_prefix, uint64_t n,
