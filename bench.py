@@ -338,6 +338,56 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     return out
 
 
+
+def bench_rect(args, eng, torch, dev, steps, warmup):
+    """benchmark/rectangular_01.cpp:24-52: curr = 1; 70 times curr *= f (13-term f in 3 variables, fp64).  The timed
+    unit is the whole chain, as in the reference; every intermediate stays in HBM (the product of step i is the
+    operand of step i+1 through its device pointers), which is row 8(f).1 of the scope table in miniature."""
+    from obake_b200 import _capi, workloads as wl
+    from obake_b200.engine import raw_view
+
+    f = wl.rect_base("u64", True)
+    fk = torch.from_numpy(np.ascontiguousarray(f.keys).view(np.int64)).to(dev)
+    fc = torch.from_numpy(np.ascontiguousarray(f.cfs).view(np.int64).reshape(-1, 1)).to(dev)
+    one_k = torch.zeros((1, 1), dtype=torch.int64, device=dev)
+    one_c = torch.from_numpy(np.array([[1.0]]).view(np.int64)).to(dev)
+    vf = raw_view(f.nterms, 1, 0, 3, 0, _capi.OBK_CF_F64, 1, _capi.OBK_MEM_DEVICE, fk.data_ptr(), fc.data_ptr())
+
+    def chain():
+        cur = None
+        vcur = raw_view(1, 1, 0, 3, 0, _capi.OBK_CF_F64, 1, _capi.OBK_MEM_DEVICE, one_k.data_ptr(), one_c.data_ptr())
+        prods, launches, sizes = 0, 0, []
+        for i in range(70):
+            nxt = eng.mul_views(vf, vcur, result_mem=_capi.OBK_MEM_DEVICE)
+            prods += nxt.stats["term_products"]
+            launches += nxt.stats["total_launches"]
+            if cur is not None:
+                cur.free()
+            cur = nxt
+            vcur = raw_view(cur.nterms, 1, 0, 3, 0, _capi.OBK_CF_F64, 1, _capi.OBK_MEM_DEVICE, cur.keys_ptr, cur.cfs_ptr)
+            if (i + 1) % 10 == 0:
+                sizes.append(cur.nterms)
+        n = cur.nterms
+        cur.free()
+        return prods, launches, n, sizes
+
+    for _ in range(max(1, warmup)):
+        chain()
+    times = []
+    for _ in range(steps):
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        prods, launches, n, sizes = chain()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    return {"value": prods / (ms * 1e-3), "ms_per_chain": ms, "products": prods, "final_terms": n,
+            "sizes_every_10": sizes, "launches": launches,
+            "expected_final_terms": 1284816}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -367,6 +417,14 @@ def main():
     for o in args.opt:
         k, v = o.split("=")
         eng.set_option(k, int(v))
+    if args.workload.upper() == "RECT":
+        r = bench_rect(args, eng, torch, dev, max(2, args.steps // 2), 1)
+        print(json.dumps({"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": max(2, args.steps // 2),
+                          "warmup": 1, "ms_per_step": r["ms_per_chain"], "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "RECT", "description": "rectangular_01: 70 chained 13-term products, fp64, device-resident chain", **r}}))
+        eng.close()
+        return 0
     res = bench_workload(args.workload, args, eng, torch, dev, rank, world, args.steps, args.warmup)
     f, g, limit = res.pop("_operands")
     also = {}

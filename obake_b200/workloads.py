@@ -228,6 +228,13 @@ def named(name: str):
         n = int(name[1:])
         f, g = fateman(n, 4, "u64")
         return f, g, None, f"Fateman (1+x+y+z+t)^{n} * ((1+x+y+z+t)^{n}+1), packed u64, exact integer"
+    if name == "F30W":
+        # BASELINE config 3 variant: every coefficient times 2^40 -> two-limb inputs, 3-limb accumulators
+        # would overflow, so n is 24 here: inputs <= 88 bits, products <= 192 bits with the term-count margin
+        f, g = fateman(24, 4, "u64")
+        f = Operand(f.symbols, f.expos, np.array([int(c) << 40 for c in f.cfs], dtype=object), f.tname, f.psize)
+        g = Operand(g.symbols, g.expos, np.array([int(c) << 40 for c in g.cfs], dtype=object), g.tname, g.psize)
+        return f, g, None, "Fateman n=24 with every coefficient scaled by 2^40 (two-limb inputs, three-limb accumulators)"
     if name == "D5":
         f, g = fateman(14, 5, "u64")
         return f, g, None, "dense_02: (1+x+y+z+t+u)^14 * (..+1), packed u64, exact integer"
