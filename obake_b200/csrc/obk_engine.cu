@@ -1409,6 +1409,10 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                         const double run = (double)tot_mults / (double)std::max<uint64_t>(ts.na + ts.nb, 1) / (double)nsegs;
                         lg = run >= 16.0 ? 5 : (run >= 4.0 ? 3 : 0);
                     }
+                    // rectangular products (a handful of left terms against a long right operand): fewer left terms
+                    // than threads would leave most lanes idle -- spread each left term's run over threads/nx lanes
+                    const uint64_t nleft = std::max<uint64_t>(ts.on ? std::max(ts.na, ts.nb) : snx, 1);
+                    while ((nleft << (lg + 1)) <= threads) ++lg;
                 }
                 P.lg = lg;
                 st.group_lanes = 1u << lg;
