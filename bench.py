@@ -299,6 +299,8 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     }
     if info_last:
         out["exchange"] = {k: info_last[k] for k in ("partial_terms", "sent_rows", "recv_rows", "bytes_sent", "nsegs")}
+        if "timing_ms" in info_last:
+            out["exchange"]["timing_ms"] = info_last["timing_ms"]
     # ---- end to end: host (pinned) operands in, host result out, through the same public call ---------------
     if with_e2e and world == 1:
         for _ in range(min(warmup, 2)):

@@ -58,9 +58,14 @@ def exchange_partials(keys: torch.Tensor, cfs: torch.Tensor, send_counts, group=
 def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result_mem=_capi.OBK_MEM_DEVICE):
     """This rank's share of x*y: partial product -> all-to-all by owner -> merge.  Returns (Product holding the
     segments this rank owns, info dict)."""
+    import os
+    import time
+    timing = os.environ.get("OBK_DIST_TIMING") == "1"
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", engine.device)
+    t0 = time.perf_counter()
     part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
+    t1 = time.perf_counter()
     nsegs = _capi.OBK_EXCHANGE_MOD  # fixed modulus: owner ranges are the same on every rank
     W, L = part.key_words, part.cf_limbs
     pk = device_tensor(part.keys_ptr, (part.nterms, W), dev)
@@ -71,11 +76,16 @@ def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result
             "nsegs": nsegs}
     is_f64 = part.is_f64
     torch.cuda.current_stream(dev).synchronize()
+    t2 = time.perf_counter()
     view = raw_view(rkeys.shape[0], W, vx.key_signed, vx.nvars, vx.psize,
                     _capi.OBK_CF_F64 if is_f64 else _capi.OBK_CF_INT, L, _capi.OBK_MEM_DEVICE,
                     rkeys.data_ptr() if rkeys.numel() else 0, rcfs.data_ptr() if rcfs.numel() else 0,
                     vx.key_bits or 64)
     merged = engine.merge_view(view, nsegs, result_mem)
     info["merge_stats"] = merged.stats
+    if timing:
+        t3 = time.perf_counter()
+        info["timing_ms"] = {"partial": (t1 - t0) * 1e3, "exchange": (t2 - t1) * 1e3, "merge": (t3 - t2) * 1e3,
+                             "partial_device_ms": part.stats["ms_total"], "merge_device_ms": merged.stats["ms_total"]}
     part.free()
     return merged, info
