@@ -673,12 +673,13 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
         enum : uint32_t { LX = 0, LY = 1, LP = 2, LDONE = 3 };
         uint32_t lst = LX, lpass = 0;
         uint64_t xi = (uint64_t)gid - (uint64_t)ngroups; // wraps; the first LX step adds ngroups back
-        uint32_t t = 0, y1 = 0, h = 0, probes = 0;
+        uint32_t t = 0, y1 = 0, h = 0;
         uint64_t kx[W], k[W];
         uint64_t cx[XCW > 0 ? XCW : 1];
         uint64_t p[ACCW > 0 ? ACCW : 1];
-        for (;;) {
-            if (*(volatile uint32_t *)&s_over) break;
+        for (uint32_t trip = 0;; ++trip) {
+            // the overflow flag is polled every 16 trips: a full table cannot trap a lane for longer than that
+            if ((trip & 15u) == 0u && *(volatile uint32_t *)&s_over) break;
             if (!__any_sync(0xffffffffu, lst != LDONE)) break;
             if (lst == LX) {
                 xi += ngroups;
@@ -739,7 +740,6 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
                     }
                 }
                 h = slot_hash<W>(k, P.log2_cap);
-                probes = 0;
                 t += G;
                 lst = LP;
             }
@@ -776,8 +776,7 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
                             // else: the slot is being updated by another thread; try again next trip
                         }
                     } else {
-                        h = (h + 1u) & cmask;
-                        if (++probes > cap) s_over = 1;
+                        h = (h + 1u) & cmask; // the table is never completely full (max_fill < cap): probing ends
                     }
                 } else if (st == ST_EMPTY) {
                     if (atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
