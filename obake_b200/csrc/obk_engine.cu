@@ -279,21 +279,18 @@ void device_scan(obk_engine *e, Scratch &sc, const uint32_t *in, uint32_t *out, 
         return;
     }
     const uint64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    if (nb > (uint64_t)SCAN_BLOCK) {
+    if (nb > (1ull << 22)) { // 2^34 items
         e->err = "scan too large";
         throw obk_fail{OBK_ERR_UNSUPPORTED};
     }
     uint32_t *bs = sc.alloc<uint32_t>(nb + 1);
     uint32_t *bp = sc.alloc<uint32_t>(nb + 2);
-    uint32_t *dummy = sc.alloc<uint32_t>(4);
     k_scan_local<<<(unsigned)nb, SCAN_THREADS, 0, e->stream>>>(in, out, bs, n);
-    k_scan_local<<<1, SCAN_THREADS, 0, e->stream>>>(bs, bp, dummy, nb);
-    // grand total = dummy[0]
-    k_scan_add<<<(unsigned)nb, SCAN_THREADS, 0, e->stream>>>(out, bp, n, dummy);
+    k_scan_small<<<1, SCAN_THREADS, 0, e->stream>>>(bs, bp, nb); // any nb; bp[nb] = grand total
+    k_scan_add<<<(unsigned)nb, SCAN_THREADS, 0, e->stream>>>(out, bp, n, bp + nb);
     e->launches += 3;
     sc.release(bs);
     sc.release(bp);
-    sc.release(dummy);
 }
 
 struct SortedY {

@@ -438,3 +438,15 @@ def test_two_sided_truncation(engine):
             check_f64(engine, fa, ga, limit=7)
     finally:
         engine.set_option("two_sided", 1)
+
+
+def test_many_bins_scan(engine):
+    """Large bin counts (fine estimator modulus x degree range) go through the multi-level scan."""
+    f, g = wl.sparse_mp(9, "u64")
+    try:
+        engine.set_option("table_slots", 1024)   # small tables -> many segments and a fine estimator modulus
+        p = engine.mul(f, g, limit=60)
+        r = orc.poly_mul(f, g, limit=60, nthreads=NT)
+        assert p.as_dict() == as_key_dict(r["keys"], r["cfs"])
+    finally:
+        engine.set_option("table_slots", 0)
