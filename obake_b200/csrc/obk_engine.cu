@@ -1317,6 +1317,12 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                              "allowed value (table size overflow)";
                     return OBK_ERR_TABLE_OVERFLOW;
                 }
+                if ((uint64_t)nsegs * cap >= (1ull << 32)) {
+                    // offsets of the staged terms are 32-bit
+                    e->err = "The homomorphic multiplication of two polynomials would produce more than 2^32 terms "
+                             "(table size overflow)";
+                    return OBK_ERR_TABLE_OVERFLOW;
+                }
                 CU_CHECK(e, cudaEventRecord(e->ev[4], s));
                 SortedY ys, xs{};
                 uint32_t *xseg = nullptr, *aseg = nullptr, *bseg = nullptr;
