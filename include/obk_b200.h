@@ -128,9 +128,12 @@ obk_status obk_engine_create(int device, obk_engine **out);
 void obk_engine_destroy(obk_engine *e);
 /* Launch on the caller's stream (e.g. torch's current stream) instead of the engine's own. */
 obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream);
-/* Tunables: "nsegs" (force the segment modulus, -1 = auto), "table_slots", "threads", "group_lanes" (0 = auto),
- * "fill_pct", "fence" (1: fence.acq_rel.cta around the slot lock), "regroup" (1 = default: series-table grouping for HOST results only; 2: always; 0: leave the result in the
- * engine's own segmentation), "kernel" (-1 auto, 0 scatter, 1 rows), "max_retries". */
+/* Tunables (development / tests): "nsegs" (force the segment modulus, -1 = auto), "table_slots", "threads",
+ * "group_lanes" (0 = auto), "fill_pct", "ctas_per_sm", "max_retries",
+ * "kernel"    -1 auto, 0 segment-owner scatter, 1 row-blocked dense path (if the operands qualify),
+ * "row_threads" 512 | 1024, "two_sided" 0 off, 1 auto, 2 always (truncated products),
+ * "fence"     1: fence.acq_rel.cta around the slot lock (memory-model form of the protocol),
+ * "regroup"   1 (default): series-table grouping for HOST results only; 2: always; 0: never. */
 obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value);
 const char *obk_last_error(const obk_engine *e);
 const char *obk_status_string(obk_status s);

@@ -461,7 +461,6 @@ struct EstimateIn {
     uint64_t tot_mults;
     unsigned threads;
     const TwoSided *ts = nullptr; // optional: two-sided truncation (xk/xdeg/nx then describe the FULL left operand)
-    const uint64_t *xc = nullptr;
 };
 
 // Product-size estimate (stands in for poly_mul_estimate_product_size, polynomial.hpp:478-794): a sampled
