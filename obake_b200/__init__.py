@@ -15,8 +15,8 @@ from . import kpack, workloads  # noqa: F401
 
 def __getattr__(name):
     # engine (ctypes + the CUDA library) is imported lazily so that CPU-only tooling can use kpack / workloads
-    if name in ("Engine", "Product", "engine"):
-        from . import engine as _e
+    if name in ("Engine", "Product"):
+        import importlib
 
-        return _e if name == "engine" else getattr(_e, name)
+        return getattr(importlib.import_module(".engine", __name__), name)
     raise AttributeError(name)
