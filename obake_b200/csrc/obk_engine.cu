@@ -47,7 +47,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_lx_batch = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
 };
@@ -1420,6 +1420,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 st.group_lanes = 1u << lg;
                 P.max_fill = max_fill;
                 P.fence = e->opt_fence ? 1u : 0u;
+                P.lx_batch = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(32, e->opt_lx_batch));
                 P.okeys = stage_k;
                 P.ocfs = stage_c;
                 P.counts = counts;
@@ -1726,6 +1727,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "row_threads") e->opt_row_threads = value;
     else if (n == "two_sided") e->opt_two_sided = value;
     else if (n == "ctas_per_sm") e->opt_ctas_per_sm = value;
+    else if (n == "lx_batch") e->opt_lx_batch = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
     else if (n == "group_lanes") e->opt_group_lanes = value;

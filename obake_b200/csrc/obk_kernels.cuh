@@ -593,6 +593,7 @@ struct MulParams {
     uint32_t lg; // log2(lanes per left term)
     uint32_t max_fill;
     uint32_t fence; // 1: fence.acq_rel.cta around the slot lock (validation build of the protocol)
+    uint32_t lx_batch; // lanes that must be waiting for a new left term before the LX step is issued (1 = always)
     // staging output: [segment][cap] slots, counts per segment
     uint64_t *okeys;
     uint64_t *ocfs;
@@ -681,7 +682,12 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
             // the overflow flag is polled every 16 trips: a full table cannot trap a lane for longer than that
             if ((trip & 15u) == 0u && *(volatile uint32_t *)&s_over) break;
             if (!__any_sync(0xffffffffu, lst != LDONE)) break;
-            if (lst == LX) {
+            // The LX body (next left term: ~40 instructions, 4-5 loads) is worth issuing only when several lanes
+            // need it: lanes wait in LX until at least `lx_batch` of them do, or nothing else can make progress.
+            const uint32_t m_lx = __ballot_sync(0xffffffffu, lst == LX);
+            const uint32_t m_busy = __ballot_sync(0xffffffffu, lst == LY || lst == LP);
+            const bool run_lx = __popc(m_lx) >= (int)(P.lx_batch ? P.lx_batch : 1u) || m_busy == 0u;
+            if (run_lx && lst == LX) {
                 xi += ngroups;
                 const bool pb = TWO && lpass != 0;
                 if (xi >= (pb ? P.b.nx : P.nx)) {
