@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--also", default="S12", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
+    ap.add_argument("--mgpu-mode", default="both", choices=["both", "exchange", "owner"],
+                    help="N>1: left-operand sharding + all-to-all + merge (the contract design), owner-computes "
+                         "(zero exchange), or both (value = the faster, both reported)")
     return ap.parse_args()
 
 
@@ -183,7 +186,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------
-def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with_e2e=True):
+def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with_e2e=True, mgpu_mode="exchange"):
     from obake_b200 import _capi, workloads as wl
     from obake_b200.engine import needed_limbs, raw_view
 
@@ -217,6 +220,8 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         if world == 1:
             p = eng.mul_views(vfd, vgd, limit=limit, result_mem=_capi.OBK_MEM_DEVICE)
             return p, {}
+        if mgpu_mode == "owner":
+            return obd.owner_mul(eng, vfd, vgd, limit=limit)
         return obd.sharded_mul(eng, vfd, vgd, limit=limit)
 
     def barrier():
@@ -245,7 +250,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         times.append(e0.elapsed_time(e1))
         st = info.get("partial_stats", p.stats)
         kernel_ms.append(st["ms_mul"])
-        launches += st["total_launches"] + (info["merge_stats"]["total_launches"] if info else 0)
+        launches += st["total_launches"] + (info["merge_stats"]["total_launches"] if info and "merge_stats" in info else 0)
         stats_last, info_last = st, info
         products = st["term_products"]
         nterms_out = p.nterms
@@ -325,11 +330,16 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         for _ in range(max(3, steps // 2)):
             barrier()
             t0 = time.perf_counter()
-            p, info = obd.sharded_mul(eng, vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
+            if mgpu_mode == "owner":
+                p, info = obd.owner_mul(eng, vfh, vgh, limit=limit)
+                hk_, hc_ = p.keys, p.cf_limb_array  # device -> host read of this rank's share
+                d2h = int(hk_.nbytes + hc_.nbytes)
+            else:
+                p, info = obd.sharded_mul(eng, vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
+                d2h = p.stats["d2h_bytes"]
             torch.cuda.synchronize(dev)
             et.append(time.perf_counter() - t0)
             h2d = info["partial_stats"]["h2d_bytes"]
-            d2h = p.stats["d2h_bytes"]
             p.free()
         t = torch.tensor([float(np.mean(et))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -427,7 +437,11 @@ def main():
                           "config": {"workload": "RECT", "description": "rectangular_01: 70 chained 13-term products, fp64, device-resident chain", **r}}))
         eng.close()
         return 0
-    res = bench_workload(args.workload, args, eng, torch, dev, rank, world, args.steps, args.warmup)
+    modes = ["exchange"] if world == 1 else (["exchange", "owner"] if args.mgpu_mode == "both" else [args.mgpu_mode])
+    results = {m: bench_workload(args.workload, args, eng, torch, dev, rank, world, args.steps, args.warmup, mgpu_mode=m)
+               for m in modes}
+    best = max(results, key=lambda m: results[m]["value"])
+    res = results[best]
     f, g, limit = res.pop("_operands")
     also = {}
     if world == 1 and args.also:
@@ -445,8 +459,11 @@ def main():
         "config": {"workload": args.workload, "description": res["description"], "truncation": res["limit"],
                    "term_products": res["products"], "terms_out": res["terms_out"],
                    "l2": "256 MB buffer written between timed steps (L2 flush)",
-                   "parallelism": "single GPU" if world == 1 else
-                   f"left operand sharded over {world} GPUs, NCCL all-to-all of partial segments, owner merge",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"left operand sharded over {world} GPUs, NCCL all-to-all of partial segments, owner merge"
+                       if best == "exchange" else
+                       f"owner-computes over {world} GPUs: both operands on every rank, each rank forms the output "
+                       f"rows/segments it owns, no exchange (SURVEY 8e zero-exchange alternative)"),
                    "engine": res["stats"]},
         "roofline": res["roofline"], "clocks": res["clocks"], "gpu_launches": res["gpu_launches"],
     }
@@ -454,6 +471,10 @@ def main():
         line["e2e"] = res["e2e"]
     if "exchange" in res:
         line["config"]["exchange"] = res["exchange"]
+    if world > 1:
+        line["config"]["multi_gpu_modes"] = {m: {"value": r["value"], "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"],
+                                                 "e2e": r.get("e2e", {}).get("value")} for m, r in results.items()}
+        line["config"]["multi_gpu_mode_reported"] = best
     if also:
         line["also"] = also
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

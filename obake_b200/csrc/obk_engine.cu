@@ -47,7 +47,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_lx_batch = 1, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_lx_batch = 1, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
 };
@@ -694,7 +694,7 @@ struct RowsResult {
 // Returns done=false when the operands are not dense enough (the caller then runs the scatter kernel).
 RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx, const uint64_t *dyk,
                     const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, uint64_t tot_mults,
-                    unsigned threads, bool forced, bool uns, uint32_t rank, uint32_t nranks, obk_stats &st)
+                    unsigned threads, bool forced, bool uns, uint32_t rank, uint32_t nranks, bool owner, obk_stats &st)
 {
     RowsResult R;
     cudaStream_t s = e->stream;
@@ -715,7 +715,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         Y.nrows = hy;
         rows_phase_b(e, sc, dyk, dyc, ny, delta, Y);
     }
-    if (nranks > 1) {
+    if (nranks > 1 && !owner) {
         // multi-GPU: this rank multiplies a contiguous slice of the left ROWS (row numbers come out of a hash
         // table, so a slice is a pseudo-random, balanced subset) by every right row
         const uint32_t b = (uint32_t)((uint64_t)X.nrows * rank / nranks);
@@ -740,7 +740,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     for (auto v : ly) Y.sum_len += v;
     const double iters = std::min((double)X.sum_len * (double)Y.nrows, (double)Y.sum_len * (double)X.nrows);
     // measured costs: ~40 warp instructions per convolution step vs ~22 per product in the scatter kernel
-    if (!forced && iters * 40.0 * (double)nranks > (double)tot_mults * 22.0 * 0.7) return R;
+    if (!forced && iters * 40.0 * (double)(owner ? 1u : nranks) > (double)tot_mults * 22.0 * 0.7) return R;
 
     const uint32_t wave = (uint32_t)e->sm_count;
     // ---- symbolic row product: the set of output rows ------------------------------------------------------
@@ -812,6 +812,14 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     sc.release(offs);
     sc.release(off64);
 
+    if (owner) {
+        // owner-computes: this rank forms a contiguous slice of the output rows (their order comes out of hash tables:
+        // a slice is a balanced pseudo-random subset); every rank derives the same list from the same operands
+        const uint32_t b = (uint32_t)((uint64_t)nro * rank / nranks);
+        const uint32_t c = (uint32_t)((uint64_t)nro * (rank + 1) / nranks) - b;
+        or_hi += b;
+        nro = c;
+    }
     // ---- gather directory: right rows sorted by a fine prime modulus (2-3 rows per run) ------------------------
     const uint32_t mG = next_prime(std::max<uint32_t>(Y.nrows / 2, 3));
     uint64_t *iota = sc.alloc<uint64_t>(Y.nrows);
@@ -995,6 +1003,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         int64_t lim_base = 0, degmin_y = 0;
         int64_t *xdeg = nullptr, *ydeg = nullptr;
         TwoSided ts;
+        // multi-GPU "owner-computes" mode (zero-exchange alternative): both operands are used whole on every
+        // rank and rank r forms only the output segments / output rows it owns -- no partial products, no exchange.
+        const bool owner = rq.nranks > 1 && e->opt_mgpu_owner != 0 && !rq.merge;
         const uint64_t *sxk = nullptr, *sxc = nullptr; // this rank's slice of the left operand
         const int64_t *sxdeg = nullptr;
         uint64_t snx = 0, x_begin = 0;
@@ -1036,7 +1047,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             st.d2h_bytes += sizeof(StatsOut) * 2;
             // multi-GPU: from here on this rank only sees its slice of the left operand's terms;
             // the checks above and the accumulator width below use the FULL operands so that every rank agrees.
-            if (rq.nranks > 1) {
+            if (rq.nranks > 1 && !owner) {
                 x_begin = nx_full * rq.rank / rq.nranks;
                 snx = nx_full * (rq.rank + 1) / rq.nranks - x_begin;
                 sxk = dxk + x_begin * W;
@@ -1267,7 +1278,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok
             && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
             rows = run_rows(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, nx_full * ny, threads, e->opt_kernel == 1,
-                            !f64 && hs_anyneg == 0, rq.rank, rq.nranks, st);
+                            !f64 && hs_anyneg == 0, rq.rank, rq.nranks, owner, st);
         }
 
         uint64_t *rk = nullptr, *rc = nullptr, *off64 = nullptr;
@@ -1394,6 +1405,18 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 P.lim_base = lim_base;
                 P.seg_list = nullptr;
                 P.nseg_list = nsegs;
+                uint32_t *own_list = nullptr;
+                if (owner) {
+                    const uint32_t a = (uint32_t)((uint64_t)nsegs * rq.rank / rq.nranks);
+                    const uint32_t b = (uint32_t)((uint64_t)nsegs * (rq.rank + 1) / rq.nranks);
+                    std::vector<uint32_t> hl(b - a);
+                    for (uint32_t i = a; i < b; ++i) hl[i - a] = i;
+                    own_list = sc.alloc<uint32_t>(std::max<uint32_t>(b - a, 1));
+                    if (b > a) CU_CHECK(e, cudaMemcpyAsync(own_list, hl.data(), (size_t)(b - a) * 4, cudaMemcpyHostToDevice, s));
+                    CU_CHECK(e, cudaStreamSynchronize(s)); // hl goes out of scope
+                    P.seg_list = own_list;
+                    P.nseg_list = b - a;
+                }
                 P.cursor = dflags + 1;
                 P.log2_cap = log2_cap;
                 uint32_t lg = 0;
@@ -1426,7 +1449,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 P.counts = counts;
                 P.flags = dflags;
                 CU_CHECK(e, cudaEventRecord(e->ev[5], s));
-                launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(nsegs, (uint64_t)e->sm_count * (uint64_t)std::max<int64_t>(1, e->opt_ctas_per_sm)), threads, smem_mul);
+                launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(std::max<uint32_t>(P.nseg_list, 1), (uint64_t)e->sm_count * (uint64_t)std::max<int64_t>(1, e->opt_ctas_per_sm)), threads, smem_mul);
                 CU_CHECK(e, cudaEventRecord(e->ev[6], s));
                 st.mul_launches += 1;
                 device_scan(e, sc, counts, offs, nsegs);
@@ -1460,7 +1483,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 sc.release(offs);
                 sc.release(dflags);
                 st.retries += 1;
-                if ((int64_t)st.retries > e->opt_max_retries || rq.merge) {
+                if ((int64_t)st.retries > e->opt_max_retries || rq.merge || owner) {
                     e->err = "The homomorphic multiplication of two polynomials resulted in a segment table whose size "
                              "is larger than the maximum allowed value (shared-memory table overflow after "
                              + std::to_string(st.retries) + " finer segmentations)";
@@ -1492,8 +1515,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         // A device-resident product keeps the engine's own segmentation (seg_kind OBK_SEG_KEY_MOD); the series-table
         // grouping is produced when the result is handed to the host (the container rebuild needs it) or on request
         // (option regroup = 2).  regroup = 0 never regroups.
-        const bool regroup = rq.nranks <= 1 && (e->opt_regroup == 2 || (e->opt_regroup == 1 && rq.result_mem == OBK_MEM_HOST));
-        if (rq.nranks > 1) {
+        const bool regroup = (rq.nranks <= 1 || owner) && (e->opt_regroup == 2 || (e->opt_regroup == 1 && rq.result_mem == OBK_MEM_HOST));
+        if (rq.nranks > 1 && !owner) {
             // multi-GPU partial product: group by key mod OBK_EXCHANGE_MOD, a fixed prime every rank uses, so the
             // rows destined to one owner are contiguous whatever kernel and segmentation produced them
             const uint32_t mx = OBK_EXCHANGE_MOD;
@@ -1592,7 +1615,14 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         }
         CU_CHECK(e, cudaEventRecord(e->ev[8], s));
         CU_CHECK(e, cudaStreamSynchronize(s));
-        if (rq.send_counts) {
+        if (owner) {
+            // this rank's share of the whole job's term products (the shares of all ranks add up to tot_n_mults)
+            st.term_products = tot_mults * (rq.rank + 1) / rq.nranks - tot_mults * rq.rank / rq.nranks;
+            if (rq.send_counts) {
+                std::memset(rq.send_counts, 0, sizeof(uint64_t) * rq.nranks);
+                rq.send_counts[rq.rank] = total;
+            }
+        } else if (rq.send_counts) {
             for (uint32_t g = 0; g < rq.nranks; ++g) {
                 const uint64_t a = (uint64_t)nsegs * g / rq.nranks, b = (uint64_t)nsegs * (g + 1) / rq.nranks;
                 rq.send_counts[g] = own->seg_offsets[b] - own->seg_offsets[a];
@@ -1728,6 +1758,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "two_sided") e->opt_two_sided = value;
     else if (n == "ctas_per_sm") e->opt_ctas_per_sm = value;
     else if (n == "lx_batch") e->opt_lx_batch = value;
+    else if (n == "mgpu_owner") e->opt_mgpu_owner = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
     else if (n == "group_lanes") e->opt_group_lanes = value;

@@ -55,6 +55,40 @@ def exchange_partials(keys: torch.Tensor, cfs: torch.Tensor, send_counts, group=
     return rkeys, rcfs, recv_counts
 
 
+def owner_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None):
+    """Zero-exchange alternative: every rank holds both operands and forms only the output segments /
+    output rows it owns, so there is no partial product, no all-to-all and no merge.  Returns (Product in DEVICE
+    memory with this rank's share of the result, info dict).  If a shared-memory segment table overflows on any
+    rank, ALL ranks retry with a finer segmentation (they must agree on it: ownership is defined by it)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", engine.device)
+    engine.set_option("mgpu_owner", 1)
+    fill = 62
+    try:
+        for attempt in range(6):
+            part, failed = None, 0
+            try:
+                part, counts = engine.mul_partial_views(vx, vy, rank, world, limit, idx)
+            except OverflowError as ex:
+                if "segment table" not in str(ex):
+                    raise
+                failed = 1
+            flag = torch.tensor([failed], dtype=torch.int64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()) == 0:
+                return part, {"mode": "owner", "partial_stats": part.stats, "attempts": attempt + 1,
+                              "sent_rows": 0, "recv_rows": 0, "bytes_sent": 0, "partial_terms": part.nterms,
+                              "nsegs": part.stats["nsegs"]}
+            if part is not None:
+                part.free()
+            fill = max(4, fill // 2)
+            engine.set_option("fill_pct", fill)
+        raise OverflowError("owner-computes product: segment tables keep overflowing")
+    finally:
+        engine.set_option("mgpu_owner", 0)
+        engine.set_option("fill_pct", 62)
+
+
 def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result_mem=_capi.OBK_MEM_DEVICE):
     """This rank's share of x*y: partial product -> all-to-all by owner -> merge.  Returns (Product holding the
     segments this rank owns, info dict)."""

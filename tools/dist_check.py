@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Multi-GPU parity check (run under torchrun): sharded product -> NCCL all-to-all -> owner merge, gathered on
-rank 0 and compared with the CPU oracle.  Used by tests/test_dist_gpu.py."""
+"""Multi-GPU parity check (run under torchrun): both multi-GPU modes -- left-operand sharding + NCCL all-to-all +
+owner merge ("exchange", the contract design) and owner-computes ("owner", zero exchange) -- gathered on rank 0
+and compared with the CPU oracle.  Used by tests/test_dist_gpu.py."""
 import os
 import sys
 
@@ -11,6 +12,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
+
+
+def reference_dict(orc, f, g, limit, idx):
+    r = orc.poly_mul(f, g, limit=limit, idx=idx, nthreads=os.cpu_count() or 1)
+    cfs = r["cfs"] if isinstance(r["cfs"], list) else r["cfs"].tolist()
+    if r["keys"].shape[1] == 1:
+        return dict(zip(r["keys"][:, 0].tolist(), cfs))
+    return {tuple(k): c for k, c in zip(r["keys"].tolist(), cfs)}
 
 
 def main():
@@ -28,6 +37,8 @@ def main():
     cases = []
     f, g = wl.fateman(10, 4, "u64")
     cases.append(("fateman10", f, g, None, None))
+    f16, g16 = wl.fateman(16, 4, "u64")
+    cases.append(("fateman16 (row kernel)", f16, g16, None, None))
     f, g = wl.sparse_mp(7, "i64")
     cases.append(("sparse7", f, g, None, None))
     cases.append(("sparse7 trunc 30", f, g, 30, None))
@@ -38,35 +49,34 @@ def main():
     for name, f, g, limit, idx in cases:
         lin = None if f.is_f64 else max(engine.needed_limbs(f.cfs), engine.needed_limbs(g.cfs))
         hx, hy = engine.HostOperand(f, lin), engine.HostOperand(g, lin)
-        p, info = obd.sharded_mul(eng, hx.view, hy.view, limit=limit, idx=idx, result_mem=_capi.OBK_MEM_HOST)
-        mine = p.as_dict()
-        nsegs = info["nsegs"]
-        a, b = obd.owner_ranges(nsegs, world)[rank]
-        keys = p.keys
-        if len(keys):
-            seg = (keys % np.uint64(nsegs)).sum(axis=1) % nsegs if keys.shape[1] > 1 or f.tname == "u64" else None
-            if seg is not None:
-                assert ((seg >= a) & (seg < b)).all(), "rank holds a segment it does not own"
-        gathered = [None] * world
-        dist.all_gather_object(gathered, mine)
-        if rank == 0:
-            full = {}
-            for d in gathered:
-                assert not (set(full) & set(d))
-                full.update(d)
-            r = orc.poly_mul(f, g, limit=limit, idx=idx, nthreads=os.cpu_count() or 1)
-            if r["keys"].shape[1] == 1:
-                ref = dict(zip(r["keys"][:, 0].tolist(), r["cfs"] if isinstance(r["cfs"], list) else r["cfs"].tolist()))
+        ref = reference_dict(orc, f, g, limit, idx) if rank == 0 else None
+        for mode in ("exchange", "owner"):
+            if mode == "exchange":
+                p, info = obd.sharded_mul(eng, hx.view, hy.view, limit=limit, idx=idx, result_mem=_capi.OBK_MEM_HOST)
             else:
-                ref = {tuple(k): c for k, c in zip(r["keys"].tolist(), r["cfs"] if isinstance(r["cfs"], list) else r["cfs"].tolist())}
-            if f.is_f64:
-                ok = set(full) == set(ref) and all(abs(full[k] - ref[k]) <= 1e-12 * max(abs(ref[k]), 1e-300) + 1e-3 for k in ref)
-            else:
-                ok = full == ref
-            print(f"[dist_check] {name}: world={world} terms={len(full)} nsegs={nsegs} sent_rows(rank0)={info['sent_rows']} ok={ok}",
-                  flush=True)
-            ok_all &= ok
-        p.free()
+                p, info = obd.owner_mul(eng, hx.view, hy.view, limit=limit, idx=idx)
+            mine = p.as_dict()
+            if mode == "exchange" and p.nterms:
+                a, b = obd.owner_ranges(info["nsegs"], world)[rank]
+                seg = (p.keys % np.uint64(info["nsegs"])).sum(axis=1) % info["nsegs"]
+                if f.tname == "u64":
+                    assert ((seg >= a) & (seg < b)).all(), "rank holds a segment it does not own"
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            if rank == 0:
+                full = {}
+                for d in gathered:
+                    assert not (set(full) & set(d)), "two ranks hold the same key"
+                    full.update(d)
+                if f.is_f64:
+                    ok = set(full) == set(ref) and all(
+                        abs(full[k] - ref[k]) <= 1e-12 * max(abs(ref[k]), 1e-300) + 1e-3 for k in ref)
+                else:
+                    ok = full == ref
+                print(f"[dist_check] {name} [{mode}]: world={world} terms={len(full)} kernel={info['partial_stats']['kernel']} "
+                      f"sent_rows(rank0)={info['sent_rows']} ok={ok}", flush=True)
+                ok_all &= ok
+            p.free()
     flag = torch.tensor([1 if ok_all else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
