@@ -163,15 +163,17 @@ class Product:
         if self.on_device:
             import torch  # plumbing only: copy a device buffer back for inspection
 
-            nbytes = int(np.prod(shape)) * C.sizeof(ctype)
-            out = np.empty(shape, dtype=np.dtype(ctype))
-            if nbytes:
-                cudart = torch.cuda.cudart()
-                torch.cuda.synchronize()
-                err = cudart.cudaMemcpy(out.ctypes.data, ptr, nbytes, 2)  # cudaMemcpyDeviceToHost
-                if int(err) != 0:
-                    raise ObkCudaError(f"cudaMemcpy failed: {err}")
-            return out
+            class _Dev:
+                pass
+
+            n = int(np.prod(shape))
+            if n == 0:
+                return np.empty(shape, dtype=np.dtype(ctype))
+            d = _Dev()
+            d.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 3,
+                                          "strides": None}
+            t = torch.as_tensor(d, device=torch.device("cuda", self._engine.device))
+            return t.cpu().numpy().view(np.dtype(ctype)).reshape(shape).copy()
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape).copy()
 
     @property
