@@ -47,7 +47,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_lx_batch = 1, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_lx_batch = 1, opt_scatter = 2, opt_refill_min = 12, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
 };
@@ -362,12 +362,12 @@ void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, un
                 e->err = "internal: two-sided pass in merge mode";                                                     \
                 throw obk_fail{OBK_ERR_INVALID_ARG};                                                                   \
             } else {                                                                                                   \
-                auto fn = k_mul<W, M, true>;                                                                           \
+                auto fn = e->opt_scatter == 1 ? k_mul<W, M, true> : k_mul2<W, M, true>;                                \
                 CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
                 fn<<<grid, threads, smem, e->stream>>>(P);                                                             \
             }                                                                                                          \
         } else {                                                                                                       \
-            auto fn = k_mul<W, M, false>;                                                                              \
+            auto fn = e->opt_scatter == 1 ? k_mul<W, M, false> : k_mul2<W, M, false>;                                  \
             CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
             fn<<<grid, threads, smem, e->stream>>>(P);                                                                 \
         }                                                                                                              \
@@ -391,6 +391,28 @@ void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, un
 #undef OBK_CASE
     e->launches += 1;
     CU_CHECK(e, cudaGetLastError());
+}
+
+// Work units of k_mul2: 32 left terms x one slice of their runs.  Long runs are cut so that a segment yields at
+// least ~4 units per warp (a rectangular product has a handful of left terms, the owner-side merge has one).
+void plan_units(obk_engine *e, MulParams &P, unsigned threads, double avg_run, uint64_t max_run)
+{
+    const uint64_t nch = std::max<uint64_t>(1, ((P.nx + 31) >> 5) + (P.npass > 1 ? ((P.b.nx + 31) >> 5) : 0));
+    const uint64_t want = 4ull * (threads / 32);
+    uint64_t R = 1;
+    if (nch < want) {
+        R = (want + nch - 1) / nch;
+        const uint64_t by_run = (uint64_t)std::max(1.0, avg_run / 8.0);
+        R = std::max<uint64_t>(1, std::min<uint64_t>(R, by_run));
+    }
+    // a unit's products are indexed with 32 bits: 32 slices of at most ceil(max_run / R) terms each
+    R = std::max<uint64_t>(R, (max_run >> 25) + 1);
+    if (nch * R >= (1ull << 31)) {
+        e->err = "operands too large for the work-unit index";
+        throw obk_fail{OBK_ERR_UNSUPPORTED};
+    }
+    P.rslices = (uint32_t)R;
+    P.refill_min = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(32, e->opt_refill_min));
 }
 
 void launch_mul(obk_engine *e, int W, int mode, const MulParams &P, unsigned grid, unsigned threads, size_t smem)
@@ -544,6 +566,8 @@ uint64_t estimate_terms(obk_engine *e, Scratch &sc, const EstimateIn &in)
     P.counts = dcounts;
     P.flags = dflags;
     const size_t smem_sym = (size_t)sym_cap * (8 * W + 4);
+    plan_units(e, P, in.threads, (double)in.tot_mults / (double)std::max<uint64_t>(P.nx + (P.npass > 1 ? P.b.nx : 0), 1) / (double)mE,
+               std::max(in.nx, in.ny));
     launch_mul(e, W, CF_SYM, P, (unsigned)std::min<uint64_t>(S, (uint64_t)e->sm_count), in.threads, smem_sym);
     std::vector<uint32_t> hcounts(S);
     CU_CHECK(e, cudaMemcpyAsync(hcounts.data(), dcounts, S * 4, cudaMemcpyDeviceToHost, s));
@@ -780,6 +804,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         P.okeys = stage;
         P.counts = counts;
         P.flags = dflags;
+        plan_units(e, P, threads, (double)Y.nrows / (double)mR, Y.nrows);
         launch_mul(e, 1, CF_SYM, P, std::min<uint32_t>(mR, wave), threads, (size_t)sym_cap * 12);
         device_scan(e, sc, counts, offs, mR);
         uint32_t hflag[4], htot = 0;
@@ -807,19 +832,23 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     uint64_t *off64 = sc.alloc<uint64_t>((size_t)mR + 1);
     k_compact<<<std::min<uint32_t>(mR, 4096), 256, 0, s>>>(stage, nullptr, counts, offs, sym_cap, 1, 0, or_hi, nullptr, off64, mR);
     e->launches += 1;
+    if (owner) {
+        // owner-computes: this rank forms the output rows of a contiguous range of the symbolic product's segments.
+        // The CONTENT of a segment (row keys congruent mod mR) is the same on every rank, the order inside it is
+        // not (it comes out of a hash table filled by racing threads), so the cut must fall on segment boundaries;
+        // mR itself is a function of the operands only (estimate and retries count distinct keys).
+        const uint32_t sa = (uint32_t)((uint64_t)mR * rank / nranks), sb = (uint32_t)((uint64_t)mR * (rank + 1) / nranks);
+        uint32_t hb[2] = {0, 0};
+        CU_CHECK(e, cudaMemcpyAsync(&hb[0], offs + sa, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaMemcpyAsync(&hb[1], offs + sb, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        or_hi += hb[0];
+        nro = hb[1] - hb[0];
+    }
     sc.release(stage);
     sc.release(counts);
     sc.release(offs);
     sc.release(off64);
-
-    if (owner) {
-        // owner-computes: this rank forms a contiguous slice of the output rows (their order comes out of hash tables:
-        // a slice is a balanced pseudo-random subset); every rank derives the same list from the same operands
-        const uint32_t b = (uint32_t)((uint64_t)nro * rank / nranks);
-        const uint32_t c = (uint32_t)((uint64_t)nro * (rank + 1) / nranks) - b;
-        or_hi += b;
-        nro = c;
-    }
     // ---- gather directory: right rows sorted by a fine prime modulus (2-3 rows per run) ------------------------
     const uint32_t mG = next_prime(std::max<uint32_t>(Y.nrows / 2, 3));
     uint64_t *iota = sc.alloc<uint64_t>(Y.nrows);
@@ -1448,6 +1477,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 P.ocfs = stage_c;
                 P.counts = counts;
                 P.flags = dflags;
+                plan_units(e, P, threads,
+                           (double)tot_mults / (double)std::max<uint64_t>(P.nx + (P.npass > 1 ? P.b.nx : 0), 1) / (double)nsegs,
+                           std::max(snx, ny));
                 CU_CHECK(e, cudaEventRecord(e->ev[5], s));
                 launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(std::max<uint32_t>(P.nseg_list, 1), (uint64_t)e->sm_count * (uint64_t)std::max<int64_t>(1, e->opt_ctas_per_sm)), threads, smem_mul);
                 CU_CHECK(e, cudaEventRecord(e->ev[6], s));
@@ -1758,6 +1790,8 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "two_sided") e->opt_two_sided = value;
     else if (n == "ctas_per_sm") e->opt_ctas_per_sm = value;
     else if (n == "lx_batch") e->opt_lx_batch = value;
+    else if (n == "scatter") e->opt_scatter = value;
+    else if (n == "refill_min") e->opt_refill_min = value;
     else if (n == "mgpu_owner") e->opt_mgpu_owner = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;

@@ -594,6 +594,9 @@ struct MulParams {
     uint32_t max_fill;
     uint32_t fence; // 1: fence.acq_rel.cta around the slot lock (validation build of the protocol)
     uint32_t lx_batch; // lanes that must be waiting for a new left term before the LX step is issued (1 = always)
+    // k_mul2 (warp-cooperative expansion): every left term's run is cut into `rslices` slices (work unit = 32 left
+    // terms x one slice) and idle lanes are refilled once at least `refill_min` of a warp's lanes are idle
+    uint32_t rslices, refill_min;
     // staging output: [segment][cap] slots, counts per segment
     uint64_t *okeys;
     uint64_t *ocfs;
@@ -845,6 +848,309 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
                 P.counts[seg] = over ? 0u : s_out;
                 if (over) atomicAdd(&P.flags[0], 1u);
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mul2 -- the same segment-owner product with WARP-COOPERATIVE expansion of the term products.
+//
+// k_mul gives every lane its own left term and lets it walk that term's run; lanes sit in different phases of
+// their walk, so each trip of the warp loop issues the "next left term", "next product" and "probe" bodies for
+// a third of the lanes each (ncu: 12 of 32 threads active, 13 warp instructions per product).  Here a WARP takes
+// a work unit of 32 consecutive left terms (loaded converged and coalesced), scans their run lengths, and the
+// products of the unit form one index space [0, T): any idle lane is handed the next product index, finds the
+// owning left term by a 5-step binary search over the scanned lengths (shuffles), fetches that term's key and
+// coefficient from the owner lane and forms the product.  Product formation therefore always runs with every idle
+// lane busy, whatever the run lengths are (5 terms in S12, 10^5 in a rectangular product, 0 in most runs of a
+// heavily truncated one), and the only divergent code left is the probe attempt itself.  Units are handed out by
+// a per-CTA counter; `rslices` cuts long runs so that a product with a handful of left terms still yields enough
+// units for 32 warps.  Slot protocol, truncation window, two-sided passes and flush are those of k_mul.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, uint32_t src)
+{
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, (int)src);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), (int)src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <int W, int MODE, bool TWO>
+__global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
+{
+    using T = CfTraits<MODE>;
+    constexpr int ACCW = T::SYM ? 0 : T::LACC;
+    constexpr int CW = T::SYM ? 0 : T::LIN;
+    constexpr int XCW = (T::SYM || T::ADD) ? 0 : CW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t cap = 1u << P.log2_cap;
+    uint64_t *tkeys = reinterpret_cast<uint64_t *>(smem_raw);                    // [W][cap]
+    uint64_t *tacc = tkeys + (size_t)W * cap;                                   // [ACCW][cap]
+    uint32_t *tstate = reinterpret_cast<uint32_t *>(tacc + (size_t)ACCW * cap); // [cap]
+    __shared__ uint32_t s_seg, s_count, s_out, s_over, s_unit;
+
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t cmask = cap - 1u;
+    const uint32_t R = P.rslices ? P.rslices : 1u;
+    const uint32_t nchA = (uint32_t)((P.nx + 31u) >> 5);
+    const uint32_t nchB = (TWO && P.npass > 1) ? (uint32_t)((P.b.nx + 31u) >> 5) : 0u;
+    const uint32_t nunits = (nchA + nchB) * R;
+    const uint32_t refill_min = P.refill_min ? P.refill_min : 1u;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s_seg = atomicAdd(P.cursor, 1u);
+            s_count = 0;
+            s_out = 0;
+            s_over = 0;
+            s_unit = 0;
+        }
+        for (uint32_t h = tid; h < cap; h += nthr) tstate[h] = ST_EMPTY;
+        __syncthreads();
+        const uint32_t work = s_seg;
+        if (work >= P.nseg_list) break;
+        const uint32_t seg = P.seg_list ? P.seg_list[work] : work;
+
+        // ---- warp state: the current unit -----------------------------------------------------------------
+        uint32_t Tn = 0, next = 0; // products of the unit, next product index to hand out
+        bool more = true;          // units remain
+        uint64_t kx[W];
+        uint64_t cx[XCW > 0 ? XCW : 1];
+        uint32_t ybase = 0, sincl = 0; // first right term of the lane's run minus its exclusive offset; inclusive scan
+        const uint64_t *ykp = P.yk, *ycp = P.yc;
+#pragma unroll
+        for (int w = 0; w < W; ++w) kx[w] = 0;
+        cx[0] = 0;
+        // ---- lane state: one product in flight ------------------------------------------------------------
+        bool pend = false;
+        uint64_t k[W];
+        uint64_t p[ACCW > 0 ? ACCW : 1];
+        uint32_t h = 0;
+        for (uint32_t trip = 0;; ++trip) {
+            // the overflow flag is polled every 16 trips: a full table cannot trap a lane for longer than that
+            if ((trip & 15u) == 0u && *(volatile uint32_t *)&s_over) break;
+            const uint32_t need = __ballot_sync(0xffffffffu, !pend);
+            const uint32_t nneed = __popc(need);
+            if (nneed >= refill_min || nneed == 32u) {
+                while (next >= Tn && more) {
+                    // ---- next unit: 32 left terms x one slice of their runs (converged, coalesced) ---------
+                    uint32_t u = 0;
+                    if (lane == 0) u = atomicAdd(&s_unit, 1u);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= nunits) {
+                        more = false;
+                        break;
+                    }
+                    uint32_t c = u, r = 0;
+                    if (R > 1u) {
+                        c = u / R;
+                        r = u - c * R;
+                    }
+                    const bool pb = TWO && c >= nchA;
+                    const uint64_t xi = (uint64_t)(pb ? c - nchA : c) * 32u + lane;
+                    uint32_t len = 0, y0 = 0;
+                    if (xi < (pb ? P.b.nx : P.nx)) {
+                        const uint64_t *xkp = pb ? P.b.xk : P.xk;
+                        const uint32_t *yoffp = pb ? P.b.yoff : P.yoff;
+#pragma unroll
+                        for (int w = 0; w < W; ++w) kx[w] = __ldg(xkp + xi * W + w);
+                        const uint32_t bx = __ldg((pb ? P.b.xseg : P.xseg) + xi);
+                        const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
+                        uint32_t y1;
+                        bool any = true;
+                        if (P.trunc) {
+                            const uint32_t dbits = pb ? P.b.dbits : P.dbits, ndeg = pb ? P.b.ndeg : P.ndeg;
+                            const uint32_t dlo = pb ? P.b.dlo : P.dlo;
+                            const int64_t rr = (pb ? P.b.lim_base : P.lim_base) - __ldg((pb ? P.b.xdeg : P.xdeg) + xi);
+                            any = rr >= (int64_t)dlo;
+                            const uint32_t d = rr >= (int64_t)ndeg ? ndeg - 1u : (uint32_t)(rr < 0 ? 0 : rr);
+                            y0 = __ldg(yoffp + ((size_t)by << dbits) + dlo);
+                            y1 = __ldg(yoffp + ((size_t)by << dbits) + d + 1u);
+                        } else {
+                            y0 = __ldg(yoffp + by);
+                            y1 = __ldg(yoffp + by + 1u);
+                        }
+                        if (any && y1 > y0) {
+                            len = y1 - y0;
+                            if (R > 1u) {
+                                const uint32_t a = (uint32_t)(((uint64_t)len * r) / R);
+                                const uint32_t b = (uint32_t)(((uint64_t)len * (r + 1u)) / R);
+                                y0 += a;
+                                len = b - a;
+                            }
+                        }
+                        if constexpr (XCW > 0) {
+                            const uint64_t *xcp = pb ? P.b.xc : P.xc;
+#pragma unroll
+                            for (int cc = 0; cc < XCW; ++cc) cx[cc] = __ldg(xcp + xi * XCW + cc);
+                        }
+                    }
+                    uint32_t sc = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, sc, o);
+                        if ((int)lane >= o) sc += t;
+                    }
+                    sincl = sc;
+                    ybase = y0 - (sc - len);
+                    Tn = __shfl_sync(0xffffffffu, sc, 31);
+                    next = 0;
+                    ykp = (TWO && pb) ? P.b.yk : P.yk;
+                    ycp = (TWO && pb) ? P.b.yc : P.yc;
+                }
+                if (next < Tn) {
+                    // ---- hand the next product indices to the idle lanes ------------------------------------
+                    const uint32_t avail = Tn - next;
+                    const uint32_t rank = __popc(need & lt_mask);
+                    const bool get = !pend && rank < avail;
+                    const uint32_t idx = next + (get ? rank : 0u);
+                    uint32_t own = 0; // number of lanes whose inclusive offset is <= idx = the owner lane
+#pragma unroll
+                    for (uint32_t step = 16; step; step >>= 1) {
+                        const uint32_t v = __shfl_sync(0xffffffffu, sincl, (int)(own + step - 1u));
+                        if (v <= idx) own += step;
+                    }
+                    const uint32_t yb = __shfl_sync(0xffffffffu, ybase, (int)own);
+                    uint64_t kxo[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) kxo[w] = shfl_u64(kx[w], own);
+                    uint64_t cxo[XCW > 0 ? XCW : 1];
+#pragma unroll
+                    for (int cc = 0; cc < XCW; ++cc) cxo[cc] = shfl_u64(cx[cc], own);
+                    if (get) {
+                        const size_t t = (size_t)(yb + idx);
+#pragma unroll
+                        for (int w = 0; w < W; ++w) k[w] = kxo[w] + __ldg(ykp + t * W + w); // monomial_mul
+                        if constexpr (!T::SYM) {
+                            uint64_t cy[CW];
+#pragma unroll
+                            for (int cc = 0; cc < CW; ++cc) cy[cc] = __ldg(ycp + t * CW + cc);
+                            if constexpr (T::ADD) {
+#pragma unroll
+                                for (int cc = 0; cc < CW; ++cc) p[cc] = cy[cc];
+                            } else if constexpr (T::F64) {
+                                // cf += c1*c2 with two roundings (no FP_FAST_FMA in the reference build, fma3.hpp:65-72)
+                                p[0] = (uint64_t)__double_as_longlong(
+                                    __dmul_rn(__longlong_as_double((long long)cxo[0]), __longlong_as_double((long long)cy[0])));
+                            } else {
+                                cf_mul<T::LIN, T::LACC>(cxo, cy, p);
+                            }
+                        }
+                        h = slot_hash<W>(k, P.log2_cap);
+                        pend = true;
+                    }
+                    next += nneed < avail ? nneed : avail;
+                } else if (nneed == 32u) {
+                    break; // no unit left and nothing in flight
+                }
+            }
+            bool inserted = false;
+            if (pend) {
+                // ---- one find-or-insert attempt ------------------------------------------------------------
+                const uint32_t st = *(volatile uint32_t *)&tstate[h];
+                if (st >= ST_FULL) {
+                    bool eq = true;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
+                    if (eq) {
+                        if constexpr (T::SYM) {
+                            pend = false;
+                        } else {
+                            if (st == ST_FULL && atomicExch(&tstate[h], ST_BUSY) == ST_FULL) {
+                                slot_fence(P.fence);
+                                if constexpr (T::F64) {
+                                    double a = __longlong_as_double((long long)*(volatile uint64_t *)&tacc[h]);
+                                    a = __dadd_rn(a, __longlong_as_double((long long)p[0]));
+                                    *(volatile uint64_t *)&tacc[h] = (uint64_t)__double_as_longlong(a);
+                                } else {
+                                    uint64_t a[ACCW];
+#pragma unroll
+                                    for (int l = 0; l < ACCW; ++l) a[l] = *(volatile uint64_t *)&tacc[(size_t)l * cap + h];
+                                    limbs_add<ACCW>(a, p);
+#pragma unroll
+                                    for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = a[l];
+                                }
+                                slot_fence(P.fence);
+                                *(volatile uint32_t *)&tstate[h] = ST_FULL;
+                                pend = false;
+                            }
+                            // else: the slot is being updated by another thread; try again next trip
+                        }
+                    } else {
+                        h = (h + 1u) & cmask; // the table is never completely full (max_fill < cap): probing ends
+                    }
+                } else if (st == ST_EMPTY) {
+                    if (atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
+#pragma unroll
+                        for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
+#pragma unroll
+                        for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = p[l];
+                        slot_fence(P.fence);
+                        *(volatile uint32_t *)&tstate[h] = ST_FULL;
+                        inserted = true;
+                        pend = false;
+                    }
+                }
+                // ST_INIT: another thread is writing this slot's key; look again next trip
+            }
+            // occupancy: one shared atomic per warp and trip instead of one per insertion
+            const uint32_t ins = __ballot_sync(0xffffffffu, inserted);
+            if (ins && lane == (uint32_t)(__ffs(ins) - 1)) {
+                const uint32_t n = __popc(ins);
+                if (atomicAdd(&s_count, n) + n > P.max_fill) s_over = 1;
+            }
+        }
+        __syncthreads();
+        // ---- flush: erase zeros (polynomial.hpp:1528-1540) and stage the segment -------------------
+        const bool over = s_over != 0;
+        uint64_t *ok = nullptr, *oc = nullptr;
+        if constexpr (T::SYM) {
+            if (P.okeys != nullptr) ok = P.okeys + (size_t)work * cap * W;
+        } else {
+            ok = P.okeys + (size_t)seg * cap * W;
+            oc = P.ocfs + (size_t)seg * cap * ACCW;
+        }
+        if (ok != nullptr && !over) {
+            for (uint32_t h0 = 0; h0 < cap; h0 += nthr) {
+                const uint32_t hh = h0 + tid;
+                bool live = hh < cap && tstate[hh] == ST_FULL;
+                uint64_t a[ACCW > 0 ? ACCW : 1];
+                if constexpr (!T::SYM) {
+                    if (live) {
+                        bool nz = false;
+#pragma unroll
+                        for (int l = 0; l < ACCW; ++l) {
+                            a[l] = tacc[(size_t)l * cap + hh];
+                            nz |= a[l] != 0;
+                        }
+                        if constexpr (T::F64) nz = __longlong_as_double((long long)a[0]) != 0.0;
+                        live = nz;
+                    }
+                }
+                const uint32_t b = __ballot_sync(0xffffffffu, live);
+                if (b == 0u) continue;
+                uint32_t base = 0;
+                const uint32_t leader = (uint32_t)(__ffs(b) - 1);
+                if (lane == leader) base = atomicAdd(&s_out, __popc(b));
+                base = __shfl_sync(0xffffffffu, base, (int)leader);
+                if (live) {
+                    const uint32_t pos = base + __popc(b & lt_mask);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) ok[(size_t)pos * W + w] = tkeys[(size_t)w * cap + hh];
+#pragma unroll
+                    for (int l = 0; l < ACCW; ++l) oc[(size_t)pos * ACCW + l] = a[l];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if constexpr (T::SYM) {
+                P.counts[work] = over ? 0xffffffffu : s_count;
+            } else {
+                P.counts[seg] = over ? 0u : s_out;
+            }
+            if (over) atomicAdd(&P.flags[0], 1u);
         }
     }
 }
