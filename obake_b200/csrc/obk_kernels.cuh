@@ -948,7 +948,11 @@ __global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
                         r = u - c * R;
                     }
                     const bool pb = TWO && c >= nchA;
-                    const uint64_t xi = (uint64_t)(pb ? c - nchA : c) * 32u + lane;
+                    // lane l takes left term c + l * nch: the 32 terms of a unit are far apart in the operand's order.
+                    // Neighbouring terms differ by a small exponent vector d, and x + y = (x + d) + (y - d) whenever
+                    // y - d is a term too, so products formed side by side would keep hitting the same slot and lose
+                    // the slot lock to each other (ncu: 27 % of the lock attempts failed with contiguous units).
+                    const uint64_t xi = (uint64_t)(pb ? c - nchA : c) + (uint64_t)lane * (pb ? nchB : nchA);
                     uint32_t len = 0, y0 = 0;
                     if (xi < (pb ? P.b.nx : P.nx)) {
                         const uint64_t *xkp = pb ? P.b.xk : P.xk;
@@ -1047,52 +1051,56 @@ __global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
             }
             bool inserted = false;
             if (pend) {
-                // ---- one find-or-insert attempt ------------------------------------------------------------
+                // ---- one find-or-insert attempt: a single path for "accumulate into my key's slot" and "claim an
+                // empty slot" (the two differ only in the lock value and in where the old accumulator comes from), so
+                // the lanes of a warp do not serialise on the kind of slot they found ---------------------------------
                 const uint32_t st = *(volatile uint32_t *)&tstate[h];
-                if (st >= ST_FULL) {
-                    bool eq = true;
+                bool eq = true;
 #pragma unroll
-                    for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
-                    if (eq) {
-                        if constexpr (T::SYM) {
-                            pend = false;
-                        } else {
-                            if (st == ST_FULL && atomicExch(&tstate[h], ST_BUSY) == ST_FULL) {
-                                slot_fence(P.fence);
-                                if constexpr (T::F64) {
-                                    double a = __longlong_as_double((long long)*(volatile uint64_t *)&tacc[h]);
-                                    a = __dadd_rn(a, __longlong_as_double((long long)p[0]));
-                                    *(volatile uint64_t *)&tacc[h] = (uint64_t)__double_as_longlong(a);
-                                } else {
-                                    uint64_t a[ACCW];
-#pragma unroll
-                                    for (int l = 0; l < ACCW; ++l) a[l] = *(volatile uint64_t *)&tacc[(size_t)l * cap + h];
-                                    limbs_add<ACCW>(a, p);
-#pragma unroll
-                                    for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = a[l];
-                                }
-                                slot_fence(P.fence);
-                                *(volatile uint32_t *)&tstate[h] = ST_FULL;
-                                pend = false;
-                            }
-                            // else: the slot is being updated by another thread; try again next trip
-                        }
-                    } else {
-                        h = (h + 1u) & cmask; // the table is never completely full (max_fill < cap): probing ends
-                    }
-                } else if (st == ST_EMPTY) {
-                    if (atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
+                for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
+                const bool ins = st == ST_EMPTY;
+                if constexpr (T::SYM) {
+                    if (st >= ST_FULL) {
+                        if (eq) pend = false; else h = (h + 1u) & cmask;
+                    } else if (ins && atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
 #pragma unroll
                         for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
-#pragma unroll
-                        for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = p[l];
                         slot_fence(P.fence);
                         *(volatile uint32_t *)&tstate[h] = ST_FULL;
                         inserted = true;
                         pend = false;
                     }
+                } else {
+                    if (ins || (st == ST_FULL && eq)) {
+                        if (atomicCAS(&tstate[h], st, ins ? (uint32_t)ST_INIT : (uint32_t)ST_BUSY) == st) {
+                            slot_fence(P.fence);
+                            uint64_t a[ACCW];
+#pragma unroll
+                            for (int l = 0; l < ACCW; ++l) a[l] = ins ? 0ull : *(volatile uint64_t *)&tacc[(size_t)l * cap + h];
+                            if constexpr (T::F64) {
+                                a[0] = ins ? p[0]
+                                           : (uint64_t)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a[0]),
+                                                                                      __longlong_as_double((long long)p[0])));
+                            } else {
+                                limbs_add<ACCW>(a, p);
+                            }
+                            if (ins) {
+#pragma unroll
+                                for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
+                            }
+#pragma unroll
+                            for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = a[l];
+                            slot_fence(P.fence);
+                            *(volatile uint32_t *)&tstate[h] = ST_FULL;
+                            inserted = ins;
+                            pend = false;
+                        }
+                        // else: lost the race for the slot; look again next trip
+                    } else if (st >= ST_FULL && !eq) {
+                        h = (h + 1u) & cmask; // the table is never completely full (max_fill < cap): probing ends
+                    }
+                    // ST_INIT, or my key's slot is BUSY: another thread is writing it; look again next trip
                 }
-                // ST_INIT: another thread is writing this slot's key; look again next trip
             }
             // occupancy: one shared atomic per warp and trip instead of one per insertion
             const uint32_t ins = __ballot_sync(0xffffffffu, inserted);
