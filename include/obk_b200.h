@@ -81,8 +81,9 @@ enum { OBK_SEG_HASH_POW2 = 0, OBK_SEG_KEY_MOD = 1 };
  * 2^log2_nsegs and a term of group s satisfies hash(key) & (nsegs - 1) == s, i.e. it belongs in table s of a
  * series with that many segments (series.hpp:396-400,1294-1305), so a host series can be rebuilt table-parallel.
  * seg_kind == OBK_SEG_KEY_MOD (products left in DEVICE memory, partial products of the multi-GPU path): group s
- * holds the keys with sum_w(word_w mod nsegs) mod nsegs == s (the engine's prime segmentation; nsegs = 1 after
- * the row kernel, 4093 for multi-GPU partials).
+ * holds the keys with sum_w(word_w mod nsegs) mod nsegs == s; nsegs = 1 for a product left on the device (both
+ * kernels write their terms straight to the final arrays in no particular order; `keys`/`cfs` may be allocated
+ * larger than nterms), 4093 for multi-GPU partials.
  * No coefficient is zero (polynomial.hpp:1528-1540). */
 typedef struct obk_poly_result {
     uint64_t nterms;
@@ -111,7 +112,8 @@ typedef struct obk_stats {
     uint32_t retries;       /* segment-table overflows that forced a finer segmentation */
     uint32_t kernel;        /* 0: scatter (segment-owner hash tables), 1: row-blocked dense path */
     uint32_t table_slots;   /* slots of one shared-memory segment table */
-    uint32_t group_lanes;   /* lanes cooperating on one left-operand term */
+    uint32_t group_lanes;   /* scatter kernel: slices each left term's run is cut into (work unit = 32 left terms x
+                             * one slice); row kernel: 32 (one warp per output row) */
     uint32_t mul_launches;  /* launches of the product kernel (1 + retries) */
     uint32_t total_launches;/* all kernels launched by this call */
     uint32_t reserved;
@@ -129,7 +131,8 @@ void obk_engine_destroy(obk_engine *e);
 /* Launch on the caller's stream (e.g. torch's current stream) instead of the engine's own. */
 obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream);
 /* Tunables (development / tests): "nsegs" (force the segment modulus, -1 = auto), "table_slots", "threads",
- * "group_lanes" (0 = auto), "fill_pct", "ctas_per_sm", "max_retries",
+ * "refill_min" (idle lanes of a warp that trigger the next hand-out of products), "fill_pct", "ctas_per_sm",
+ * "max_retries",
  * "kernel"    -1 auto, 0 segment-owner scatter, 1 row-blocked dense path (if the operands qualify),
  * "row_threads" 512 | 1024, "two_sided" 0 off, 1 auto, 2 always (truncated products),
  * "fence"     1: fence.acq_rel.cta around the slot lock (memory-model form of the protocol),

@@ -47,9 +47,10 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_lx_batch = 1, opt_scatter = 2, opt_refill_min = 12, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_group_lanes = 0, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
+    uint32_t last_rslices = 1;
 };
 
 namespace
@@ -362,12 +363,12 @@ void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, un
                 e->err = "internal: two-sided pass in merge mode";                                                     \
                 throw obk_fail{OBK_ERR_INVALID_ARG};                                                                   \
             } else {                                                                                                   \
-                auto fn = e->opt_scatter == 1 ? k_mul<W, M, true> : k_mul2<W, M, true>;                                \
+                auto fn = k_mul<W, M, true>;                                                                          \
                 CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
                 fn<<<grid, threads, smem, e->stream>>>(P);                                                             \
             }                                                                                                          \
         } else {                                                                                                       \
-            auto fn = e->opt_scatter == 1 ? k_mul<W, M, false> : k_mul2<W, M, false>;                                  \
+            auto fn = k_mul<W, M, false>;                                                                             \
             CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
             fn<<<grid, threads, smem, e->stream>>>(P);                                                                 \
         }                                                                                                              \
@@ -393,7 +394,7 @@ void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, un
     CU_CHECK(e, cudaGetLastError());
 }
 
-// Work units of k_mul2: 32 left terms x one slice of their runs.  Long runs are cut so that a segment yields at
+// Work units of k_mul: 32 left terms x one slice of their runs.  Long runs are cut so that a segment yields at
 // least ~4 units per warp (a rectangular product has a handful of left terms, the owner-side merge has one).
 void plan_units(obk_engine *e, MulParams &P, unsigned threads, double avg_run, uint64_t max_run)
 {
@@ -412,6 +413,7 @@ void plan_units(obk_engine *e, MulParams &P, unsigned threads, double avg_run, u
         throw obk_fail{OBK_ERR_UNSUPPORTED};
     }
     P.rslices = (uint32_t)R;
+    e->last_rslices = (uint32_t)R;
     P.refill_min = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(32, e->opt_refill_min));
 }
 
@@ -561,7 +563,6 @@ uint64_t estimate_terms(obk_engine *e, Scratch &sc, const EstimateIn &in)
     P.log2_cap = sym_log2_cap;
     const double run = (double)in.tot_mults / (double)in.nx / (double)mE;
     (void)run;
-    P.lg = 0;
     P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
     P.counts = dcounts;
     P.flags = dflags;
@@ -799,8 +800,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         P.nseg_list = mR;
         P.cursor = dflags + 1;
         P.log2_cap = sym_log2_cap;
-        P.lg = 0;
-        P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
+            P.max_fill = (uint32_t)((uint64_t)sym_cap * 9 / 10);
         P.okeys = stage;
         P.counts = counts;
         P.flags = dflags;
@@ -1310,7 +1310,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                             !f64 && hs_anyneg == 0, rq.rank, rq.nranks, owner, st);
         }
 
-        uint64_t *rk = nullptr, *rc = nullptr, *off64 = nullptr;
+        uint64_t *rk = nullptr, *rc = nullptr;
         uint64_t total = 0;
         uint32_t nsegs = 1;
         float ms_prep_extra = 0;
@@ -1322,10 +1322,6 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             st.nsegs = rows.m;
             st.nterms_out = total;
             st.kernel = 1;
-            off64 = sc.alloc<uint64_t>(2);
-            const uint64_t h2[2] = {0, total};
-            CU_CHECK(e, cudaMemcpyAsync(off64, h2, 16, cudaMemcpyHostToDevice, s));
-            CU_CHECK(e, cudaStreamSynchronize(s));
             CU_CHECK(e, cudaEventRecord(e->ev[3], s));
         } else {
             // ---- product-size estimate (poly_mul_estimate_product_size, polynomial.hpp:478-794) -------------
@@ -1348,8 +1344,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             CU_CHECK(e, cudaEventRecord(e->ev[3], s));
 
             // ---- sort the right operand, multiply, retry with a finer segmentation on table overflow --------
-            uint64_t *stage_k = nullptr, *stage_c = nullptr;
-            uint32_t *counts = nullptr, *offs = nullptr, *dflags = nullptr;
+            uint32_t *dflags = nullptr;
             for (unsigned attempt = 0;; ++attempt) {
                 if (((uint64_t)nsegs << dbits) > max_bins) {
                     e->err = "The homomorphic multiplication of two polynomials needs more segment bins than the maximum "
@@ -1374,13 +1369,13 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                                                                                                        L.is_signed, xseg);
                     e->launches += 1;
                 }
-                stage_k = sc.alloc<uint64_t>((uint64_t)nsegs * cap * W);
-                stage_c = sc.alloc<uint64_t>((uint64_t)nsegs * cap * accw);
-                counts = sc.alloc<uint32_t>((uint64_t)nsegs + 1);
-                offs = sc.alloc<uint32_t>((uint64_t)nsegs + 2);
+                // final term arrays, sized for the worst case that does not overflow a table (max_fill terms per
+                // segment): the kernel writes every segment straight to its reserved range, no staging or compaction
+                const uint64_t out_bound = std::max<uint64_t>((uint64_t)nsegs * max_fill, 1);
+                rk = sc.alloc<uint64_t>(out_bound * W);
+                rc = sc.alloc<uint64_t>(out_bound * accw);
                 dflags = sc.alloc<uint32_t>(4);
                 CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
-                CU_CHECK(e, cudaMemsetAsync(counts, 0, ((uint64_t)nsegs + 1) * 4, s));
                 MulParams P{};
                 uint64_t *zero_key = nullptr;
                 if (rq.merge) {
@@ -1448,47 +1443,25 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 }
                 P.cursor = dflags + 1;
                 P.log2_cap = log2_cap;
-                uint32_t lg = 0;
-                if (rq.merge) {
-                    while ((1u << (lg + 1)) <= threads) ++lg;
-                } else if (e->opt_group_lanes > 0) {
-                    while ((1ll << (lg + 1)) <= e->opt_group_lanes && lg < 5) ++lg;
-                } else {
-                    // one lane per left term: with the per-lane state machine this is the fastest mapping on every
-                    // untruncated workload measured (S12 38.6 vs 30.2 G/s at 4 lanes; F20 58.8 vs 38.2 G/s at 32 lanes).
-                    // Two-sided truncation leaves few left terms with long, very uneven runs (a degree-0 term pairs
-                    // with a whole bucket): split each run over a warp so that no single lane owns it.
-                    lg = 0;
-                    if (ts.on) {
-                        const double run = (double)tot_mults / (double)std::max<uint64_t>(ts.na + ts.nb, 1) / (double)nsegs;
-                        lg = run >= 16.0 ? 5 : (run >= 4.0 ? 3 : 0);
-                    }
-                    // rectangular products (a handful of left terms against a long right operand): fewer left terms
-                    // than threads would leave most lanes idle -- spread each left term's run over threads/nx lanes
-                    const uint64_t nleft = std::max<uint64_t>(ts.on ? std::max(ts.na, ts.nb) : snx, 1);
-                    while ((nleft << (lg + 1)) <= threads) ++lg;
-                }
-                P.lg = lg;
-                st.group_lanes = 1u << lg;
                 P.max_fill = max_fill;
                 P.fence = e->opt_fence ? 1u : 0u;
-                P.lx_batch = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(32, e->opt_lx_batch));
-                P.okeys = stage_k;
-                P.ocfs = stage_c;
-                P.counts = counts;
+                P.okeys = rk;
+                P.ocfs = rc;
+                P.counts = nullptr;
                 P.flags = dflags;
+                P.out_cursor = dflags + 2;
                 plan_units(e, P, threads,
                            (double)tot_mults / (double)std::max<uint64_t>(P.nx + (P.npass > 1 ? P.b.nx : 0), 1) / (double)nsegs,
                            std::max(snx, ny));
+                st.group_lanes = e->last_rslices;
                 CU_CHECK(e, cudaEventRecord(e->ev[5], s));
                 launch_mul(e, W, mode, P, (unsigned)std::min<uint64_t>(std::max<uint32_t>(P.nseg_list, 1), (uint64_t)e->sm_count * (uint64_t)std::max<int64_t>(1, e->opt_ctas_per_sm)), threads, smem_mul);
                 CU_CHECK(e, cudaEventRecord(e->ev[6], s));
                 st.mul_launches += 1;
-                device_scan(e, sc, counts, offs, nsegs);
-                uint32_t hflag[4], htotal = 0;
+                uint32_t hflag[4];
                 CU_CHECK(e, cudaMemcpyAsync(hflag, dflags, 16, cudaMemcpyDeviceToHost, s));
-                CU_CHECK(e, cudaMemcpyAsync(&htotal, offs + nsegs, 4, cudaMemcpyDeviceToHost, s));
                 CU_CHECK(e, cudaStreamSynchronize(s));
+                const uint32_t htotal = hflag[2];
                 float ms = 0;
                 cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
                 ms_prep_extra += ms;
@@ -1508,11 +1481,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     total = htotal;
                     break;
                 }
-                // some segment's table filled up: finer segmentation (the HBM staging is re-made)
-                sc.release(stage_k);
-                sc.release(stage_c);
-                sc.release(counts);
-                sc.release(offs);
+                // some segment's table filled up: finer segmentation
+                sc.release(rk);
+                sc.release(rc);
                 sc.release(dflags);
                 st.retries += 1;
                 if ((int64_t)st.retries > e->opt_max_retries || rq.merge || owner) {
@@ -1527,17 +1498,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             st.nsegs = nsegs;
             st.nterms_out = total;
 
-            // ---- segment-ordered dense result ---------------------------------------------------------------
-            rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * W);
-            rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
-            off64 = sc.alloc<uint64_t>((uint64_t)nsegs + 1);
-            k_compact<<<(unsigned)std::min<uint64_t>(nsegs, 4096), 256, 0, s>>>(stage_k, stage_c, counts, offs, cap, W, accw, rk, rc,
-                                                                            off64, nsegs);
-            e->launches += 1;
-            CU_CHECK(e, cudaGetLastError());
-            sc.release(stage_k);
-            sc.release(stage_c);
-
+            sc.release(dflags);
         }
 
         // ---- regroup the way a series stores its terms: table hash & (2^k - 1) (series.hpp:396-400) ---------
@@ -1609,12 +1570,13 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
 
         ResultOwner *own = static_cast<ResultOwner *>(out->owner);
         if (!own) {
+            // a product left on the device is one group: both kernels write their terms in no particular order
             own = new ResultOwner{e};
             out->owner = own;
-            const size_t ngr = rows.done ? 1 : (size_t)nsegs;
-            out_groups = (uint32_t)ngr;
-            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * (ngr + 1));
-            CU_CHECK(e, cudaMemcpyAsync(own->seg_offsets, off64, (ngr + 1) * 8, cudaMemcpyDeviceToHost, s));
+            out_groups = 1;
+            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * 2);
+            own->seg_offsets[0] = 0;
+            own->seg_offsets[1] = total;
         }
         st.d2h_bytes += ((uint64_t)out_groups + 1) * 8;
         out->nterms = total;
@@ -1789,13 +1751,10 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "row_threads") e->opt_row_threads = value;
     else if (n == "two_sided") e->opt_two_sided = value;
     else if (n == "ctas_per_sm") e->opt_ctas_per_sm = value;
-    else if (n == "lx_batch") e->opt_lx_batch = value;
-    else if (n == "scatter") e->opt_scatter = value;
     else if (n == "refill_min") e->opt_refill_min = value;
     else if (n == "mgpu_owner") e->opt_mgpu_owner = value;
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
-    else if (n == "group_lanes") e->opt_group_lanes = value;
     else if (n == "kernel") e->opt_kernel = value;
     else if (n == "max_retries") e->opt_max_retries = value;
     else if (n == "fill_pct") e->opt_fill_pct = value;

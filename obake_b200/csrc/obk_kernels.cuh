@@ -590,11 +590,10 @@ struct MulParams {
     uint32_t *cursor;
     // shared-memory table geometry
     uint32_t log2_cap;
-    uint32_t lg; // log2(lanes per left term)
     uint32_t max_fill;
     uint32_t fence; // 1: fence.acq_rel.cta around the slot lock (validation build of the protocol)
     uint32_t lx_batch; // lanes that must be waiting for a new left term before the LX step is issued (1 = always)
-    // k_mul2 (warp-cooperative expansion): every left term's run is cut into `rslices` slices (work unit = 32 left
+    // k_mul (warp-cooperative expansion): every left term's run is cut into `rslices` slices (work unit = 32 left
     // terms x one slice) and idle lanes are refilled once at least `refill_min` of a warp's lanes are idle
     uint32_t rslices, refill_min;
     // staging output: [segment][cap] slots, counts per segment
@@ -602,6 +601,9 @@ struct MulParams {
     uint64_t *ocfs;
     uint32_t *counts;
     uint32_t *flags; // [0] = number of segments whose table overflowed
+    // k_mul: when set, okeys/ocfs are the FINAL term arrays and every segment reserves its range with one atomic
+    // on this counter (its final value is the number of terms); counts is then unused
+    uint32_t *out_cursor;
 };
 
 enum : uint32_t { ST_EMPTY = 0, ST_INIT = 1, ST_FULL = 2, ST_BUSY = 3 };
@@ -631,241 +633,26 @@ __device__ __forceinline__ void slot_fence(uint32_t fence)
     if (fence) asm volatile("fence.acq_rel.cta;" ::: "memory"); else asm volatile("" ::: "memory");
 }
 
-// One CTA owns one output segment (polynomial.hpp:1421-1553, dense_par_functor): its open-addressing
-// table lives in shared memory; every left term x_i pairs with the right bucket (seg - bucket(x_i))
-// mod nsegs (:1449-1456); truncation keeps the prefix of that bucket with deg_j <= limit - deg_i
-// (compute_end_idx2, :1187-1238 -- the bucket is degree-sorted, so the prefix is one table lookup).
-template <int W, int MODE, bool TWO>
-__global__ void __launch_bounds__(1024) k_mul(const MulParams P)
-{
-    using T = CfTraits<MODE>;
-    constexpr int ACCW = T::SYM ? 0 : T::LACC;
-    constexpr int CW = T::SYM ? 0 : T::LIN;         // limbs of a right-operand coefficient
-    constexpr int XCW = (T::SYM || T::ADD) ? 0 : CW;  // limbs of a left-operand coefficient
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t cap = 1u << P.log2_cap;
-    uint64_t *tkeys = reinterpret_cast<uint64_t *>(smem_raw);           // [W][cap]
-    uint64_t *tacc = tkeys + (size_t)W * cap;                          // [ACCW][cap]
-    uint32_t *tstate = reinterpret_cast<uint32_t *>(tacc + (size_t)ACCW * cap); // [cap]
-    __shared__ uint32_t s_seg, s_count, s_out, s_over;
-
-    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-    const uint32_t G = 1u << P.lg;
-    const uint32_t gid = tid >> P.lg, lg_lane = tid & (G - 1), ngroups = nthr >> P.lg;
-    const uint32_t cmask = cap - 1u;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            s_seg = atomicAdd(P.cursor, 1u);
-            s_count = 0;
-            s_out = 0;
-            s_over = 0;
-        }
-        for (uint32_t h = tid; h < cap; h += nthr) tstate[h] = ST_EMPTY;
-        __syncthreads();
-        const uint32_t work = s_seg;
-        if (work >= P.nseg_list) break;
-        const uint32_t seg = P.seg_list ? P.seg_list[work] : work;
-
-        // Per-lane state machine.  A lane walks its own sequence of (left term, right term) pairs and keeps at most
-        // one product in flight; every trip of the warp-converged loop below lets EVERY lane advance one step --
-        // fetch the next left term (LX), form the next product (LY), or make one probe attempt (LP).  A lane that
-        // finishes its probe early starts on its next pair in the following trip instead of idling until the slowest
-        // lane of a 32-product batch is done: the nested-loop form of this kernel ran with 7-8 of 32 lanes active
-        // (ncu, profiles/r01a_*), i.e. 18-22 warp instructions per product.
-        enum : uint32_t { LX = 0, LY = 1, LP = 2, LDONE = 3 };
-        uint32_t lst = LX, lpass = 0;
-        uint64_t xi = (uint64_t)gid - (uint64_t)ngroups; // wraps; the first LX step adds ngroups back
-        uint32_t t = 0, y1 = 0, h = 0;
-        uint64_t kx[W], k[W];
-        uint64_t cx[XCW > 0 ? XCW : 1];
-        uint64_t p[ACCW > 0 ? ACCW : 1];
-        for (uint32_t trip = 0;; ++trip) {
-            // the overflow flag is polled every 16 trips: a full table cannot trap a lane for longer than that
-            if ((trip & 15u) == 0u && *(volatile uint32_t *)&s_over) break;
-            if (!__any_sync(0xffffffffu, lst != LDONE)) break;
-            // The LX body (next left term: ~40 instructions, 4-5 loads) is worth issuing only when several lanes
-            // need it: lanes wait in LX until at least `lx_batch` of them do, or nothing else can make progress.
-            const uint32_t m_lx = __ballot_sync(0xffffffffu, lst == LX);
-            const uint32_t m_busy = __ballot_sync(0xffffffffu, lst == LY || lst == LP);
-            const bool run_lx = __popc(m_lx) >= (int)(P.lx_batch ? P.lx_batch : 1u) || m_busy == 0u;
-            if (run_lx && lst == LX) {
-                xi += ngroups;
-                const bool pb = TWO && lpass != 0;
-                if (xi >= (pb ? P.b.nx : P.nx)) {
-                    if (TWO && !pb && P.npass > 1) {
-                        lpass = 1; // roles swapped: continue with the second pass's left list
-                        xi = (uint64_t)gid - (uint64_t)ngroups;
-                    } else {
-                        lst = LDONE;
-                    }
-                } else {
-                    const uint64_t *xkp = pb ? P.b.xk : P.xk;
-                    const uint32_t *yoffp = pb ? P.b.yoff : P.yoff;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) kx[w] = __ldg(xkp + xi * W + w);
-                    const uint32_t bx = __ldg((pb ? P.b.xseg : P.xseg) + xi);
-                    const uint32_t by = seg >= bx ? seg - bx : seg + P.nsegs - bx; // (seg - bx) mod m
-                    uint32_t y0;
-                    bool any = true;
-                    if (P.trunc) {
-                        const uint32_t dbits = pb ? P.b.dbits : P.dbits, ndeg = pb ? P.b.ndeg : P.ndeg;
-                        const uint32_t dlo = pb ? P.b.dlo : P.dlo;
-                        const int64_t r = (pb ? P.b.lim_base : P.lim_base) - __ldg((pb ? P.b.xdeg : P.xdeg) + xi);
-                        any = r >= (int64_t)dlo;
-                        const uint32_t d = r >= (int64_t)ndeg ? ndeg - 1u : (uint32_t)(r < 0 ? 0 : r);
-                        y0 = __ldg(yoffp + ((size_t)by << dbits) + dlo);
-                        y1 = __ldg(yoffp + ((size_t)by << dbits) + d + 1u);
-                    } else {
-                        y0 = __ldg(yoffp + by);
-                        y1 = __ldg(yoffp + by + 1u);
-                    }
-                    t = y0 + lg_lane;
-                    if (any && t < y1) {
-                        const uint64_t *xcp = pb ? P.b.xc : P.xc;
-#pragma unroll
-                        for (int c = 0; c < XCW; ++c) cx[c] = __ldg(xcp + xi * XCW + c);
-                        lst = LY;
-                    }
-                }
-            }
-            if (lst == LY) {
-#pragma unroll
-                for (int w = 0; w < W; ++w) k[w] = kx[w] + __ldg(((TWO && lpass) ? P.b.yk : P.yk) + (size_t)t * W + w); // monomial_mul
-                if constexpr (!T::SYM) {
-                    uint64_t cy[CW];
-#pragma unroll
-                    for (int c = 0; c < CW; ++c) cy[c] = __ldg(((TWO && lpass) ? P.b.yc : P.yc) + (size_t)t * CW + c);
-                    if constexpr (T::ADD) {
-#pragma unroll
-                        for (int c = 0; c < CW; ++c) p[c] = cy[c];
-                    } else if constexpr (T::F64) {
-                        // cf += c1*c2 with two roundings (no FP_FAST_FMA in the reference build, fma3.hpp:65-72)
-                        p[0] = (uint64_t)__double_as_longlong(
-                            __dmul_rn(__longlong_as_double((long long)cx[0]), __longlong_as_double((long long)cy[0])));
-                    } else {
-                        cf_mul<T::LIN, T::LACC>(cx, cy, p);
-                    }
-                }
-                h = slot_hash<W>(k, P.log2_cap);
-                t += G;
-                lst = LP;
-            }
-            if (lst == LP) {
-                // ---- one find-or-insert attempt ------------------------------------------------------------
-                bool fin = false;
-                const uint32_t st = *(volatile uint32_t *)&tstate[h];
-                if (st >= ST_FULL) {
-                    bool eq = true;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
-                    if (eq) {
-                        if constexpr (T::SYM) {
-                            fin = true;
-                        } else {
-                            if (st == ST_FULL && atomicExch(&tstate[h], ST_BUSY) == ST_FULL) {
-                                slot_fence(P.fence);
-                                if constexpr (T::F64) {
-                                    double a = __longlong_as_double((long long)*(volatile uint64_t *)&tacc[h]);
-                                    a = __dadd_rn(a, __longlong_as_double((long long)p[0]));
-                                    *(volatile uint64_t *)&tacc[h] = (uint64_t)__double_as_longlong(a);
-                                } else {
-                                    uint64_t a[ACCW];
-#pragma unroll
-                                    for (int l = 0; l < ACCW; ++l) a[l] = *(volatile uint64_t *)&tacc[(size_t)l * cap + h];
-                                    limbs_add<ACCW>(a, p);
-#pragma unroll
-                                    for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = a[l];
-                                }
-                                slot_fence(P.fence);
-                                *(volatile uint32_t *)&tstate[h] = ST_FULL;
-                                fin = true;
-                            }
-                            // else: the slot is being updated by another thread; try again next trip
-                        }
-                    } else {
-                        h = (h + 1u) & cmask; // the table is never completely full (max_fill < cap): probing ends
-                    }
-                } else if (st == ST_EMPTY) {
-                    if (atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
-#pragma unroll
-                        for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
-#pragma unroll
-                        for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = p[l];
-                        slot_fence(P.fence);
-                        *(volatile uint32_t *)&tstate[h] = ST_FULL;
-                        if (atomicAdd(&s_count, 1u) + 1u > P.max_fill) s_over = 1;
-                        fin = true;
-                    }
-                }
-                // ST_INIT: another thread is writing this slot's key; look again next trip
-                if (fin) lst = t < y1 ? LY : LX;
-            }
-        }
-        __syncthreads();
-        // ---- flush: erase zeros (polynomial.hpp:1528-1540) and stage the segment -------------------
-        const bool over = s_over != 0;
-        if constexpr (T::SYM) {
-            if (P.okeys != nullptr && !over) {
-                // symbolic product: stage the distinct keys of this segment (row-blocked path)
-                uint64_t *ok = P.okeys + (size_t)work * cap * W;
-                for (uint32_t h = tid; h < cap; h += nthr) {
-                    if (tstate[h] != ST_FULL) continue;
-                    const uint32_t pos = atomicAdd(&s_out, 1u);
-#pragma unroll
-                    for (int w = 0; w < W; ++w) ok[(size_t)pos * W + w] = tkeys[(size_t)w * cap + h];
-                }
-            }
-            if (tid == 0) {
-                P.counts[work] = over ? 0xffffffffu : s_count;
-                if (over) atomicAdd(&P.flags[0], 1u);
-            }
-        } else {
-            if (!over) {
-                uint64_t *ok = P.okeys + (size_t)seg * cap * W;
-                uint64_t *oc = P.ocfs + (size_t)seg * cap * ACCW;
-                for (uint32_t h = tid; h < cap; h += nthr) {
-                    if (tstate[h] != ST_FULL) continue;
-                    uint64_t a[ACCW];
-                    bool nz = false;
-#pragma unroll
-                    for (int l = 0; l < ACCW; ++l) {
-                        a[l] = tacc[(size_t)l * cap + h];
-                        nz |= a[l] != 0;
-                    }
-                    if constexpr (T::F64) nz = __longlong_as_double((long long)a[0]) != 0.0;
-                    if (!nz) continue;
-                    const uint32_t pos = atomicAdd(&s_out, 1u);
-#pragma unroll
-                    for (int w = 0; w < W; ++w) ok[(size_t)pos * W + w] = tkeys[(size_t)w * cap + h];
-#pragma unroll
-                    for (int l = 0; l < ACCW; ++l) oc[(size_t)pos * ACCW + l] = a[l];
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                P.counts[seg] = over ? 0u : s_out;
-                if (over) atomicAdd(&P.flags[0], 1u);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// k_mul2 -- the same segment-owner product with WARP-COOPERATIVE expansion of the term products.
+// k_mul -- the segment-owner product.
 //
-// k_mul gives every lane its own left term and lets it walk that term's run; lanes sit in different phases of
-// their walk, so each trip of the warp loop issues the "next left term", "next product" and "probe" bodies for
-// a third of the lanes each (ncu: 12 of 32 threads active, 13 warp instructions per product).  Here a WARP takes
-// a work unit of 32 consecutive left terms (loaded converged and coalesced), scans their run lengths, and the
-// products of the unit form one index space [0, T): any idle lane is handed the next product index, finds the
-// owning left term by a 5-step binary search over the scanned lengths (shuffles), fetches that term's key and
-// coefficient from the owner lane and forms the product.  Product formation therefore always runs with every idle
-// lane busy, whatever the run lengths are (5 terms in S12, 10^5 in a rectangular product, 0 in most runs of a
-// heavily truncated one), and the only divergent code left is the probe attempt itself.  Units are handed out by
-// a per-CTA counter; `rslices` cuts long runs so that a product with a handful of left terms still yields enough
-// units for 32 warps.  Slot protocol, truncation window, two-sided passes and flush are those of k_mul.
+// One CTA owns one output segment (polynomial.hpp:1421-1553, dense_par_functor): its open-addressing table lives
+// in shared memory; every left term x_i pairs with the right bucket (seg - bucket(x_i)) mod nsegs (:1449-1456);
+// truncation keeps the prefix of that bucket with deg_j <= limit - deg_i (compute_end_idx2, :1187-1238 -- the
+// bucket is degree-sorted, so the prefix is one table lookup).
+//
+// Term products are expanded WARP-COOPERATIVELY.  (The first two versions of this kernel gave every lane its own
+// left term and let it walk that term's run; lanes then sit in different phases of their walk and each trip of the
+// warp loop issues the "next left term", "next product" and "probe" bodies for a third of the lanes each -- ncu:
+// 12 of 32 threads active, 13 warp instructions per product; profiles/r01_k_mul_S12_*.)  Here a WARP takes a work
+// unit of 32 left terms, scans their run lengths, and the products of the unit form one index space [0, T): any
+// idle lane is handed the next product index, finds the owning left term by a 5-step binary search over the
+// scanned lengths (shuffles), fetches that term's key and coefficient from the owner lane and forms the product.
+// Product formation therefore runs with every idle lane busy whatever the run lengths are (5 terms in S12, 10^5
+// in a rectangular product, 0 in most runs of a heavily truncated one), and the only divergent code left is the
+// probe attempt itself.  Units are handed out by a per-CTA counter; `rslices` cuts long runs so that a product
+// with a handful of left terms (or the one-term "left operand" of the owner-side merge) still yields enough units
+// for 32 warps.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, uint32_t src)
 {
@@ -875,7 +662,7 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, uint32_t src)
 }
 
 template <int W, int MODE, bool TWO>
-__global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
+__global__ void __launch_bounds__(1024) k_mul(const MulParams P)
 {
     using T = CfTraits<MODE>;
     constexpr int ACCW = T::SYM ? 0 : T::LACC;
@@ -886,7 +673,7 @@ __global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
     uint64_t *tkeys = reinterpret_cast<uint64_t *>(smem_raw);                    // [W][cap]
     uint64_t *tacc = tkeys + (size_t)W * cap;                                   // [ACCW][cap]
     uint32_t *tstate = reinterpret_cast<uint32_t *>(tacc + (size_t)ACCW * cap); // [cap]
-    __shared__ uint32_t s_seg, s_count, s_out, s_over, s_unit;
+    __shared__ uint32_t s_seg, s_count, s_out, s_over, s_unit, s_base, s_pos;
 
     const uint32_t tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -926,10 +713,17 @@ __global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
         bool pend = false;
         uint64_t k[W];
         uint64_t p[ACCW > 0 ? ACCW : 1];
-        uint32_t h = 0;
+        uint32_t h = 0, nins = 0;
         for (uint32_t trip = 0;; ++trip) {
-            // the overflow flag is polled every 16 trips: a full table cannot trap a lane for longer than that
-            if ((trip & 15u) == 0u && *(volatile uint32_t *)&s_over) break;
+            // Every 16 trips: report this warp's insertions (one shared atomic per warp instead of one per insertion;
+            // the table has 10 % of headroom above max_fill and a lane never writes outside it) and poll the overflow
+            // flag, so a full table cannot trap a lane for longer than that.
+            if ((trip & 15u) == 0u) {
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, nins);
+                nins = 0;
+                if (tot && lane == 0 && atomicAdd(&s_count, tot) + tot > P.max_fill) s_over = 1;
+                if (__any_sync(0xffffffffu, *(volatile uint32_t *)&s_over != 0u)) break; // warp-uniform exit
+            }
             const uint32_t need = __ballot_sync(0xffffffffu, !pend);
             const uint32_t nneed = __popc(need);
             if (nneed >= refill_min || nneed == 32u) {
@@ -1102,52 +896,78 @@ __global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
                     // ST_INIT, or my key's slot is BUSY: another thread is writing it; look again next trip
                 }
             }
-            // occupancy: one shared atomic per warp and trip instead of one per insertion
-            const uint32_t ins = __ballot_sync(0xffffffffu, inserted);
-            if (ins && lane == (uint32_t)(__ffs(ins) - 1)) {
-                const uint32_t n = __popc(ins);
-                if (atomicAdd(&s_count, n) + n > P.max_fill) s_over = 1;
-            }
+            nins += inserted ? 1u : 0u;
+        }
+        // insertions not yet reported (the loop was left between two polls)
+        {
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, nins);
+            if (tot && lane == 0 && atomicAdd(&s_count, tot) + tot > P.max_fill) s_over = 1;
         }
         __syncthreads();
-        // ---- flush: erase zeros (polynomial.hpp:1528-1540) and stage the segment -------------------
+        // ---- flush: erase zeros (polynomial.hpp:1528-1540) and write the segment out --------------------------
+        // Products (P.out_cursor set): the segment's non-zero terms are counted first, one global atomic reserves
+        // their range in the FINAL arrays and the terms are written there -- no staging area, no compaction pass.
+        // Symbolic products that keep their keys (row path) stage them per segment for k_compact.
         const bool over = s_over != 0;
         uint64_t *ok = nullptr, *oc = nullptr;
+        bool direct = false;
         if constexpr (T::SYM) {
             if (P.okeys != nullptr) ok = P.okeys + (size_t)work * cap * W;
         } else {
-            ok = P.okeys + (size_t)seg * cap * W;
-            oc = P.ocfs + (size_t)seg * cap * ACCW;
+            direct = P.out_cursor != nullptr;
+            ok = direct ? P.okeys : P.okeys + (size_t)seg * cap * W;
+            oc = direct ? P.ocfs : P.ocfs + (size_t)seg * cap * ACCW;
+        }
+        auto slot_live = [&](uint32_t hh, uint64_t(&a)[ACCW > 0 ? ACCW : 1]) -> bool {
+            bool live = hh < cap && tstate[hh] == ST_FULL;
+            if constexpr (!T::SYM) {
+                if (live) {
+                    bool nz = false;
+#pragma unroll
+                    for (int l = 0; l < ACCW; ++l) {
+                        a[l] = tacc[(size_t)l * cap + hh];
+                        nz |= a[l] != 0;
+                    }
+                    if constexpr (T::F64) nz = __longlong_as_double((long long)a[0]) != 0.0;
+                    live = nz;
+                }
+            }
+            return live;
+        };
+        if (direct && !over) {
+            uint32_t mine = 0;
+            for (uint32_t h0 = 0; h0 < cap; h0 += nthr) {
+                uint64_t a[ACCW > 0 ? ACCW : 1];
+                mine += slot_live(h0 + tid, a) ? 1u : 0u;
+            }
+            mine = __reduce_add_sync(0xffffffffu, mine);
+            if (lane == 0 && mine) atomicAdd(&s_out, mine);
+            __syncthreads();
+            if (tid == 0) {
+                s_base = atomicAdd(P.out_cursor, s_out);
+                s_pos = 0;
+            }
+            __syncthreads();
         }
         if (ok != nullptr && !over) {
+            const size_t obase = direct ? (size_t)s_base : 0;
+            uint32_t *ctr = direct ? &s_pos : &s_out;
             for (uint32_t h0 = 0; h0 < cap; h0 += nthr) {
                 const uint32_t hh = h0 + tid;
-                bool live = hh < cap && tstate[hh] == ST_FULL;
                 uint64_t a[ACCW > 0 ? ACCW : 1];
-                if constexpr (!T::SYM) {
-                    if (live) {
-                        bool nz = false;
-#pragma unroll
-                        for (int l = 0; l < ACCW; ++l) {
-                            a[l] = tacc[(size_t)l * cap + hh];
-                            nz |= a[l] != 0;
-                        }
-                        if constexpr (T::F64) nz = __longlong_as_double((long long)a[0]) != 0.0;
-                        live = nz;
-                    }
-                }
+                const bool live = slot_live(hh, a);
                 const uint32_t b = __ballot_sync(0xffffffffu, live);
                 if (b == 0u) continue;
                 uint32_t base = 0;
                 const uint32_t leader = (uint32_t)(__ffs(b) - 1);
-                if (lane == leader) base = atomicAdd(&s_out, __popc(b));
+                if (lane == leader) base = atomicAdd(ctr, __popc(b));
                 base = __shfl_sync(0xffffffffu, base, (int)leader);
                 if (live) {
-                    const uint32_t pos = base + __popc(b & lt_mask);
+                    const size_t pos = obase + base + __popc(b & lt_mask);
 #pragma unroll
-                    for (int w = 0; w < W; ++w) ok[(size_t)pos * W + w] = tkeys[(size_t)w * cap + hh];
+                    for (int w = 0; w < W; ++w) ok[pos * W + w] = tkeys[(size_t)w * cap + hh];
 #pragma unroll
-                    for (int l = 0; l < ACCW; ++l) oc[(size_t)pos * ACCW + l] = a[l];
+                    for (int l = 0; l < ACCW; ++l) oc[pos * ACCW + l] = a[l];
                 }
             }
         }
@@ -1156,7 +976,7 @@ __global__ void __launch_bounds__(1024) k_mul2(const MulParams P)
             if constexpr (T::SYM) {
                 P.counts[work] = over ? 0xffffffffu : s_count;
             } else {
-                P.counts[seg] = over ? 0u : s_out;
+                if (!direct) P.counts[seg] = over ? 0u : s_out;
             }
             if (over) atomicAdd(&P.flags[0], 1u);
         }

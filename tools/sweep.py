@@ -33,7 +33,7 @@ def main():
                 st = p.stats
                 best = st if best is None or st["ms_mul"] < best["ms_mul"] else best
                 p.free()
-            print(dict(zip(keys, combo)), "ms_mul %.3f ms_total %.3f nsegs %d slots %d lanes %d retries %d Gprod/s %.2f" % (
+            print(dict(zip(keys, combo)), "ms_mul %.3f ms_total %.3f nsegs %d slots %d slices %d retries %d Gprod/s %.2f" % (
                 best["ms_mul"], best["ms_total"], best["nsegs"], best["table_slots"], best["group_lanes"], best["retries"],
                 best["term_products"] / best["ms_mul"] / 1e6), flush=True)
         except Exception as ex:  # noqa: BLE001
