@@ -175,6 +175,21 @@ obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk
 obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t nsegs, uint32_t result_mem,
                           obk_poly_result *out, obk_stats *stats);
 
+/* ---- the steps either side of the product, on the same device layout ------------------------------
+ * Operands and results may stay in DEVICE memory, so a chain such as f *= g; h = f + 1; truncate(h) never leaves
+ * HBM (benchmark/dense.hpp:28-32, rectangular_01.cpp:42-47, audi_01.cpp:32-42). */
+
+/* Series addition / subtraction of two polynomials over the SAME symbol set (series.hpp:2195-2991, the
+ * identical-symbol-set branch of series_default_addsub_impl): out = x + y or x - y, exact for integers (the result
+ * uses as many limbs as the sum needs, at most 3), terms that cancel are erased. */
+obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int subtract, uint32_t result_mem,
+                           obk_poly_result *out, obk_stats *stats);
+
+/* truncate_degree(x, limit) / truncate_p_degree(x, limit, symbols) (polynomial.hpp:2364-2445): keeps the terms
+ * with !(limit < degree), the degree taken in the key's integer type T as in obk_trunc. */
+obk_status obk_poly_truncate_degree(obk_engine *e, const obk_poly_view *x, const obk_trunc *t, uint32_t result_mem,
+                                    obk_poly_result *out, obk_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,7 @@ SYMBOLS = [
     "obk_engine_create", "obk_engine_destroy", "obk_engine_set_stream", "obk_engine_set_option",
     "obk_last_error", "obk_status_string", "obk_version", "obk_poly_mul", "obk_result_free",
     "obk_overflow_check", "obk_key_degrees", "obk_poly_mul_partial", "obk_poly_merge",
+    "obk_poly_addsub", "obk_poly_truncate_degree",
 ]
 
 _LIB = None
@@ -99,5 +100,11 @@ def lib():
     L.obk_poly_merge.restype = C.c_int
     L.obk_poly_merge.argtypes = [C.c_void_p, C.POINTER(PolyView), C.c_uint32, C.c_uint32, C.POINTER(PolyResult),
                                  C.POINTER(Stats)]
+    L.obk_poly_addsub.restype = C.c_int
+    L.obk_poly_addsub.argtypes = [C.c_void_p, C.POINTER(PolyView), C.POINTER(PolyView), C.c_int, C.c_uint32,
+                                  C.POINTER(PolyResult), C.POINTER(Stats)]
+    L.obk_poly_truncate_degree.restype = C.c_int
+    L.obk_poly_truncate_degree.argtypes = [C.c_void_p, C.POINTER(PolyView), C.POINTER(Trunc), C.c_uint32,
+                                           C.POINTER(PolyResult), C.POINTER(Stats)]
     _LIB = L
     return L

@@ -938,6 +938,142 @@ void set_empty_result(obk_poly_result *out, const obk_poly_view *x, int cf_limbs
     out->owner = own;
 }
 
+struct TailIn {
+    uint64_t *rk, *rc; // device term arrays (scratch-owned)
+    uint64_t total;
+    int W, accw;
+    bool f64;
+    uint32_t is_signed;
+    uint64_t tot_mults; // sparsity hint for the series-table sizing rule
+    uint32_t result_mem;
+    uint32_t nranks; // > 1 and !owner: multi-GPU partial product, grouped by key mod OBK_EXCHANGE_MOD
+    bool owner;
+    uint32_t nsegs_out; // out: groups when a multi-GPU partial
+};
+
+// Common tail of every entry point that returns terms: optional regrouping (series tables for the host, exchange
+// groups for a multi-GPU partial), result ownership, device -> host copy.  Records events 7 and 8.
+void emit_result(obk_engine *e, Scratch &sc, TailIn &in, obk_poly_result *out, obk_stats &st)
+{
+    cudaStream_t s = e->stream;
+    uint64_t *rk = in.rk, *rc = in.rc;
+    const uint64_t total = in.total, tot_mults = in.tot_mults;
+    const int W = in.W, accw = in.accw;
+    const bool f64 = in.f64, owner = in.owner;
+    uint32_t nsegs = 1;
+    // ---- regroup the way a series stores its terms: table hash & (2^k - 1) (series.hpp:396-400) ---------
+    // k follows the reference's sizing rule (polynomial.hpp:870-902).  Partial products of the multi-GPU
+    // path keep the engine's own segmentation (key mod nsegs): the all-to-all needs owner ranges contiguous.
+    uint32_t out_groups = nsegs, out_log2 = 0, seg_kind = 1;
+    // A device-resident product keeps the engine's own segmentation (seg_kind OBK_SEG_KEY_MOD); the series-table
+    // grouping is produced when the result is handed to the host (the container rebuild needs it) or on request
+    // (option regroup = 2).  regroup = 0 never regroups.
+    const bool regroup = (in.nranks <= 1 || owner) && (e->opt_regroup == 2 || (e->opt_regroup == 1 && in.result_mem == OBK_MEM_HOST));
+    if (in.nranks > 1 && !owner) {
+        // multi-GPU partial product: group by key mod OBK_EXCHANGE_MOD, a fixed prime every rank uses, so the
+        // rows destined to one owner are contiguous whatever kernel and segmentation produced them
+        const uint32_t mx = OBK_EXCHANGE_MOD;
+        auto *own = new ResultOwner{e};
+        out->owner = own;
+        own->seg_offsets = (uint64_t *)std::calloc((size_t)mx + 1, sizeof(uint64_t));
+        if (total > 0) {
+            SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, mx, in.is_signed, false, 0, 0, true);
+            sc.release(rk);
+            sc.release(rc);
+            rk = g.keys;
+            rc = g.cfs;
+            std::vector<uint32_t> h32((size_t)mx + 1);
+            CU_CHECK(e, cudaMemcpyAsync(h32.data(), g.off, h32.size() * 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            sc.release(g.off);
+            for (size_t i = 0; i <= mx; ++i) own->seg_offsets[i] = h32[i];
+        }
+        out_groups = mx;
+        nsegs = mx;
+        seg_kind = 1;
+    }
+    if (regroup) {
+        const double term_bytes = 8.0 * W + 8.0 * accw;
+        const double est_sp = tot_mults ? (double)total / (double)tot_mults : 1.0;
+        const double seg_kb = est_sp >= 1e-3 ? 200.0 : 20.0;
+        const uint64_t est_nsegs = (uint64_t)((double)total * term_bytes / (seg_kb * 1024.0));
+        while ((est_nsegs >> out_log2) != 0 && out_log2 < 22) ++out_log2; // nbits()
+        if (total > 0 && out_log2 > 0) {
+            SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, 1u << out_log2, 0, true, 0, 0, true);
+            sc.release(rk);
+            sc.release(rc);
+            rk = g.keys;
+            rc = g.cfs;
+            // widen the 32-bit offsets
+            std::vector<uint32_t> h32((1u << out_log2) + 1);
+            CU_CHECK(e, cudaMemcpyAsync(h32.data(), g.off, h32.size() * 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            sc.release(g.off);
+            out_groups = 1u << out_log2;
+            seg_kind = 0;
+            auto *own = new ResultOwner{e};
+            out->owner = own;
+            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * ((size_t)out_groups + 1));
+            for (size_t i = 0; i <= out_groups; ++i) own->seg_offsets[i] = h32[i];
+        } else {
+            out_groups = 1;
+            out_log2 = 0;
+            seg_kind = 0;
+            auto *own = new ResultOwner{e};
+            out->owner = own;
+            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * 2);
+            own->seg_offsets[0] = 0;
+            own->seg_offsets[1] = total;
+        }
+    }
+    CU_CHECK(e, cudaEventRecord(e->ev[7], s));
+
+    ResultOwner *own = static_cast<ResultOwner *>(out->owner);
+    if (!own) {
+        // a product left on the device is one group: both kernels write their terms in no particular order
+        own = new ResultOwner{e};
+        out->owner = own;
+        out_groups = 1;
+        own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * 2);
+        own->seg_offsets[0] = 0;
+        own->seg_offsets[1] = total;
+    }
+    st.d2h_bytes += ((uint64_t)out_groups + 1) * 8;
+    out->nterms = total;
+    out->key_words = W;
+    out->cf_kind = f64 ? OBK_CF_F64 : OBK_CF_INT;
+    out->cf_limbs = f64 ? 1 : accw;
+    out->log2_nsegs = out_log2;
+    out->nsegs = out_groups;
+    out->seg_kind = seg_kind;
+    out->mem = in.result_mem;
+    out->seg_offsets = own->seg_offsets;
+    st.log2_nsegs = out_log2;
+    if (in.result_mem == OBK_MEM_DEVICE) {
+        sc.detach(rk);
+        sc.detach(rc);
+        own->dkeys = rk;
+        own->dcfs = rc;
+        out->keys = rk;
+        out->cfs = rc;
+    } else {
+        own->pk = pinned_acquire(e, total * W * 8);
+        own->pc = pinned_acquire(e, total * accw * 8);
+        out->keys = (uint64_t *)e->pinned[own->pk].ptr;
+        out->cfs = e->pinned[own->pc].ptr;
+        if (total) {
+            CU_CHECK(e, cudaMemcpyAsync(out->keys, rk, total * W * 8, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaMemcpyAsync(out->cfs, rc, total * accw * 8, cudaMemcpyDeviceToHost, s));
+        }
+        st.d2h_bytes += total * (W + accw) * 8;
+    }
+    CU_CHECK(e, cudaEventRecord(e->ev[8], s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    in.nsegs_out = nsegs;
+    in.rk = rk;
+    in.rc = rc;
+}
+
 struct MulRequest {
     const obk_poly_view *x, *y;
     const obk_trunc *t;
@@ -989,7 +1125,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         }
         const int W = (int)y->key_words;
         const bool f64 = y->cf_kind == OBK_CF_F64;
-        const int CWx = f64 ? 1 : (int)x->cf_limbs, CWy = f64 ? 1 : (int)y->cf_limbs;
+        int CWx = f64 ? 1 : (int)x->cf_limbs, CWy = f64 ? 1 : (int)y->cf_limbs;
         const Layout L = make_layout(*y);
         Scratch sc(e);
         cudaStream_t s = e->stream;
@@ -1074,6 +1210,29 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             CU_CHECK(e, cudaStreamSynchronize(s));
             if (x == y) hs[1] = hs[0];
             st.d2h_bytes += sizeof(StatsOut) * 2;
+            if (!f64) {
+                // Input limbs are whatever the VALUES need (1 or 2), not what the caller's arrays carry: a product
+                // left in HBM with a 3-limb accumulator is a valid operand of the next product as long as its
+                // coefficients fit two limbs, and operands of different widths are brought to a common one.
+                const unsigned bits_in = std::max(hs[0].cfbits, hs[1].cfbits) + 1;
+                const int need = (int)std::max(1u, (bits_in + 63) / 64);
+                if (need > 2) {
+                    e->err = "3-limb input coefficients are not supported (inputs are 1 or 2 limbs): the operands need "
+                             + std::to_string(bits_in) + " bits";
+                    return OBK_ERR_UNSUPPORTED;
+                }
+                auto renorm = [&](const uint64_t *&dc, uint64_t n, int cw) {
+                    uint64_t *o = sc.alloc<uint64_t>(n * need);
+                    k_widen_cfs<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, s>>>(dc, n, cw, need, 0, 0, o);
+                    e->launches += 1;
+                    dc = o;
+                };
+                const bool same_c = dxc == dyc;
+                if (CWy != need) renorm(dyc, ny, CWy);
+                if (same_c) dxc = dyc;
+                else if (CWx != need) renorm(dxc, nx_full, CWx);
+                CWx = CWy = need;
+            }
             // multi-GPU: from here on this rank only sees its slice of the left operand's terms;
             // the checks above and the accumulator width below use the FULL operands so that every rank agrees.
             if (rq.nranks > 1 && !owner) {
@@ -1501,114 +1660,10 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             sc.release(dflags);
         }
 
-        // ---- regroup the way a series stores its terms: table hash & (2^k - 1) (series.hpp:396-400) ---------
-        // k follows the reference's sizing rule (polynomial.hpp:870-902).  Partial products of the multi-GPU
-        // path keep the engine's own segmentation (key mod nsegs): the all-to-all needs owner ranges contiguous.
-        uint32_t out_groups = nsegs, out_log2 = 0, seg_kind = 1;
-        // A device-resident product keeps the engine's own segmentation (seg_kind OBK_SEG_KEY_MOD); the series-table
-        // grouping is produced when the result is handed to the host (the container rebuild needs it) or on request
-        // (option regroup = 2).  regroup = 0 never regroups.
-        const bool regroup = (rq.nranks <= 1 || owner) && (e->opt_regroup == 2 || (e->opt_regroup == 1 && rq.result_mem == OBK_MEM_HOST));
-        if (rq.nranks > 1 && !owner) {
-            // multi-GPU partial product: group by key mod OBK_EXCHANGE_MOD, a fixed prime every rank uses, so the
-            // rows destined to one owner are contiguous whatever kernel and segmentation produced them
-            const uint32_t mx = OBK_EXCHANGE_MOD;
-            auto *own = new ResultOwner{e};
-            out->owner = own;
-            own->seg_offsets = (uint64_t *)std::calloc((size_t)mx + 1, sizeof(uint64_t));
-            if (total > 0) {
-                SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, mx, L.is_signed, false, 0, 0, true);
-                sc.release(rk);
-                sc.release(rc);
-                rk = g.keys;
-                rc = g.cfs;
-                std::vector<uint32_t> h32((size_t)mx + 1);
-                CU_CHECK(e, cudaMemcpyAsync(h32.data(), g.off, h32.size() * 4, cudaMemcpyDeviceToHost, s));
-                CU_CHECK(e, cudaStreamSynchronize(s));
-                sc.release(g.off);
-                for (size_t i = 0; i <= mx; ++i) own->seg_offsets[i] = h32[i];
-            }
-            out_groups = mx;
-            nsegs = mx;
-            seg_kind = 1;
-        }
-        if (regroup) {
-            const double term_bytes = 8.0 * W + 8.0 * accw;
-            const double est_sp = tot_mults ? (double)total / (double)tot_mults : 1.0;
-            const double seg_kb = est_sp >= 1e-3 ? 200.0 : 20.0;
-            const uint64_t est_nsegs = (uint64_t)((double)total * term_bytes / (seg_kb * 1024.0));
-            while ((est_nsegs >> out_log2) != 0 && out_log2 < 22) ++out_log2; // nbits()
-            if (total > 0 && out_log2 > 0) {
-                SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, 1u << out_log2, 0, true, 0, 0, true);
-                sc.release(rk);
-                sc.release(rc);
-                rk = g.keys;
-                rc = g.cfs;
-                // widen the 32-bit offsets
-                std::vector<uint32_t> h32((1u << out_log2) + 1);
-                CU_CHECK(e, cudaMemcpyAsync(h32.data(), g.off, h32.size() * 4, cudaMemcpyDeviceToHost, s));
-                CU_CHECK(e, cudaStreamSynchronize(s));
-                sc.release(g.off);
-                out_groups = 1u << out_log2;
-                seg_kind = 0;
-                auto *own = new ResultOwner{e};
-                out->owner = own;
-                own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * ((size_t)out_groups + 1));
-                for (size_t i = 0; i <= out_groups; ++i) own->seg_offsets[i] = h32[i];
-            } else {
-                out_groups = 1;
-                out_log2 = 0;
-                seg_kind = 0;
-                auto *own = new ResultOwner{e};
-                out->owner = own;
-                own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * 2);
-                own->seg_offsets[0] = 0;
-                own->seg_offsets[1] = total;
-            }
-        }
-        CU_CHECK(e, cudaEventRecord(e->ev[7], s));
-
+        TailIn tin{rk, rc, total, W, accw, f64, L.is_signed, tot_mults, rq.result_mem, rq.nranks, owner, 1};
+        emit_result(e, sc, tin, out, st);
         ResultOwner *own = static_cast<ResultOwner *>(out->owner);
-        if (!own) {
-            // a product left on the device is one group: both kernels write their terms in no particular order
-            own = new ResultOwner{e};
-            out->owner = own;
-            out_groups = 1;
-            own->seg_offsets = (uint64_t *)std::malloc(sizeof(uint64_t) * 2);
-            own->seg_offsets[0] = 0;
-            own->seg_offsets[1] = total;
-        }
-        st.d2h_bytes += ((uint64_t)out_groups + 1) * 8;
-        out->nterms = total;
-        out->key_words = W;
-        out->cf_kind = f64 ? OBK_CF_F64 : OBK_CF_INT;
-        out->cf_limbs = f64 ? 1 : accw;
-        out->log2_nsegs = out_log2;
-        out->nsegs = out_groups;
-        out->seg_kind = seg_kind;
-        out->mem = rq.result_mem;
-        out->seg_offsets = own->seg_offsets;
-        st.log2_nsegs = out_log2;
-        if (rq.result_mem == OBK_MEM_DEVICE) {
-            sc.detach(rk);
-            sc.detach(rc);
-            own->dkeys = rk;
-            own->dcfs = rc;
-            out->keys = rk;
-            out->cfs = rc;
-        } else {
-            own->pk = pinned_acquire(e, total * W * 8);
-            own->pc = pinned_acquire(e, total * accw * 8);
-            out->keys = (uint64_t *)e->pinned[own->pk].ptr;
-            out->cfs = e->pinned[own->pc].ptr;
-            if (total) {
-                CU_CHECK(e, cudaMemcpyAsync(out->keys, rk, total * W * 8, cudaMemcpyDeviceToHost, s));
-                CU_CHECK(e, cudaMemcpyAsync(out->cfs, rc, total * accw * 8, cudaMemcpyDeviceToHost, s));
-            }
-            st.d2h_bytes += total * (W + accw) * 8;
-        }
-        CU_CHECK(e, cudaEventRecord(e->ev[8], s));
-        CU_CHECK(e, cudaStreamSynchronize(s));
+        if (rq.nranks > 1 && !owner) nsegs = tin.nsegs_out;
         if (owner) {
             // this rank's share of the whole job's term products (the shares of all ranks add up to tot_n_mults)
             st.term_products = tot_mults * (rq.rank + 1) / rq.nranks - tot_mults * rq.rank / rq.nranks;
@@ -1798,6 +1853,193 @@ obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t ns
     rq.merge = true;
     rq.merge_nsegs = nsegs ? nsegs : 1;
     return run_mul(e, rq, out, stats);
+}
+
+obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int subtract, uint32_t result_mem,
+                           obk_poly_result *out, obk_stats *stats)
+{
+    if (!e || !out) return OBK_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    uint64_t *cat_k = nullptr, *cat_c = nullptr;
+    obk_status rc_status = OBK_OK;
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        validate_view(e, x, "x");
+        validate_view(e, y, "y");
+        if (x->key_words != y->key_words || x->key_signed != y->key_signed || x->nvars != y->nvars || x->psize != y->psize
+            || x->cf_kind != y->cf_kind || (x->key_bits == 32) != (y->key_bits == 32)) {
+            e->err = "operands have different key layouts or coefficient kinds";
+            return OBK_ERR_INVALID_ARG;
+        }
+        const bool f64 = x->cf_kind == OBK_CF_F64;
+        const int W = (int)x->key_words;
+        const uint64_t nx = x->nterms, ny = y->nterms, n = nx + ny;
+        if (n == 0) {
+            set_empty_result(out, x, 1, result_mem);
+            if (stats) *stats = obk_stats{};
+            return OBK_OK;
+        }
+        if (n >= (1ull << 31)) {
+            e->err = "operands with 2^31 or more terms are not supported";
+            return OBK_ERR_UNSUPPORTED;
+        }
+        cudaStream_t s = e->stream;
+        int lout = 1;
+        {
+            Scratch sc(e);
+            const obk_poly_view *vs[2] = {x, y};
+            const uint64_t *dk[2] = {nullptr, nullptr}, *dc[2] = {nullptr, nullptr};
+            for (int i = 0; i < 2; ++i) {
+                const obk_poly_view *v = vs[i];
+                const int cw = f64 ? 1 : (int)v->cf_limbs;
+                if (v->nterms == 0) continue;
+                if (v->mem == OBK_MEM_DEVICE) {
+                    dk[i] = v->keys;
+                    dc[i] = (const uint64_t *)v->cfs;
+                } else {
+                    uint64_t *k = sc.alloc<uint64_t>(v->nterms * W);
+                    uint64_t *c = sc.alloc<uint64_t>(v->nterms * cw);
+                    CU_CHECK(e, cudaMemcpyAsync(k, v->keys, v->nterms * W * 8, cudaMemcpyHostToDevice, s));
+                    CU_CHECK(e, cudaMemcpyAsync(c, v->cfs, v->nterms * cw * 8, cudaMemcpyHostToDevice, s));
+                    dk[i] = k;
+                    dc[i] = c;
+                }
+            }
+            if (!f64) {
+                // exact sum: one more bit than the wider operand, plus the sign
+                const Layout L = make_layout(*x);
+                StatsOut *dstats = sc.alloc<StatsOut>(2);
+                k_stats_init<<<2, 64, 0, s>>>(dstats, 2);
+                for (int i = 0; i < 2; ++i) {
+                    if (vs[i]->nterms == 0) continue;
+                    const unsigned g = (unsigned)std::min<uint64_t>((vs[i]->nterms + 255) / 256, 1024);
+                    k_term_stats<<<g, 256, 0, s>>>(dk[i], dc[i], vs[i]->nterms, L, 0, 0, (int)vs[i]->cf_limbs, nullptr, dstats + i);
+                }
+                StatsOut hs[2];
+                CU_CHECK(e, cudaMemcpyAsync(hs, dstats, sizeof(hs), cudaMemcpyDeviceToHost, s));
+                CU_CHECK(e, cudaStreamSynchronize(s));
+                const unsigned bits = std::max(hs[0].cfbits, hs[1].cfbits) + 2;
+                lout = (int)((bits + 63) / 64);
+                if (lout > 3) {
+                    e->err = "coefficient overflow beyond 3 limbs: the exact sum needs " + std::to_string(bits) + " bits";
+                    return OBK_ERR_CF_OVERFLOW;
+                }
+            }
+            // merge input: x's terms followed by (+/-) y's terms
+            if (cudaMallocAsync((void **)&cat_k, n * W * 8, s) != cudaSuccess
+                || cudaMallocAsync((void **)&cat_c, n * (size_t)lout * 8, s) != cudaSuccess) {
+                cudaGetLastError();
+                e->err = "device allocation failed";
+                throw obk_fail{OBK_ERR_NOMEM};
+            }
+            uint64_t off = 0;
+            for (int i = 0; i < 2; ++i) {
+                const uint64_t ni = vs[i]->nterms;
+                if (ni == 0) continue;
+                CU_CHECK(e, cudaMemcpyAsync(cat_k + off * W, dk[i], ni * W * 8, cudaMemcpyDeviceToDevice, s));
+                const unsigned g = (unsigned)std::min<uint64_t>((ni + 255) / 256, 4096);
+                k_widen_cfs<<<g, 256, 0, s>>>(dc[i], ni, f64 ? 1 : (int)vs[i]->cf_limbs, lout, (i == 1 && subtract) ? 1 : 0, f64 ? 1 : 0,
+                                             cat_c + off * lout);
+                off += ni;
+            }
+            CU_CHECK(e, cudaGetLastError());
+        }
+        obk_poly_view terms = *x;
+        terms.nterms = n;
+        terms.cf_limbs = f64 ? 1 : (uint32_t)lout;
+        terms.mem = OBK_MEM_DEVICE;
+        terms.keys = cat_k;
+        terms.cfs = cat_c;
+        MulRequest rq{nullptr, &terms, nullptr, result_mem};
+        rq.merge = true;
+        rc_status = run_mul(e, rq, out, stats);
+    } catch (const obk_fail &f) {
+        rc_status = f.st;
+    }
+    if (cat_k) cudaFreeAsync(cat_k, e->stream);
+    if (cat_c) cudaFreeAsync(cat_c, e->stream);
+    return rc_status;
+}
+
+obk_status obk_poly_truncate_degree(obk_engine *e, const obk_poly_view *x, const obk_trunc *t, uint32_t result_mem,
+                                    obk_poly_result *out, obk_stats *stats)
+{
+    if (!e || !out || !x || !t) return OBK_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    obk_stats st{};
+    e->launches = 0;
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        validate_view(e, x, "x");
+        const bool f64 = x->cf_kind == OBK_CF_F64;
+        const int W = (int)x->key_words, cw = f64 ? 1 : (int)x->cf_limbs;
+        const uint64_t n = x->nterms;
+        if (n == 0) {
+            set_empty_result(out, x, cw, result_mem);
+            if (stats) *stats = st;
+            return OBK_OK;
+        }
+        const Layout L = make_layout(*x);
+        uint64_t var_mask = L.nvars >= 64 ? ~0ull : ((1ull << L.nvars) - 1);
+        if (t->partial) {
+            var_mask = 0;
+            for (uint32_t i = 0; i < t->nidx; ++i) {
+                if (t->idx[i] >= L.nvars) {
+                    e->err = "partial-degree index outside the symbol set";
+                    return OBK_ERR_INVALID_ARG;
+                }
+                var_mask |= 1ull << t->idx[i];
+            }
+        }
+        Scratch sc(e);
+        cudaStream_t s = e->stream;
+        CU_CHECK(e, cudaEventRecord(e->ev[0], s));
+        const uint64_t *dk = x->keys, *dc = (const uint64_t *)x->cfs;
+        if (x->mem == OBK_MEM_HOST) {
+            uint64_t *k = sc.alloc<uint64_t>(n * W);
+            uint64_t *c = sc.alloc<uint64_t>(n * cw);
+            CU_CHECK(e, cudaMemcpyAsync(k, x->keys, n * W * 8, cudaMemcpyHostToDevice, s));
+            CU_CHECK(e, cudaMemcpyAsync(c, x->cfs, n * cw * 8, cudaMemcpyHostToDevice, s));
+            st.h2d_bytes += n * (W + cw) * 8;
+            dk = k;
+            dc = c;
+        }
+        StatsOut *dstats = sc.alloc<StatsOut>(1);
+        int64_t *deg = sc.alloc<int64_t>(n);
+        uint32_t *flag = sc.alloc<uint32_t>(n + 1);
+        uint32_t *pos = sc.alloc<uint32_t>(n + 2);
+        const unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 1024);
+        k_stats_init<<<1, 64, 0, s>>>(dstats, 1);
+        k_term_stats<<<g, 256, 0, s>>>(dk, dk, n, L, var_mask, 2 /* keys only */, 1, deg, dstats);
+        k_flag_keep<<<g, 256, 0, s>>>(deg, n, t->limit, L.is_signed ? 0 : 1, flag);
+        e->launches += 3;
+        device_scan(e, sc, flag, pos, n);
+        uint32_t htot = 0;
+        CU_CHECK(e, cudaMemcpyAsync(&htot, pos + n, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        const uint64_t total = htot;
+        uint64_t *rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * W);
+        uint64_t *rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * cw);
+        int64_t *odeg = sc.alloc<int64_t>(std::max<uint64_t>(total, 1));
+        k_select<<<g, 256, 0, s>>>(dk, dc, deg, n, W, cw, pos, rk, rc, odeg);
+        e->launches += 1;
+        CU_CHECK(e, cudaGetLastError());
+        st.nterms_out = total;
+        st.acc_limbs = cw;
+        TailIn tin{rk, rc, total, W, cw, f64, L.is_signed, n, result_mem, 1, false, 1};
+        emit_result(e, sc, tin, out, st);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->ev[0], e->ev[8]);
+        st.ms_total = ms;
+        st.total_launches = e->launches;
+        if (stats) *stats = st;
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        if (out->owner) obk_result_free(e, out);
+        std::memset(out, 0, sizeof(*out));
+        cudaStreamSynchronize(e->stream);
+        return f.st;
+    }
 }
 
 void obk_result_free(obk_engine *e, obk_poly_result *r)

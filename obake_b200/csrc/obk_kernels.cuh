@@ -278,7 +278,17 @@ __global__ void __launch_bounds__(256) k_bin_count_smem(const uint64_t *__restri
             }
             if (dbits) bin = (bin << dbits) | (uint32_t)(deg[i] - degmin);
             mybin[j] = bin;
-            myrank[j] = atomicAdd(&sh_hist[bin], 1u);
+        }
+        // lanes of a warp that fall into the same bin share ONE shared-memory atomic (degree-skewed operands put
+        // most terms into a few bins: one atomic per lane serialises on them)
+        const uint32_t peers = __match_any_sync(0xffffffffu, mybin[j]);
+        if (mybin[j] != 0xffffffffu) {
+            const uint32_t lane = threadIdx.x & 31u;
+            const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+            uint32_t r0 = 0;
+            if (lane == leader) r0 = atomicAdd(&sh_hist[mybin[j]], (uint32_t)__popc(peers));
+            r0 = __shfl_sync(peers, r0, (int)leader);
+            myrank[j] = r0 + (uint32_t)__popc(peers & ((1u << lane) - 1u));
         }
     }
     __syncthreads();
@@ -431,6 +441,42 @@ __global__ void __launch_bounds__(256) k_select(const uint64_t *__restrict__ key
     }
 }
 
+// truncate_degree / truncate_p_degree (polynomial.hpp:2364-2445): keep term t iff !(limit < deg(t)), compared in
+// the key's integer type T (unsigned T: unsigned comparison).
+__global__ void __launch_bounds__(256) k_flag_keep(const int64_t *__restrict__ deg, uint64_t n, int64_t limit, int uns,
+                                                   uint32_t *__restrict__ flag)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        flag[i] = uns ? ((uint64_t)deg[i] <= (uint64_t)limit) : (deg[i] <= limit);
+}
+
+// Series addition / subtraction (series.hpp:2195-2991) is a merge of the two term lists: copy one operand's
+// coefficients into the merge input, sign-extended from lin to lout limbs and negated if asked (fp64: sign flip).
+__global__ void __launch_bounds__(256) k_widen_cfs(const uint64_t *__restrict__ in, uint64_t n, int lin, int lout, int negate,
+                                                   int f64, uint64_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (f64) {
+            out[i] = negate ? in[i] ^ 0x8000000000000000ULL : in[i];
+            continue;
+        }
+        uint64_t v[3];
+        const uint64_t ext = (uint64_t)((long long)in[i * lin + lin - 1] >> 63);
+        for (int l = 0; l < 3; ++l) v[l] = l < lin ? in[i * lin + l] : ext;
+        if (negate) {
+            uint64_t c = 1;
+            for (int l = 0; l < 3; ++l) {
+                const uint64_t t = ~v[l] + c;
+                c = (c && t == 0) ? 1 : 0;
+                v[l] = t;
+            }
+        }
+        for (int l = 0; l < lout; ++l) out[i * lout + l] = v[l];
+    }
+}
+
 // tot_n_mults of a truncated product (polynomial.hpp:574-623): for each left term the number of right
 // terms whose degree passes the limit, via the degree histogram's prefix sums.
 __global__ void __launch_bounds__(256) k_deg_hist(const int64_t *__restrict__ deg, uint64_t n, int64_t degmin,
@@ -443,8 +489,13 @@ __global__ void __launch_bounds__(256) k_deg_hist(const int64_t *__restrict__ de
     if (ndeg_smem) {
         for (uint32_t b = threadIdx.x; b < ndeg_smem; b += blockDim.x) sh_dh[b] = 0;
         __syncthreads();
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-            atomicAdd(&sh_dh[(uint32_t)(deg[i] - degmin)], 1u);
+        // a handful of degrees shared by 10^5 terms: lanes holding the same degree elect one to add their count
+        const uint64_t nround = (n + 31) / 32 * 32;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+            const uint32_t d = i < n ? (uint32_t)(deg[i] - degmin) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (d != 0xffffffffu && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&sh_dh[d], (uint32_t)__popc(peers));
+        }
         __syncthreads();
         for (uint32_t b = threadIdx.x; b < ndeg_smem; b += blockDim.x)
             if (sh_dh[b]) atomicAdd(&hist[b], sh_dh[b]);

@@ -297,6 +297,47 @@ class Engine:
             _raise(rc, self.last_error())
         return Product(self, res, st), [int(c) for c in counts]
 
+    def view_of(self, prod: "Product", like: PolyView) -> PolyView:
+        """View over a product this engine left in DEVICE (or host) memory, so that it can be the operand of the
+        next call without leaving HBM (f *= g chains).  `like` supplies the key layout."""
+        return raw_view(prod.nterms, prod.key_words, like.key_signed, like.nvars, like.psize,
+                        _capi.OBK_CF_F64 if prod.is_f64 else _capi.OBK_CF_INT, prod.cf_limbs,
+                        OBK_MEM_DEVICE if prod.on_device else OBK_MEM_HOST, prod.keys_ptr, prod.cfs_ptr,
+                        like.key_bits or 64)
+
+    def addsub_views(self, vx: PolyView, vy: PolyView, subtract=False, result_mem=OBK_MEM_HOST) -> Product:
+        """x + y / x - y over the same symbol set (series.hpp:2195-2991) on the engine's layout."""
+        res, st = PolyResult(), Stats()
+        rc = _capi.lib().obk_poly_addsub(self._h, C.byref(vx), C.byref(vy), 1 if subtract else 0, int(result_mem),
+                                         C.byref(res), C.byref(st))
+        if rc != 0:
+            _raise(rc, self.last_error())
+        return Product(self, res, st)
+
+    def add(self, x, y, result_mem=OBK_MEM_HOST) -> Product:
+        hx, hy = HostOperand(x), HostOperand(y)  # keep the marshalled arrays alive across the call
+        return self.addsub_views(hx.view, hy.view, False, result_mem)
+
+    def sub(self, x, y, result_mem=OBK_MEM_HOST) -> Product:
+        hx, hy = HostOperand(x), HostOperand(y)
+        return self.addsub_views(hx.view, hy.view, True, result_mem)
+
+    def truncate_degree_view(self, vx: PolyView, limit, idx=None, result_mem=OBK_MEM_HOST) -> Product:
+        """truncate_degree(x, limit) / truncate_p_degree(x, limit, symbols at positions idx)
+        (polynomial.hpp:2364-2445): keeps the terms with not (limit < degree)."""
+        keep = []
+        tr = self._trunc(limit, idx, keep)
+        res, st = PolyResult(), Stats()
+        rc = _capi.lib().obk_poly_truncate_degree(self._h, C.byref(vx), C.byref(tr), int(result_mem), C.byref(res),
+                                                  C.byref(st))
+        if rc != 0:
+            _raise(rc, self.last_error())
+        return Product(self, res, st)
+
+    def truncate_degree(self, x, limit, idx=None, result_mem=OBK_MEM_HOST) -> Product:
+        hx = HostOperand(x)
+        return self.truncate_degree_view(hx.view, limit, idx, result_mem)
+
     def merge_view(self, vterms: PolyView, nsegs: int, result_mem=OBK_MEM_HOST) -> Product:
         res, st = PolyResult(), Stats()
         rc = _capi.lib().obk_poly_merge(self._h, C.byref(vterms), int(nsegs), int(result_mem), C.byref(res),

@@ -91,3 +91,23 @@ def overflow_check(x_expos, y_expos, lim_min: int, lim_max: int) -> bool:
         if mn < lim_min or mx > lim_max:
             return False
     return True
+
+
+def poly_addsub(x: dict, y: dict, subtract: bool = False) -> dict:
+    """x + y or x - y for two polynomials over the SAME symbol set: the identical-symbol-set branch of
+    series_default_addsub_impl (include/obake/series.hpp:2195-2991): every term of the second operand is inserted
+    into a copy of the first with its coefficient added (or subtracted, a new term enters negated), and terms whose
+    coefficient becomes zero are erased (series_add_term_table, series.hpp:683-792)."""
+    out = dict(x)
+    for e, c in y.items():
+        if e in out:
+            out[e] = out[e] - c if subtract else out[e] + c
+        else:
+            out[e] = -c if subtract else c
+    return {k: v for k, v in out.items() if v != 0}
+
+
+def truncate_degree(x: dict, max_deg, idx=None) -> dict:
+    """truncate_degree / truncate_p_degree (include/obake/polynomials/polynomial.hpp:2364-2445): filter() keeping
+    the terms with not (max_deg < degree); partial degree over the symbol positions idx."""
+    return {e: c for e, c in x.items() if not (max_deg < degree(e, idx))}
