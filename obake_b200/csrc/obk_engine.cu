@@ -34,6 +34,11 @@ struct PinnedBlock {
     bool in_use;
 };
 
+struct ArenaChunk {
+    char *base;
+    size_t size;
+};
+
 } // namespace
 
 struct obk_engine {
@@ -51,6 +56,10 @@ struct obk_engine {
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
     uint32_t last_rslices = 1;
+    // scratch arena (see Scratch)
+    std::vector<ArenaChunk> arena;
+    size_t arena_chunk = 0, arena_off = 0;
+    int arena_depth = 0;
 };
 
 namespace
@@ -76,16 +85,25 @@ struct obk_fail {
     obk_status st;
 };
 
-// Stream-ordered scratch allocations released when the call ends.
+// Scratch memory of one call.  Small buffers (the dozens of offset tables, flags and sorted copies a call needs) are
+// bump-allocated from a per-engine arena that persists across calls -- a call used to spend more host time in
+// cudaMallocAsync / cudaFreeAsync (about 60 pairs) than the GPU spent in its kernels for the small benchmarks.
+// Large buffers and everything that may be handed to the caller (alloc_out) come from the driver's stream-ordered
+// pool.  The arena is reset when the outermost Scratch of a call dies; all work is ordered on the engine's stream,
+// so the next call may reuse it.
+constexpr size_t ARENA_MAX_ALLOC = 8u << 20;
+constexpr size_t ARENA_MIN_CHUNK = 64u << 20;
+
 struct Scratch {
     obk_engine *e;
-    std::vector<void *> ptrs;
-    explicit Scratch(obk_engine *e_) : e(e_) {}
-    template <typename T>
-    T *alloc(size_t n)
+    std::vector<void *> ptrs; // stream-ordered allocations owned by this object
+    explicit Scratch(obk_engine *e_) : e(e_)
+    {
+        ++e->arena_depth;
+    }
+    void *pool_alloc(size_t bytes)
     {
         void *p = nullptr;
-        size_t bytes = (std::max<size_t>(n * sizeof(T), 16) + 255) / 256 * 256;
         cudaError_t err = cudaMallocAsync(&p, bytes, e->stream);
         if (err != cudaSuccess) {
             e->err = std::string("device allocation of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(err);
@@ -93,26 +111,89 @@ struct Scratch {
             throw obk_fail{OBK_ERR_NOMEM};
         }
         ptrs.push_back(p);
-        return static_cast<T *>(p);
+        return p;
+    }
+    void *arena_alloc(size_t bytes)
+    {
+        for (;;) {
+            if (e->arena_chunk < e->arena.size()) {
+                ArenaChunk &c = e->arena[e->arena_chunk];
+                if (e->arena_off + bytes <= c.size) {
+                    void *p = c.base + e->arena_off;
+                    e->arena_off += bytes;
+                    return p;
+                }
+                ++e->arena_chunk;
+                e->arena_off = 0;
+                continue;
+            }
+            const size_t last = e->arena.empty() ? 0 : e->arena.back().size;
+            const size_t sz = std::max(std::max(ARENA_MIN_CHUNK, 2 * last), bytes);
+            void *base = nullptr;
+            if (cudaMalloc(&base, sz) != cudaSuccess) {
+                cudaGetLastError();
+                e->err = "device allocation of the scratch arena failed";
+                throw obk_fail{OBK_ERR_NOMEM};
+            }
+            e->arena.push_back({static_cast<char *>(base), sz});
+        }
+    }
+    static size_t round_up(size_t bytes)
+    {
+        return (std::max<size_t>(bytes, 16) + 255) / 256 * 256;
+    }
+    template <typename T>
+    T *alloc(size_t n)
+    {
+        const size_t bytes = round_up(n * sizeof(T));
+        return static_cast<T *>(bytes <= ARENA_MAX_ALLOC ? arena_alloc(bytes) : pool_alloc(bytes));
+    }
+    // buffers that may outlive the call (results): never from the arena
+    template <typename T>
+    T *alloc_out(size_t n)
+    {
+        return static_cast<T *>(pool_alloc(round_up(n * sizeof(T))));
     }
     void release(void *p)
     {
         for (auto &q : ptrs)
-            if (q == p) {
+            if (q == p && q) {
                 cudaFreeAsync(q, e->stream);
                 q = nullptr;
             }
+        // arena memory is reclaimed wholesale at the end of the call
     }
     // hand ownership to the caller
     void detach(void *p)
     {
         for (auto &q : ptrs)
-            if (q == p) q = nullptr;
+            if (q == p) {
+                q = nullptr;
+                return;
+            }
+        e->err = "internal: result buffer was not allocated with alloc_out";
+        throw obk_fail{OBK_ERR_INVALID_ARG};
     }
     ~Scratch()
     {
         for (auto q : ptrs)
             if (q) cudaFreeAsync(q, e->stream);
+        if (--e->arena_depth == 0) {
+            if (e->arena.size() > 1) {
+                // the call outgrew the arena: replace the chunks by one of the total size (rare; cudaFree synchronises)
+                size_t total = 0;
+                for (auto &c : e->arena) {
+                    total += c.size;
+                    cudaFree(c.base);
+                }
+                e->arena.clear();
+                void *base = nullptr;
+                if (cudaMalloc(&base, total) == cudaSuccess) e->arena.push_back({static_cast<char *>(base), total});
+                else cudaGetLastError();
+            }
+            e->arena_chunk = 0;
+            e->arena_off = 0;
+        }
     }
 };
 
@@ -303,7 +384,8 @@ struct SortedY {
 // Counting sort of an operand by (segment, degree index).  pow2: segment = hash & (m-1) (m a power of two,
 // used to regroup the result the way a series stores it); otherwise segment = key mod m.
 SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uint64_t *cfs, const int64_t *deg, uint64_t n,
-                     int W, int CW, uint32_t m, uint32_t is_signed, bool pow2, int dbits, int64_t degmin, bool with_cfs)
+                     int W, int CW, uint32_t m, uint32_t is_signed, bool pow2, int dbits, int64_t degmin, bool with_cfs,
+                     bool persistent = false)
 {
     SortedY r;
     const uint64_t nbins = (uint64_t)m << dbits;
@@ -311,8 +393,8 @@ SortedY sort_operand(obk_engine *e, Scratch &sc, const uint64_t *keys, const uin
     uint32_t *bin_of = sc.alloc<uint32_t>(n);
     uint32_t *rank_of = sc.alloc<uint32_t>(n);
     r.off = sc.alloc<uint32_t>(nbins + 1);
-    r.keys = sc.alloc<uint64_t>(n * W);
-    if (with_cfs) r.cfs = sc.alloc<uint64_t>(n * CW);
+    r.keys = persistent ? sc.alloc_out<uint64_t>(n * W) : sc.alloc<uint64_t>(n * W);
+    if (with_cfs) r.cfs = persistent ? sc.alloc_out<uint64_t>(n * CW) : sc.alloc<uint64_t>(n * CW);
     CU_CHECK(e, cudaMemsetAsync(cnt, 0, (nbins + 1) * sizeof(uint32_t), e->stream));
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
     if (nbins <= 8192 && n >= 8192) {
@@ -751,8 +833,8 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         X.nrows = c;
         if (c == 0) {
             R.done = true;
-            R.rk = sc.alloc<uint64_t>(1);
-            R.rc = sc.alloc<uint64_t>(accw);
+            R.rk = sc.alloc_out<uint64_t>(1);
+            R.rc = sc.alloc_out<uint64_t>(accw);
             return R;
         }
     }
@@ -911,8 +993,8 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         CU_CHECK(e, cudaStreamSynchronize(s));
         total = htot;
     }
-    R.rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1));
-    R.rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * accw);
+    R.rk = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1));
+    R.rc = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1) * accw);
     if (total) launch_rows(e, mode, uns, P, 0, 0, roffs, delta, R.rk, R.rc, true);
     R.total = total;
     R.nro = nro;
@@ -977,7 +1059,7 @@ void emit_result(obk_engine *e, Scratch &sc, TailIn &in, obk_poly_result *out, o
         out->owner = own;
         own->seg_offsets = (uint64_t *)std::calloc((size_t)mx + 1, sizeof(uint64_t));
         if (total > 0) {
-            SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, mx, in.is_signed, false, 0, 0, true);
+            SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, mx, in.is_signed, false, 0, 0, true, true);
             sc.release(rk);
             sc.release(rc);
             rk = g.keys;
@@ -999,7 +1081,7 @@ void emit_result(obk_engine *e, Scratch &sc, TailIn &in, obk_poly_result *out, o
         const uint64_t est_nsegs = (uint64_t)((double)total * term_bytes / (seg_kb * 1024.0));
         while ((est_nsegs >> out_log2) != 0 && out_log2 < 22) ++out_log2; // nbits()
         if (total > 0 && out_log2 > 0) {
-            SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, 1u << out_log2, 0, true, 0, 0, true);
+            SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, 1u << out_log2, 0, true, 0, 0, true, true);
             sc.release(rk);
             sc.release(rc);
             rk = g.keys;
@@ -1531,8 +1613,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 // final term arrays, sized for the worst case that does not overflow a table (max_fill terms per
                 // segment): the kernel writes every segment straight to its reserved range, no staging or compaction
                 const uint64_t out_bound = std::max<uint64_t>((uint64_t)nsegs * max_fill, 1);
-                rk = sc.alloc<uint64_t>(out_bound * W);
-                rc = sc.alloc<uint64_t>(out_bound * accw);
+                rk = sc.alloc_out<uint64_t>(out_bound * W);
+                rc = sc.alloc_out<uint64_t>(out_bound * accw);
                 dflags = sc.alloc<uint32_t>(4);
                 CU_CHECK(e, cudaMemsetAsync(dflags, 0, 16, s));
                 MulParams P{};
@@ -1782,6 +1864,7 @@ void obk_engine_destroy(obk_engine *e)
     for (auto &b : e->pinned)
         if (b.ptr) cudaFreeHost(b.ptr);
     for (auto &ev : e->ev) cudaEventDestroy(ev);
+    for (auto &c : e->arena) cudaFree(c.base);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -2018,8 +2101,8 @@ obk_status obk_poly_truncate_degree(obk_engine *e, const obk_poly_view *x, const
         CU_CHECK(e, cudaMemcpyAsync(&htot, pos + n, 4, cudaMemcpyDeviceToHost, s));
         CU_CHECK(e, cudaStreamSynchronize(s));
         const uint64_t total = htot;
-        uint64_t *rk = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * W);
-        uint64_t *rc = sc.alloc<uint64_t>(std::max<uint64_t>(total, 1) * cw);
+        uint64_t *rk = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1) * W);
+        uint64_t *rc = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1) * cw);
         int64_t *odeg = sc.alloc<int64_t>(std::max<uint64_t>(total, 1));
         k_select<<<g, 256, 0, s>>>(dk, dc, deg, n, W, cw, pos, rk, rc, odeg);
         e->launches += 1;
