@@ -1691,6 +1691,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 P.counts = nullptr;
                 P.flags = dflags;
                 P.out_cursor = dflags + 2;
+                P.uns = (!f64 && !rq.merge && hs_anyneg == 0) ? 1u : 0u;
                 plan_units(e, P, threads,
                            (double)tot_mults / (double)std::max<uint64_t>(P.nx + (P.npass > 1 ? P.b.nx : 0), 1) / (double)nsegs,
                            std::max(snx, ny));

@@ -554,9 +554,18 @@ OBK_TRAITS(CF_ADDF, 1, 1, true, false, true)
 
 // p (LACC limbs, two's complement) = a * b for LIN-limb two's-complement inputs.
 template <int LIN, int LACC>
-__device__ __forceinline__ void cf_mul(const uint64_t *a, const uint64_t *b, uint64_t *p)
+__device__ __forceinline__ void cf_mul(const uint64_t *a, const uint64_t *b, uint64_t *p, bool uns = false)
 {
     if constexpr (LIN == 1) {
+        if (uns) {
+            // no negative coefficient in either operand: plain unsigned product, no sign fix-ups
+            p[0] = a[0] * b[0];
+            if constexpr (LACC >= 2) {
+                p[1] = __umul64hi(a[0], b[0]);
+                if constexpr (LACC >= 3) p[2] = 0;
+            }
+            return;
+        }
         const long long x = (long long)a[0], y = (long long)b[0];
         p[0] = (uint64_t)(x * y);
         if constexpr (LACC >= 2) {
@@ -647,6 +656,7 @@ struct MulParams {
     // k_mul (warp-cooperative expansion): every left term's run is cut into `rslices` slices (work unit = 32 left
     // terms x one slice) and idle lanes are refilled once at least `refill_min` of a warp's lanes are idle
     uint32_t rslices, refill_min;
+    uint32_t uns; // 1: no coefficient is negative (unsigned 64x64 products)
     // staging output: [segment][cap] slots, counts per segment
     uint64_t *okeys;
     uint64_t *ocfs;
@@ -662,6 +672,12 @@ enum : uint32_t { ST_EMPTY = 0, ST_INIT = 1, ST_FULL = 2, ST_BUSY = 3 };
 template <int W>
 __device__ __forceinline__ uint32_t slot_hash(const uint64_t (&k)[W], uint32_t log2_cap)
 {
+    if constexpr (W == 1) {
+        // one packed word: multilinear hash of its two halves (2 IMAD + shift); the top bits of
+        // lo * A + hi * B mod 2^32 are flat for the arithmetic progressions a segment's keys form
+        const uint32_t x = (uint32_t)k[0] * 0x9E3779B1u + (uint32_t)(k[0] >> 32) * 0x85EBCA77u;
+        return (x ^ (x >> 15)) * 0x2C1B3C6Du >> (32 - log2_cap);
+    }
     // multiply-shift over the whole key: the top bits of the product depend on every key bit
     uint64_t h = k[0] * 0x9E3779B97F4A7C15ULL;
 #pragma unroll
@@ -883,7 +899,7 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
                                 p[0] = (uint64_t)__double_as_longlong(
                                     __dmul_rn(__longlong_as_double((long long)cxo[0]), __longlong_as_double((long long)cy[0])));
                             } else {
-                                cf_mul<T::LIN, T::LACC>(cxo, cy, p);
+                                cf_mul<T::LIN, T::LACC>(cxo, cy, p, P.uns != 0u);
                             }
                         }
                         h = slot_hash<W>(k, P.log2_cap);
