@@ -29,6 +29,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "term_products_per_s"
 UNIT = "term-products/s"
+PX = [None]  # multi-GPU: the peer-window exchange (obake_b200.dist.PeerExchange)
 
 
 def parse_args():
@@ -41,9 +42,12 @@ def parse_args():
     ap.add_argument("--also", default="S12", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
-    ap.add_argument("--mgpu-mode", default="both", choices=["both", "exchange", "owner"],
-                    help="N>1: left-operand sharding + all-to-all + merge (the contract design), owner-computes "
-                         "(zero exchange), or both (value = the faster, both reported)")
+    ap.add_argument("--mgpu-mode", default="push", choices=["all", "both", "exchange", "push", "owner"],
+                    help="N>1: left-operand sharding + NCCL all-to-all + merge (the contract design), the same with "
+                         "the exchange fused into the producer as P2P stores into NVLink peer windows (push), "
+                         "owner-computes (zero exchange), or all (value = the fastest, all reported; modes measured later in "
+                         "one process run a few percent slower, so the default measures the push design alone and "
+                         "falls back to exchange when CUDA IPC is unavailable)")
     return ap.parse_args()
 
 
@@ -222,6 +226,8 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
             return p, {}
         if mgpu_mode == "owner":
             return obd.owner_mul(eng, vfd, vgd, limit=limit)
+        if mgpu_mode == "push":
+            return PX[0].pushed_mul(vfd, vgd, limit=limit)
         return obd.sharded_mul(eng, vfd, vgd, limit=limit)
 
     def barrier():
@@ -303,7 +309,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         "lin": lin, "lacc": int(lacc), "f64": f64, "limit": limit,
     }
     if info_last:
-        out["exchange"] = {k: info_last[k] for k in ("partial_terms", "sent_rows", "recv_rows", "bytes_sent", "nsegs")}
+        out["exchange"] = {k: info_last.get(k) for k in ("partial_terms", "sent_rows", "recv_rows", "bytes_sent", "nsegs")}
         if "timing_ms" in info_last:
             out["exchange"]["timing_ms"] = info_last["timing_ms"]
     # ---- end to end: host (pinned) operands in, host result out, through the same public call ---------------
@@ -334,6 +340,9 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
                 p, info = obd.owner_mul(eng, vfh, vgh, limit=limit)
                 hk_, hc_ = p.keys, p.cf_limb_array  # device -> host read of this rank's share
                 d2h = int(hk_.nbytes + hc_.nbytes)
+            elif mgpu_mode == "push":
+                p, info = PX[0].pushed_mul(vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
+                d2h = p.stats["d2h_bytes"]
             else:
                 p, info = obd.sharded_mul(eng, vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
                 d2h = p.stats["d2h_bytes"]
@@ -437,7 +446,17 @@ def main():
                           "config": {"workload": "RECT", "description": "rectangular_01: 70 chained 13-term products, fp64, device-resident chain", **r}}))
         eng.close()
         return 0
-    modes = ["exchange"] if world == 1 else (["exchange", "owner"] if args.mgpu_mode == "both" else [args.mgpu_mode])
+    modes = ["exchange"] if world == 1 else {"all": ["exchange", "push", "owner"], "both": ["exchange", "owner"]}.get(
+        args.mgpu_mode, [args.mgpu_mode])
+    if world > 1 and "push" in modes:
+        from obake_b200 import dist as obd
+
+        try:
+            PX[0] = obd.PeerExchange(eng, window_bytes=1 << 30)
+        except Exception as ex:  # noqa: BLE001 -- CUDA IPC unavailable: report the NCCL modes only
+            if rank == 0:
+                sys.stderr.write(f"push mode unavailable: {ex}\n")
+            modes = [m for m in modes if m != "push"] or ["exchange"]
     results = {m: bench_workload(args.workload, args, eng, torch, dev, rank, world, args.steps, args.warmup, mgpu_mode=m)
                for m in modes}
     best = max(results, key=lambda m: results[m]["value"])
@@ -462,6 +481,9 @@ def main():
                    "parallelism": "single GPU" if world == 1 else (
                        f"left operand sharded over {world} GPUs, NCCL all-to-all of partial segments, owner merge"
                        if best == "exchange" else
+                       f"left operand sharded over {world} GPUs, partial terms pushed into the owners' NVLink peer "
+                       f"windows by the producing rank (P2P stores, one all-reduce as barrier), owner merge"
+                       if best == "push" else
                        f"owner-computes over {world} GPUs: both operands on every rank, each rank forms the output "
                        f"rows/segments it owns, no exchange (SURVEY 8e zero-exchange alternative)"),
                    "engine": res["stats"]},
@@ -490,6 +512,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if PX[0] is not None:
+            PX[0].close()
         dist.barrier()
         dist.destroy_process_group()
     eng.close()

@@ -175,6 +175,36 @@ obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk
 obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t nsegs, uint32_t result_mem,
                           obk_poly_result *out, obk_stats *stats);
 
+/* ---- multi-GPU exchange fused into the producer (NVLink peer memory) -------------------------------------------
+ * Instead of returning its partial product, a rank writes every partial term straight into the receive window of
+ * the rank that owns it (P2P stores over NVLink, the slot range reserved with one remote atomic per destination and
+ * CTA).  A window is 2 halves ("parities", alternated step by step so that a fast rank may already push step k+1
+ * while a slow one still merges step k) of `window_bytes` each: [0] term counter, [4] overflow flag, records from
+ * byte 256.  How the peers' windows get mapped into this process is the caller's business (obk_peer_window_alloc /
+ * _open use CUDA IPC; any symmetric-memory allocator works): the engine only sees device pointers.
+ * Protocol per step: obk_poly_mul_push on every rank; one stream-ordered collective on the engine's stream as the
+ * barrier (e.g. an all-reduce of one word); obk_peer_merge on every rank. */
+typedef struct obk_peer_windows {
+    uint32_t nranks;
+    uint32_t rank;
+    uint32_t parity;       /* 0 | 1: the half used by this step */
+    uint32_t reserved;
+    uint64_t window_bytes; /* bytes of ONE half */
+    void *const *base;     /* nranks device pointers: rank g's window as mapped in this process (base[rank] = own) */
+} obk_peer_windows;
+
+/* cudaMalloc'ed window of 2 * window_bytes, zeroed headers, and its 64-byte CUDA IPC handle. */
+obk_status obk_peer_window_alloc(obk_engine *e, uint64_t window_bytes, void **base, void *ipc_handle64);
+obk_status obk_peer_window_open(obk_engine *e, const void *ipc_handle64, void **base);
+obk_status obk_peer_window_close(obk_engine *e, void *base, int own);
+/* obk_poly_mul_partial + push of the partial terms to their owners; stats->acc_limbs is the limb count pushed. */
+obk_status obk_poly_mul_push(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
+                             const obk_peer_windows *w, obk_stats *stats);
+/* Sum what arrived in this rank's window (same as obk_poly_merge on the received records) and clear the window's
+ * header for its next use.  `like` supplies the key layout and coefficient kind, `acc_limbs` the pushed limb count. */
+obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_poly_view *like, uint32_t acc_limbs,
+                          uint32_t result_mem, obk_poly_result *out, obk_stats *stats);
+
 /* ---- the steps either side of the product, on the same device layout ------------------------------
  * Operands and results may stay in DEVICE memory, so a chain such as f *= g; h = f + 1; truncate(h) never leaves
  * HBM (benchmark/dense.hpp:28-32, rectangular_01.cpp:42-47, audi_01.cpp:32-42). */

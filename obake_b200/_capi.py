@@ -31,6 +31,11 @@ class Trunc(C.Structure):
     _fields_ = [("limit", C.c_int64), ("nidx", C.c_uint32), ("partial", C.c_uint32), ("idx", C.c_void_p)]
 
 
+class PeerWindows(C.Structure):
+    _fields_ = [("nranks", C.c_uint32), ("rank", C.c_uint32), ("parity", C.c_uint32), ("reserved", C.c_uint32),
+                ("window_bytes", C.c_uint64), ("base", C.POINTER(C.c_void_p))]
+
+
 class PolyResult(C.Structure):
     _fields_ = [("nterms", C.c_uint64), ("key_words", C.c_uint32), ("cf_kind", C.c_uint32),
                 ("cf_limbs", C.c_uint32), ("log2_nsegs", C.c_uint32), ("mem", C.c_uint32), ("nsegs", C.c_uint32),
@@ -57,6 +62,7 @@ SYMBOLS = [
     "obk_last_error", "obk_status_string", "obk_version", "obk_poly_mul", "obk_result_free",
     "obk_overflow_check", "obk_key_degrees", "obk_poly_mul_partial", "obk_poly_merge",
     "obk_poly_addsub", "obk_poly_truncate_degree",
+    "obk_peer_window_alloc", "obk_peer_window_open", "obk_peer_window_close", "obk_poly_mul_push", "obk_peer_merge",
 ]
 
 _LIB = None
@@ -106,5 +112,17 @@ def lib():
     L.obk_poly_truncate_degree.restype = C.c_int
     L.obk_poly_truncate_degree.argtypes = [C.c_void_p, C.POINTER(PolyView), C.POINTER(Trunc), C.c_uint32,
                                            C.POINTER(PolyResult), C.POINTER(Stats)]
+    L.obk_peer_window_alloc.restype = C.c_int
+    L.obk_peer_window_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]
+    L.obk_peer_window_open.restype = C.c_int
+    L.obk_peer_window_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.obk_peer_window_close.restype = C.c_int
+    L.obk_peer_window_close.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.obk_poly_mul_push.restype = C.c_int
+    L.obk_poly_mul_push.argtypes = [C.c_void_p, C.POINTER(PolyView), C.POINTER(PolyView), C.POINTER(Trunc),
+                                    C.POINTER(PeerWindows), C.POINTER(Stats)]
+    L.obk_peer_merge.restype = C.c_int
+    L.obk_peer_merge.argtypes = [C.c_void_p, C.POINTER(PeerWindows), C.POINTER(PolyView), C.c_uint32, C.c_uint32,
+                                 C.POINTER(PolyResult), C.POINTER(Stats)]
     _LIB = L
     return L

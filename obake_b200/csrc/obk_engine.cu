@@ -1163,6 +1163,8 @@ struct MulRequest {
     // sharding of the left operand (multi-GPU): this call multiplies x[shard_rank] slice only
     uint32_t rank = 0, nranks = 1;
     uint64_t *send_counts = nullptr;
+    // push mode (multi-GPU): the partial terms go straight to their owners' windows, nothing is returned
+    const obk_peer_windows *push = nullptr;
     // merge mode: x is ignored, y holds acc-limb coefficients to be summed by key
     bool merge = false;
     uint32_t merge_nsegs = 1;
@@ -1743,6 +1745,52 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             sc.release(dflags);
         }
 
+        if (rq.push) {
+            const obk_peer_windows &pw = *rq.push;
+            PushParams PP{};
+            PP.keys = rk;
+            PP.cfs = rc;
+            PP.n = total;
+            PP.W = W;
+            PP.L = accw;
+            PP.is_signed = L.is_signed;
+            PP.mod = OBK_EXCHANGE_MOD;
+            PP.nranks = pw.nranks;
+            PP.cap = (pw.window_bytes - PUSH_HEADER) / ((uint64_t)8 * (W + accw));
+            for (uint32_t g = 0; g < pw.nranks; ++g) {
+                PP.win[g] = static_cast<unsigned char *>(pw.base[g]) + (size_t)pw.parity * pw.window_bytes;
+                PP.first_group[g] = (uint32_t)((uint64_t)OBK_EXCHANGE_MOD * g / pw.nranks);
+            }
+            PP.first_group[pw.nranks] = OBK_EXCHANGE_MOD;
+            uint32_t *dover = sc.alloc<uint32_t>(4);
+            CU_CHECK(e, cudaMemsetAsync(dover, 0, 16, s));
+            PP.local_overflow = dover;
+            if (total) {
+                const unsigned g = (unsigned)std::min<uint64_t>((total + 256 * PUSH_ITEMS - 1) / (256 * PUSH_ITEMS), 4 * (uint64_t)e->sm_count);
+                k_push<<<g, 256, 0, s>>>(PP);
+                e->launches += 1;
+                CU_CHECK(e, cudaGetLastError());
+            }
+            uint32_t hover = 0;
+            CU_CHECK(e, cudaMemcpyAsync(&hover, dover, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaEventRecord(e->ev[7], s));
+            CU_CHECK(e, cudaEventRecord(e->ev[8], s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            if (hover) {
+                e->err = "peer window too small for the pushed partial terms (window_bytes = " + std::to_string(pw.window_bytes) + ")";
+                return OBK_ERR_TABLE_OVERFLOW;
+            }
+            set_empty_result(out, x, accw, OBK_MEM_DEVICE);
+            st.nterms_out = total;
+            float msx;
+            cudaEventElapsedTime(&msx, e->ev[0], e->ev[8]);
+            st.ms_total = msx;
+            cudaEventElapsedTime(&msx, e->ev[5], e->ev[6]);
+            st.ms_mul = msx;
+            st.total_launches = e->launches;
+            if (stats) *stats = st;
+            return OBK_OK;
+        }
         TailIn tin{rk, rc, total, W, accw, f64, L.is_signed, tot_mults, rq.result_mem, rq.nranks, owner, 1};
         emit_result(e, sc, tin, out, st);
         ResultOwner *own = static_cast<ResultOwner *>(out->owner);
@@ -1937,6 +1985,134 @@ obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t ns
     rq.merge = true;
     rq.merge_nsegs = nsegs ? nsegs : 1;
     return run_mul(e, rq, out, stats);
+}
+
+obk_status obk_peer_window_alloc(obk_engine *e, uint64_t window_bytes, void **base, void *ipc_handle64)
+{
+    if (!e || !base || window_bytes < 4096) return OBK_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        void *p = nullptr;
+        CU_CHECK(e, cudaMalloc(&p, 2 * window_bytes));
+        CU_CHECK(e, cudaMemset(p, 0, PUSH_HEADER));
+        CU_CHECK(e, cudaMemset(static_cast<char *>(p) + window_bytes, 0, PUSH_HEADER));
+        if (ipc_handle64) {
+            cudaIpcMemHandle_t h;
+            cudaError_t err = cudaIpcGetMemHandle(&h, p);
+            if (err != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(p);
+                e->err = std::string("cudaIpcGetMemHandle failed: ") + cudaGetErrorString(err);
+                return OBK_ERR_CUDA;
+            }
+            std::memcpy(ipc_handle64, &h, 64);
+        }
+        *base = p;
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        return f.st;
+    }
+}
+
+obk_status obk_peer_window_open(obk_engine *e, const void *ipc_handle64, void **base)
+{
+    if (!e || !ipc_handle64 || !base) return OBK_ERR_INVALID_ARG;
+    cudaSetDevice(e->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle64, 64);
+    void *p = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        e->err = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(err);
+        return OBK_ERR_CUDA;
+    }
+    *base = p;
+    return OBK_OK;
+}
+
+obk_status obk_peer_window_close(obk_engine *e, void *base, int own)
+{
+    if (!e || !base) return OBK_ERR_INVALID_ARG;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    cudaError_t err = own ? cudaFree(base) : cudaIpcCloseMemHandle(base);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return OBK_ERR_CUDA;
+    }
+    return OBK_OK;
+}
+
+static bool check_windows(obk_engine *e, const obk_peer_windows *w)
+{
+    if (!w || !w->base || w->nranks == 0 || w->nranks > (uint32_t)PUSH_MAX_RANKS || w->rank >= w->nranks || w->parity > 1
+        || w->window_bytes < 4096) {
+        e->err = "invalid peer windows (1..16 ranks, parity 0|1, window_bytes >= 4096)";
+        return false;
+    }
+    for (uint32_t g = 0; g < w->nranks; ++g)
+        if (!w->base[g]) {
+            e->err = "invalid peer windows: null base pointer";
+            return false;
+        }
+    return true;
+}
+
+obk_status obk_poly_mul_push(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
+                             const obk_peer_windows *w, obk_stats *stats)
+{
+    if (!e) return OBK_ERR_INVALID_ARG;
+    if (!check_windows(e, w)) return OBK_ERR_INVALID_ARG;
+    MulRequest rq{x, y, t, OBK_MEM_DEVICE};
+    rq.rank = w->rank;
+    rq.nranks = w->nranks;
+    rq.push = w;
+    obk_poly_result dummy{};
+    const obk_status st = run_mul(e, rq, &dummy, stats);
+    if (dummy.owner) obk_result_free(e, &dummy);
+    return st;
+}
+
+obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_poly_view *like, uint32_t acc_limbs,
+                          uint32_t result_mem, obk_poly_result *out, obk_stats *stats)
+{
+    if (!e || !like || !out) return OBK_ERR_INVALID_ARG;
+    if (!check_windows(e, w)) return OBK_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        unsigned char *win = static_cast<unsigned char *>(w->base[w->rank]) + (size_t)w->parity * w->window_bytes;
+        uint32_t hdr[2] = {0, 0};
+        CU_CHECK(e, cudaMemcpyAsync(hdr, win, 8, cudaMemcpyDeviceToHost, e->stream));
+        CU_CHECK(e, cudaStreamSynchronize(e->stream));
+        const bool f64 = like->cf_kind == OBK_CF_F64;
+        const uint32_t L = f64 ? 1u : acc_limbs;
+        if (L < 1 || L > 3) {
+            e->err = "acc_limbs must be in [1,3]";
+            return OBK_ERR_INVALID_ARG;
+        }
+        const uint64_t cap = (w->window_bytes - PUSH_HEADER) / ((uint64_t)8 * (like->key_words + L));
+        if (hdr[1] != 0 || hdr[0] > cap) {
+            CU_CHECK(e, cudaMemsetAsync(win, 0, 8, e->stream));
+            e->err = "peer window overflow: " + std::to_string(hdr[0]) + " terms were pushed into a window of " + std::to_string(cap);
+            return OBK_ERR_TABLE_OVERFLOW;
+        }
+        obk_poly_view terms = *like;
+        terms.nterms = hdr[0];
+        terms.cf_limbs = L;
+        terms.mem = OBK_MEM_DEVICE;
+        terms.keys = reinterpret_cast<const uint64_t *>(win + PUSH_HEADER);
+        terms.cfs = terms.keys + cap * like->key_words;
+        MulRequest rq{nullptr, &terms, nullptr, result_mem};
+        rq.merge = true;
+        const obk_status st = run_mul(e, rq, out, stats);
+        CU_CHECK(e, cudaMemsetAsync(win, 0, 8, e->stream));
+        return st;
+    } catch (const obk_fail &f) {
+        return f.st;
+    }
 }
 
 obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int subtract, uint32_t result_mem,

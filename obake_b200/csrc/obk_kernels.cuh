@@ -1070,6 +1070,89 @@ __global__ void __launch_bounds__(256) k_compact(const uint64_t *__restrict__ sk
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// k_push -- multi-GPU exchange fused into the producer: every term of this rank's partial product is written
+// straight into the receive window of the rank that owns it, over NVLink peer memory (plain P2P stores; the slot
+// range is reserved with ONE remote atomic per destination and CTA).  Replaces regroup-by-owner + D2H of the
+// group offsets + all-to-all of counts + two NCCL all-to-alls.  Ownership is the same rule as the NCCL path:
+// group = key mod OBK_EXCHANGE_MOD, contiguous group ranges per rank.
+// Window layout (one per rank and step parity): [0] term counter, [4] overflow flag, records from byte 256:
+// keys[cap][W] then cfs[cap][L].
+// ------------------------------------------------------------------------------------------------
+constexpr int PUSH_MAX_RANKS = 16;
+constexpr int PUSH_ITEMS = 4;
+constexpr uint32_t PUSH_HEADER = 256;
+
+struct PushParams {
+    const uint64_t *keys;
+    const uint64_t *cfs;
+    uint64_t n;
+    int W, L;
+    uint32_t is_signed, mod, nranks;
+    uint64_t cap;                        // terms one window can hold
+    unsigned char *win[PUSH_MAX_RANKS];  // rank g's window (this step's parity) as mapped in this process
+    uint32_t first_group[PUSH_MAX_RANKS + 1]; // rank g owns groups [first_group[g], first_group[g+1])
+    uint32_t *local_overflow;            // set when some window was too small
+};
+
+__global__ void __launch_bounds__(256) k_push(const PushParams P)
+{
+    __shared__ uint32_t s_cnt[PUSH_MAX_RANKS], s_base[PUSH_MAX_RANKS];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    for (uint64_t tile = (uint64_t)blockIdx.x * blockDim.x * PUSH_ITEMS; tile < P.n; tile += (uint64_t)gridDim.x * blockDim.x * PUSH_ITEMS) {
+        if (tid < PUSH_MAX_RANKS) s_cnt[tid] = 0;
+        __syncthreads();
+        uint32_t dest[PUSH_ITEMS], rank_in[PUSH_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PUSH_ITEMS; ++j) {
+            const uint64_t i = tile + (uint64_t)j * blockDim.x + tid;
+            uint32_t g = 0xffffffffu;
+            if (i < P.n) {
+                const uint32_t grp = key_segment(P.keys + i * P.W, P.W, P.mod, P.is_signed);
+                g = (uint32_t)(((uint64_t)grp * P.nranks) / P.mod);
+                while (g + 1 < P.nranks && grp >= P.first_group[g + 1]) ++g;
+                while (g > 0 && grp < P.first_group[g]) --g;
+            }
+            dest[j] = g;
+            const uint32_t peers = __match_any_sync(0xffffffffu, g);
+            if (g != 0xffffffffu) {
+                const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+                uint32_t b0 = 0;
+                if (lane == leader) b0 = atomicAdd(&s_cnt[g], (uint32_t)__popc(peers));
+                b0 = __shfl_sync(peers, b0, (int)leader);
+                rank_in[j] = b0 + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            }
+        }
+        __syncthreads();
+        if (tid < P.nranks) {
+            const uint32_t c = s_cnt[tid];
+            uint32_t b = 0;
+            if (c) {
+                b = atomicAdd(reinterpret_cast<uint32_t *>(P.win[tid]), c); // remote atomic over NVLink (local for own rank)
+                if ((uint64_t)b + c > P.cap) {
+                    reinterpret_cast<volatile uint32_t *>(P.win[tid])[1] = 1u;
+                    *P.local_overflow = 1u;
+                    b = 0xffffffffu;
+                }
+            }
+            s_base[tid] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PUSH_ITEMS; ++j) {
+            const uint32_t g = dest[j];
+            if (g == 0xffffffffu || s_base[g] == 0xffffffffu) continue;
+            const uint64_t i = tile + (uint64_t)j * blockDim.x + tid;
+            const uint64_t dst = (uint64_t)s_base[g] + rank_in[j];
+            uint64_t *wk = reinterpret_cast<uint64_t *>(P.win[g] + PUSH_HEADER);
+            uint64_t *wc = wk + P.cap * (uint64_t)P.W;
+            for (int w = 0; w < P.W; ++w) wk[dst * P.W + w] = P.keys[i * P.W + w];
+            for (int l = 0; l < P.L; ++l) wc[dst * P.L + l] = P.cfs[i * P.L + l];
+        }
+        __syncthreads();
+    }
+}
+
 // ================================================================================================
 // Row-blocked dense path ("kernel 1").
 //

@@ -13,8 +13,10 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+import ctypes as C
+
 from . import _capi
-from .engine import Engine, Product, raw_view
+from .engine import Engine, Product, _raise, raw_view
 
 
 class _DevArray:
@@ -123,3 +125,90 @@ def sharded_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None, result
                              "partial_device_ms": part.stats["ms_total"], "merge_device_ms": merged.stats["ms_total"]}
     part.free()
     return merged, info
+
+
+class PeerExchange:
+    """Receive windows in NVLink peer memory for the fused push exchange (include/obk_b200.h, obk_peer_windows).
+
+    Every rank allocates one window (2 parities of `window_bytes`), exports it with CUDA IPC and opens the windows
+    of its peers; the 64-byte handles travel through torch.distributed (plumbing).  `pushed_mul` then replaces
+    regroup-by-owner + all-to-all of counts + two NCCL all-to-alls by P2P stores issued by the producing rank, with
+    ONE one-word all-reduce as the stream-ordered barrier between the pushes and the owner-side merge."""
+
+    def __init__(self, engine: Engine, window_bytes: int = 1 << 30, group=None):
+        self.engine, self.group = engine, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.window_bytes = int(window_bytes)
+        self.parity = 0
+        L = _capi.lib()
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        rc = L.obk_peer_window_alloc(engine._h, self.window_bytes, C.byref(own), handle)
+        if rc != 0:
+            _raise(rc, engine.last_error())
+        self._own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._base = (C.c_void_p * self.world)()
+        self._opened = []
+        for g in range(self.world):
+            if g == self.rank:
+                self._base[g] = own.value
+                continue
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[g])
+            rc = L.obk_peer_window_open(engine._h, buf, C.byref(p))
+            if rc != 0:
+                _raise(rc, engine.last_error())
+            self._base[g] = p.value
+            self._opened.append(p)
+        dev = torch.device("cuda", engine.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.barrier(group=group)
+
+    def _windows(self) -> _capi.PeerWindows:
+        return _capi.PeerWindows(self.world, self.rank, self.parity, 0, self.window_bytes,
+                                 C.cast(self._base, C.POINTER(C.c_void_p)))
+
+    def pushed_mul(self, vx, vy, limit=None, idx=None, result_mem=_capi.OBK_MEM_DEVICE):
+        """This rank's share of x*y: partial product pushed to the owners' windows -> barrier -> merge."""
+        eng, L = self.engine, _capi.lib()
+        keep = []
+        tr = eng._trunc(limit, idx, keep)
+        w = self._windows()
+        st = _capi.Stats()
+        rc = L.obk_poly_mul_push(eng._h, C.byref(vx), C.byref(vy), C.byref(tr) if tr is not None else None,
+                                 C.byref(w), C.byref(st))
+        failed = 0
+        if rc != 0:
+            failed, msg = rc, eng.last_error()
+        # the barrier: stream-ordered, carries the failure flag so that every rank takes the same branch
+        self._flag.fill_(failed)
+        dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
+        res, mst = _capi.PolyResult(), _capi.Stats()
+        acc = int(st.acc_limbs) if rc == 0 and st.acc_limbs else 1
+        if rc == 0:
+            rc2 = L.obk_peer_merge(eng._h, C.byref(w), C.byref(vx), acc, int(result_mem), C.byref(res), C.byref(mst))
+        self.parity ^= 1
+        if int(self._flag.item()) != 0 or rc != 0:
+            if rc == 0 and rc2 == 0 and res.owner:
+                L.obk_result_free(eng._h, C.byref(res))
+            _raise(rc or int(self._flag.item()), msg if rc != 0 else "a peer failed in the pushed product")
+        if rc2 != 0:
+            _raise(rc2, eng.last_error())
+        merged = Product(eng, res, mst)
+        info = {"mode": "push", "partial_stats": st.as_dict(), "merge_stats": merged.stats,
+                "partial_terms": int(st.nterms_out), "recv_rows": int(mst.term_products), "nsegs": _capi.OBK_EXCHANGE_MOD,
+                "sent_rows": None, "bytes_sent": None}
+        return merged, info
+
+    def close(self):
+        L = _capi.lib()
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            L.obk_peer_window_close(self.engine._h, p, 0)
+        self._opened = []
+        dist.barrier(group=self.group)
+        if self._own:
+            L.obk_peer_window_close(self.engine._h, self._own, 1)
+            self._own = None

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Multi-GPU parity check (run under torchrun): both multi-GPU modes -- left-operand sharding + NCCL all-to-all +
-owner merge ("exchange", the contract design) and owner-computes ("owner", zero exchange) -- gathered on rank 0
-and compared with the CPU oracle.  Used by tests/test_dist_gpu.py."""
+"""Multi-GPU parity check (run under torchrun): the three multi-GPU modes -- left-operand sharding + NCCL all-to-all +
+owner merge ("exchange", the contract design), the same with the exchange fused into the producer as P2P stores into
+the owners' NVLink peer windows ("push"), and owner-computes ("owner", zero exchange) -- gathered on rank 0 and
+compared with the CPU oracle.  Used by tests/test_dist_gpu.py."""
 import os
 import sys
 
@@ -46,17 +47,20 @@ def main():
     fa, ga = wl.audi("u64", 4, nvars=6, n=6)
     cases.append(("audi66 d_packed f64", fa, ga, 6, None))
     ok_all = True
+    px = obd.PeerExchange(eng, window_bytes=64 << 20)
     for name, f, g, limit, idx in cases:
         lin = None if f.is_f64 else max(engine.needed_limbs(f.cfs), engine.needed_limbs(g.cfs))
         hx, hy = engine.HostOperand(f, lin), engine.HostOperand(g, lin)
         ref = reference_dict(orc, f, g, limit, idx) if rank == 0 else None
-        for mode in ("exchange", "owner"):
+        for mode in ("exchange", "push", "owner"):
             if mode == "exchange":
                 p, info = obd.sharded_mul(eng, hx.view, hy.view, limit=limit, idx=idx, result_mem=_capi.OBK_MEM_HOST)
+            elif mode == "push":
+                p, info = px.pushed_mul(hx.view, hy.view, limit=limit, idx=idx, result_mem=_capi.OBK_MEM_HOST)
             else:
                 p, info = obd.owner_mul(eng, hx.view, hy.view, limit=limit, idx=idx)
             mine = p.as_dict()
-            if mode == "exchange" and p.nterms:
+            if mode in ("exchange", "push") and p.nterms:
                 a, b = obd.owner_ranges(info["nsegs"], world)[rank]
                 seg = (p.keys % np.uint64(info["nsegs"])).sum(axis=1) % info["nsegs"]
                 if f.tname == "u64":
@@ -77,6 +81,7 @@ def main():
                       f"sent_rows(rank0)={info['sent_rows']} ok={ok}", flush=True)
                 ok_all &= ok
             p.free()
+    px.close()
     flag = torch.tensor([1 if ok_all else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
