@@ -1767,7 +1767,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             PP.local_overflow = dover;
             if (total) {
                 const unsigned g = (unsigned)std::min<uint64_t>((total + 256 * PUSH_ITEMS - 1) / (256 * PUSH_ITEMS), 4 * (uint64_t)e->sm_count);
-                k_push<<<g, 256, 0, s>>>(PP);
+                const size_t psm = (size_t)256 * PUSH_ITEMS * 8 * (W + accw);
+                CU_CHECK(e, cudaFuncSetAttribute(k_push, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+                k_push<<<g, 256, psm, s>>>(PP);
                 e->launches += 1;
                 CU_CHECK(e, cudaGetLastError());
             }

@@ -1097,9 +1097,16 @@ struct PushParams {
 
 __global__ void __launch_bounds__(256) k_push(const PushParams P)
 {
-    __shared__ uint32_t s_cnt[PUSH_MAX_RANKS], s_base[PUSH_MAX_RANKS];
+    // The records of a tile are first sorted by destination in shared memory, then each destination's run is copied
+    // out with consecutive threads writing consecutive words: NVLink sees 256-byte contiguous stores instead of
+    // scattered 8-byte ones (the scattered version spent 0.57 ms on 0.55 M terms at 8 GPUs).
+    extern __shared__ __align__(16) unsigned char push_smem[];
+    __shared__ uint32_t s_cnt[PUSH_MAX_RANKS], s_base[PUSH_MAX_RANKS], s_off[PUSH_MAX_RANKS + 1];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    for (uint64_t tile = (uint64_t)blockIdx.x * blockDim.x * PUSH_ITEMS; tile < P.n; tile += (uint64_t)gridDim.x * blockDim.x * PUSH_ITEMS) {
+    const uint32_t tile_terms = blockDim.x * PUSH_ITEMS;
+    uint64_t *sk = reinterpret_cast<uint64_t *>(push_smem);      // [tile_terms][W]
+    uint64_t *scf = sk + (size_t)tile_terms * P.W;              // [tile_terms][L]
+    for (uint64_t tile = (uint64_t)blockIdx.x * tile_terms; tile < P.n; tile += (uint64_t)gridDim.x * tile_terms) {
         if (tid < PUSH_MAX_RANKS) s_cnt[tid] = 0;
         __syncthreads();
         uint32_t dest[PUSH_ITEMS], rank_in[PUSH_ITEMS];
@@ -1114,6 +1121,7 @@ __global__ void __launch_bounds__(256) k_push(const PushParams P)
                 while (g > 0 && grp < P.first_group[g]) --g;
             }
             dest[j] = g;
+            rank_in[j] = 0;
             const uint32_t peers = __match_any_sync(0xffffffffu, g);
             if (g != 0xffffffffu) {
                 const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
@@ -1137,17 +1145,38 @@ __global__ void __launch_bounds__(256) k_push(const PushParams P)
             }
             s_base[tid] = b;
         }
+        if (tid == 0) {
+            uint32_t o = 0;
+            for (uint32_t g = 0; g < P.nranks; ++g) {
+                s_off[g] = o;
+                o += s_cnt[g];
+            }
+            s_off[P.nranks] = o;
+        }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < PUSH_ITEMS; ++j) {
             const uint32_t g = dest[j];
-            if (g == 0xffffffffu || s_base[g] == 0xffffffffu) continue;
+            if (g == 0xffffffffu) continue;
             const uint64_t i = tile + (uint64_t)j * blockDim.x + tid;
-            const uint64_t dst = (uint64_t)s_base[g] + rank_in[j];
-            uint64_t *wk = reinterpret_cast<uint64_t *>(P.win[g] + PUSH_HEADER);
-            uint64_t *wc = wk + P.cap * (uint64_t)P.W;
-            for (int w = 0; w < P.W; ++w) wk[dst * P.W + w] = P.keys[i * P.W + w];
-            for (int l = 0; l < P.L; ++l) wc[dst * P.L + l] = P.cfs[i * P.L + l];
+            const uint32_t pos = s_off[g] + rank_in[j];
+            for (int w = 0; w < P.W; ++w) sk[(size_t)pos * P.W + w] = P.keys[i * P.W + w];
+            for (int l = 0; l < P.L; ++l) scf[(size_t)pos * P.L + l] = P.cfs[i * P.L + l];
+        }
+        __syncthreads();
+        const uint32_t nrec = s_off[P.nranks];
+        for (int part = 0; part < 2; ++part) {
+            const uint32_t wpr = part == 0 ? (uint32_t)P.W : (uint32_t)P.L; // words per record
+            const uint64_t *src = part == 0 ? sk : scf;
+            for (uint32_t q = tid; q < nrec * wpr; q += blockDim.x) {
+                const uint32_t r = q / wpr, wi = q - r * wpr;
+                uint32_t g = 0;
+                while (g + 1 < P.nranks && r >= s_off[g + 1]) ++g;
+                if (s_base[g] == 0xffffffffu) continue;
+                uint64_t *wk = reinterpret_cast<uint64_t *>(P.win[g] + PUSH_HEADER);
+                uint64_t *dstp = part == 0 ? wk : wk + P.cap * (uint64_t)P.W;
+                dstp[((uint64_t)s_base[g] + (r - s_off[g])) * wpr + wi] = src[q];
+            }
         }
         __syncthreads();
     }
