@@ -1284,15 +1284,18 @@ __device__ __forceinline__ void row_mac(uint64_t (&z)[LACC], uint64_t x, uint64_
     if constexpr (LACC == 1) {
         z[0] += x * y;
     } else {
-        const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32);
-        const uint64_t p00 = (uint64_t)x0 * y0;
-        const uint64_t t = (uint64_t)x0 * y1 + (p00 >> 32);
-        const uint64_t u = (uint64_t)x1 * y0 + (uint32_t)t;
-        const uint64_t lo = (u << 32) | (uint32_t)p00;
-        uint64_t hi = (uint64_t)x1 * y1 + (t >> 32) + (u >> 32);
-        if constexpr (!UNS) {
-            // signed correction of the high half: hi_s = hi_u - (x < 0 ? y : 0) - (y < 0 ? x : 0)
-            hi -= ((long long)x < 0 ? y : 0ull) + ((long long)y < 0 ? x : 0ull);
+        // The 64x64->128 product as ONE 128-bit multiply: the compiler lowers it to 3 IMAD.WIDE + 1 IMAD.WIDE.X with
+        // the carries chained through predicates (20 SASS instructions per convolution step including the operand
+        // fetch; the hand-split 32-bit form took 26, x*y next to __umul64hi 24).
+        uint64_t lo, hi;
+        if constexpr (UNS) {
+            const unsigned __int128 p = (unsigned __int128)x * y;
+            lo = (uint64_t)p;
+            hi = (uint64_t)(p >> 64);
+        } else {
+            const __int128 p = (__int128)(long long)x * (long long)y;
+            lo = (uint64_t)p;
+            hi = (uint64_t)((unsigned __int128)p >> 64);
         }
         if constexpr (LACC == 2) {
             asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(z[0]), "+l"(z[1]) : "l"(lo), "l"(hi));
@@ -1342,7 +1345,12 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
+    // per-warp staging of the current row pair (double-buffered): the convolution reads x[i] as a broadcast LDS and
+    // y[(lane - i) & 31] as a conflict-free LDS instead of four SHFL per step
+    __shared__ __align__(16) uint64_t s_pair[BT / 32][2][2][32];
     const uint32_t lane = threadIdx.x & 31u;
+    uint64_t(*wp)[2][32] = s_pair[threadIdx.x >> 5];
+    uint32_t pbuf = 0;
     const uint64_t *xr_hi = P.xr_hi, *yr_hi = P.yr_hi;
     const uint32_t *xr_sl = P.xr_sl, *yr_off = P.yr_off, *yr_il = P.yr_il;
     if (P.dir_in_smem) {
@@ -1438,12 +1446,17 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
                     len1 = len2;
                     len2 = tl;
                 }
+                const uint64_t *px = wp[pbuf][0], *py = wp[pbuf][1];
+                wp[pbuf][0][lane] = X;
+                wp[pbuf][1][lane] = Y;
+                pbuf ^= 1u;
+                __syncwarp(); // the other buffer is free: every lane passed this point after finishing the pair before last
                 if (len1 + len2 <= 33u) {
                     // the output row fits 32 lanes: the wrapped-around lanes of the rotation read zeros of the
                     // longer row, so every lane accumulates unconditionally into its low output
                     for (uint32_t i = 0; i < len1; ++i) {
-                        const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
-                        const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                        const uint64_t xi = px[i];
+                        const uint64_t yv = py[(lane - i) & 31u];
                         if constexpr (F64) {
                             d0 = __dadd_rn(d0, __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv)));
                         } else {
@@ -1452,8 +1465,8 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
                     }
                 } else {
                     for (uint32_t i = 0; i < len1; ++i) {
-                        const uint64_t xi = __shfl_sync(0xffffffffu, X, (int)i);
-                        const uint64_t yv = __shfl_sync(0xffffffffu, Y, (int)((lane - i) & 31u));
+                        const uint64_t xi = px[i];
+                        const uint64_t yv = py[(lane - i) & 31u];
                         // lane >= i: the rotated value belongs to output lo = lane, else to output lo = lane + 32;
                         // mask the INPUT so both accumulators run branch-free multiply-adds
                         const bool lowhalf = lane >= i;
