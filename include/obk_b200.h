@@ -209,6 +209,11 @@ obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_po
  * Operands and results may stay in DEVICE memory, so a chain such as f *= g; h = f + 1; truncate(h) never leaves
  * HBM (benchmark/dense.hpp:28-32, rectangular_01.cpp:42-47, audi_01.cpp:32-42). */
 
+/* Copy a polynomial's terms into engine-owned HOST or DEVICE memory: the upload that starts a device-resident
+ * chain (what poly_mul_impl_mt_hm's term copy, polynomial.hpp:828-833, does once per product in the reference) and
+ * the download that ends it (a HOST copy arrives grouped the way a series stores its terms). */
+obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_mem, obk_poly_result *out);
+
 /* Series addition / subtraction of two polynomials over the SAME symbol set (series.hpp:2195-2991, the
  * identical-symbol-set branch of series_default_addsub_impl): out = x + y or x - y, exact for integers (the result
  * uses as many limbs as the sum needs, at most 3), terms that cancel are erased. */

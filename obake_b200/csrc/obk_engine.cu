@@ -2224,6 +2224,42 @@ obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly
     return rc_status;
 }
 
+obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_mem, obk_poly_result *out)
+{
+    if (!e || !out || !x) return OBK_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    obk_stats st{};
+    e->launches = 0;
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        validate_view(e, x, "x");
+        const bool f64 = x->cf_kind == OBK_CF_F64;
+        const int W = (int)x->key_words, cw = f64 ? 1 : (int)x->cf_limbs;
+        const uint64_t n = x->nterms;
+        if (n == 0) {
+            set_empty_result(out, x, cw, result_mem);
+            return OBK_OK;
+        }
+        const Layout L = make_layout(*x);
+        Scratch sc(e);
+        cudaStream_t s = e->stream;
+        CU_CHECK(e, cudaEventRecord(e->ev[0], s));
+        uint64_t *rk = sc.alloc_out<uint64_t>(n * W);
+        uint64_t *rc = sc.alloc_out<uint64_t>(n * cw);
+        const cudaMemcpyKind kind = x->mem == OBK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        CU_CHECK(e, cudaMemcpyAsync(rk, x->keys, n * W * 8, kind, s));
+        CU_CHECK(e, cudaMemcpyAsync(rc, x->cfs, n * cw * 8, kind, s));
+        TailIn tin{rk, rc, n, W, cw, f64, L.is_signed, n, result_mem, 1, false, 1};
+        emit_result(e, sc, tin, out, st);
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        if (out->owner) obk_result_free(e, out);
+        std::memset(out, 0, sizeof(*out));
+        cudaStreamSynchronize(e->stream);
+        return f.st;
+    }
+}
+
 obk_status obk_poly_truncate_degree(obk_engine *e, const obk_poly_view *x, const obk_trunc *t, uint32_t result_mem,
                                     obk_poly_result *out, obk_stats *stats)
 {

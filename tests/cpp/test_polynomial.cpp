@@ -12,6 +12,7 @@
 #include <string>
 
 #include <obake/polynomials/polynomial.hpp>
+#include <obake/b200/device_polynomial.hpp>
 
 using namespace obake;
 
@@ -292,6 +293,53 @@ static void fateman_test()
     REQUIRE(sum == pow(integer(5), 24) + pow(integer(5), 12));
 }
 
+// Device-resident chains: the operand-building loops of the reference's benchmarks (f *= tmp,
+// benchmark/dense.hpp:28-32; g = f + 1, :34; truncated products, audi_01.cpp:32-42) with every intermediate in HBM,
+// compared with the same chain through the host container.
+template <typename K, typename C>
+static void device_chain_test()
+{
+    using poly_t = polynomial<K, C>;
+    using dpoly_t = b200::device_polynomial<K, C>;
+    const symbol_set ss{"t", "x", "y", "z"};
+    auto [t, x, y, z] = make_polynomials<poly_t>(ss, "t", "x", "y", "z");
+    const poly_t tmp = x + y * 2 - z + t * 3 + 1;
+    poly_t f = tmp;
+    dpoly_t df(tmp);
+    const dpoly_t dtmp(tmp);
+    REQUIRE(df.size() == tmp.size());
+    REQUIRE(df.to_host() == tmp);
+    for (int i = 1; i < 7; ++i) {
+        f *= tmp;
+        df = df * dtmp; // never leaves the GPU
+    }
+    REQUIRE(df.size() == f.size());
+    REQUIRE(df.to_host() == f);
+    // g = f + tmp, h = f - f, products and truncation
+    const poly_t g = f + tmp;
+    const dpoly_t dg = df + dtmp;
+    REQUIRE(dg.to_host() == g);
+    REQUIRE((df - df).empty());
+    REQUIRE((dg - dtmp).to_host() == f);
+    const poly_t full = f * g;
+    const dpoly_t dfull = df * dg;
+    REQUIRE(dfull.to_host() == full);
+    REQUIRE(truncated_mul(df, dg, 9).to_host() == truncated_mul(f, g, 9));
+    REQUIRE(truncated_mul(df, dg, 5, symbol_set{"x", "z"}).to_host() == truncated_mul(f, g, 5, symbol_set{"x", "z"}));
+    REQUIRE(truncate_degree(dfull, 8).to_host() == truncate_degree(full, 8));
+    REQUIRE(truncate_p_degree(dfull, 3, symbol_set{"t", "y"}).to_host() == truncate_p_degree(full, 3, symbol_set{"t", "y"}));
+    REQUIRE(truncate_degree(dfull, -1).to_host() == truncate_degree(full, -1));
+    // empty operands and mismatched symbol sets
+    poly_t e0;
+    e0.set_symbol_set(ss);
+    const dpoly_t de(e0);
+    REQUIRE((df * de).empty());
+    REQUIRE((df + de).to_host() == f);
+    auto [a] = make_polynomials<poly_t>(symbol_set{"a"}, "a");
+    const dpoly_t da(a);
+    REQUIRES_THROWS_CONTAINS(df * da, std::invalid_argument, "share the symbol set");
+}
+
 int main(int argc, char **argv)
 {
     const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
@@ -318,6 +366,9 @@ int main(int argc, char **argv)
         large_tests<packed_monomial<std::int64_t>, integer>();
         large_tests<d_packed_monomial<std::int64_t, 3>, double>();
         fateman_test();
+        device_chain_test<packed_monomial<std::uint64_t>, integer>();
+        device_chain_test<packed_monomial<std::int64_t>, double>();
+        device_chain_test<d_packed_monomial<std::int64_t, 2>, integer>();
     }
     std::printf("%s: %d checks, %d failures%s\n", g_fail ? "FAILED" : "OK", g_checks, g_fail, cpu_only ? " (host-only subset)" : "");
     return g_fail ? 1 : 0;
