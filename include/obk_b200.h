@@ -214,6 +214,15 @@ obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_po
  * the download that ends it (a HOST copy arrives grouped the way a series stores its terms). */
 obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_mem, obk_poly_result *out);
 
+/* Symbol-set extension (series_sym_extender, series.hpp:539-625, with key_merge_symbols,
+ * src/polynomials/packed_monomial.cpp:234-292 / d_packed_monomial.hpp:473-520): re-express x over a larger symbol
+ * set of `new_nvars` symbols; pos[j] (strictly increasing, host memory, x->nvars entries) is the position of x's
+ * j-th symbol in the new set, the new symbols get exponent 0.  Every key is re-packed with the Kronecker deltas of
+ * the new size; an exponent outside the new limits fails with OBK_ERR_KEY_OVERFLOW (the reference's kpacker throws
+ * std::overflow_error), too many symbols for one packed word with OBK_ERR_INVALID_ARG. */
+obk_status obk_poly_extend_symbols(obk_engine *e, const obk_poly_view *x, uint32_t new_nvars, const uint32_t *pos,
+                                   uint32_t result_mem, obk_poly_result *out);
+
 /* Series addition / subtraction of two polynomials over the SAME symbol set (series.hpp:2195-2991, the
  * identical-symbol-set branch of series_default_addsub_impl): out = x + y or x - y, exact for integers (the result
  * uses as many limbs as the sum needs, at most 3), terms that cancel are erased. */

@@ -61,7 +61,7 @@ SYMBOLS = [
     "obk_engine_create", "obk_engine_destroy", "obk_engine_set_stream", "obk_engine_set_option",
     "obk_last_error", "obk_status_string", "obk_version", "obk_poly_mul", "obk_result_free",
     "obk_overflow_check", "obk_key_degrees", "obk_poly_mul_partial", "obk_poly_merge",
-    "obk_poly_addsub", "obk_poly_truncate_degree", "obk_poly_copy",
+    "obk_poly_addsub", "obk_poly_truncate_degree", "obk_poly_copy", "obk_poly_extend_symbols",
     "obk_peer_window_alloc", "obk_peer_window_open", "obk_peer_window_close", "obk_poly_mul_push", "obk_peer_merge",
 ]
 
@@ -114,6 +114,9 @@ def lib():
                                            C.POINTER(PolyResult), C.POINTER(Stats)]
     L.obk_poly_copy.restype = C.c_int
     L.obk_poly_copy.argtypes = [C.c_void_p, C.POINTER(PolyView), C.c_uint32, C.POINTER(PolyResult)]
+    L.obk_poly_extend_symbols.restype = C.c_int
+    L.obk_poly_extend_symbols.argtypes = [C.c_void_p, C.POINTER(PolyView), C.c_uint32, C.c_void_p, C.c_uint32,
+                                          C.POINTER(PolyResult)]
     L.obk_peer_window_alloc.restype = C.c_int
     L.obk_peer_window_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p]
     L.obk_peer_window_open.restype = C.c_int

@@ -2260,6 +2260,90 @@ obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_
     }
 }
 
+obk_status obk_poly_extend_symbols(obk_engine *e, const obk_poly_view *x, uint32_t new_nvars, const uint32_t *pos,
+                                   uint32_t result_mem, obk_poly_result *out)
+{
+    if (!e || !out || !x) return OBK_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    obk_stats st{};
+    e->launches = 0;
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        validate_view(e, x, "x");
+        if (new_nvars < x->nvars || new_nvars > (uint32_t)MAX_VARS || (x->nvars && !pos)) {
+            e->err = "symbol-set extension: the new symbol set must contain the old one (at most 64 symbols)";
+            return OBK_ERR_INVALID_ARG;
+        }
+        for (uint32_t j = 0; j < x->nvars; ++j)
+            if (pos[j] >= new_nvars || (j && pos[j] <= pos[j - 1])) {
+                e->err = "symbol-set extension: positions must be strictly increasing and inside the new symbol set";
+                return OBK_ERR_INVALID_ARG;
+            }
+        obk_poly_view nv = *x;
+        nv.nvars = new_nvars;
+        nv.key_words = x->psize ? std::max(1u, (new_nvars + x->psize - 1) / x->psize) : 1u;
+        if (x->psize == 0 && new_nvars > key_max_size(*x)) {
+            e->err = "Invalid size specified in the constructor of a Kronecker packer: too many symbols for one packed word";
+            return OBK_ERR_INVALID_ARG;
+        }
+        if (nv.key_words > 4) {
+            e->err = "symbol-set extension: key_words must be in [1,4]";
+            return OBK_ERR_UNSUPPORTED;
+        }
+        const bool f64 = x->cf_kind == OBK_CF_F64;
+        const int W = (int)x->key_words, Wn = (int)nv.key_words, cw = f64 ? 1 : (int)x->cf_limbs;
+        const uint64_t n = x->nterms;
+        if (n == 0) {
+            set_empty_result(out, &nv, cw, result_mem);
+            return OBK_OK;
+        }
+        ExtendParams P{};
+        P.lo = make_layout(*x);
+        P.ln = make_layout(nv);
+        i128 lmin = 0, lmax = 0;
+        component_lims(nv, P.ln.wsize ? P.ln.wsize : 1, lmin, lmax);
+        P.lim_max_new = (uint64_t)lmax;
+        for (uint32_t j = 0; j < x->nvars; ++j) P.pos[j] = pos[j];
+        P.n = n;
+        Scratch sc(e);
+        cudaStream_t s = e->stream;
+        CU_CHECK(e, cudaEventRecord(e->ev[0], s));
+        const uint64_t *dk = x->keys;
+        uint64_t *rk = sc.alloc_out<uint64_t>(n * Wn);
+        uint64_t *rc = sc.alloc_out<uint64_t>(n * cw);
+        if (x->mem == OBK_MEM_HOST) {
+            uint64_t *k = sc.alloc<uint64_t>(n * W);
+            CU_CHECK(e, cudaMemcpyAsync(k, x->keys, n * W * 8, cudaMemcpyHostToDevice, s));
+            dk = k;
+        }
+        CU_CHECK(e, cudaMemcpyAsync(rc, x->cfs, n * cw * 8, x->mem == OBK_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+        uint32_t *dover = sc.alloc<uint32_t>(4);
+        CU_CHECK(e, cudaMemsetAsync(dover, 0, 16, s));
+        P.keys = dk;
+        P.okeys = rk;
+        P.overflow = dover;
+        k_extend_symbols<<<(unsigned)std::min<uint64_t>((n + 127) / 128, 4096), 128, 0, s>>>(P);
+        e->launches += 1;
+        CU_CHECK(e, cudaGetLastError());
+        uint32_t hover = 0;
+        CU_CHECK(e, cudaMemcpyAsync(&hover, dover, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        if (hover) {
+            e->err = "Cannot push a value to this Kronecker packer: an exponent is outside the range allowed by the "
+                     "extended symbol set (overflow while merging symbols)";
+            return OBK_ERR_KEY_OVERFLOW;
+        }
+        TailIn tin{rk, rc, n, Wn, cw, f64, P.ln.is_signed, n, result_mem, 1, false, 1};
+        emit_result(e, sc, tin, out, st);
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        if (out->owner) obk_result_free(e, out);
+        std::memset(out, 0, sizeof(*out));
+        cudaStreamSynchronize(e->stream);
+        return f.st;
+    }
+}
+
 obk_status obk_poly_truncate_degree(obk_engine *e, const obk_poly_view *x, const obk_trunc *t, uint32_t result_mem,
                                     obk_poly_result *out, obk_stats *stats)
 {

@@ -477,6 +477,51 @@ __global__ void __launch_bounds__(256) k_widen_cfs(const uint64_t *__restrict__ 
     }
 }
 
+// Symbol-set extension (series_sym_extender, series.hpp:539-625; key_merge_symbols,
+// src/polynomials/packed_monomial.cpp:234-292, d_packed_monomial.hpp:473-520): every key is unpacked, its exponents
+// are moved to their positions in the larger symbol set (zeros for the new symbols) and packed again with the
+// deltas of the new size.  An exponent outside the new limits sets *overflow (the reference's kpacker throws).
+struct ExtendParams {
+    const uint64_t *keys;
+    uint64_t n;
+    Layout lo, ln;          // old and new key layouts
+    uint64_t lim_max_new;   // largest component value of the new layout (bit pattern of T)
+    uint32_t pos[MAX_VARS]; // position of old variable j in the new symbol set
+    uint64_t *okeys;
+    uint32_t *overflow;
+};
+
+__global__ void __launch_bounds__(128) k_extend_symbols(const ExtendParams P)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        int64_t en[MAX_VARS];
+        for (uint32_t v = 0; v < P.ln.nvars; ++v) en[v] = 0;
+        uint32_t vi = 0;
+        bool bad = false;
+        for (uint32_t w = 0; w < P.lo.W; ++w) {
+            uint64_t v = P.keys[i * P.lo.W + w] - P.lo.klim_min;
+            for (uint32_t j = 0; j < P.lo.wsize && vi < P.lo.nvars; ++j, ++vi) {
+                const uint64_t q = v / P.lo.delta;
+                const int64_t e = (int64_t)(v - q * P.lo.delta) + P.lo.lim_min;
+                v = q;
+                en[P.pos[vi]] = e;
+                bad |= P.ln.is_signed ? (e < P.ln.lim_min || e > (int64_t)P.lim_max_new) : ((uint64_t)e > P.lim_max_new);
+            }
+        }
+        if (bad) *P.overflow = 1u;
+        uint32_t base = 0;
+        for (uint32_t w = 0; w < P.ln.W; ++w) {
+            // Horner from the highest digit of the word: value = sum_j e_j * delta^j (kpack.hpp:262-267)
+            const uint32_t cnt = min(P.ln.wsize, P.ln.nvars - base);
+            uint64_t val = 0;
+            for (uint32_t j = cnt; j-- > 0;) val = val * P.ln.delta + (uint64_t)en[base + j];
+            P.okeys[i * P.ln.W + w] = val;
+            base += P.ln.wsize;
+        }
+    }
+}
+
 // tot_n_mults of a truncated product (polynomial.hpp:574-623): for each left term the number of right
 // terms whose degree passes the limit, via the degree histogram's prefix sums.
 __global__ void __launch_bounds__(256) k_deg_hist(const int64_t *__restrict__ deg, uint64_t n, int64_t degmin,

@@ -338,6 +338,21 @@ class Engine:
         hx = HostOperand(x)
         return self.truncate_degree_view(hx.view, limit, idx, result_mem)
 
+    def extend_symbols_view(self, vx: PolyView, new_nvars: int, pos, result_mem=OBK_MEM_HOST) -> Product:
+        """Re-express x over a larger symbol set (series_sym_extender, series.hpp:539-625): pos[j] is the position
+        of x's j-th symbol in the new set; every key is re-packed on the device."""
+        pa = np.ascontiguousarray([int(p) for p in pos], dtype=np.uint32)
+        res = PolyResult()
+        rc = _capi.lib().obk_poly_extend_symbols(self._h, C.byref(vx), int(new_nvars),
+                                                 pa.ctypes.data if len(pa) else None, int(result_mem), C.byref(res))
+        if rc != 0:
+            _raise(rc, self.last_error())
+        return Product(self, res, Stats())
+
+    def extend_symbols(self, x, new_nvars: int, pos, result_mem=OBK_MEM_HOST) -> Product:
+        hx = HostOperand(x)
+        return self.extend_symbols_view(hx.view, new_nvars, pos, result_mem)
+
     def merge_view(self, vterms: PolyView, nsegs: int, result_mem=OBK_MEM_HOST) -> Product:
         res, st = PolyResult(), Stats()
         rc = _capi.lib().obk_poly_merge(self._h, C.byref(vterms), int(nsegs), int(result_mem), C.byref(res),

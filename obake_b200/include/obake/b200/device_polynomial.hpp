@@ -10,8 +10,8 @@
 //     f + g, f - g                                    obk_poly_addsub          (series.hpp:2195-2991, identical symbol sets)
 //     truncate_degree / truncate_p_degree             obk_poly_truncate_degree (polynomial.hpp:2364-2445)
 //     f.to_host()                                     download + container rebuild, once
-// Operands of one operation must share the symbol set (merging symbol sets re-packs every key, series.hpp:539-625,
-// and is host work in this repository: extend on the host before uploading).  Errors are the host mirror's:
+//     operands over different symbol sets           obk_poly_extend_symbols  (series.hpp:539-625: keys re-packed on the device)
+// Errors are the host mirror's:
 // std::overflow_error / std::invalid_argument / std::runtime_error (obake/b200/engine.hpp).
 #ifndef OBAKE_B200_DEVICE_POLYNOMIAL_HPP
 #define OBAKE_B200_DEVICE_POLYNOMIAL_HPP
@@ -43,10 +43,25 @@ class device_polynomial
         }
         m_res = obk_poly_result{};
     }
-    static void same_ss(const device_polynomial &a, const device_polynomial &b)
+    // Operands over different symbol sets are re-expressed over the union ON THE DEVICE (series_sym_extender,
+    // series.hpp:539-625 -> obk_poly_extend_symbols) as poly_mul_impl does on the host (polynomial.hpp:1955-2010).
+    static void unify(const device_polynomial &a, const device_polynomial &b, device_polynomial &ta, device_polynomial &tb,
+                      const device_polynomial *&pa, const device_polynomial *&pb)
     {
-        if (!(a.m_ss == b.m_ss)) {
-            throw std::invalid_argument("device_polynomial operands must share the symbol set (extend on the host first)");
+        pa = &a;
+        pb = &b;
+        if (a.m_ss == b.m_ss) {
+            return;
+        }
+        std::vector<std::size_t> posa, posb;
+        const symbol_set u = merge_symbol_sets(a.m_ss, b.m_ss, posa, posb);
+        if (!(u == a.m_ss)) {
+            ta = a.extend(u, posa);
+            pa = &ta;
+        }
+        if (!(u == b.m_ss)) {
+            tb = b.extend(u, posb);
+            pb = &tb;
         }
     }
     static device_polynomial adopt(const symbol_set &ss, const obk_poly_result &r)
@@ -145,6 +160,22 @@ public:
         v.cfs = m_res.cfs;
         return v;
     }
+    // this polynomial over the larger symbol set u; pos[j] = position in u of the j-th symbol of this one
+    device_polynomial extend(const symbol_set &u, const std::vector<std::size_t> &pos) const
+    {
+        device_polynomial r;
+        r.m_ss = u;
+        if (empty()) {
+            return r;
+        }
+        std::vector<std::uint32_t> p32(pos.begin(), pos.end());
+        const obk_poly_view v = view();
+        auto &eng = engine::instance();
+        std::lock_guard<std::mutex> g(eng.mutex());
+        eng.check(::obk_poly_extend_symbols(eng.handle(), &v, static_cast<std::uint32_t>(u.size()), p32.data(), OBK_MEM_DEVICE,
+                                            &r.m_res));
+        return r;
+    }
     // download + host container rebuild
     polynomial<K, C> to_host() const
     {
@@ -177,9 +208,12 @@ public:
     }
 
     // ---- the product (poly_mul_impl_identical_ss seam, polynomial.hpp:1878-1929) -------------------------------
-    static device_polynomial mul(const device_polynomial &a, const device_polynomial &b, const ::obake::detail::trunc_args &ta)
+    static device_polynomial mul(const device_polynomial &a0, const device_polynomial &b0, const ::obake::detail::trunc_args &ta)
     {
-        same_ss(a, b);
+        device_polynomial xa, xb;
+        const device_polynomial *pa, *pb;
+        unify(a0, b0, xa, xb, pa, pb);
+        const device_polynomial &a = *pa, &b = *pb;
         if (a.empty() || b.empty() || ta.reject_all) {
             device_polynomial r;
             r.m_ss = a.m_ss;
@@ -217,14 +251,18 @@ public:
         ::obake::detail::trunc_args ta;
         ::obake::detail::reduce_limit<T>(ta, max_degree);
         ta.partial = true;
-        ta.idx = ss_intersect_idx(s, a.m_ss);
+        std::vector<std::size_t> posa, posb;
+        ta.idx = ss_intersect_idx(s, merge_symbol_sets(a.m_ss, b.m_ss, posa, posb)); // positions in the MERGED set
         return mul(a, b, ta);
     }
 
     // ---- addition / subtraction (series.hpp:2195-2991, identical symbol sets) ----------------------------------
-    static device_polynomial addsub(const device_polynomial &a, const device_polynomial &b, bool subtract)
+    static device_polynomial addsub(const device_polynomial &a0, const device_polynomial &b0, bool subtract)
     {
-        same_ss(a, b);
+        device_polynomial xa, xb;
+        const device_polynomial *pa, *pb;
+        unify(a0, b0, xa, xb, pa, pb);
+        const device_polynomial &a = *pa, &b = *pb;
         const obk_poly_view va = a.view(), vb = b.view();
         obk_poly_result r{};
         auto &eng = engine::instance();

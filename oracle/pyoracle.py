@@ -111,3 +111,16 @@ def truncate_degree(x: dict, max_deg, idx=None) -> dict:
     """truncate_degree / truncate_p_degree (include/obake/polynomials/polynomial.hpp:2364-2445): filter() keeping
     the terms with not (max_deg < degree); partial degree over the symbol positions idx."""
     return {e: c for e, c in x.items() if not (max_deg < degree(e, idx))}
+
+
+def extend_symbols(x: dict, new_nvars: int, pos) -> dict:
+    """series_sym_extender (include/obake/series.hpp:539-625) on exponent tuples: x's j-th exponent moves to
+    position pos[j] of the larger symbol set, new symbols get exponent 0 (key_merge_symbols,
+    src/polynomials/packed_monomial.cpp:234-292)."""
+    out = {}
+    for e, c in x.items():
+        n = [0] * new_nvars
+        for j, v in enumerate(e):
+            n[pos[j]] = v
+        out[tuple(n)] = c
+    return out

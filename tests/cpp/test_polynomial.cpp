@@ -335,9 +335,15 @@ static void device_chain_test()
     const dpoly_t de(e0);
     REQUIRE((df * de).empty());
     REQUIRE((df + de).to_host() == f);
-    auto [a] = make_polynomials<poly_t>(symbol_set{"a"}, "a");
-    const dpoly_t da(a);
-    REQUIRES_THROWS_CONTAINS(df * da, std::invalid_argument, "share the symbol set");
+    // different symbol sets: the keys are re-packed over the union on the device (series.hpp:539-625)
+    auto [a, y2] = make_polynomials<poly_t>(symbol_set{"a", "y"}, "a", "y");
+    const poly_t q = a * 3 + y2 * y2 - 2;
+    const dpoly_t dq(q);
+    REQUIRE((df * dq).get_symbol_set() == symbol_set{"a", "t", "x", "y", "z"});
+    REQUIRE((df * dq).to_host() == f * q);
+    REQUIRE((dq + df).to_host() == q + f);
+    REQUIRE((dq - df).to_host() == q - f);
+    REQUIRE(truncated_mul(df, dq, 6, symbol_set{"a", "x"}).to_host() == truncated_mul(f, q, 6, symbol_set{"a", "x"}));
 }
 
 int main(int argc, char **argv)

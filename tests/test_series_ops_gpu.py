@@ -88,6 +88,51 @@ def test_truncate_degree(engine, tn):
         assert p.as_dict() == packed(pyoracle.truncate_degree(xd, 9, idx), x), idx
 
 
+@pytest.mark.parametrize("tn,psize", [("u64", 0), ("i64", 0), ("u64", 2), ("i64", 4)])
+def test_extend_symbols(engine, tn, psize):
+    """series_sym_extender on the device: keys re-packed over a larger symbol set (series.hpp:539-625)."""
+    rng = np.random.default_rng(12)
+    x = wl.random_poly(rng, 1500, 3, 11, 30, tn, psize, signed_expos=(tn == "i64"))
+    pos, nn = [1, 2, 5], 7
+    big = wl.Operand(tuple("abcdefg"), np.zeros((1, nn), dtype=np.int64), np.zeros(1), tn, psize)
+    p = engine.extend_symbols(x, nn, pos)
+    assert p.key_words == big.key_words
+    assert p.as_dict() == packed(pyoracle.extend_symbols(x.to_dict(), nn, pos), big)
+    # identity extension and device-resident operand
+    hx = HostOperand(x)
+    d = engine.extend_symbols_view(hx.view, 3, [0, 1, 2], result_mem=_capi.OBK_MEM_DEVICE)
+    assert d.on_device and d.as_dict() == packed(x.to_dict(), x)
+    d.free()
+    # an exponent that fits 3 packed symbols but not 7 (per word: psize symbols): the reference's kpacker throws
+    if psize == 0:
+        lim7 = kpack.lims(tn, nn)[1]
+        assert kpack.lims(tn, 3)[1] > lim7
+        y = wl.from_dict(("a", "b", "c"), {(lim7 + 1, 0, 1): 3, (1, 1, 1): 2}, tn)
+        with pytest.raises(OverflowError):
+            engine.extend_symbols(y, nn, pos)
+        with pytest.raises(ValueError):
+            engine.extend_symbols(y, kpack.tables(tn)["max_size"] + 1, pos)  # too many symbols for one word
+    with pytest.raises(ValueError):
+        engine.extend_symbols(x, nn, [2, 1, 5])
+
+
+def test_product_after_extension(engine):
+    """x(a,b) * y(b,c): both operands extended to (a,b,c) on the device, then multiplied without leaving HBM."""
+    rng = np.random.default_rng(13)
+    x = wl.random_poly(rng, 800, 2, 40, 20, "u64")
+    y = wl.random_poly(rng, 700, 2, 40, 20, "u64")
+    hx, hy = HostOperand(x), HostOperand(y)
+    dx = engine.extend_symbols_view(hx.view, 3, [0, 1], result_mem=_capi.OBK_MEM_DEVICE)
+    dy = engine.extend_symbols_view(hy.view, 3, [1, 2], result_mem=_capi.OBK_MEM_DEVICE)
+    like = wl.Operand(("a", "b", "c"), np.zeros((1, 3), dtype=np.int64), np.zeros(1), "u64")
+    hl = HostOperand(like)
+    p = engine.mul_views(engine.view_of(dx, hl.view), engine.view_of(dy, hl.view))
+    ref = pyoracle.poly_mul(pyoracle.extend_symbols(x.to_dict(), 3, [0, 1]), pyoracle.extend_symbols(y.to_dict(), 3, [1, 2]))
+    assert p.as_dict() == packed(ref, like)
+    for q in (dx, dy, p):
+        q.free()
+
+
 def test_device_resident_chain(engine):
     """f *= g twice, + g, truncated: every intermediate stays in HBM; only the last result is read back."""
     f, g = wl.fateman(6, 3, "u64")
