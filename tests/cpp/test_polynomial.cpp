@@ -13,6 +13,7 @@
 
 #include <obake/polynomials/polynomial.hpp>
 #include <obake/b200/device_polynomial.hpp>
+#include <obake/power_series/power_series.hpp>
 
 using namespace obake;
 
@@ -346,6 +347,98 @@ static void device_chain_test()
     REQUIRE(truncated_mul(df, dq, 6, symbol_set{"a", "x"}).to_host() == truncated_mul(f, q, 6, symbol_set{"a", "x"}));
 }
 
+// test/power_series_01.cpp:384-560 ("multiplication"): truncation policies of p_series products
+static void p_series_tests()
+{
+    using pm_t = packed_monomial<std::int32_t>;
+    using ps_t = p_series<pm_t, double>;
+    {
+        auto [x, y] = make_p_series<ps_t>("x", "y");
+        auto ret = x * y;
+        REQUIRE(ret.get_symbol_set() == symbol_set{"x", "y"});
+        REQUIRE(ret.size() == 1u);
+        REQUIRE(get_truncation(ret).index() == 0u);
+        REQUIRE(ret.begin()->first == pm_t{1, 1});
+        REQUIRE(ret.begin()->second == 1);
+    }
+    {
+        auto [x, y] = make_p_series_t<ps_t>(3, "x", "y");
+        auto ret = x * y;
+        REQUIRE(ret.size() == 1u);
+        REQUIRE(get_truncation(ret).index() == 1u);
+        REQUIRE(std::get<1>(get_truncation(ret)) == 3);
+        REQUIRE(ret.begin()->first == pm_t{1, 1});
+    }
+    {
+        auto [x, y] = make_p_series_t<ps_t>(1, "x", "y");
+        auto ret = x * y;
+        REQUIRE(ret.get_symbol_set() == symbol_set{"x", "y"});
+        REQUIRE(ret.empty());
+        REQUIRE(std::get<1>(get_truncation(ret)) == 1);
+    }
+    {
+        auto [x, y] = make_p_series_p<ps_t>(3, symbol_set{"a", "b"}, "x", "y");
+        auto ret = x * y;
+        REQUIRE(ret.size() == 1u);
+        REQUIRE(get_truncation(ret).index() == 2u);
+        REQUIRE(std::get<2>(get_truncation(ret)) == std::pair{std::int32_t(3), symbol_set{"a", "b"}});
+    }
+    {
+        auto [x, y] = make_p_series_p<ps_t>(1, symbol_set{"x", "y", "z"}, "x", "y");
+        auto ret = x * y;
+        REQUIRE(ret.empty());
+        REQUIRE(get_truncation(ret).index() == 2u);
+    }
+    {
+        auto [x] = make_p_series_t<ps_t>(3, "x");
+        auto [y] = make_p_series_t<ps_t>(2, "y");
+        REQUIRES_THROWS_CONTAINS(x * y, std::invalid_argument,
+                                 "Unable to multiply two power series if their truncation levels do not match");
+    }
+    {
+        auto [x] = make_p_series_p<ps_t>(3, symbol_set{"a", "b"}, "x");
+        auto [y] = make_p_series_p<ps_t>(3, symbol_set{"a", "c"}, "y");
+        REQUIRES_THROWS_CONTAINS(x * y, std::invalid_argument,
+                                 "Unable to multiply two power series if their truncation levels do not match");
+    }
+    {
+        auto [x] = make_p_series_t<ps_t>(3, "x");
+        auto [y] = make_p_series_p<ps_t>(2, symbol_set{"a"}, "y");
+        REQUIRES_THROWS_CONTAINS(x * y, std::invalid_argument,
+                                 "Unable to multiply two power series if their truncation policies do not match");
+    }
+    {
+        auto [x, y] = make_p_series_t<ps_t>(3, "x", "y");
+        unset_truncation(y);
+        auto ret = x * y;
+        REQUIRE(ret.size() == 1u);
+        REQUIRE(std::get<1>(get_truncation(ret)) == 3);
+    }
+    {
+        auto [x, y] = make_p_series_t<ps_t>(1, "x", "y");
+        unset_truncation(x);
+        auto ret = x * y;
+        REQUIRE(ret.empty());
+        REQUIRE(std::get<1>(get_truncation(ret)) == 1);
+    }
+    // a truncated power: (1 + x + y)^8 kept to total degree 4 at every step == truncate_degree of the full power
+    {
+        using pi_t = p_series<packed_monomial<std::int64_t>, integer>;
+        auto [x, y] = make_p_series_t<pi_t>(symbol_set{"x", "y"}, 4, "x", "y");
+        pi_t one(polynomial<packed_monomial<std::int64_t>, integer>(1));
+        one.poly() = x.poly() * 0 + 1; // constant over {x, y}
+        pi_t b = x + y + one;
+        pi_t acc = b;
+        auto full = b.poly();
+        for (int i = 1; i < 8; ++i) {
+            acc *= b;
+            full = full * b.poly();
+        }
+        REQUIRE(acc.poly() == truncate_degree(full, 4));
+        REQUIRE(std::get<1>(get_truncation(acc)) == 4);
+    }
+}
+
 int main(int argc, char **argv)
 {
     const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
@@ -372,6 +465,7 @@ int main(int argc, char **argv)
         large_tests<packed_monomial<std::int64_t>, integer>();
         large_tests<d_packed_monomial<std::int64_t, 3>, double>();
         fateman_test();
+        p_series_tests();
         device_chain_test<packed_monomial<std::uint64_t>, integer>();
         device_chain_test<packed_monomial<std::int64_t>, double>();
         device_chain_test<d_packed_monomial<std::int64_t, 2>, integer>();
