@@ -1390,16 +1390,18 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
-    // per-warp staging of the current row pair (double-buffered): the convolution reads x[i] as a broadcast LDS and
-    // y[(lane - i) & 31] as a conflict-free LDS instead of four SHFL per step
-    __shared__ __align__(16) uint64_t s_pair[BT / 32][2][2][32];
+    // Per-warp staging of the current row pair at the start of the dynamic shared memory (double-buffered, 96 words
+    // per buffer: x[32], then y TWICE so that y[(lane - i) mod 32] is the plain address yy[32 + lane - i]): the
+    // convolution reads x[i] as a broadcast LDS and the rotated y as a conflict-free LDS with an immediate offset
+    // instead of four SHFL (or an LDS plus three address instructions) per step.
+    constexpr uint32_t PAIR_WORDS = 96;
     const uint32_t lane = threadIdx.x & 31u;
-    uint64_t(*wp)[2][32] = s_pair[threadIdx.x >> 5];
+    uint64_t *wp = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)(threadIdx.x >> 5) * 2u * PAIR_WORDS;
     uint32_t pbuf = 0;
     const uint64_t *xr_hi = P.xr_hi, *yr_hi = P.yr_hi;
     const uint32_t *xr_sl = P.xr_sl, *yr_off = P.yr_off, *yr_il = P.yr_il;
     if (P.dir_in_smem) {
-        unsigned char *p = smem_raw;
+        unsigned char *p = smem_raw + (size_t)(BT / 32) * 2u * PAIR_WORDS * 8u;
         uint64_t *s_xhi = reinterpret_cast<uint64_t *>(p);
         p += P.b_xhi;
         uint64_t *s_yhi = reinterpret_cast<uint64_t *>(p);
@@ -1491,17 +1493,20 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
                     len1 = len2;
                     len2 = tl;
                 }
-                const uint64_t *px = wp[pbuf][0], *py = wp[pbuf][1];
-                wp[pbuf][0][lane] = X;
-                wp[pbuf][1][lane] = Y;
+                uint64_t *pb = wp + pbuf * PAIR_WORDS;
+                const uint64_t *px = pb, *py = pb + 64u + lane; // py[-i] = y[(lane - i) mod 32]
+                pb[lane] = X;
+                pb[32u + lane] = Y;
+                pb[64u + lane] = Y;
                 pbuf ^= 1u;
                 __syncwarp(); // the other buffer is free: every lane passed this point after finishing the pair before last
                 if (len1 + len2 <= 33u) {
                     // the output row fits 32 lanes: the wrapped-around lanes of the rotation read zeros of the
                     // longer row, so every lane accumulates unconditionally into its low output
+#pragma unroll 4
                     for (uint32_t i = 0; i < len1; ++i) {
                         const uint64_t xi = px[i];
-                        const uint64_t yv = py[(lane - i) & 31u];
+                        const uint64_t yv = *(py - i);
                         if constexpr (F64) {
                             d0 = __dadd_rn(d0, __dmul_rn(__longlong_as_double((long long)xi), __longlong_as_double((long long)yv)));
                         } else {
@@ -1509,9 +1514,10 @@ __global__ void __launch_bounds__(BT, 1) k_rowconv(const RowParams P)
                         }
                     }
                 } else {
+#pragma unroll 4
                     for (uint32_t i = 0; i < len1; ++i) {
                         const uint64_t xi = px[i];
-                        const uint64_t yv = py[(lane - i) & 31u];
+                        const uint64_t yv = *(py - i);
                         // lane >= i: the rotated value belongs to output lo = lane, else to output lo = lane + 32;
                         // mask the INPUT so both accumulators run branch-free multiply-adds
                         const bool lowhalf = lane >= i;
