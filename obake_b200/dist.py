@@ -172,24 +172,35 @@ class PeerExchange:
 
     def pushed_mul(self, vx, vy, limit=None, idx=None, result_mem=_capi.OBK_MEM_DEVICE):
         """This rank's share of x*y: partial product pushed to the owners' windows -> barrier -> merge."""
+        import os
+        import time
+        timing = os.environ.get("OBK_DIST_TIMING") == "1"
         eng, L = self.engine, _capi.lib()
         keep = []
         tr = eng._trunc(limit, idx, keep)
         w = self._windows()
         st = _capi.Stats()
+        t0 = time.perf_counter()
         rc = L.obk_poly_mul_push(eng._h, C.byref(vx), C.byref(vy), C.byref(tr) if tr is not None else None,
                                  C.byref(w), C.byref(st))
+        t1 = time.perf_counter()
         failed = 0
         if rc != 0:
             failed, msg = rc, eng.last_error()
         # the barrier: stream-ordered, carries the failure flag so that every rank takes the same branch
         self._flag.fill_(failed)
         dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
+        if timing:
+            torch.cuda.current_stream().synchronize()
+        t2 = time.perf_counter()
         res, mst = _capi.PolyResult(), _capi.Stats()
         acc = int(st.acc_limbs) if rc == 0 and st.acc_limbs else 1
         if rc == 0:
             rc2 = L.obk_peer_merge(eng._h, C.byref(w), C.byref(vx), acc, int(result_mem), C.byref(res), C.byref(mst))
+        t3 = time.perf_counter()
         self.parity ^= 1
+        self._last_timing = {"push": (t1 - t0) * 1e3, "barrier": (t2 - t1) * 1e3, "merge": (t3 - t2) * 1e3,
+                             "partial_device_ms": float(st.ms_total), "merge_device_ms": float(mst.ms_total)} if timing else None
         if int(self._flag.item()) != 0 or rc != 0:
             if rc == 0 and rc2 == 0 and res.owner:
                 L.obk_result_free(eng._h, C.byref(res))
@@ -200,6 +211,8 @@ class PeerExchange:
         info = {"mode": "push", "partial_stats": st.as_dict(), "merge_stats": merged.stats,
                 "partial_terms": int(st.nterms_out), "recv_rows": int(mst.term_products), "nsegs": _capi.OBK_EXCHANGE_MOD,
                 "sent_rows": None, "bytes_sent": None}
+        if self._last_timing:
+            info["timing_ms"] = self._last_timing
         return merged, info
 
     def close(self):
