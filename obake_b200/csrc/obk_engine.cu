@@ -980,8 +980,9 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     const size_t dir_bytes = (size_t)P.b_xhi + P.b_yhi + P.b_yil + P.b_xsl + P.b_yoff + 128;
     // a multi-GPU slice offsets X.row_hi by a row count: bulk copies need 16-byte aligned sources
     const bool aligned = ((uintptr_t)X.row_hi % 16 == 0);
-    // the per-warp row staging (96 words x 2 buffers per warp) sits at the start of the dynamic shared memory
-    const size_t stage_bytes = (size_t)(e->opt_row_threads <= 512 ? 16 : 32) * 2 * 96 * 8;
+    // the per-warp row staging (96 words x 2 buffers) and short-pair queue (64 words) sit at the start of the
+    // dynamic shared memory
+    const size_t stage_bytes = (size_t)(e->opt_row_threads <= 512 ? 16 : 32) * (2 * 96 + 64) * 8;
     P.dir_in_smem = (dir_bytes + stage_bytes + 2048 <= e->smem_optin && aligned) ? 1u : 0u;
     CU_CHECK(e, cudaEventRecord(e->ev[5], s));
     if (nro) launch_rows(e, mode, uns, P, wave, stage_bytes + (P.dir_in_smem ? dir_bytes : 0), nullptr, delta, nullptr, nullptr, false);
