@@ -852,8 +852,16 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     const uint32_t wave = (uint32_t)e->sm_count;
     // ---- symbolic row product: the set of output rows ------------------------------------------------------
     const uint64_t row_pairs = (uint64_t)X.nrows * Y.nrows;
-    EstimateIn ein{X.row_hi, nullptr, X.nrows, Y.row_hi, nullptr, Y.nrows, 1, 0, 0, 0, 1, false, 0, row_pairs, threads};
-    R.est_rows = estimate_terms(e, sc, ein);
+    if (row_pairs <= (8ull << 20)) {
+        // A small symbolic product (a multi-GPU slice, Fateman n <= 20) costs less than estimating it: the sampled
+        // estimate is three launches and a host round trip.  Size for 32 output rows per operand row (dense operands
+        // produce ~7) -- the segment count is then set by the amount of work anyway -- and let the overflow retry
+        // below handle a product that turns out sparser.
+        R.est_rows = std::min<uint64_t>(row_pairs, 32ull * std::max(X.nrows, Y.nrows));
+    } else {
+        EstimateIn ein{X.row_hi, nullptr, X.nrows, Y.row_hi, nullptr, Y.nrows, 1, 0, 0, 0, 1, false, 0, row_pairs, threads};
+        R.est_rows = estimate_terms(e, sc, ein);
+    }
     const uint32_t sym_log2_cap = pick_log2_cap(e, 1, 0);
     const uint32_t sym_cap = 1u << sym_log2_cap;
     uint32_t mR = pick_nsegs(R.est_rows, 0.5 * sym_cap, row_pairs, wave);
