@@ -159,6 +159,15 @@ class Product:
             return np.zeros(2, dtype=np.uint64)
         return np.ctypeslib.as_array(C.cast(self._res.seg_offsets, C.POINTER(C.c_uint64)), (n,)).copy()
 
+    def table_stats(self) -> dict:
+        """What series::table_stats() reports for a series rebuilt from this result (series.hpp:1386-1409): number
+        of terms and tables, smallest / largest / average table, bytes of the SoA term arrays."""
+        so = self.seg_offsets.astype(np.int64)
+        sizes = np.diff(so) if len(so) > 1 else np.zeros(1, dtype=np.int64)
+        return {"total_terms": self.nterms, "n_tables": int(len(sizes)), "min_table": int(sizes.min()),
+                "max_table": int(sizes.max()), "avg_table": float(sizes.mean()),
+                "bytes": self.nterms * 8 * (self.key_words + self.cf_limbs)}
+
     def _host_array(self, ptr, shape, ctype):
         if self.on_device:
             import torch  # plumbing only: copy a device buffer back for inspection

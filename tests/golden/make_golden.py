@@ -88,7 +88,33 @@ KNOWN = {
 }
 
 
+def series_ops_cases():
+    """Hand-checkable cases for the steps either side of the product (series add/sub, series.hpp:2195-2991;
+    truncate_degree / truncate_p_degree, polynomial.hpp:2364-2445; series_sym_extender, series.hpp:539-625), in the
+    exponent-tuple form the Python oracle uses.  The expected outputs are written out by hand in
+    tests/test_oracle.py::test_series_ops_golden; this file carries the same cases for the GPU tests."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"))
+    import pyoracle
+
+    def pack(d):
+        return [[list(k), v] for k, v in sorted(d.items())]
+
+    x = {(1, 0): 1, (0, 1): 1}
+    y = {(1, 0): 1, (0, 1): -1}
+    b = {(0, 0): 1, (1, 0): 1, (0, 1): 1}
+    p = pyoracle.poly_mul(pyoracle.poly_mul(b, b), b)
+    return [
+        {"op": "add", "x": pack(x), "y": pack(y), "out": pack(pyoracle.poly_addsub(x, y))},
+        {"op": "sub", "x": pack(x), "y": pack(y), "out": pack(pyoracle.poly_addsub(x, y, True))},
+        {"op": "truncate", "x": pack(p), "limit": 2, "idx": None, "out": pack(pyoracle.truncate_degree(p, 2))},
+        {"op": "truncate", "x": pack(p), "limit": 1, "idx": [0], "out": pack(pyoracle.truncate_degree(p, 1, [0]))},
+        {"op": "extend", "x": pack(b), "new_nvars": 4, "pos": [1, 3], "out": pack(pyoracle.extend_symbols(b, 4, [1, 3]))},
+    ]
+
+
 def main():
+    with open(os.path.join(HERE, "series_ops.json"), "w") as f:
+        json.dump(series_ops_cases(), f, indent=1)
     if not os.path.isdir(REF):
         print("reference tree not present; nothing regenerated", file=sys.stderr)
         return 1

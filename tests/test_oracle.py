@@ -196,3 +196,35 @@ def test_wide_coefficients_three_limbs():
     y2 = wl.random_poly(rng, 20, 2, 7, 70, "u64")
     r = orc.poly_mul(x2, y2)
     assert orc.result_to_dict(r, x2) == pyoracle.poly_mul(x2.to_dict(), y2.to_dict())
+
+
+def test_series_ops_golden():
+    """The Python oracle's series add/sub, degree truncation and symbol-set extension against answers written out
+    by hand, and against the committed fixture (tests/golden/series_ops.json, tests/golden/make_golden.py)."""
+    x = {(1, 0): 1, (0, 1): 1}   # x + y
+    y = {(1, 0): 1, (0, 1): -1}  # x - y
+    assert pyoracle.poly_addsub(x, y) == {(1, 0): 2}            # 2x: the y terms cancel and are erased
+    assert pyoracle.poly_addsub(x, y, True) == {(0, 1): 2}      # 2y
+    assert pyoracle.poly_addsub({}, y, True) == {(1, 0): -1, (0, 1): 1}
+    b = {(0, 0): 1, (1, 0): 1, (0, 1): 1}
+    p = pyoracle.poly_mul(pyoracle.poly_mul(b, b), b)           # (1 + x + y)^3
+    assert pyoracle.truncate_degree(p, 2) == {(0, 0): 1, (1, 0): 3, (0, 1): 3, (2, 0): 3, (1, 1): 6, (0, 2): 3}
+    assert pyoracle.truncate_degree(p, -1) == {}
+    # partial degree over x only: keep x^0 and x^1 with every power of y
+    assert pyoracle.truncate_degree(p, 1, [0]) == {(0, 0): 1, (0, 1): 3, (0, 2): 3, (0, 3): 1, (1, 0): 3, (1, 1): 6,
+                                                   (1, 2): 3}
+    assert pyoracle.extend_symbols(b, 4, [1, 3]) == {(0, 0, 0, 0): 1, (0, 1, 0, 0): 1, (0, 0, 0, 1): 1}
+    with open(os.path.join(HERE, "golden", "series_ops.json")) as f:
+        cases = json.load(f)
+
+    def unpack(lst):
+        return {tuple(k): v for k, v in lst}
+
+    for c in cases:
+        if c["op"] in ("add", "sub"):
+            got = pyoracle.poly_addsub(unpack(c["x"]), unpack(c["y"]), c["op"] == "sub")
+        elif c["op"] == "truncate":
+            got = pyoracle.truncate_degree(unpack(c["x"]), c["limit"], c["idx"])
+        else:
+            got = pyoracle.extend_symbols(unpack(c["x"]), c["new_nvars"], c["pos"])
+        assert got == unpack(c["out"]), c["op"]
