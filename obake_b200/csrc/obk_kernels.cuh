@@ -10,9 +10,14 @@
 //   k_term_stats   per-variable exponent min/max (overflow check), (partial) degrees, coefficient width
 //   k_bin_count / k_scan_* / k_bin_scatter   counting sort of the right operand by (bucket, degree)
 //   k_deg_hist / k_count_mults               tot_n_mults of a truncated product
-//   k_mul          the product: one CTA owns one output segment's open-addressing table in shared memory
-//   k_compact      segment-ordered dense output
-//   k_merge        multi-GPU owner-side merge of partial segments
+//   k_mul          the product: one CTA owns one output segment's open-addressing table in shared memory; term
+//                  products are expanded warp-cooperatively and every segment is written straight to the final
+//                  arrays (also: symbolic key-only products, the owner-side merge of the multi-GPU path)
+//   k_rowconv      row-blocked dense path: one warp owns one output row, register accumulation
+//                  (k_row_insert / k_row_flags / k_row_keys / k_row_fill / k_row_pack build the rows,
+//                  k_compact orders the symbolic row product, k_row_expand turns rows back into terms)
+//   k_push         multi-GPU: partial terms written straight into the owners' NVLink peer windows
+//   k_widen_cfs / k_flag_keep / k_select / k_extend_symbols   series add/sub, degree truncation, symbol extension
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
