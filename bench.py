@@ -287,12 +287,13 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     peak, peak_src = measured_peak()
     per_launch_products = rank_products  # the slowest rank's kernel and the products it formed
     achieved = B * per_launch_products / (kernel_mean * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as tf:
             tj = json.load(tf).get(name.upper())
             if tj and world == 1:
                 traffic = tj["traffic_bytes"]
+                ncu_note = {k: tj[k] for k in ("issue_active_pct", "warp_instructions", "limiter", "source") if k in tj}
     except Exception:
         traffic = None
     out = {
@@ -304,7 +305,8 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
                      "kernel": "k_rowconv" if stats_last.get("kernel") == 1 else "k_mul",
                      "algorithmic_bytes_per_launch": B * per_launch_products, "algorithmic_bytes_per_product": B,
                      "peak_source": peak_src, "kernel_ms": kernel_mean,
-                     "kernel_share_of_step": kernel_mean / ms},
+                     "kernel_share_of_step": kernel_mean / ms,
+                     "ncu": ncu_note},
         "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
         "lin": lin, "lacc": int(lacc), "f64": f64, "limit": limit,
     }
