@@ -1415,6 +1415,15 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     return OBK_ERR_UNSUPPORTED;
                 }
             }
+            // A limit no pair can exceed (limit >= max degree of x + max degree of y; the reference's own
+            // sparse_02_truncated benchmark runs with one) is no truncation: drop the degree sort, the per-term degree
+            // lookups and the (segment x degree) offset table, and let dense operands take the row path.
+            if (trunc) {
+                const i128 lim0 = L.is_signed ? (i128)rq.t->limit : (i128)(uint64_t)rq.t->limit;
+                const i128 top = unord(hs[0].dmax, L.is_signed) + unord(hs[1].dmax, L.is_signed);
+                const i128 big0 = (i128)1 << 62;
+                if (top < big0 && top > -big0 && lim0 >= top) trunc = false;
+            }
             // truncation geometry
             if (trunc) {
                 const i128 dminx = unord(hs[0].dmin, L.is_signed), dmaxx = unord(hs[0].dmax, L.is_signed);
