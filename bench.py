@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="F30")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--also", default="S12", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
+    ap.add_argument("--also", default="S12,S16T,AUDI,AUDID,F20,D5,RECT", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
     ap.add_argument("--mgpu-mode", default="push", choices=["all", "both", "exchange", "push", "owner"],
@@ -138,9 +138,10 @@ def operand_arrays(op, lin):
     return keys, cfs
 
 
-def cpu_reference_run(f, g, limit, threads, budget_products=3.0e9):
-    """Time the oracle (CPU restatement of obake's algorithm) on a bounded sample of the workload: the first
-    rows of the left operand so that at most `budget_products` term products are formed."""
+def cpu_reference_run(f, g, limit, threads, budget_products=2.0e10):
+    """Time the oracle (CPU restatement of obake's algorithm).  Every named workload is run WHOLE (F30: 2.15e9
+    products, under a second on 16 cores); only a product beyond `budget_products` would be cut to the first rows
+    of the left operand, and the returned sample string says so."""
     import orc
 
     nx = f.nterms
@@ -165,10 +166,10 @@ def run_reference(args):
     f, g, limit, desc = wl.named(args.workload)
     cores = orc.lib().orc_hardware_concurrency()
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_run(f, g, limit, cores, budget_products=2.0e8)
+        cpu_reference_run(f, g, limit, cores)
     vals, secs, sample, prods = [], [], "", 0
     for _ in range(max(1, args.steps)):
-        v, s, prods, sample = cpu_reference_run(f, g, limit, cores, budget_products=1.5e9)
+        v, s, prods, sample = cpu_reference_run(f, g, limit, cores)
         vals.append(v)
         secs.append(s)
     value = float(np.mean(vals))
@@ -190,6 +191,36 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------
+def check_parity(name, f, g, limit, p, info, torch, dev, rank, world, mgpu_mode):
+    from obake_b200 import _capi, verify
+
+    keys = p.keys
+    cfs = p.cfs if p.is_f64 else p.cf_limb_array
+    ws = None
+    own_ok = True
+    if world > 1:
+        import torch.distributed as dist
+
+        def ws(vals):
+            t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return [int(v) for v in t.tolist()]
+
+        if mgpu_mode in ("exchange", "push") and p.nterms and not f.tname.startswith("i"):
+            # ownership rule of the exchange: group = key mod 4093, contiguous group ranges per rank
+            m = _capi.OBK_EXCHANGE_MOD
+            grp = (keys % np.uint64(m)).sum(axis=1) % np.uint64(m)
+            a, b = m * rank // world, m * (rank + 1) // world
+            own_ok = bool(((grp >= a) & (grp < b)).all())
+    res = verify.check_product(name, f, g, limit, keys, cfs, p.is_f64, ws)
+    if world > 1:
+        bad_owner, = ws([0 if own_ok else 1])
+        res["ownership_ok"] = bad_owner == 0
+        if res["ok"] is not None:
+            res["ok"] = bool(res["ok"] and bad_owner == 0)
+    return res
+
+
 def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with_e2e=True, mgpu_mode="exchange"):
     from obake_b200 import _capi, workloads as wl
     from obake_b200.engine import needed_limbs, raw_view
@@ -245,7 +276,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     times, kernel_ms, launches = [], [], 0
     stats_last, nterms_out, products, info_last = None, 0, 0, {}
     t_wall0 = time.perf_counter()
-    for _ in range(steps):
+    for it in range(steps):
         flush.zero_()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -260,9 +291,14 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         stats_last, info_last = st, info
         products = st["term_products"]
         nterms_out = p.nterms
-        p.free()
+        if it + 1 < steps:
+            p.free()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
+    # ---- parity of the launch that was just timed (oracle-free: closed forms, evaluation checksum, pinned counts;
+    # obake_b200/verify.py).  N > 1: every rank checks ITS share, the verdicts and checksums are all-reduced.
+    parity = check_parity(name, f, g, limit, p, info, torch, dev, rank, world, mgpu_mode)
+    p.free()
     ms = float(np.mean(times))
     rank_products = products
     if world > 1:
@@ -308,7 +344,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
                      "kernel_share_of_step": kernel_mean / ms,
                      "ncu": ncu_note},
         "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
-        "lin": lin, "lacc": int(lacc), "f64": f64, "limit": limit,
+        "lin": lin, "lacc": int(lacc), "f64": f64, "limit": limit, "parity": parity,
     }
     if info_last:
         out["exchange"] = {k: info_last.get(k) for k in ("partial_terms", "sent_rows", "recv_rows", "bytes_sent", "nsegs")}
@@ -376,7 +412,7 @@ def bench_rect(args, eng, torch, dev, steps, warmup):
     one_c = torch.from_numpy(np.array([[1.0]]).view(np.int64)).to(dev)
     vf = raw_view(f.nterms, 1, 0, 3, 0, _capi.OBK_CF_F64, 1, _capi.OBK_MEM_DEVICE, fk.data_ptr(), fc.data_ptr())
 
-    def chain():
+    def chain(check=False):
         cur = None
         vcur = raw_view(1, 1, 0, 3, 0, _capi.OBK_CF_F64, 1, _capi.OBK_MEM_DEVICE, one_k.data_ptr(), one_c.data_ptr())
         prods, launches, sizes = 0, 0, []
@@ -391,8 +427,9 @@ def bench_rect(args, eng, torch, dev, steps, warmup):
             if (i + 1) % 10 == 0:
                 sizes.append(cur.nterms)
         n = cur.nterms
+        total = float(cur.cfs.sum()) if check else None
         cur.free()
-        return prods, launches, n, sizes
+        return prods, launches, n, sizes, total
 
     for _ in range(max(1, warmup)):
         chain()
@@ -401,14 +438,20 @@ def bench_rect(args, eng, torch, dev, steps, warmup):
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        prods, launches, n, sizes = chain()
+        prods, launches, n, sizes, _tot = chain()
         e1.record()
         torch.cuda.synchronize(dev)
         times.append(e0.elapsed_time(e1))
     ms = float(np.mean(times))
+    # parity (untimed run): term count pinned by the survey's restatement, sum of coefficients = f(1,1,1)^70 = 16^70
+    _p, _l, n_chk, _s, tot = chain(check=True)
+    want = float(16 ** 70)
+    parity = {"checked": True, "terms": int(n_chk), "terms_expected": 1284816, "sum_rel_err": abs(tot - want) / want,
+              "ok": bool(n_chk == 1284816 and abs(tot - want) <= 1e-12 * want),
+              "how": "final term count; sum of coefficients == f(1,1,1)^70 = 16^70 within relative 1e-12"}
     return {"value": prods / (ms * 1e-3), "ms_per_chain": ms, "products": prods, "final_terms": n,
             "sizes_every_10": sizes, "launches": launches,
-            "expected_final_terms": 1284816}
+            "expected_final_terms": 1284816, "parity": parity}
 
 
 def main():
@@ -466,12 +509,21 @@ def main():
     f, g, limit = res.pop("_operands")
     also = {}
     if world == 1 and args.also:
-        for nm in [s for s in args.also.split(",") if s]:
+        for nm in [s for s in args.also.split(",") if s and s.upper() != args.workload.upper()]:
+            if nm.upper() == "RECT":
+                r = bench_rect(args, eng, torch, dev, 3, 1)
+                also["RECT"] = {"value": r["value"], "ms_per_step": r["ms_per_chain"], "products": r["products"],
+                                "terms_out": r["final_terms"], "launches": r["launches"], "parity": r["parity"],
+                                "note": "rectangular_01: 70 chained 13-term fp64 products, every intermediate resident in HBM"}
+                continue
             r = bench_workload(nm, args, eng, torch, dev, rank, world, max(3, args.steps // 2), 3, with_e2e=True)
             r.pop("_operands")
             also[nm] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"],
-                        "roofline_frac": r["roofline"]["frac"], "e2e": r.get("e2e", {}).get("value"),
-                        "terms_out": r["terms_out"], "products": r["products"], "stats": r["stats"]}
+                        "kernel": r["roofline"]["kernel"], "roofline_frac": r["roofline"]["frac"],
+                        "roofline_note": r["roofline"].get("note"),
+                        "e2e": r.get("e2e", {}).get("value"), "e2e_ms": r.get("e2e", {}).get("ms_per_step"),
+                        "terms_out": r["terms_out"], "products": r["products"], "parity": r["parity"],
+                        "stats": r["stats"]}
     line = {
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
@@ -490,6 +542,7 @@ def main():
                        f"rows/segments it owns, no exchange (SURVEY 8e zero-exchange alternative)"),
                    "engine": res["stats"]},
         "roofline": res["roofline"], "clocks": res["clocks"], "gpu_launches": res["gpu_launches"],
+        "parity": res["parity"],
     }
     if "e2e" in res:
         line["e2e"] = res["e2e"]

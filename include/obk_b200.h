@@ -205,6 +205,11 @@ obk_status obk_poly_mul_push(obk_engine *e, const obk_poly_view *x, const obk_po
 obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_poly_view *like, uint32_t acc_limbs,
                           uint32_t result_mem, obk_poly_result *out, obk_stats *stats);
 
+/* Error path of the protocol: when ANY rank's obk_poly_mul_push failed, no rank calls obk_peer_merge for that step;
+ * every rank instead clears the header of its own window (this step's parity) after the barrier, so that what the
+ * peers had already pushed is not merged when the parity is reused two steps later. */
+obk_status obk_peer_window_reset(obk_engine *e, const obk_peer_windows *w);
+
 /* ---- the steps either side of the product, on the same device layout ------------------------------
  * Operands and results may stay in DEVICE memory, so a chain such as f *= g; h = f + 1; truncate(h) never leaves
  * HBM (benchmark/dense.hpp:28-32, rectangular_01.cpp:42-47, audi_01.cpp:32-42). */

@@ -52,7 +52,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 0, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
     uint32_t last_rslices = 1;
@@ -635,6 +635,7 @@ uint64_t estimate_terms(obk_engine *e, Scratch &sc, const EstimateIn &in)
         P.b.lim_base = ts.lim_base_b;
     }
     P.nsegs = mE;
+    P.fence = e->opt_fence ? 1u : 0u;
     P.dbits = in.dbits;
     P.ndeg = in.ndeg;
     P.trunc = in.trunc;
@@ -886,6 +887,7 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
         P.yk = ys.keys;
         P.yoff = ys.off;
         P.nsegs = mR;
+        P.fence = e->opt_fence ? 1u : 0u;
         P.ndeg = 1;
         P.nseg_list = mR;
         P.cursor = dflags + 1;
@@ -1290,7 +1292,11 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 }
                 xdeg = sc.alloc<int64_t>(nx_full);
                 ydeg = (x == y) ? xdeg : sc.alloc<int64_t>(ny);
+            } else {
+                // untruncated: the statistics pass still reports the total-degree extrema (d_packed degree check)
+                var_mask = L.nvars >= 64 ? ~0ull : ((1ull << L.nvars) - 1);
             }
+            const bool full_mask = var_mask == (L.nvars >= 64 ? ~0ull : ((1ull << L.nvars) - 1));
             StatsOut *dstats = sc.alloc<StatsOut>(2);
             k_stats_init<<<2, 64, 0, s>>>(dstats, 2);
             // NOTE: k_stats_init indexes by global thread; fix up: one block per struct
@@ -1336,13 +1342,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 sxk = dxk + x_begin * W;
                 sxc = dxc + x_begin * CWx;
                 if (xdeg) sxdeg = xdeg + x_begin;
-                if (snx == 0) {
-                    // more ranks than left-operand terms: this rank has nothing to multiply
-                    set_empty_result(out, x, f64 ? 1 : 1, rq.result_mem);
-                    if (rq.send_counts) std::memset(rq.send_counts, 0, sizeof(uint64_t) * rq.nranks);
-                    if (stats) *stats = st;
-                    return OBK_OK;
-                }
+                // snx may be 0 (more ranks than left-operand terms): the rank still takes every decision below --
+                // overflow verdict, accumulator width -- so that all ranks agree, and returns an empty share after them
             } else {
                 sxk = dxk;
                 sxc = dxc;
@@ -1360,14 +1361,20 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     const i128 mx = unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);
                     if (mn < lim_min || mx > lim_max) ok = false;
                 }
-                if (ok && L.psize != 0 && !trunc) {
+                if (ok && L.psize != 0) {
                     // d_packed: the total degree of a product must stay representable in T.  The total-degree
                     // extrema are only computed when var_mask covers every variable; recompute cheaply from
                     // the per-variable extrema as a conservative bound only if that bound fails.
                     i128 dmax = 0, dmin = 0;
-                    for (uint32_t v = 0; v < L.nvars; ++v) {
-                        dmax += unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);
-                        dmin += unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
+                    if (full_mask) {
+                        // the reference's own quantity: extrema of the total degrees (d_packed_monomial.hpp:880-894)
+                        dmax = unord(hs[0].dmax, L.is_signed) + unord(hs[1].dmax, L.is_signed);
+                        dmin = unord(hs[0].dmin, L.is_signed) + unord(hs[1].dmin, L.is_signed);
+                    } else {
+                        for (uint32_t v = 0; v < L.nvars; ++v) {
+                            dmax += unord(hs[0].emax[v], L.is_signed) + unord(hs[1].emax[v], L.is_signed);
+                            dmin += unord(hs[0].emin[v], L.is_signed) + unord(hs[1].emin[v], L.is_signed);
+                        }
                     }
                     const bool b32 = y->key_bits == 32;
                     const i128 tmax = L.is_signed ? (b32 ? (i128)INT32_MAX : (i128)INT64_MAX)
@@ -1414,6 +1421,14 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     e->err = "3-limb input coefficients are not supported (inputs are 1 or 2 limbs)";
                     return OBK_ERR_UNSUPPORTED;
                 }
+            }
+            if (snx == 0) {
+                // nothing to multiply on this rank; the stats carry the limb count every other rank uses
+                set_empty_result(out, x, f64 ? 1 : (int)st.acc_limbs, rq.result_mem);
+                if (rq.send_counts) std::memset(rq.send_counts, 0, sizeof(uint64_t) * rq.nranks);
+                st.total_launches = e->launches;
+                if (stats) *stats = st;
+                return OBK_OK;
             }
             // A limit no pair can exceed (limit >= max degree of x + max degree of y; the reference's own
             // sparse_02_truncated benchmark runs with one) is no truncation: drop the degree sort, the per-term degree
@@ -1750,7 +1765,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 sc.release(rc);
                 sc.release(dflags);
                 st.retries += 1;
-                if ((int64_t)st.retries > e->opt_max_retries || rq.merge || owner) {
+                if ((int64_t)st.retries > e->opt_max_retries || owner) {
                     e->err = "The homomorphic multiplication of two polynomials resulted in a segment table whose size "
                              "is larger than the maximum allowed value (shared-memory table overflow after "
                              + std::to_string(st.retries) + " finer segmentations)";
@@ -2080,6 +2095,21 @@ static bool check_windows(obk_engine *e, const obk_peer_windows *w)
             return false;
         }
     return true;
+}
+
+obk_status obk_peer_window_reset(obk_engine *e, const obk_peer_windows *w)
+{
+    if (!e) return OBK_ERR_INVALID_ARG;
+    if (!check_windows(e, w)) return OBK_ERR_INVALID_ARG;
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        unsigned char *win = static_cast<unsigned char *>(w->base[w->rank]) + (size_t)w->parity * w->window_bytes;
+        CU_CHECK(e, cudaMemsetAsync(win, 0, 8, e->stream));
+        CU_CHECK(e, cudaStreamSynchronize(e->stream));
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        return f.st;
+    }
 }
 
 obk_status obk_poly_mul_push(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,

@@ -738,16 +738,37 @@ __device__ __forceinline__ uint32_t slot_hash(const uint64_t (&k)[W], uint32_t l
 }
 
 // Slot lock protocol.  A slot's state word goes EMPTY -> INIT -> FULL and then FULL <-> BUSY; key and
-// accumulator limbs are only written by the thread that moved the state to INIT or BUSY.  All of it is
-// shared-memory traffic of ONE SM, which the LSU / shared-memory pipeline performs in issue order, so a
-// store to the limbs followed by the store that releases the state cannot be observed out of order by
-// another warp of the CTA; the acquiring side only touches the limbs after the atomic exchange returned
-// FULL (a control dependency).  That is why the default build uses compiler barriers only; fence != 0
-// adds fence.acq_rel.cta on both sides (the PTX-memory-model form of the same protocol), used by the tests
-// to cross-check the fence-free path.
-__device__ __forceinline__ void slot_fence(uint32_t fence)
+// accumulator limbs are only written by the thread that moved the state to INIT or BUSY.  In PTX-memory-model
+// terms: the state is read with ld.acquire.cta, locked with atom.acquire.cta.cas and released with
+// st.release.cta, so the key / limb accesses of successive owners of a slot are ordered by release-acquire
+// pairs on the state word.  For shared memory ptxas lowers the two acquire forms to the plain LDS / ATOMS.CAS
+// (the shared-memory pipe of one SM performs accesses in issue order) and the release to MEMBAR.ALL.CTA + STS
+// (profiles/r02_sass_slot_lock.txt): the only cost of the model-clean protocol is one MEMBAR per accumulated
+// product.  fence == 0 (option "fence") replaces the release by a plain store behind a compiler barrier -- the
+// hardware-order argument alone -- and exists to measure that cost; the default is fence = 1.
+__device__ __forceinline__ uint32_t slot_ld_acquire(const uint32_t *p)
 {
-    if (fence) asm volatile("fence.acq_rel.cta;" ::: "memory"); else asm volatile("" ::: "memory");
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t slot_cas_acquire(uint32_t *p, uint32_t cmp, uint32_t val)
+{
+    uint32_t old;
+    asm volatile("atom.acquire.cta.shared.cas.b32 %0, [%1], %2, %3;"
+                 : "=r"(old)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(cmp), "r"(val)
+                 : "memory");
+    return old;
+}
+__device__ __forceinline__ void slot_st_release(uint32_t *p, uint32_t val, uint32_t fence)
+{
+    if (fence) {
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(val) : "memory");
+    } else {
+        asm volatile("" ::: "memory");
+        *(volatile uint32_t *)p = val;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -965,7 +986,7 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
                 // ---- one find-or-insert attempt: a single path for "accumulate into my key's slot" and "claim an
                 // empty slot" (the two differ only in the lock value and in where the old accumulator comes from), so
                 // the lanes of a warp do not serialise on the kind of slot they found ---------------------------------
-                const uint32_t st = *(volatile uint32_t *)&tstate[h];
+                const uint32_t st = slot_ld_acquire(&tstate[h]);
                 bool eq = true;
 #pragma unroll
                 for (int w = 0; w < W; ++w) eq &= (*(volatile uint64_t *)&tkeys[(size_t)w * cap + h] == k[w]);
@@ -973,18 +994,16 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
                 if constexpr (T::SYM) {
                     if (st >= ST_FULL) {
                         if (eq) pend = false; else h = (h + 1u) & cmask;
-                    } else if (ins && atomicCAS(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
+                    } else if (ins && slot_cas_acquire(&tstate[h], ST_EMPTY, ST_INIT) == ST_EMPTY) {
 #pragma unroll
                         for (int w = 0; w < W; ++w) *(volatile uint64_t *)&tkeys[(size_t)w * cap + h] = k[w];
-                        slot_fence(P.fence);
-                        *(volatile uint32_t *)&tstate[h] = ST_FULL;
+                        slot_st_release(&tstate[h], ST_FULL, P.fence);
                         inserted = true;
                         pend = false;
                     }
                 } else {
                     if (ins || (st == ST_FULL && eq)) {
-                        if (atomicCAS(&tstate[h], st, ins ? (uint32_t)ST_INIT : (uint32_t)ST_BUSY) == st) {
-                            slot_fence(P.fence);
+                        if (slot_cas_acquire(&tstate[h], st, ins ? (uint32_t)ST_INIT : (uint32_t)ST_BUSY) == st) {
                             uint64_t a[ACCW];
 #pragma unroll
                             for (int l = 0; l < ACCW; ++l) a[l] = ins ? 0ull : *(volatile uint64_t *)&tacc[(size_t)l * cap + h];
@@ -1001,8 +1020,7 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
                             }
 #pragma unroll
                             for (int l = 0; l < ACCW; ++l) *(volatile uint64_t *)&tacc[(size_t)l * cap + h] = a[l];
-                            slot_fence(P.fence);
-                            *(volatile uint32_t *)&tstate[h] = ST_FULL;
+                            slot_st_release(&tstate[h], ST_FULL, P.fence);
                             inserted = ins;
                             pend = false;
                         }

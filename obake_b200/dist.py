@@ -141,6 +141,9 @@ class PeerExchange:
         self.window_bytes = int(window_bytes)
         self.parity = 0
         L = _capi.lib()
+        # The all-reduce between the pushes and the merge is only a barrier for the engine's work if both run on
+        # the SAME stream: bind the engine to torch's current stream (NCCL collectives are ordered on it).
+        engine.set_stream(torch.cuda.current_stream(torch.device("cuda", engine.device)).cuda_stream)
         own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
         rc = L.obk_peer_window_alloc(engine._h, self.window_bytes, C.byref(own), handle)
@@ -194,7 +197,9 @@ class PeerExchange:
             torch.cuda.current_stream().synchronize()
         t2 = time.perf_counter()
         res, mst = _capi.PolyResult(), _capi.Stats()
+        # every rank computes the accumulator width from the FULL operands (also a rank whose slice is empty)
         acc = int(st.acc_limbs) if rc == 0 and st.acc_limbs else 1
+        rc2 = 0
         if rc == 0:
             rc2 = L.obk_peer_merge(eng._h, C.byref(w), C.byref(vx), acc, int(result_mem), C.byref(res), C.byref(mst))
         t3 = time.perf_counter()
@@ -204,6 +209,11 @@ class PeerExchange:
         if int(self._flag.item()) != 0 or rc != 0:
             if rc == 0 and rc2 == 0 and res.owner:
                 L.obk_result_free(eng._h, C.byref(res))
+            # a rank whose own push failed has not merged: whatever the peers already pushed into its window must not
+            # survive until this parity is reused (obk_peer_merge is the only other place that clears the header).
+            # Stream-ordered behind the all-reduce, i.e. after every peer's push of this step has landed.
+            if rc != 0:
+                L.obk_peer_window_reset(eng._h, C.byref(w))
             _raise(rc or int(self._flag.item()), msg if rc != 0 else "a peer failed in the pushed product")
         if rc2 != 0:
             _raise(rc2, eng.last_error())

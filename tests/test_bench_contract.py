@@ -20,6 +20,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["sample"] == "full workload"  # the reference arm runs the same configuration, never a sample
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "F20" and "model" not in d["config"]
     assert d["gpu_launches"] == 0

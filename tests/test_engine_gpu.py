@@ -306,7 +306,7 @@ def test_skewed_buckets_force_retry(engine):
     assert p.nterms == 2 * n - 1
 
 
-DEFAULTS = {"nsegs": -1, "refill_min": 16, "table_slots": 0, "threads": 1024, "fence": 0, "fill_pct": 62}
+DEFAULTS = {"nsegs": -1, "refill_min": 16, "table_slots": 0, "threads": 1024, "fence": 1, "fill_pct": 62}
 
 
 def test_forced_geometry_options(engine):
@@ -316,7 +316,7 @@ def test_forced_geometry_options(engine):
     ref = check_exact(engine, x, y).as_dict()
     try:
         for opts in ({"nsegs": 1}, {"nsegs": 128}, {"nsegs": 1000}, {"refill_min": 1}, {"refill_min": 32},
-                     {"table_slots": 1024, "threads": 256}, {"threads": 64}, {"fence": 1}, {"fill_pct": 85}):
+                     {"table_slots": 1024, "threads": 256}, {"threads": 64}, {"fence": 0}, {"fill_pct": 85}):
             for k, v in opts.items():
                 engine.set_option(k, v)
             assert engine.mul(x, y).as_dict() == ref, opts
