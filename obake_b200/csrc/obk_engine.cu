@@ -17,6 +17,7 @@
 #include "../../include/obk_b200.h"
 #include "../include/obake/kpack.hpp"
 #include "obk_kernels.cuh"
+#include "obk_planes.cuh"
 
 using namespace obk;
 
@@ -52,7 +53,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1,
+    int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1, opt_plane_cfg = 0,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
     uint32_t last_rslices = 1;
@@ -1018,6 +1019,235 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
     return R;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plane-blocked dense path (obk_planes.cuh, "kernel 2")
+// ------------------------------------------------------------------------------------------------
+struct PlaneSide {
+    RowSide set;               // open-addressing set of the plane keys hi2 = key / delta^2, and their numbering
+    uint64_t *mat = nullptr;   // [planes][PL_BLOB]: row-length table + rows in their staged layout
+    uint32_t *pinfo = nullptr; // [planes][4]: rows, terms, longest row, -
+    uint32_t nplanes = 0;
+};
+
+void planes_build(obk_engine *e, Scratch &sc, const uint64_t *keys, const uint64_t *cfs, uint64_t n, uint64_t delta, PlaneSide &p)
+{
+    cudaStream_t s = e->stream;
+    const uint32_t cap = 1u << p.set.log2_cap;
+    p.set.nrows = p.nplanes;
+    p.set.row_hi = sc.alloc<uint64_t>(p.nplanes);
+    p.mat = sc.alloc<uint64_t>((size_t)p.nplanes * PL_BLOB);
+    p.pinfo = sc.alloc<uint32_t>((size_t)p.nplanes * 4);
+    CU_CHECK(e, cudaMemsetAsync(p.mat, 0, (size_t)p.nplanes * PL_BLOB * 8, s));
+    CU_CHECK(e, cudaMemsetAsync(p.pinfo, 0, (size_t)p.nplanes * 16, s));
+    k_row_keys<<<(cap + 255) / 256, 256, 0, s>>>(p.set.tab, cap, p.set.rank, p.set.row_hi);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
+    k_plane_fill<<<grid, 256, 0, s>>>(keys, cfs, n, delta, p.set.tab, p.set.log2_cap, p.set.rank, p.mat, p.pinfo);
+    e->launches += 2;
+}
+
+// Geometry of the plane kernel: consumer warps (= virtual output rows per unit) and CTAs per SM.
+struct PlaneCfg {
+    uint32_t nw, ctas;
+};
+PlaneCfg plane_cfg(const obk_engine *e)
+{
+    switch (e->opt_plane_cfg) {
+        case 1: return {16, 1};
+        case 2: return {8, 3};
+        default: return {16, 2};
+    }
+}
+
+template <int LACC, bool F64, bool UNS, int NW, int MINB>
+void launch_planes_c(obk_engine *e, const PlaneParams &P, unsigned grid)
+{
+    auto fn = k_planeconv<LACC, F64, UNS, NW, MINB>;
+    const size_t smem = (size_t)P.nstage * pl_stage_bytes(P.ra_max, P.rb_max);
+    CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<grid, (NW + 1) * 32, smem, e->stream>>>(P);
+    e->launches += 1;
+    CU_CHECK(e, cudaGetLastError());
+}
+
+template <int LACC, bool F64, bool UNS>
+void launch_planes_t(obk_engine *e, const PlaneParams &P, unsigned grid)
+{
+    switch (e->opt_plane_cfg) {
+        case 1: launch_planes_c<LACC, F64, UNS, 16, 1>(e, P, grid); break;
+        case 2: launch_planes_c<LACC, F64, UNS, 8, 3>(e, P, grid); break;
+        default: launch_planes_c<LACC, F64, UNS, 16, 2>(e, P, grid); break;
+    }
+}
+
+void launch_planes(obk_engine *e, int mode, bool uns, const PlaneParams &P, unsigned grid)
+{
+    switch (mode) {
+        case CF_I1A1: launch_planes_t<1, false, false>(e, P, grid); break;
+        case CF_I1A2: uns ? launch_planes_t<2, false, true>(e, P, grid) : launch_planes_t<2, false, false>(e, P, grid); break;
+        case CF_I1A3: uns ? launch_planes_t<3, false, true>(e, P, grid) : launch_planes_t<3, false, false>(e, P, grid); break;
+        case CF_F64: launch_planes_t<1, true, false>(e, P, grid); break;
+        default: e->err = "internal: coefficient mode not supported by the plane path"; throw obk_fail{OBK_ERR_INVALID_ARG};
+    }
+}
+
+// Returns done=false when the operands do not qualify (the caller then tries the row path / the scatter kernel).
+RowsResult run_planes(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx, const uint64_t *dyk,
+                      const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, bool forced, bool uns, uint32_t rank,
+                      uint32_t nranks, bool owner, uint32_t rows_max_x, uint32_t rows_max_y, obk_stats &st)
+{
+    RowsResult R;
+    cudaStream_t s = e->stream;
+    const uint64_t delta = L.delta;
+    if (delta >= (1ull << 32)) return R; // delta^2 must fit 64 bits
+    const PlaneCfg cfg = plane_cfg(e);
+    const uint32_t stage_bytes = pl_stage_bytes(rows_max_x, rows_max_y);
+    // shared memory of one SM (228 KB) shared by cfg.ctas resident CTAs, 1 KB reserved per CTA
+    const uint32_t nstage = (uint32_t)std::min<size_t>(PL_MAX_STAGES, (std::min<size_t>(e->smem_optin, (228u << 10) / cfg.ctas - 1024) - 512) / stage_bytes);
+    if (nstage < 2 || rows_max_x > (uint32_t)PL_ROWS || rows_max_y > (uint32_t)PL_ROWS) return R;
+    const uint64_t d2 = delta * delta;
+    PlaneSide X, Y;
+    const bool same = dxk == dyk && nx == ny;
+    rows_phase_a(e, sc, dxk, nx, d2, X.set);
+    if (!same) rows_phase_a(e, sc, dyk, ny, d2, Y.set);
+    uint32_t hx = 0, hy = 0;
+    CU_CHECK(e, cudaMemcpyAsync(&hx, X.set.rank + (1u << X.set.log2_cap), 4, cudaMemcpyDeviceToHost, s));
+    if (!same) CU_CHECK(e, cudaMemcpyAsync(&hy, Y.set.rank + (1u << Y.set.log2_cap), 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    if (same) hy = hx;
+    // dense enough?  planes cost 8 KB each and a staged pair is only worth its copy with enough terms in it
+    const uint64_t plane_pairs = (uint64_t)hx * hy;
+    const bool dense = (double)nx >= 8.0 * hx && (double)ny >= 8.0 * hy;
+    if (plane_pairs > (1ull << 21) || hx >= (1u << 24) || hy >= (1u << 24) || (!forced && !dense)) return R;
+    X.nplanes = hx;
+    planes_build(e, sc, dxk, dxc, nx, delta, X);
+    if (same) {
+        Y = X;
+    } else {
+        Y.nplanes = hy;
+        planes_build(e, sc, dyk, dyc, ny, delta, Y);
+    }
+    // multi-GPU partial product: this rank multiplies a contiguous slice of the left PLANES by every right plane
+    uint32_t x_first = 0, nxp = X.nplanes;
+    if (nranks > 1 && !owner) {
+        x_first = (uint32_t)((uint64_t)X.nplanes * rank / nranks);
+        nxp = (uint32_t)((uint64_t)X.nplanes * (rank + 1) / nranks) - x_first;
+        if (nxp == 0) {
+            R.done = true;
+            R.rk = sc.alloc_out<uint64_t>(1);
+            R.rc = sc.alloc_out<uint64_t>(accw);
+            return R;
+        }
+    }
+    const uint64_t npairs = (uint64_t)nxp * Y.nplanes;
+    // ---- symbolic plane product ------------------------------------------------------------------------------
+    uint32_t l2 = 4;
+    while ((1ull << l2) < 2 * npairs) ++l2;
+    const uint32_t cap = 1u << l2;
+    uint64_t *tab = sc.alloc<uint64_t>(cap);
+    uint32_t *cnt = sc.alloc<uint32_t>(cap), *nrows = sc.alloc<uint32_t>(2 * (size_t)cap), *flags = sc.alloc<uint32_t>((size_t)cap + 1);
+    uint32_t *rnk = sc.alloc<uint32_t>((size_t)cap + 2);
+    unsigned long long *work = sc.alloc<unsigned long long>(cap);
+    CU_CHECK(e, cudaMemsetAsync(tab, 0xFF, (size_t)cap * 8, s));
+    CU_CHECK(e, cudaMemsetAsync(cnt, 0, (size_t)cap * 4, s));
+    CU_CHECK(e, cudaMemsetAsync(nrows, 0, (size_t)cap * 8, s));
+    CU_CHECK(e, cudaMemsetAsync(work, 0, (size_t)cap * 8, s));
+    const unsigned gp = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 2048);
+    k_plane_sym_insert<<<gp, 256, 0, s>>>(X.set.row_hi + x_first, X.pinfo + 4 * (size_t)x_first, nxp, Y.set.row_hi, Y.pinfo, Y.nplanes,
+                                          tab, l2, cnt, work, nrows);
+    k_row_flags<<<(cap + 255) / 256, 256, 0, s>>>(tab, cap, flags);
+    e->launches += 2;
+    device_scan(e, sc, flags, rnk, cap);
+    uint32_t nout = 0;
+    CU_CHECK(e, cudaMemcpyAsync(&nout, rnk + cap, 4, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    uint64_t *okey = sc.alloc<uint64_t>(nout);
+    uint32_t *ocnt = sc.alloc<uint32_t>((size_t)nout + 1), *onrows = sc.alloc<uint32_t>((size_t)nout + 1);
+    unsigned long long *owork = sc.alloc<unsigned long long>(nout);
+    uint32_t *pair_off = sc.alloc<uint32_t>((size_t)nout + 2), *fill = sc.alloc<uint32_t>(nout);
+    uint32_t *row_base = sc.alloc<uint32_t>((size_t)nout + 2);
+    uint2 *pairs = sc.alloc<uint2>(npairs);
+    uint32_t *totals = sc.alloc<uint32_t>(4);
+    k_plane_sym_compact<<<(cap + 255) / 256, 256, 0, s>>>(tab, cap, rnk, cnt, work, nrows, okey, ocnt, owork, onrows);
+    e->launches += 1;
+    device_scan(e, sc, ocnt, pair_off, nout);
+    CU_CHECK(e, cudaMemsetAsync(fill, 0, (size_t)nout * 4, s));
+    k_plane_sym_fill<<<gp, 256, 0, s>>>(X.set.row_hi + x_first, nxp, Y.set.row_hi, Y.nplanes, x_first, tab, l2, rnk, pair_off, fill, pairs);
+    // units: every plane has at most 63 rows, each with a low and a high half -> at most ceil(126 / NW) blocks
+    const uint32_t max_units = nout * ((2 * (2 * PL_ROWS - 1) + cfg.nw - 1) / cfg.nw);
+    uint32_t *units = sc.alloc<uint32_t>(std::max<uint32_t>(max_units, 1));
+    k_plane_units<<<1, 1024, 0, s>>>(owork, onrows, nout, cfg.nw, row_base, units, totals);
+    e->launches += 2;
+    uint32_t htot[2] = {0, 0};
+    CU_CHECK(e, cudaMemcpyAsync(htot, totals, 8, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    const uint32_t nunits = htot[0], nro = htot[1];
+    // ---- the product ----------------------------------------------------------------------------------------
+    uint64_t *omat = sc.alloc<uint64_t>((size_t)std::max<uint32_t>(nro, 1) * 64 * accw);
+    uint64_t *or_hi = sc.alloc<uint64_t>(std::max<uint32_t>(nro, 1));
+    uint32_t *or_cnt = sc.alloc<uint32_t>(2 * (size_t)nro + 1);
+    uint32_t *roffs = sc.alloc<uint32_t>(2 * (size_t)nro + 2);
+    uint32_t *cursor = sc.alloc<uint32_t>(4);
+    CU_CHECK(e, cudaMemsetAsync(cursor, 0, 16, s));
+    CU_CHECK(e, cudaMemsetAsync(or_cnt, 0, (2 * (size_t)nro + 1) * 4, s)); // rows of units this rank does not own stay empty
+    PlaneParams P{};
+    P.xmat = X.mat;
+    P.ymat = Y.mat;
+    P.xinfo = X.pinfo;
+    P.yinfo = Y.pinfo;
+    P.pairs = pairs;
+    P.pair_off = pair_off;
+    P.okey = okey;
+    P.onrows = onrows;
+    P.row_base = row_base;
+    P.units = units;
+    P.nunits = nunits;
+    P.unit_first = owner ? rank : 0;
+    P.unit_step = owner ? nranks : 1;
+    P.cursor = cursor;
+    P.delta = delta;
+    P.or_hi = or_hi;
+    P.omat = omat;
+    P.or_cnt = or_cnt;
+    P.ra_max = rows_max_x;
+    P.rb_max = rows_max_y;
+    P.nstage = nstage;
+    const uint32_t my_units = owner ? (nunits + nranks - 1 - rank) / nranks : nunits;
+    const unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(my_units, (uint32_t)e->sm_count * cfg.ctas));
+    CU_CHECK(e, cudaEventRecord(e->ev[5], s));
+    launch_planes(e, mode, uns, P, grid);
+    CU_CHECK(e, cudaEventRecord(e->ev[6], s));
+    st.mul_launches += 1;
+    uint64_t total = 0;
+    if (nro) {
+        device_scan(e, sc, or_cnt, roffs, 2 * (uint64_t)nro);
+        uint32_t ht = 0;
+        CU_CHECK(e, cudaMemcpyAsync(&ht, roffs + 2 * (size_t)nro, 4, cudaMemcpyDeviceToHost, s));
+        CU_CHECK(e, cudaStreamSynchronize(s));
+        total = ht;
+    }
+    R.rk = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1));
+    R.rc = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1) * accw);
+    if (total) {
+        const unsigned ge = (unsigned)std::min<uint32_t>((2 * nro + 7) / 8, 8192);
+        switch (mode) {
+            case CF_I1A1: k_plane_expand<1, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, nro, delta, R.rk, R.rc); break;
+            case CF_I1A2: k_plane_expand<2, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, nro, delta, R.rk, R.rc); break;
+            case CF_I1A3: k_plane_expand<3, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, nro, delta, R.rk, R.rc); break;
+            default: k_plane_expand<1, true><<<ge, 256, 0, s>>>(or_hi, omat, roffs, nro, delta, R.rk, R.rc); break;
+        }
+        e->launches += 1;
+        CU_CHECK(e, cudaGetLastError());
+    }
+    R.total = total;
+    R.nro = nro;
+    R.m = nout;
+    R.est_rows = nro;
+    R.done = true;
+    st.table_slots = 64;
+    st.group_lanes = 32;
+    return R;
+}
+
 void set_empty_result(obk_poly_result *out, const obk_poly_view *x, int cf_limbs, uint32_t mem)
 {
     std::memset(out, 0, sizeof(*out));
@@ -1274,6 +1504,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         bool trunc = false;
         unsigned hs_anyneg = 1;
         bool rows_ok = false; // every exponent >= 0 and the first symbol's exponents < 32 in both operands
+        bool planes_ok = false; // ... and the second symbol's exponents < 32 as well (plane-blocked path)
+        uint32_t plane_rows[2] = {PL_ROWS, PL_ROWS}; // largest second-symbol exponent + 1 of each operand
         uint64_t tot_mults = 0;
         if (!rq.merge) {
             trunc = rq.t != nullptr;
@@ -1394,6 +1626,11 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                           && hs[0].nonfinite == 0 && hs[1].nonfinite == 0;
                 for (uint32_t v = 0; v < L.nvars; ++v)
                     if (unord(hs[0].emin[v], L.is_signed) < 0 || unord(hs[1].emin[v], L.is_signed) < 0) rows_ok = false;
+                planes_ok = L.nvars >= 3 && unord(hs[0].emax[1], L.is_signed) < 32 && unord(hs[1].emax[1], L.is_signed) < 32;
+                if (planes_ok && rows_ok) {
+                    plane_rows[0] = (uint32_t)unord(hs[0].emax[1], L.is_signed) + 1u;
+                    plane_rows[1] = (uint32_t)unord(hs[1].emax[1], L.is_signed) + 1u;
+                }
             }
             // a-priori accumulator width: |sum| <= min(nx,ny) * max|c1| * max|c2|
             if (f64) {
@@ -1581,7 +1818,15 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
 
         // ---- dense operands: row-blocked path (register accumulation, no table) --------------------------------
         RowsResult rows;
-        if (!rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
+        int dense_kernel = 1;
+        if (!rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 3 && CWx == 1 && (e->opt_kernel == -1 || e->opt_kernel == 2)
+            && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok && planes_ok
+            && (e->opt_kernel == 2 || tot_mults >= (1ull << 22))) {
+            rows = run_planes(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, e->opt_kernel == 2, !f64 && hs_anyneg == 0,
+                              rq.rank, rq.nranks, owner, plane_rows[0], plane_rows[1], st);
+            if (rows.done) dense_kernel = 2;
+        }
+        if (!rows.done && e->opt_kernel != 2 && !rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok
             && (e->opt_kernel == 1 || tot_mults >= (1ull << 22))) {
             rows = run_rows(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, nx_full * ny, threads, e->opt_kernel == 1,
@@ -1599,7 +1844,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             st.est_nterms = rows.est_rows;
             st.nsegs = rows.m;
             st.nterms_out = total;
-            st.kernel = 1;
+            st.kernel = dense_kernel;
             CU_CHECK(e, cudaEventRecord(e->ev[3], s));
         } else {
             // ---- product-size estimate (poly_mul_estimate_product_size, polynomial.hpp:478-794) -------------
@@ -1980,6 +2225,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "table_slots") e->opt_table_slots = value;
     else if (n == "threads") e->opt_threads = value;
     else if (n == "kernel") e->opt_kernel = value;
+    else if (n == "plane_cfg") e->opt_plane_cfg = value;
     else if (n == "max_retries") e->opt_max_retries = value;
     else if (n == "fill_pct") e->opt_fill_pct = value;
     else {

@@ -400,10 +400,51 @@ def test_row_path_forced(engine):
         engine.set_option("kernel", -1)
 
 
+def test_plane_path_forced(engine):
+    """The plane-blocked dense kernel (2-D tiles staged by TMA, carry-save accumulators) against the oracle:
+    unsigned and signed coefficients, 1-3 limb accumulators, fp64, holes in the planes, squares, and the three
+    sub-warp modes (output rows of <= 8, <= 16, <= 32 and up to 63 entries)."""
+    rng = np.random.default_rng(31)
+    engine.set_option("kernel", 2)
+    try:
+        for nvars, max0, maxrest, fill, bits, tn, sgn in ((3, 9, 5, 0.9, 20, "u64", True), (4, 31, 3, 0.6, 61, "u64", False),
+                                                           (3, 15, 31, 1.0, 30, "i64", True), (3, 31, 6, 0.3, 8, "i64", False),
+                                                           (5, 4, 2, 1.0, 40, "u64", False), (4, 3, 3, 0.8, 62, "u64", False),
+                                                           (3, 31, 31, 0.5, 45, "u64", True), (4, 7, 7, 1.0, 12, "u64", False)):
+            x = dense_poly(rng, nvars, max0, maxrest, fill, bits, tn, signed_cfs=sgn)
+            y = dense_poly(rng, nvars, max0, maxrest, fill, bits, tn, signed_cfs=sgn)
+            p = check_exact(engine, x, y)
+            assert p.stats["kernel"] == 2, "plane path was not taken"
+            p = check_exact(engine, x, x)
+            assert p.stats["kernel"] == 2
+        # exact cancellation: (a+b+c)(a-b+c) ...
+        sy = ("a", "b", "c")
+        u = wl.from_dict(sy, {(1, 0, 0): 1, (0, 1, 0): 1, (0, 0, 1): 3}, "i64")
+        v = wl.from_dict(sy, {(1, 0, 0): 1, (0, 1, 0): -1, (0, 0, 1): 3}, "i64")
+        p = check_exact(engine, u, v)
+        assert p.stats["kernel"] == 2
+        # fp64
+        x = dense_poly(rng, 3, 12, 6, 0.8, 0, "u64", f64=True)
+        y = dense_poly(rng, 3, 12, 6, 0.8, 0, "u64", f64=True)
+        p = check_f64(engine, x, y)
+        assert p.stats["kernel"] == 2
+        # Fateman closed form
+        f, g = wl.fateman(14, 4, "u64")
+        p = engine.mul(f, g)
+        assert p.stats["kernel"] == 2
+        assert p.as_dict() == {kpack.pack(k, "u64"): v for k, v in wl.fateman_expected(14).items()}
+        # 1-limb accumulator (mod 2^64 arithmetic) and a 5-variable dense product
+        f, g = wl.fateman(6, 5, "u64")
+        p = check_exact(engine, f, g)
+        assert p.stats["kernel"] == 2 and p.stats["acc_limbs"] == 1
+    finally:
+        engine.set_option("kernel", -1)
+
+
 def test_row_path_auto_selection(engine):
     f, g = wl.fateman(16, 4, "u64")
     p = check_exact(engine, f, g)
-    assert p.stats["kernel"] == 1          # dense: rows
+    assert p.stats["kernel"] in (1, 2)     # dense: rows or planes
     fs, gs = wl.sparse_mp(9, "u64")
     p = engine.mul(fs, gs)
     assert p.stats["kernel"] == 0          # sparse: segment-owner scatter
