@@ -1053,8 +1053,8 @@ PlaneCfg plane_cfg(const obk_engine *e)
 {
     switch (e->opt_plane_cfg) {
         case 1: return {16, 1};
-        case 2: return {8, 3};
-        default: return {16, 2};
+        case 2: return {16, 2};
+        default: return {8, 3};
     }
 }
 
@@ -1074,8 +1074,8 @@ void launch_planes_t(obk_engine *e, const PlaneParams &P, unsigned grid)
 {
     switch (e->opt_plane_cfg) {
         case 1: launch_planes_c<LACC, F64, UNS, 16, 1>(e, P, grid); break;
-        case 2: launch_planes_c<LACC, F64, UNS, 8, 3>(e, P, grid); break;
-        default: launch_planes_c<LACC, F64, UNS, 16, 2>(e, P, grid); break;
+        case 2: launch_planes_c<LACC, F64, UNS, 16, 2>(e, P, grid); break;
+        default: launch_planes_c<LACC, F64, UNS, 8, 3>(e, P, grid); break;
     }
 }
 

@@ -322,16 +322,45 @@ struct PlaneDesc {
     uint32_t rows;   // onrows[plane]
 };
 
-// steps i0, i0+2, ... < n of one row pair: z[lane] += x[i] * y[lane - i].  Steps run in pairs (one LDS.128 for two
-// scalars): a scalar row is zero beyond its length and so is the pad after it, an odd count is rounded up for free.
+// Shared-memory loads by 32-bit shared-window address.  (With generic pointers the compiler re-derived the window base
+// -- S2R SR_CgaCtaId, LEA -- at every use: a quarter of the per-pair bookkeeping.)  asm volatile keeps them between the
+// mbarrier wait and the mbarrier arrive of their stage.
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a)
+{
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_2u64(uint32_t a, uint64_t &v0, uint64_t &v1)
+{
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
+// steps i0, i0+2, ... < n of one row pair: z[lane] += x[i] * y[lane - i]; px / py are the shared addresses of x[0]
+// and of y[lane].  Steps run in pairs (one LDS.128 for two scalars): a scalar row is zero beyond its length and so is
+// the pad after it, an odd count is rounded up for free.
 template <class Acc>
-__device__ __forceinline__ void conv_steps(Acc &z, const uint64_t *px, const uint64_t *py, uint32_t i0, uint32_t n)
+__device__ __forceinline__ void conv_steps(Acc &z, uint32_t px, uint32_t py, uint32_t i0, uint32_t n)
 {
 #pragma unroll 2
     for (uint32_t i = i0; i < n; i += 2) {
-        const ulonglong2 xx = *reinterpret_cast<const ulonglong2 *>(px + i);
-        z.mac(xx.x, *(py - i));
-        z.mac(xx.y, *(py - i - 1));
+        uint64_t x0, x1;
+        lds_2u64(px + 8u * i, x0, x1);
+        const uint64_t y0 = lds_u64(py - 8u * i), y1 = lds_u64(py - 8u * i - 8u);
+        z.mac(x0, y0);
+        z.mac(x1, y1);
     }
 }
 
@@ -447,47 +476,58 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_planeconv(const PlanePa
         gsub = 0;
     };
 
+    const uint32_t smem0 = smem_u32(smem_raw);
     uint32_t s = 0, ph = 0;
     for (;;) {
         mbar_wait(&s_full[s], ph);
-        const PlaneDesc d = *stageDesc(s);
+        const uint32_t aA = smem0 + s * stage_bytes, aB = aA + wordsA * 8u; // shared addresses of the two blobs
+        const uint4 dd = lds_u32x4(aB + wordsB * 8u);
+        PlaneDesc d;
+        d.plane = dd.x;
+        d.v0 = dd.y;
+        d.flags = dd.z;
+        d.rows = dd.w;
         if (d.flags & 2u) break;
         const uint32_t R = d.rows & 0xffu, V = pl_virtual_rows(d.rows);
         const uint32_t v = d.v0 + warp;
         const uint32_t h = v >= R ? 1u : 0u;   // 1: the high half (outputs 32..63) of the row
         const uint32_t j = h ? v - R : v;       // my output row inside the plane
         if (v < V) {
-            const uint64_t *sA = blobA(s) + PL_HDR, *sB = blobB(s) + PL_HDR;
-            const uint32_t *lenA = reinterpret_cast<const uint32_t *>(blobA(s)), *lenB = reinterpret_cast<const uint32_t *>(blobB(s));
             // row pairs (b, j - b): lane b looks at its candidate
-            uint32_t la = lenA[lane];
+            uint32_t la = lds_u32(aA + 4u * lane);
             const uint32_t jb = j - lane;
-            uint32_t lb = jb < (uint32_t)PL_ROWS ? lenB[jb] : 0u;
+            uint32_t lb = jb < (uint32_t)PL_ROWS ? lds_u32(aB + 4u * jb) : 0u;
             // the high half only sees pairs whose output reaches beyond 32 entries
             const bool valid = la != 0u && lb != 0u && (h == 0u || la + lb > 33u);
             if (!valid) la = lb = 0u;
             const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
             if (vmask) {
                 const uint32_t L = __reduce_max_sync(0xffffffffu, valid ? la + lb - 1u : 0u);
+                // shared addresses of A[0][0] and of B[j][lane (+32)]: row b of A is + b * 512, row j - b of B is - b * 512
+                const uint32_t rowA0 = aA + (PL_HDR + 32u) * 8u, rowBj = aB + (PL_HDR + 32u) * 8u + j * (PL_PITCH * 8u);
                 if (L > 16u) {
                     // ---- one row pair per trip, the whole warp on one pair; the SHORTER row supplies the scalars.
-                    // First the pairs whose B row is the shorter one, then the others: inside each run the pointers are
-                    // affine in b and the only per-pair lookups are two shuffles ----
+                    // First the pairs whose B row is the shorter one, then the others ----
                     const uint32_t bmask = __ballot_sync(0xffffffffu, valid && lb < la);
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {
-                        uint32_t m = pass == 0 ? bmask : (vmask & ~bmask);
-                        const uint32_t sl = pass == 0 ? lb : la, ll = pass == 0 ? la : lb; // scalar-row / vector-row length by lane
+                    const uint32_t voff = (lane + 32u * h) * 8u;
+                    {
+                        uint32_t m = bmask; // B row shorter: scalars from B, vector = A row
                         while (m) {
                             const uint32_t b = (uint32_t)__ffs(m) - 1u;
                             m &= m - 1u;
-                            const uint32_t n = __shfl_sync(0xffffffffu, sl, (int)b), ly = __shfl_sync(0xffffffffu, ll, (int)b);
-                            const uint64_t *ra = sA + (size_t)b * PL_PITCH + 32, *rb = sB + (size_t)(j - b) * PL_PITCH + 32;
-                            const uint64_t *px = pass == 0 ? rb : ra;
-                            const uint64_t *py = (pass == 0 ? ra : rb) + lane + 32u * h;
-                            // outputs i + m (m < ly) reach the high half only from step 33 - ly on
+                            const uint32_t n = __shfl_sync(0xffffffffu, lb, (int)b), ly = __shfl_sync(0xffffffffu, la, (int)b);
+                            const uint32_t i0 = h ? ((33u - ly) & ~1u) : 0u; // outputs reach the high half from step 33 - ly on
+                            conv_steps(z, rowBj - b * (PL_PITCH * 8u), rowA0 + b * (PL_PITCH * 8u) + voff, i0, n);
+                        }
+                    }
+                    {
+                        uint32_t m = vmask & ~bmask; // scalars from A, vector = B row
+                        while (m) {
+                            const uint32_t b = (uint32_t)__ffs(m) - 1u;
+                            m &= m - 1u;
+                            const uint32_t n = __shfl_sync(0xffffffffu, la, (int)b), ly = __shfl_sync(0xffffffffu, lb, (int)b);
                             const uint32_t i0 = h ? ((33u - ly) & ~1u) : 0u;
-                            conv_steps(z, px, py, i0, n);
+                            conv_steps(z, rowA0 + b * (PL_PITCH * 8u), rowBj - b * (PL_PITCH * 8u) + voff, i0, n);
                         }
                     }
                 } else {
@@ -503,10 +543,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_planeconv(const PlanePa
                         const uint32_t b = b0 + g;
                         const uint32_t a1 = __shfl_sync(0xffffffffu, la, (int)(b & 31u)), b1 = __shfl_sync(0xffffffffu, lb, (int)(b & 31u));
                         const bool live = b <= bhi && a1 != 0u;
-                        const uint64_t *ra = sA + (size_t)b * PL_PITCH + 32, *rb = sB + (size_t)(j - b) * PL_PITCH + 32;
+                        const uint32_t ra = rowA0 + b * (PL_PITCH * 8u), rb = rowBj - b * (PL_PITCH * 8u);
                         const bool a_short = a1 <= b1;
-                        const uint64_t *px = live ? (a_short ? ra : rb) : sA; // sA[0..32) is a zero run
-                        const uint64_t *py = (live ? (a_short ? rb : ra) : sA + 32) + lg;
+                        // a dead group multiplies the zero run in front of A's row 0
+                        const uint32_t px = live ? (a_short ? ra : rb) : rowA0 - 32u * 8u;
+                        const uint32_t py = (live ? (a_short ? rb : ra) : rowA0) + lg * 8u;
                         const uint32_t n = live ? (a_short ? a1 : b1) : 0u;
                         const uint32_t trips = __reduce_max_sync(0xffffffffu, n);
                         conv_steps(zs, px, py, 0u, trips);
