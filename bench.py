@@ -338,7 +338,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         "stats": {k: (float(v) if isinstance(v, float) else int(v)) for k, v in stats_last.items()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/traffic.json)",
-                     "kernel": "k_rowconv" if stats_last.get("kernel") == 1 else "k_mul",
+                     "kernel": {1: "k_rowconv", 2: "k_planeconv"}.get(stats_last.get("kernel"), "k_mul"),
                      "algorithmic_bytes_per_launch": B * per_launch_products, "algorithmic_bytes_per_product": B,
                      "peak_source": peak_src, "kernel_ms": kernel_mean,
                      "kernel_share_of_step": kernel_mean / ms,
@@ -550,7 +550,9 @@ def main():
         line["config"]["exchange"] = res["exchange"]
     if world > 1:
         line["config"]["multi_gpu_modes"] = {m: {"value": r["value"], "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"],
-                                                 "e2e": r.get("e2e", {}).get("value")} for m, r in results.items()}
+                                                 "e2e": r.get("e2e", {}).get("value"), "parity_ok": r["parity"].get("ok"),
+                                                 "timing_ms": (r.get("exchange") or {}).get("timing_ms")}
+                                             for m, r in results.items()}
         line["config"]["multi_gpu_mode_reported"] = best
     if also:
         line["also"] = also

@@ -791,10 +791,14 @@ void launch_rows(obk_engine *e, int mode, bool uns, const RowParams &P, unsigned
     }
 }
 
+
 struct RowsResult {
     bool done = false;
     uint64_t *rk = nullptr, *rc = nullptr;
     uint64_t total = 0;
+    // plane path: the term count stays on the device until the call's last synchronisation when nobody needs it
+    // earlier (a product left in HBM, not regrouped): `total` is then an upper bound (the size of rk / rc)
+    const uint32_t *total_dev = nullptr;
     uint64_t est_rows = 0;
     uint32_t nro = 0, m = 0;
     float ms_rowconv = 0;
@@ -1023,26 +1027,61 @@ RowsResult run_rows(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint6
 // Plane-blocked dense path (obk_planes.cuh, "kernel 2")
 // ------------------------------------------------------------------------------------------------
 struct PlaneSide {
-    RowSide set;               // open-addressing set of the plane keys hi2 = key / delta^2, and their numbering
-    uint64_t *mat = nullptr;   // [planes][PL_BLOB]: row-length table + rows in their staged layout
-    uint32_t *pinfo = nullptr; // [planes][4]: rows, terms, longest row, -
+    uint64_t *tab = nullptr;       // open-addressing set of the plane keys hi2 = key / delta^2
+    uint32_t log2_cap = 0;
+    uint32_t *slot_id = nullptr;   // slot -> plane number
+    uint64_t *plane_key = nullptr; // plane number -> key
+    uint64_t *mat = nullptr;       // [planes][PL_BLOB]: row-length table + rows in their staged layout
+    uint32_t *pinfo = nullptr;     // [planes][4]: rows, terms, longest row, -
     uint32_t nplanes = 0;
 };
+
+// The plane sets of both operands are built BEFORE the host reads the term statistics (they only need delta), so that
+// the plane counts travel with the statistics in one round trip.
+struct PlanePre {
+    bool launched = false, same = false;
+    PlaneSide X, Y;
+    uint32_t *counters = nullptr; // device: [0] planes of x, [1] planes of y
+    uint32_t h[2] = {0, 0};       // host copies (valid after the next synchronisation)
+};
+
+void planes_insert(obk_engine *e, Scratch &sc, const uint64_t *keys, uint64_t n, uint64_t d2, PlaneSide &p, uint32_t *counter)
+{
+    cudaStream_t s = e->stream;
+    p.log2_cap = 4;
+    while ((1ull << p.log2_cap) < 2 * n) ++p.log2_cap;
+    const uint32_t cap = 1u << p.log2_cap;
+    p.tab = sc.alloc<uint64_t>(cap);
+    p.slot_id = sc.alloc<uint32_t>(cap);
+    p.plane_key = sc.alloc<uint64_t>(n);
+    CU_CHECK(e, cudaMemsetAsync(p.tab, 0xFF, (size_t)cap * 8, s));
+    k_plane_insert<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, s>>>(keys, n, d2, p.tab, p.log2_cap, p.slot_id, p.plane_key,
+                                                                                     counter);
+    e->launches += 1;
+}
+
+void planes_prepare(obk_engine *e, Scratch &sc, const uint64_t *dxk, uint64_t nx, const uint64_t *dyk, uint64_t ny, uint64_t delta,
+                    PlanePre &pre)
+{
+    pre.same = dxk == dyk && nx == ny;
+    pre.counters = sc.alloc<uint32_t>(4);
+    CU_CHECK(e, cudaMemsetAsync(pre.counters, 0, 16, e->stream));
+    planes_insert(e, sc, dxk, nx, delta * delta, pre.X, pre.counters);
+    if (!pre.same) planes_insert(e, sc, dyk, ny, delta * delta, pre.Y, pre.counters + 1);
+    CU_CHECK(e, cudaMemcpyAsync(pre.h, pre.counters, 8, cudaMemcpyDeviceToHost, e->stream));
+    pre.launched = true;
+}
 
 void planes_build(obk_engine *e, Scratch &sc, const uint64_t *keys, const uint64_t *cfs, uint64_t n, uint64_t delta, PlaneSide &p)
 {
     cudaStream_t s = e->stream;
-    const uint32_t cap = 1u << p.set.log2_cap;
-    p.set.nrows = p.nplanes;
-    p.set.row_hi = sc.alloc<uint64_t>(p.nplanes);
     p.mat = sc.alloc<uint64_t>((size_t)p.nplanes * PL_BLOB);
     p.pinfo = sc.alloc<uint32_t>((size_t)p.nplanes * 4);
     CU_CHECK(e, cudaMemsetAsync(p.mat, 0, (size_t)p.nplanes * PL_BLOB * 8, s));
     CU_CHECK(e, cudaMemsetAsync(p.pinfo, 0, (size_t)p.nplanes * 16, s));
-    k_row_keys<<<(cap + 255) / 256, 256, 0, s>>>(p.set.tab, cap, p.set.rank, p.set.row_hi);
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
-    k_plane_fill<<<grid, 256, 0, s>>>(keys, cfs, n, delta, p.set.tab, p.set.log2_cap, p.set.rank, p.mat, p.pinfo);
-    e->launches += 2;
+    k_plane_fill<<<grid, 256, 0, s>>>(keys, cfs, n, delta, p.tab, p.log2_cap, p.slot_id, p.mat, p.pinfo);
+    e->launches += 1;
 }
 
 // Geometry of the plane kernel: consumer warps (= virtual output rows per unit) and CTAs per SM.
@@ -1090,10 +1129,14 @@ void launch_planes(obk_engine *e, int mode, bool uns, const PlaneParams &P, unsi
     }
 }
 
+
 // Returns done=false when the operands do not qualify (the caller then tries the row path / the scatter kernel).
-RowsResult run_planes(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx, const uint64_t *dyk,
-                      const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, bool forced, bool uns, uint32_t rank,
-                      uint32_t nranks, bool owner, uint32_t rows_max_x, uint32_t rows_max_y, obk_stats &st)
+// Host round trips: the plane counts (with the term statistics, see PlanePre), the unit / row totals of the symbolic
+// plane product, and the term count -- the last one only if `need_total`.
+RowsResult run_planes(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx,
+                      const uint64_t *dyk, const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, bool forced, bool uns,
+                      uint32_t rank, uint32_t nranks, bool owner, uint32_t rows_max_x, uint32_t rows_max_y, bool need_total,
+                      obk_stats &st)
 {
     RowsResult R;
     cudaStream_t s = e->stream;
@@ -1104,90 +1147,66 @@ RowsResult run_planes(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uin
     // shared memory of one SM (228 KB) shared by cfg.ctas resident CTAs, 1 KB reserved per CTA
     const uint32_t nstage = (uint32_t)std::min<size_t>(PL_MAX_STAGES, (std::min<size_t>(e->smem_optin, (228u << 10) / cfg.ctas - 1024) - 512) / stage_bytes);
     if (nstage < 2 || rows_max_x > (uint32_t)PL_ROWS || rows_max_y > (uint32_t)PL_ROWS) return R;
-    const uint64_t d2 = delta * delta;
-    PlaneSide X, Y;
-    const bool same = dxk == dyk && nx == ny;
-    rows_phase_a(e, sc, dxk, nx, d2, X.set);
-    if (!same) rows_phase_a(e, sc, dyk, ny, d2, Y.set);
-    uint32_t hx = 0, hy = 0;
-    CU_CHECK(e, cudaMemcpyAsync(&hx, X.set.rank + (1u << X.set.log2_cap), 4, cudaMemcpyDeviceToHost, s));
-    if (!same) CU_CHECK(e, cudaMemcpyAsync(&hy, Y.set.rank + (1u << Y.set.log2_cap), 4, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(e, cudaStreamSynchronize(s));
-    if (same) hy = hx;
-    // dense enough?  planes cost 8 KB each and a staged pair is only worth its copy with enough terms in it
+    if (!pre.launched) {
+        planes_prepare(e, sc, dxk, nx, dyk, ny, delta, pre);
+        CU_CHECK(e, cudaStreamSynchronize(s));
+    }
+    PlaneSide &X = pre.X, &Y = pre.Y;
+    const uint32_t hx = pre.h[0], hy = pre.same ? pre.h[0] : pre.h[1];
+    // dense enough?  a plane costs 16 KB of HBM and a staged pair is only worth its copy with enough terms in it
     const uint64_t plane_pairs = (uint64_t)hx * hy;
     const bool dense = (double)nx >= 8.0 * hx && (double)ny >= 8.0 * hy;
     if (plane_pairs > (1ull << 21) || hx >= (1u << 24) || hy >= (1u << 24) || (!forced && !dense)) return R;
     X.nplanes = hx;
     planes_build(e, sc, dxk, dxc, nx, delta, X);
-    if (same) {
+    if (pre.same) {
         Y = X;
     } else {
         Y.nplanes = hy;
         planes_build(e, sc, dyk, dyc, ny, delta, Y);
     }
-    // multi-GPU partial product: this rank multiplies a contiguous slice of the left PLANES by every right plane
-    uint32_t x_first = 0, nxp = X.nplanes;
-    if (nranks > 1 && !owner) {
-        x_first = (uint32_t)((uint64_t)X.nplanes * rank / nranks);
-        nxp = (uint32_t)((uint64_t)X.nplanes * (rank + 1) / nranks) - x_first;
-        if (nxp == 0) {
-            R.done = true;
-            R.rk = sc.alloc_out<uint64_t>(1);
-            R.rc = sc.alloc_out<uint64_t>(accw);
-            return R;
-        }
-    }
-    const uint64_t npairs = (uint64_t)nxp * Y.nplanes;
+    // multi-GPU partial product (left operand sharded): this rank forms the pairs of the left planes it owns
+    const uint32_t part_nranks = (nranks > 1 && !owner) ? nranks : 1u;
+    const uint64_t npairs = plane_pairs;
     // ---- symbolic plane product ------------------------------------------------------------------------------
     uint32_t l2 = 4;
     while ((1ull << l2) < 2 * npairs) ++l2;
     const uint32_t cap = 1u << l2;
     uint64_t *tab = sc.alloc<uint64_t>(cap);
-    uint32_t *cnt = sc.alloc<uint32_t>(cap), *nrows = sc.alloc<uint32_t>(2 * (size_t)cap), *flags = sc.alloc<uint32_t>((size_t)cap + 1);
-    uint32_t *rnk = sc.alloc<uint32_t>((size_t)cap + 2);
-    unsigned long long *work = sc.alloc<unsigned long long>(cap);
+    // one zeroed block: per-slot records and work, per-plane fill cursors, counters
+    const size_t zero_words = (size_t)cap * 4 + (size_t)cap * 2 + npairs + 8;
+    uint32_t *zero = sc.alloc<uint32_t>(zero_words);
+    uint4 *rec = reinterpret_cast<uint4 *>(zero);
+    unsigned long long *work = reinterpret_cast<unsigned long long *>(zero + (size_t)cap * 4);
+    uint32_t *fill = zero + (size_t)cap * 6;
+    uint32_t *counters = fill + npairs; // [0] output planes, [1] product-kernel unit cursor
     CU_CHECK(e, cudaMemsetAsync(tab, 0xFF, (size_t)cap * 8, s));
-    CU_CHECK(e, cudaMemsetAsync(cnt, 0, (size_t)cap * 4, s));
-    CU_CHECK(e, cudaMemsetAsync(nrows, 0, (size_t)cap * 8, s));
-    CU_CHECK(e, cudaMemsetAsync(work, 0, (size_t)cap * 8, s));
-    const unsigned gp = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 2048);
-    k_plane_sym_insert<<<gp, 256, 0, s>>>(X.set.row_hi + x_first, X.pinfo + 4 * (size_t)x_first, nxp, Y.set.row_hi, Y.pinfo, Y.nplanes,
-                                          tab, l2, cnt, work, nrows);
-    k_row_flags<<<(cap + 255) / 256, 256, 0, s>>>(tab, cap, flags);
-    e->launches += 2;
-    device_scan(e, sc, flags, rnk, cap);
-    uint32_t nout = 0;
-    CU_CHECK(e, cudaMemcpyAsync(&nout, rnk + cap, 4, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(e, cudaStreamSynchronize(s));
-    uint64_t *okey = sc.alloc<uint64_t>(nout);
-    uint32_t *ocnt = sc.alloc<uint32_t>((size_t)nout + 1), *onrows = sc.alloc<uint32_t>((size_t)nout + 1);
-    unsigned long long *owork = sc.alloc<unsigned long long>(nout);
-    uint32_t *pair_off = sc.alloc<uint32_t>((size_t)nout + 2), *fill = sc.alloc<uint32_t>(nout);
-    uint32_t *row_base = sc.alloc<uint32_t>((size_t)nout + 2);
+    CU_CHECK(e, cudaMemsetAsync(zero, 0, zero_words * 4, s));
+    // everything indexed by output plane is sized by the bound nout <= npairs
+    uint64_t *okey = sc.alloc<uint64_t>(npairs);
+    uint32_t *ocnt = sc.alloc<uint32_t>(npairs + 1), *onrows = sc.alloc<uint32_t>(npairs + 1);
+    unsigned long long *owork = sc.alloc<unsigned long long>(npairs);
+    uint32_t *pair_off = sc.alloc<uint32_t>(npairs + 2), *row_base = sc.alloc<uint32_t>(npairs + 2);
     uint2 *pairs = sc.alloc<uint2>(npairs);
     uint32_t *totals = sc.alloc<uint32_t>(4);
-    k_plane_sym_compact<<<(cap + 255) / 256, 256, 0, s>>>(tab, cap, rnk, cnt, work, nrows, okey, ocnt, owork, onrows);
-    e->launches += 1;
-    device_scan(e, sc, ocnt, pair_off, nout);
-    CU_CHECK(e, cudaMemsetAsync(fill, 0, (size_t)nout * 4, s));
-    k_plane_sym_fill<<<gp, 256, 0, s>>>(X.set.row_hi + x_first, nxp, Y.set.row_hi, Y.nplanes, x_first, tab, l2, rnk, pair_off, fill, pairs);
-    // units: every plane has at most 63 rows, each with a low and a high half -> at most ceil(126 / NW) blocks
-    const uint32_t max_units = nout * ((2 * (2 * PL_ROWS - 1) + cfg.nw - 1) / cfg.nw);
-    uint32_t *units = sc.alloc<uint32_t>(std::max<uint32_t>(max_units, 1));
-    k_plane_units<<<1, 1024, 0, s>>>(owork, onrows, nout, cfg.nw, row_base, units, totals);
-    e->launches += 2;
-    uint32_t htot[2] = {0, 0};
-    CU_CHECK(e, cudaMemcpyAsync(htot, totals, 8, cudaMemcpyDeviceToHost, s));
+    const uint32_t blocks_max = (2 * (2 * PL_ROWS - 1) + cfg.nw - 1) / cfg.nw; // at most 63 rows x 2 halves per plane
+    uint32_t *units = sc.alloc<uint32_t>(std::max<uint64_t>(npairs * blocks_max, 1));
+    const unsigned gp = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 2048);
+    k_plane_sym_insert<<<gp, 256, 0, s>>>(X.plane_key, X.pinfo, X.nplanes, Y.plane_key, Y.pinfo, Y.nplanes, rank, part_nranks, tab, l2, rec,
+                                          work, okey, counters);
+    k_plane_sym_compact<<<(cap + 255) / 256, 256, 0, s>>>(tab, cap, rec, work, ocnt, owork, onrows);
+    k_plane_units<<<1, 1024, 0, s>>>(owork, onrows, ocnt, okey, counters, cfg.nw, rank, owner ? nranks : 1u, row_base, pair_off, units, totals);
+    k_plane_sym_fill<<<gp, 256, 0, s>>>(X.plane_key, X.nplanes, Y.plane_key, Y.nplanes, rank, part_nranks, tab, l2, rec, pair_off, fill, pairs);
+    e->launches += 4;
+    uint32_t htot[3] = {0, 0, 0};
+    CU_CHECK(e, cudaMemcpyAsync(htot, totals, 12, cudaMemcpyDeviceToHost, s));
     CU_CHECK(e, cudaStreamSynchronize(s));
-    const uint32_t nunits = htot[0], nro = htot[1];
+    const uint32_t nunits = htot[0], nro = htot[1], nout = htot[2];
     // ---- the product ----------------------------------------------------------------------------------------
     uint64_t *omat = sc.alloc<uint64_t>((size_t)std::max<uint32_t>(nro, 1) * 64 * accw);
     uint64_t *or_hi = sc.alloc<uint64_t>(std::max<uint32_t>(nro, 1));
     uint32_t *or_cnt = sc.alloc<uint32_t>(2 * (size_t)nro + 1);
     uint32_t *roffs = sc.alloc<uint32_t>(2 * (size_t)nro + 2);
-    uint32_t *cursor = sc.alloc<uint32_t>(4);
-    CU_CHECK(e, cudaMemsetAsync(cursor, 0, 16, s));
     CU_CHECK(e, cudaMemsetAsync(or_cnt, 0, (2 * (size_t)nro + 1) * 4, s)); // rows of units this rank does not own stay empty
     PlaneParams P{};
     P.xmat = X.mat;
@@ -1201,9 +1220,7 @@ RowsResult run_planes(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uin
     P.row_base = row_base;
     P.units = units;
     P.nunits = nunits;
-    P.unit_first = owner ? rank : 0;
-    P.unit_step = owner ? nranks : 1;
-    P.cursor = cursor;
+    P.cursor = counters + 1;
     P.delta = delta;
     P.or_hi = or_hi;
     P.omat = omat;
@@ -1211,8 +1228,7 @@ RowsResult run_planes(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uin
     P.ra_max = rows_max_x;
     P.rb_max = rows_max_y;
     P.nstage = nstage;
-    const uint32_t my_units = owner ? (nunits + nranks - 1 - rank) / nranks : nunits;
-    const unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(my_units, (uint32_t)e->sm_count * cfg.ctas));
+    const unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(nunits, (uint32_t)e->sm_count * cfg.ctas));
     CU_CHECK(e, cudaEventRecord(e->ev[5], s));
     launch_planes(e, mode, uns, P, grid);
     CU_CHECK(e, cudaEventRecord(e->ev[6], s));
@@ -1220,10 +1236,15 @@ RowsResult run_planes(obk_engine *e, Scratch &sc, const uint64_t *dxk, const uin
     uint64_t total = 0;
     if (nro) {
         device_scan(e, sc, or_cnt, roffs, 2 * (uint64_t)nro);
-        uint32_t ht = 0;
-        CU_CHECK(e, cudaMemcpyAsync(&ht, roffs + 2 * (size_t)nro, 4, cudaMemcpyDeviceToHost, s));
-        CU_CHECK(e, cudaStreamSynchronize(s));
-        total = ht;
+        if (need_total) {
+            uint32_t ht = 0;
+            CU_CHECK(e, cudaMemcpyAsync(&ht, roffs + 2 * (size_t)nro, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            total = ht;
+        } else {
+            total = (uint64_t)nro * 64; // bound: the arrays are sized for it, the count is read with the call's last sync
+            R.total_dev = roffs + 2 * (size_t)nro;
+        }
     }
     R.rk = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1));
     R.rc = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1) * accw);
@@ -1274,6 +1295,9 @@ struct TailIn {
     uint32_t nranks; // > 1 and !owner: multi-GPU partial product, grouped by key mod OBK_EXCHANGE_MOD
     bool owner;
     uint32_t nsegs_out; // out: groups when a multi-GPU partial
+    // non-null: `total` is only a bound, the term count is still on the device and is fetched with the last
+    // synchronisation of the call (only for products left in DEVICE memory as they are: no regrouping, no partial)
+    const uint32_t *total_dev = nullptr;
 };
 
 // Common tail of every entry point that returns terms: optional regrouping (series tables for the host, exchange
@@ -1392,8 +1416,20 @@ void emit_result(obk_engine *e, Scratch &sc, TailIn &in, obk_poly_result *out, o
         }
         st.d2h_bytes += total * (W + accw) * 8;
     }
+    uint32_t pend = 0;
+    if (in.total_dev) CU_CHECK(e, cudaMemcpyAsync(&pend, in.total_dev, 4, cudaMemcpyDeviceToHost, s));
     CU_CHECK(e, cudaEventRecord(e->ev[8], s));
     CU_CHECK(e, cudaStreamSynchronize(s));
+    if (in.total_dev) {
+        if (regroup || in.result_mem != OBK_MEM_DEVICE || (in.nranks > 1 && !owner)) {
+            e->err = "internal: pending term count on a path that needs it early";
+            throw obk_fail{OBK_ERR_INVALID_ARG};
+        }
+        in.total = pend;
+        out->nterms = pend;
+        own->seg_offsets[1] = pend;
+        st.nterms_out = pend;
+    }
     in.nsegs_out = nsegs;
     in.rk = rk;
     in.rc = rc;
@@ -1506,6 +1542,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         bool rows_ok = false; // every exponent >= 0 and the first symbol's exponents < 32 in both operands
         bool planes_ok = false; // ... and the second symbol's exponents < 32 as well (plane-blocked path)
         uint32_t plane_rows[2] = {PL_ROWS, PL_ROWS}; // largest second-symbol exponent + 1 of each operand
+        PlanePre plane_pre;
         uint64_t tot_mults = 0;
         if (!rq.merge) {
             trunc = rq.t != nullptr;
@@ -1538,6 +1575,11 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             if (x != y)
                 k_term_stats<<<gy, 256, 0, s>>>(dyk, dyc, ny, L, var_mask, f64 ? 1 : 0, CWy, ydeg, dstats + 1);
             e->launches += 3;
+            // dense candidates: number the planes of both operands now, so that their counts come back with the
+            // statistics (one host round trip instead of two)
+            if (!trunc && W == 1 && L.nvars >= 3 && L.delta < (1ull << 32) && (e->opt_kernel == -1 || e->opt_kernel == 2)
+                && (e->opt_kernel == 2 || (double)nx_full * (double)ny >= (double)(1ull << 22)))
+                planes_prepare(e, sc, dxk, nx_full, dyk, ny, L.delta, plane_pre);
             StatsOut hs[2];
             CU_CHECK(e, cudaMemcpyAsync(hs, dstats, sizeof(StatsOut) * (x == y ? 1 : 2), cudaMemcpyDeviceToHost, s));
             CU_CHECK(e, cudaStreamSynchronize(s));
@@ -1822,8 +1864,10 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         if (!rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 3 && CWx == 1 && (e->opt_kernel == -1 || e->opt_kernel == 2)
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok && planes_ok
             && (e->opt_kernel == 2 || tot_mults >= (1ull << 22))) {
-            rows = run_planes(e, sc, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, e->opt_kernel == 2, !f64 && hs_anyneg == 0,
-                              rq.rank, rq.nranks, owner, plane_rows[0], plane_rows[1], st);
+            // the term count may stay on the device until the end of the call when the product is left in HBM as it is
+            const bool need_total = rq.push != nullptr || (rq.nranks > 1 && !owner) || rq.result_mem != OBK_MEM_DEVICE || e->opt_regroup == 2;
+            rows = run_planes(e, sc, plane_pre, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, e->opt_kernel == 2, !f64 && hs_anyneg == 0,
+                              rq.rank, rq.nranks, owner, plane_rows[0], plane_rows[1], need_total, st);
             if (rows.done) dense_kernel = 2;
         }
         if (!rows.done && e->opt_kernel != 2 && !rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 2 && CWx == 1 && e->opt_kernel != 0
@@ -2074,7 +2118,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             return OBK_OK;
         }
         TailIn tin{rk, rc, total, W, accw, f64, L.is_signed, tot_mults, rq.result_mem, rq.nranks, owner, 1};
+        tin.total_dev = rows.done ? rows.total_dev : nullptr;
         emit_result(e, sc, tin, out, st);
+        total = tin.total;
         ResultOwner *own = static_cast<ResultOwner *>(out->owner);
         if (rq.nranks > 1 && !owner) nsegs = tin.nsegs_out;
         if (owner) {

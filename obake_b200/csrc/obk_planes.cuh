@@ -54,13 +54,47 @@ __host__ __device__ inline uint32_t pl_stage_bytes(uint32_t ra_max, uint32_t rb_
 }
 
 // ---- plane building ------------------------------------------------------------------------------------------------
-// (the plane keys hi2 = key / delta^2 are numbered with the row path's k_row_insert / k_row_flags / k_row_keys, called
-// with delta^2)
+__device__ __forceinline__ uint32_t plane_hash(uint64_t key, uint32_t log2_cap)
+{
+    return (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2_cap));
+}
+// owner rank of a plane key (multi-GPU): a function of the key alone, so every rank takes the same decision whatever
+// numbers its own tables gave the planes
+__host__ __device__ inline uint32_t plane_owner(uint64_t key, uint32_t nranks)
+{
+    return (uint32_t)(((key * 0xD6E8FEB86659FD93ULL) >> 33) % nranks);
+}
 
-// Scatter every term's coefficient into its plane's dense tile and record row lengths / row counts.
+// The set of plane keys hi2 = key / delta^2 of an operand (open addressing, global memory).  The thread that claims a
+// slot numbers the plane: no flag / scan / gather passes (the row path spends five launches on them).  Plane numbers
+// therefore depend on the race; nothing downstream may depend on them beyond "distinct and dense".
+__global__ void __launch_bounds__(256) k_plane_insert(const uint64_t *__restrict__ keys, uint64_t n, uint64_t d2, uint64_t *__restrict__ tab,
+                                                      uint32_t log2_cap, uint32_t *__restrict__ slot_id, uint64_t *__restrict__ plane_key,
+                                                      uint32_t *__restrict__ counter)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mask = (1u << log2_cap) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t hi = keys[i] / d2;
+        uint32_t h = plane_hash(hi, log2_cap);
+        for (;;) {
+            const unsigned long long old = atomicCAS((unsigned long long *)&tab[h], (unsigned long long)ROW_EMPTY, (unsigned long long)hi);
+            if (old == ROW_EMPTY) {
+                const uint32_t id = atomicAdd(counter, 1u);
+                slot_id[h] = id;
+                plane_key[id] = hi;
+                break;
+            }
+            if (old == hi) break;
+            h = (h + 1u) & mask;
+        }
+    }
+}
+
+// Scatter every term's coefficient into its plane's blob and record row lengths / row counts.
 __global__ void __launch_bounds__(256) k_plane_fill(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ cfs, uint64_t n,
                                                     uint64_t delta, const uint64_t *__restrict__ tab, uint32_t log2_cap,
-                                                    const uint32_t *__restrict__ rank, uint64_t *__restrict__ mat,
+                                                    const uint32_t *__restrict__ slot_id, uint64_t *__restrict__ mat,
                                                     uint32_t *__restrict__ pinfo)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -72,9 +106,9 @@ __global__ void __launch_bounds__(256) k_plane_fill(const uint64_t *__restrict__
         const uint64_t rem = key - hi * d2;
         const uint32_t lo1 = (uint32_t)(rem / delta);
         const uint32_t lo0 = (uint32_t)(rem - (uint64_t)lo1 * delta);
-        uint32_t h = (uint32_t)((hi * 0x9E3779B97F4A7C15ULL) >> (64 - log2_cap));
+        uint32_t h = plane_hash(hi, log2_cap);
         while (tab[h] != hi) h = (h + 1u) & mask;
-        const uint32_t p = rank[h];
+        const uint32_t p = slot_id[h];
         uint64_t *blob = mat + (size_t)p * PL_BLOB;
         blob[PL_HDR + lo1 * PL_PITCH + 32 + lo0] = cfs[i];
         atomicMax(reinterpret_cast<uint32_t *>(blob) + lo1, lo0 + 1u);
@@ -85,89 +119,83 @@ __global__ void __launch_bounds__(256) k_plane_fill(const uint64_t *__restrict__
 }
 
 // ---- symbolic plane product ----------------------------------------------------------------------------------------
-// Pass 1: every plane pair's key sum goes into an open-addressing set; per slot: pair count, work (term pairs) and
-// the number of output rows.
+// Per-slot records of the output-plane set: [0] pairs, [1] rows, [2] long-row flag (0x100), [3] output plane number.
+// Pass 1: every plane pair's key sum is inserted; the claiming thread numbers the output plane.  part_nranks > 1: this
+// rank only forms the pairs of the left planes it owns (multi-GPU partial product).
 __global__ void __launch_bounds__(256) k_plane_sym_insert(const uint64_t *__restrict__ xh, const uint32_t *__restrict__ xinfo, uint32_t nx,
                                                           const uint64_t *__restrict__ yh, const uint32_t *__restrict__ yinfo, uint32_t ny,
-                                                          uint64_t *__restrict__ tab, uint32_t log2_cap, uint32_t *__restrict__ cnt,
-                                                          unsigned long long *__restrict__ work, uint32_t *__restrict__ nrows)
+                                                          uint32_t part_rank, uint32_t part_nranks, uint64_t *__restrict__ tab,
+                                                          uint32_t log2_cap, uint4 *__restrict__ rec, unsigned long long *__restrict__ work,
+                                                          uint64_t *__restrict__ okey, uint32_t *__restrict__ counters)
 {
     const uint64_t total = (uint64_t)nx * ny, stride = (uint64_t)gridDim.x * blockDim.x;
     const uint32_t mask = (1u << log2_cap) - 1u;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const uint32_t a = (uint32_t)(i / ny), b = (uint32_t)(i - (uint64_t)a * ny);
-        const uint64_t key = xh[a] + yh[b];
-        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2_cap));
+        const uint64_t ka = xh[a];
+        if (part_nranks > 1u && plane_owner(ka, part_nranks) != part_rank) continue;
+        const uint64_t key = ka + yh[b];
+        uint32_t h = plane_hash(key, log2_cap);
         for (;;) {
             const unsigned long long old = atomicCAS((unsigned long long *)&tab[h], (unsigned long long)ROW_EMPTY, (unsigned long long)key);
-            if (old == ROW_EMPTY || old == key) break;
+            if (old == ROW_EMPTY) {
+                const uint32_t o = atomicAdd(&counters[0], 1u);
+                rec[h].w = o;
+                okey[o] = key;
+                break;
+            }
+            if (old == key) break;
             h = (h + 1u) & mask;
         }
-        atomicAdd(&cnt[h], 1u);
+        uint32_t *r = reinterpret_cast<uint32_t *>(&rec[h]);
+        atomicAdd(&r[0], 1u);
         atomicAdd(&work[h], (unsigned long long)xinfo[4 * a + 1] * yinfo[4 * b + 1]);
-        // rows of the output plane, and bit 8: some output row is longer than 32 entries (it then gets a second warp
-        // for its high half)
-        // (bit 8 is the high bit of the value, so the max keeps it once set and a later, larger row count still wins
-        // only in the low byte: combine explicitly)
-        const uint32_t rws = xinfo[4 * a] + yinfo[4 * b] - 1u;
-        const uint32_t lng = (xinfo[4 * a + 2] + yinfo[4 * b + 2] - 1u > 32u) ? 0x100u : 0u;
-        atomicMax(&nrows[2 * (size_t)h], rws);
-        if (lng) atomicOr(&nrows[2 * (size_t)h + 1], lng);
+        atomicMax(&r[1], xinfo[4 * a] + yinfo[4 * b] - 1u);
+        // some output row is longer than 32 entries: its high half gets a warp of its own
+        if (xinfo[4 * a + 2] + yinfo[4 * b + 2] - 1u > 32u) atomicOr(&r[2], 0x100u);
     }
 }
 
-// Pass 2: compact the per-slot records by output plane number (rank = exclusive scan of the occupancy flags).
-__global__ void __launch_bounds__(256) k_plane_sym_compact(const uint64_t *__restrict__ tab, uint32_t cap, const uint32_t *__restrict__ rank,
-                                                           const uint32_t *__restrict__ cnt, const unsigned long long *__restrict__ work,
-                                                           const uint32_t *__restrict__ nrows, uint64_t *__restrict__ okey,
-                                                           uint32_t *__restrict__ ocnt, unsigned long long *__restrict__ owork,
-                                                           uint32_t *__restrict__ onrows)
+// Pass 2: the per-slot records by output plane number.
+__global__ void __launch_bounds__(256) k_plane_sym_compact(const uint64_t *__restrict__ tab, uint32_t cap, const uint4 *__restrict__ rec,
+                                                           const unsigned long long *__restrict__ work, uint32_t *__restrict__ ocnt,
+                                                           unsigned long long *__restrict__ owork, uint32_t *__restrict__ onrows)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap || tab[i] == ROW_EMPTY) return;
-    const uint32_t o = rank[i];
-    okey[o] = tab[i];
-    ocnt[o] = cnt[i];
-    owork[o] = work[i];
-    onrows[o] = nrows[2 * (size_t)i] | nrows[2 * (size_t)i + 1];
+    const uint4 r = rec[i];
+    ocnt[r.w] = r.x;
+    owork[r.w] = work[i];
+    onrows[r.w] = r.y | r.z;
 }
 
-// Pass 3: the pair list, grouped by output plane.
-__global__ void __launch_bounds__(256) k_plane_sym_fill(const uint64_t *__restrict__ xh, uint32_t nx, const uint64_t *__restrict__ yh, uint32_t ny,
-                                                        uint32_t x_first, const uint64_t *__restrict__ tab, uint32_t log2_cap,
-                                                        const uint32_t *__restrict__ rank, const uint32_t *__restrict__ pair_off,
-                                                        uint32_t *__restrict__ fill, uint2 *__restrict__ pairs)
-{
-    const uint64_t total = (uint64_t)nx * ny, stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint32_t mask = (1u << log2_cap) - 1u;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const uint32_t a = (uint32_t)(i / ny), b = (uint32_t)(i - (uint64_t)a * ny);
-        const uint64_t key = xh[a] + yh[b];
-        uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ULL) >> (64 - log2_cap));
-        while (tab[h] != key) h = (h + 1u) & mask;
-        const uint32_t o = rank[h];
-        const uint32_t pos = atomicAdd(&fill[o], 1u);
-        pairs[(size_t)pair_off[o] + pos] = make_uint2(a + x_first, b);
-    }
-}
-
-// Pass 4 (one CTA): work units = (output plane, block of `nw` output rows), heaviest planes first (32 work classes
-// by bit length: a counting sort, stable inside a class); row_base = exclusive scan of the rows per plane.
+// Pass 3 (one CTA): pair_off = exclusive scan of the pairs per plane, row_base = exclusive scan of the rows per plane,
+// and the work units = (output plane, block of `nw` virtual rows), heaviest planes first (work classes by bit length:
+// a counting sort).  own_nranks > 1: only the units this rank owns (multi-GPU owner mode; ownership is a function of
+// the plane key and the block, the same on every rank).
 //   units[u] = plane | block << 24     (planes < 2^24, blocks < 2^8)
-//   totals[0] = units, totals[1] = output rows
+//   totals[0] = units, totals[1] = output rows, totals[2] = output planes
 __global__ void __launch_bounds__(1024) k_plane_units(const unsigned long long *__restrict__ owork, const uint32_t *__restrict__ onrows,
-                                                      uint32_t nout, uint32_t nw, uint32_t *__restrict__ row_base,
-                                                      uint32_t *__restrict__ units, uint32_t *__restrict__ totals)
+                                                      const uint32_t *__restrict__ ocnt, const uint64_t *__restrict__ okey,
+                                                      const uint32_t *__restrict__ counters, uint32_t nw, uint32_t own_rank,
+                                                      uint32_t own_nranks, uint32_t *__restrict__ row_base,
+                                                      uint32_t *__restrict__ pair_off, uint32_t *__restrict__ units,
+                                                      uint32_t *__restrict__ totals)
 {
     __shared__ uint32_t s_cls[65], s_tot, s_carry;
     const uint32_t tid = threadIdx.x;
+    const uint32_t nout = counters[0];
+    auto owned = [&](uint32_t o, uint32_t b) { return own_nranks <= 1u || (plane_owner(okey[o], own_nranks) + b) % own_nranks == own_rank; };
     if (tid < 65) s_cls[tid] = 0;
     if (tid == 0) s_carry = 0;
     __syncthreads();
     // units per work class
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
         const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
-        atomicAdd(&s_cls[64u - c], (pl_virtual_rows(onrows[o]) + nw - 1u) / nw); // class 0 = heaviest
+        const uint32_t nb = (pl_virtual_rows(onrows[o]) + nw - 1u) / nw;
+        uint32_t mine = 0;
+        for (uint32_t b = 0; b < nb; ++b) mine += owned(o, b) ? 1u : 0u;
+        if (mine) atomicAdd(&s_cls[64u - c], mine); // class 0 = heaviest
     }
     __syncthreads();
     if (tid == 0) {
@@ -178,36 +206,70 @@ __global__ void __launch_bounds__(1024) k_plane_units(const unsigned long long *
             acc += v;
         }
         totals[0] = acc;
+        totals[2] = nout;
     }
     __syncthreads();
-    // unit slots (order inside a class does not matter) and the row scan
+    // unit slots (the order inside a class does not matter)
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
         const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
         const uint32_t nb = (pl_virtual_rows(onrows[o]) + nw - 1u) / nw;
-        const uint32_t at = atomicAdd(&s_cls[64u - c], nb);
-        for (uint32_t b = 0; b < nb; ++b) units[at + b] = o | (b << 24);
+        uint32_t mine = 0;
+        for (uint32_t b = 0; b < nb; ++b) mine += owned(o, b) ? 1u : 0u;
+        if (mine == 0u) continue;
+        uint32_t at = atomicAdd(&s_cls[64u - c], mine);
+        for (uint32_t b = 0; b < nb; ++b)
+            if (owned(o, b)) units[at++] = o | (b << 24);
     }
-    for (uint32_t base0 = 0; base0 < nout; base0 += SCAN_BLOCK) {
-        const uint32_t base = base0 + tid * SCAN_ITEMS;
-        uint32_t v[SCAN_ITEMS], sum = 0;
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) {
-            v[j] = base + j < nout ? (onrows[base + j] & 0xffu) : 0;
-            sum += v[j];
-        }
-        uint32_t ex = block_exclusive_scan(sum, &s_tot) + s_carry;
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) {
-            if (base + j < nout) row_base[base + j] = ex;
-            ex += v[j];
-        }
+    // the two scans
+    for (int which = 0; which < 2; ++which) {
+        uint32_t *out = which == 0 ? row_base : pair_off;
         __syncthreads();
-        if (tid == 0) s_carry += s_tot;
+        if (tid == 0) s_carry = 0;
         __syncthreads();
+        for (uint32_t base0 = 0; base0 < nout; base0 += SCAN_BLOCK) {
+            const uint32_t base = base0 + tid * SCAN_ITEMS;
+            uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                v[j] = base + j < nout ? (which == 0 ? (onrows[base + j] & 0xffu) : ocnt[base + j]) : 0;
+                sum += v[j];
+            }
+            uint32_t ex = block_exclusive_scan(sum, &s_tot) + s_carry;
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                if (base + j < nout) out[base + j] = ex;
+                ex += v[j];
+            }
+            __syncthreads();
+            if (tid == 0) s_carry += s_tot;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            out[nout] = s_carry;
+            if (which == 0) totals[1] = s_carry;
+        }
     }
-    if (tid == 0) {
-        row_base[nout] = s_carry;
-        totals[1] = s_carry;
+}
+
+// Pass 4: the pair list, grouped by output plane.
+__global__ void __launch_bounds__(256) k_plane_sym_fill(const uint64_t *__restrict__ xh, uint32_t nx, const uint64_t *__restrict__ yh, uint32_t ny,
+                                                        uint32_t part_rank, uint32_t part_nranks, const uint64_t *__restrict__ tab,
+                                                        uint32_t log2_cap, const uint4 *__restrict__ rec,
+                                                        const uint32_t *__restrict__ pair_off, uint32_t *__restrict__ fill,
+                                                        uint2 *__restrict__ pairs)
+{
+    const uint64_t total = (uint64_t)nx * ny, stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mask = (1u << log2_cap) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t a = (uint32_t)(i / ny), b = (uint32_t)(i - (uint64_t)a * ny);
+        const uint64_t ka = xh[a];
+        if (part_nranks > 1u && plane_owner(ka, part_nranks) != part_rank) continue;
+        const uint64_t key = ka + yh[b];
+        uint32_t h = plane_hash(key, log2_cap);
+        while (tab[h] != key) h = (h + 1u) & mask;
+        const uint32_t o = rec[h].w;
+        const uint32_t pos = atomicAdd(&fill[o], 1u);
+        pairs[(size_t)pair_off[o] + pos] = make_uint2(a, b);
     }
 }
 
@@ -299,7 +361,6 @@ struct PlaneParams {
     const uint32_t *row_base;      // [nout + 1]
     const uint32_t *units;         // plane | block << 24, heaviest first
     uint32_t nunits;
-    uint32_t unit_first, unit_step; // this rank's units: unit_first, unit_first + unit_step, ... (multi-GPU owner mode)
     uint32_t *cursor;
     uint64_t delta;
     uint64_t *or_hi;  // [rows] row key = okey * delta + j
@@ -397,7 +458,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_planeconv(const PlanePa
             uint32_t u = 0;
             if (lane == 0) u = atomicAdd(P.cursor, 1u);
             u = __shfl_sync(0xffffffffu, u, 0);
-            const uint64_t uidx = (uint64_t)P.unit_first + (uint64_t)u * P.unit_step;
+            const uint64_t uidx = u;
             const bool quit = uidx >= P.nunits;
             uint32_t o = 0, v0 = 0, p0 = 0, p1 = 1, enc = 0, jmin = 0;
             if (!quit) {
@@ -582,7 +643,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_planeconv(const PlanePa
                 const uint32_t c = __popc(__ballot_sync(0xffffffffu, nz));
                 if (lane == 0) {
                     P.or_cnt[2 * (size_t)row + h] = c;
-                    if (h == 0u) P.or_hi[row] = __ldg(P.okey + d.plane) * P.delta + j;
+                    P.or_hi[row] = __ldg(P.okey + d.plane) * P.delta + j; // both halves: in owner mode they may sit on different ranks
                 }
             }
             z.clear();
