@@ -127,6 +127,14 @@ typedef struct obk_stats {
 
 /* Engine lifetime.  One engine = one CUDA device + one stream + a grow-only workspace. */
 obk_status obk_engine_create(int device, obk_engine **out);
+/* Single-process multi-GPU engine (obake is a single-process library: `f * g`, series.hpp:3186-3194, must be able to use
+ * the whole box without a launcher).  obk_poly_mul on such an engine takes HOST operands and returns a HOST result: one
+ * host thread per device, both operands on every device, each device forms the output segments / planes it owns (the
+ * zero-exchange design of SURVEY 8e -- ownership is a function of the keys, no term crosses NVLink), regroups its
+ * share into the same 2^k series tables and copies it back; the shares of a table are concatenated on the host.  The
+ * O(terms) entry points (addsub, truncate, copy, extend, degrees, overflow check) run on devices[0]; the partial /
+ * push / merge entry points and set_stream belong to the one-process-per-GPU design and are refused. */
+obk_status obk_engine_create_multi(const int *devices, int ndev, obk_engine **out);
 void obk_engine_destroy(obk_engine *e);
 /* Launch on the caller's stream (e.g. torch's current stream) instead of the engine's own. */
 obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream);
@@ -238,6 +246,11 @@ obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly
  * with !(limit < degree), the degree taken in the key's integer type T as in obk_trunc. */
 obk_status obk_poly_truncate_degree(obk_engine *e, const obk_poly_view *x, const obk_trunc *t, uint32_t result_mem,
                                     obk_poly_result *out, obk_stats *stats);
+
+/* Measurement support (bench.py, roofline.int_mac): "int_mac" = exact 64 x 64 -> 160-bit multiply-accumulates per second
+ * of this GPU with register-resident operands (the accumulator form of the plane-blocked dense kernel, 4 IMAD.WIDE + 2
+ * IADD3.X per product) -- the compute ceiling of the dense paths, which move almost no HBM bytes. */
+obk_status obk_microbench(obk_engine *e, const char *name, double *value);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ SYMBOLS = [
     "obk_overflow_check", "obk_key_degrees", "obk_poly_mul_partial", "obk_poly_merge",
     "obk_poly_addsub", "obk_poly_truncate_degree", "obk_poly_copy", "obk_poly_extend_symbols",
     "obk_peer_window_alloc", "obk_peer_window_open", "obk_peer_window_close", "obk_poly_mul_push", "obk_peer_merge",
-    "obk_peer_window_reset",
+    "obk_peer_window_reset", "obk_microbench", "obk_engine_create_multi",
 ]
 
 _LIB = None
@@ -130,6 +130,10 @@ def lib():
     L.obk_peer_merge.restype = C.c_int
     L.obk_peer_merge.argtypes = [C.c_void_p, C.POINTER(PeerWindows), C.POINTER(PolyView), C.c_uint32, C.c_uint32,
                                  C.POINTER(PolyResult), C.POINTER(Stats)]
+    L.obk_engine_create_multi.restype = C.c_int
+    L.obk_engine_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    L.obk_microbench.restype = C.c_int
+    L.obk_microbench.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]
     L.obk_peer_window_reset.restype = C.c_int
     L.obk_peer_window_reset.argtypes = [C.c_void_p, C.POINTER(PeerWindows)]
     _LIB = L

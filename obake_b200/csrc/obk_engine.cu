@@ -4,12 +4,14 @@
 // (include/obake/polynomials/polynomial.hpp:1878-1929, 797-1582).  There is NO CPU fallback: without a
 // CUDA device every entry point fails with OBK_ERR_CUDA.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -57,6 +59,8 @@ struct obk_engine {
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
     uint32_t last_rslices = 1;
+    // multi-device engine (obk_engine_create_multi): one single-device engine per GPU; this object then owns no stream
+    std::vector<obk_engine *> subs;
     // scratch arena (see Scratch)
     std::vector<ArenaChunk> arena;
     size_t arena_chunk = 0, arena_off = 0;
@@ -71,6 +75,7 @@ struct ResultOwner {
     void *dkeys = nullptr, *dcfs = nullptr; // device allocations (cudaMallocAsync)
     int pk = -1, pc = -1;                   // pinned block indices
     uint64_t *seg_offsets = nullptr;        // malloc
+    void *hk = nullptr, *hc = nullptr;      // malloc'ed host term arrays (multi-device engine)
 };
 
 #define CU_CHECK(e, call)                                                                                              \
@@ -1298,6 +1303,7 @@ struct TailIn {
     // non-null: `total` is only a bound, the term count is still on the device and is fetched with the last
     // synchronisation of the call (only for products left in DEVICE memory as they are: no regrouping, no partial)
     const uint32_t *total_dev = nullptr;
+    int force_log2 = -1; // >= 0: regroup into exactly 2^force_log2 series tables (shares of a multi-device product)
 };
 
 // Common tail of every entry point that returns terms: optional regrouping (series tables for the host, exchange
@@ -1347,6 +1353,7 @@ void emit_result(obk_engine *e, Scratch &sc, TailIn &in, obk_poly_result *out, o
         const double seg_kb = est_sp >= 1e-3 ? 200.0 : 20.0;
         const uint64_t est_nsegs = (uint64_t)((double)total * term_bytes / (seg_kb * 1024.0));
         while ((est_nsegs >> out_log2) != 0 && out_log2 < 22) ++out_log2; // nbits()
+        if (in.force_log2 >= 0) out_log2 = (uint32_t)in.force_log2;
         if (total > 0 && out_log2 > 0) {
             SortedY g = sort_operand(e, sc, rk, rc, nullptr, total, W, accw, 1u << out_log2, 0, true, 0, 0, true, true);
             sc.release(rk);
@@ -2167,6 +2174,24 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
 
 } // namespace
 
+// A multi-device engine forwards everything but the product to its first device (the O(terms) steps either side of the
+// product do not need more than one GPU) and reports that device's error text.
+#define OBK_FORWARD_MULTI(e, call)                                                                                     \
+    do {                                                                                                               \
+        if (!(e)->subs.empty()) {                                                                                      \
+            const obk_status _st = (call);                                                                             \
+            if (_st != OBK_OK) (e)->err = (e)->subs[0]->err;                                                           \
+            return _st;                                                                                                \
+        }                                                                                                              \
+    } while (0)
+#define OBK_REJECT_MULTI(e)                                                                                            \
+    do {                                                                                                               \
+        if (!(e)->subs.empty()) {                                                                                      \
+            (e)->err = "not available on a multi-device engine (it has no stream of its own): use a single-device engine"; \
+            return OBK_ERR_UNSUPPORTED;                                                                                \
+        }                                                                                                              \
+    } while (0)
+
 extern "C" {
 
 const char *obk_version(void)
@@ -2233,9 +2258,44 @@ obk_status obk_engine_create(int device, obk_engine **out)
     return OBK_OK;
 }
 
+obk_status obk_engine_create_multi(const int *devices, int ndev, obk_engine **out)
+{
+    if (!out || !devices || ndev < 1 || ndev > 16) return OBK_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (ndev == 1) return obk_engine_create(devices[0], out);
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) {
+                g_create_err = "obk_engine_create_multi: a device is listed twice";
+                return OBK_ERR_INVALID_ARG;
+            }
+    auto *m = new obk_engine();
+    m->device = devices[0];
+    m->own_stream = false;
+    for (int i = 0; i < ndev; ++i) {
+        obk_engine *sub = nullptr;
+        const obk_status st = obk_engine_create(devices[i], &sub);
+        if (st != OBK_OK) {
+            for (auto *q : m->subs) obk_engine_destroy(q);
+            delete m;
+            return st;
+        }
+        m->subs.push_back(sub);
+    }
+    m->sm_count = m->subs[0]->sm_count;
+    m->smem_optin = m->subs[0]->smem_optin;
+    *out = m;
+    return OBK_OK;
+}
+
 void obk_engine_destroy(obk_engine *e)
 {
     if (!e) return;
+    if (!e->subs.empty()) {
+        for (auto *q : e->subs) obk_engine_destroy(q);
+        delete e;
+        return;
+    }
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (auto &b : e->pinned)
@@ -2249,6 +2309,8 @@ void obk_engine_destroy(obk_engine *e)
 obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream)
 {
     if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+    if (!e) return OBK_ERR_INVALID_ARG;
     cudaStreamSynchronize(e->stream);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     e->stream = (cudaStream_t)cuda_stream;
@@ -2259,6 +2321,13 @@ obk_status obk_engine_set_stream(obk_engine *e, void *cuda_stream)
 obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
 {
     if (!e || !name) return OBK_ERR_INVALID_ARG;
+    for (auto *q : e->subs) {
+        const obk_status st = obk_engine_set_option(q, name, value);
+        if (st != OBK_OK) {
+            e->err = q->err;
+            return st;
+        }
+    }
     const std::string n(name);
     if (n == "nsegs") e->opt_nsegs = value;
     else if (n == "fence") e->opt_fence = value;
@@ -2286,10 +2355,14 @@ const char *obk_last_error(const obk_engine *e)
     return e ? e->err.c_str() : g_create_err.c_str();
 }
 
+static obk_status multi_mul(obk_engine *m, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t, uint32_t result_mem,
+                            obk_poly_result *out, obk_stats *stats);
+
 obk_status obk_poly_mul(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
                         uint32_t result_mem, obk_poly_result *out, obk_stats *stats)
 {
     if (!e) return OBK_ERR_INVALID_ARG;
+    if (!e->subs.empty()) return multi_mul(e, x, y, t, result_mem, out, stats);
     MulRequest rq{x, y, t, result_mem};
     return run_mul(e, rq, out, stats);
 }
@@ -2297,7 +2370,9 @@ obk_status obk_poly_mul(obk_engine *e, const obk_poly_view *x, const obk_poly_vi
 obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
                                 uint32_t rank, uint32_t nranks, obk_poly_result *out_partial, uint64_t *send_counts,
                                 obk_stats *stats)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e || nranks == 0 || rank >= nranks) return OBK_ERR_INVALID_ARG;
     MulRequest rq{x, y, t, OBK_MEM_DEVICE};
     rq.rank = rank;
@@ -2308,7 +2383,9 @@ obk_status obk_poly_mul_partial(obk_engine *e, const obk_poly_view *x, const obk
 
 obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t nsegs, uint32_t result_mem,
                           obk_poly_result *out, obk_stats *stats)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e || !terms) return OBK_ERR_INVALID_ARG;
     MulRequest rq{nullptr, terms, nullptr, result_mem};
     rq.merge = true;
@@ -2317,7 +2394,9 @@ obk_status obk_poly_merge(obk_engine *e, const obk_poly_view *terms, uint32_t ns
 }
 
 obk_status obk_peer_window_alloc(obk_engine *e, uint64_t window_bytes, void **base, void *ipc_handle64)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e || !base || window_bytes < 4096) return OBK_ERR_INVALID_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
     try {
@@ -2345,7 +2424,9 @@ obk_status obk_peer_window_alloc(obk_engine *e, uint64_t window_bytes, void **ba
 }
 
 obk_status obk_peer_window_open(obk_engine *e, const void *ipc_handle64, void **base)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e || !ipc_handle64 || !base) return OBK_ERR_INVALID_ARG;
     cudaSetDevice(e->device);
     cudaIpcMemHandle_t h;
@@ -2362,7 +2443,9 @@ obk_status obk_peer_window_open(obk_engine *e, const void *ipc_handle64, void **
 }
 
 obk_status obk_peer_window_close(obk_engine *e, void *base, int own)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e || !base) return OBK_ERR_INVALID_ARG;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
@@ -2390,7 +2473,9 @@ static bool check_windows(obk_engine *e, const obk_peer_windows *w)
 }
 
 obk_status obk_peer_window_reset(obk_engine *e, const obk_peer_windows *w)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e) return OBK_ERR_INVALID_ARG;
     if (!check_windows(e, w)) return OBK_ERR_INVALID_ARG;
     try {
@@ -2406,7 +2491,9 @@ obk_status obk_peer_window_reset(obk_engine *e, const obk_peer_windows *w)
 
 obk_status obk_poly_mul_push(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t,
                              const obk_peer_windows *w, obk_stats *stats)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e) return OBK_ERR_INVALID_ARG;
     if (!check_windows(e, w)) return OBK_ERR_INVALID_ARG;
     MulRequest rq{x, y, t, OBK_MEM_DEVICE};
@@ -2421,7 +2508,9 @@ obk_status obk_poly_mul_push(obk_engine *e, const obk_poly_view *x, const obk_po
 
 obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_poly_view *like, uint32_t acc_limbs,
                           uint32_t result_mem, obk_poly_result *out, obk_stats *stats)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_REJECT_MULTI(e);
+
     if (!e || !like || !out) return OBK_ERR_INVALID_ARG;
     if (!check_windows(e, w)) return OBK_ERR_INVALID_ARG;
     std::memset(out, 0, sizeof(*out));
@@ -2461,7 +2550,9 @@ obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_po
 
 obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int subtract, uint32_t result_mem,
                            obk_poly_result *out, obk_stats *stats)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_FORWARD_MULTI(e, obk_poly_addsub(e->subs[0], x, y, subtract, result_mem, out, stats));
+
     if (!e || !out) return OBK_ERR_INVALID_ARG;
     std::memset(out, 0, sizeof(*out));
     uint64_t *cat_k = nullptr, *cat_c = nullptr;
@@ -2565,9 +2656,8 @@ obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly
     return rc_status;
 }
 
-obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_mem, obk_poly_result *out)
+static obk_status copy_impl(obk_engine *e, const obk_poly_view *x, uint32_t result_mem, int force_log2, obk_poly_result *out)
 {
-    if (!e || !out || !x) return OBK_ERR_INVALID_ARG;
     std::memset(out, 0, sizeof(*out));
     obk_stats st{};
     e->launches = 0;
@@ -2591,6 +2681,7 @@ obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_
         CU_CHECK(e, cudaMemcpyAsync(rk, x->keys, n * W * 8, kind, s));
         CU_CHECK(e, cudaMemcpyAsync(rc, x->cfs, n * cw * 8, kind, s));
         TailIn tin{rk, rc, n, W, cw, f64, L.is_signed, n, result_mem, 1, false, 1};
+        tin.force_log2 = force_log2;
         emit_result(e, sc, tin, out, st);
         return OBK_OK;
     } catch (const obk_fail &f) {
@@ -2601,9 +2692,196 @@ obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_
     }
 }
 
+// ---- single-process multi-device product -------------------------------------------------------------------------
+// obake is a single-process library: `f * g` (series.hpp:3186-3194) must be able to use every GPU of the box without
+// a launcher.  The multi-device engine runs the zero-exchange design of SURVEY 8(e) from host threads: every device
+// gets both operands, forms only the output segments / output planes it owns (ownership is a function of the keys, so
+// the devices agree without talking), regroups its share into the SAME 2^k series tables and copies it to the host,
+// where the shares of a table are concatenated.  No term crosses NVLink; the only host-side work is one memcpy per
+// (table, device).
+static obk_status multi_mul(obk_engine *m, const obk_poly_view *x, const obk_poly_view *y, const obk_trunc *t, uint32_t result_mem,
+                            obk_poly_result *out, obk_stats *stats)
+{
+    if (!x || !y || !out) return OBK_ERR_INVALID_ARG;
+    std::memset(out, 0, sizeof(*out));
+    if (result_mem != OBK_MEM_HOST || x->mem != OBK_MEM_HOST || y->mem != OBK_MEM_HOST) {
+        m->err = "the multi-device engine takes HOST operands and returns a HOST result (device-resident chains belong to one "
+                 "device: use a single-device engine)";
+        return OBK_ERR_UNSUPPORTED;
+    }
+    const uint32_t n = (uint32_t)m->subs.size();
+    std::vector<obk_poly_result> share(n), host(n);
+    std::vector<obk_stats> sst(n);
+    std::vector<obk_status> rc(n, OBK_OK);
+    auto free_all = [&](std::vector<obk_poly_result> &v) {
+        for (uint32_t d = 0; d < n; ++d)
+            if (v[d].owner) obk_result_free(m->subs[d], &v[d]);
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    int64_t fill = m->opt_fill_pct;
+    for (int attempt = 0;; ++attempt) {
+        std::vector<std::thread> th;
+        for (uint32_t d = 0; d < n; ++d) {
+            th.emplace_back([&, d]() {
+                obk_engine *e = m->subs[d];
+                e->opt_mgpu_owner = 1;
+                e->opt_fill_pct = fill;
+                MulRequest rq{x, y, t, OBK_MEM_DEVICE};
+                rq.rank = d;
+                rq.nranks = n;
+                rc[d] = run_mul(e, rq, &share[d], &sst[d]);
+                e->opt_mgpu_owner = 0;
+                e->opt_fill_pct = m->opt_fill_pct;
+            });
+        }
+        for (auto &tt : th) tt.join();
+        bool overflow = false, failed = false;
+        for (uint32_t d = 0; d < n; ++d) {
+            if (rc[d] == OBK_ERR_TABLE_OVERFLOW && m->subs[d]->err.find("segment table") != std::string::npos) overflow = true;
+            else if (rc[d] != OBK_OK) failed = true;
+        }
+        if (!overflow && !failed) break;
+        free_all(share);
+        if (failed || attempt >= 5) {
+            for (uint32_t d = 0; d < n; ++d)
+                if (rc[d] != OBK_OK) {
+                    m->err = m->subs[d]->err;
+                    return rc[d];
+                }
+        }
+        // the devices must agree on the segmentation (ownership is defined by it): all of them retry finer
+        fill = std::max<int64_t>(4, fill / 2);
+    }
+    uint64_t total = 0, tot_mults = 0;
+    for (uint32_t d = 0; d < n; ++d) {
+        total += share[d].nterms;
+        tot_mults += sst[d].term_products;
+    }
+    const int W = (int)x->key_words;
+    const bool f64 = x->cf_kind == OBK_CF_F64;
+    uint32_t cw = 1;
+    for (uint32_t d = 0; d < n; ++d) cw = std::max(cw, share[d].cf_limbs);
+    // the reference's sizing rule for the number of series tables (polynomial.hpp:870-902), on the WHOLE result
+    uint32_t k = 0;
+    {
+        const double term_bytes = 8.0 * W + 8.0 * cw;
+        const double est_sp = tot_mults ? (double)total / (double)tot_mults : 1.0;
+        const double seg_kb = est_sp >= 1e-3 ? 200.0 : 20.0;
+        const uint64_t est_nsegs = (uint64_t)((double)total * term_bytes / (seg_kb * 1024.0));
+        while ((est_nsegs >> k) != 0 && k < 22) ++k;
+    }
+    {
+        std::vector<std::thread> th;
+        for (uint32_t d = 0; d < n; ++d) {
+            th.emplace_back([&, d]() {
+                obk_poly_view v = *x;
+                v.nterms = share[d].nterms;
+                v.cf_limbs = f64 ? 1 : share[d].cf_limbs;
+                v.mem = OBK_MEM_DEVICE;
+                v.keys = share[d].keys;
+                v.cfs = share[d].cfs;
+                rc[d] = copy_impl(m->subs[d], &v, OBK_MEM_HOST, (int)k, &host[d]);
+            });
+        }
+        for (auto &tt : th) tt.join();
+    }
+    free_all(share);
+    for (uint32_t d = 0; d < n; ++d)
+        if (rc[d] != OBK_OK) {
+            m->err = m->subs[d]->err;
+            free_all(host);
+            return rc[d];
+        }
+    // ---- concatenate the shares table by table ----------------------------------------------------------------
+    const size_t groups = (size_t)1 << k;
+    auto *own = new ResultOwner{nullptr};
+    own->seg_offsets = (uint64_t *)std::calloc(groups + 1, sizeof(uint64_t));
+    own->hk = std::malloc(std::max<uint64_t>(total, 1) * W * 8);
+    own->hc = std::malloc(std::max<uint64_t>(total, 1) * cw * 8);
+    auto seg_lo = [&](uint32_t d, size_t g) -> uint64_t {
+        const obk_poly_result &h = host[d];
+        if (h.nterms == 0) return 0;
+        return h.nsegs == groups ? h.seg_offsets[g] : (g == 0 ? 0 : h.nterms); // k == 0: one group
+    };
+    for (size_t g = 0; g < groups; ++g) {
+        uint64_t c = 0;
+        for (uint32_t d = 0; d < n; ++d) c += seg_lo(d, g + 1) - seg_lo(d, g);
+        own->seg_offsets[g + 1] = own->seg_offsets[g] + c;
+    }
+    {
+        std::vector<std::thread> th;
+        for (uint32_t d = 0; d < n; ++d) {
+            th.emplace_back([&, d]() {
+                if (host[d].nterms == 0) return;
+                const uint32_t hl = host[d].cf_limbs;
+                for (size_t g = 0; g < groups; ++g) {
+                    const uint64_t a = seg_lo(d, g), b = seg_lo(d, g + 1);
+                    if (a == b) continue;
+                    uint64_t dst = own->seg_offsets[g];
+                    for (uint32_t q = 0; q < d; ++q) dst += seg_lo(q, g + 1) - seg_lo(q, g);
+                    std::memcpy((uint64_t *)own->hk + dst * W, host[d].keys + a * W, (b - a) * W * 8);
+                    if (hl == cw) {
+                        std::memcpy((uint64_t *)own->hc + dst * cw, (const uint64_t *)host[d].cfs + a * cw, (b - a) * cw * 8);
+                    } else { // a share whose accumulators were narrower: sign-extend
+                        for (uint64_t i = a; i < b; ++i)
+                            for (uint32_t l = 0; l < cw; ++l)
+                                ((uint64_t *)own->hc)[(dst + i - a) * cw + l] =
+                                    l < hl ? ((const uint64_t *)host[d].cfs)[i * hl + l]
+                                           : (uint64_t)((int64_t)((const uint64_t *)host[d].cfs)[i * hl + hl - 1] >> 63);
+                    }
+                }
+            });
+        }
+        for (auto &tt : th) tt.join();
+    }
+    obk_stats st{};
+    st.nterms_out = total;
+    st.log2_nsegs = k;
+    for (uint32_t d = 0; d < n; ++d) {
+        st.term_products += sst[d].term_products;
+        st.h2d_bytes += sst[d].h2d_bytes;
+        st.d2h_bytes += (uint64_t)host[d].nterms * (W + host[d].cf_limbs) * 8;
+        st.ms_mul = std::max(st.ms_mul, sst[d].ms_mul);
+        st.total_launches += sst[d].total_launches;
+        st.mul_launches += sst[d].mul_launches;
+        st.retries = std::max(st.retries, sst[d].retries);
+    }
+    st.est_nterms = sst[0].est_nterms;
+    st.nsegs = sst[0].nsegs;
+    st.acc_limbs = cw;
+    st.kernel = sst[0].kernel;
+    st.table_slots = sst[0].table_slots;
+    st.group_lanes = sst[0].group_lanes;
+    st.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    free_all(host);
+    out->nterms = total;
+    out->key_words = W;
+    out->cf_kind = f64 ? OBK_CF_F64 : OBK_CF_INT;
+    out->cf_limbs = cw;
+    out->log2_nsegs = k;
+    out->mem = OBK_MEM_HOST;
+    out->nsegs = (uint32_t)groups;
+    out->seg_kind = OBK_SEG_HASH_POW2;
+    out->keys = (uint64_t *)own->hk;
+    out->cfs = own->hc;
+    out->seg_offsets = own->seg_offsets;
+    out->owner = own;
+    if (stats) *stats = st;
+    return OBK_OK;
+}
+
+obk_status obk_poly_copy(obk_engine *e, const obk_poly_view *x, uint32_t result_mem, obk_poly_result *out)
+{
+    if (!e || !out || !x) return OBK_ERR_INVALID_ARG;
+    OBK_FORWARD_MULTI(e, obk_poly_copy(e->subs[0], x, result_mem, out));
+    return copy_impl(e, x, result_mem, -1, out);
+}
+
 obk_status obk_poly_extend_symbols(obk_engine *e, const obk_poly_view *x, uint32_t new_nvars, const uint32_t *pos,
                                    uint32_t result_mem, obk_poly_result *out)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_FORWARD_MULTI(e, obk_poly_extend_symbols(e->subs[0], x, new_nvars, pos, result_mem, out));
+
     if (!e || !out || !x) return OBK_ERR_INVALID_ARG;
     std::memset(out, 0, sizeof(*out));
     obk_stats st{};
@@ -2687,7 +2965,9 @@ obk_status obk_poly_extend_symbols(obk_engine *e, const obk_poly_view *x, uint32
 
 obk_status obk_poly_truncate_degree(obk_engine *e, const obk_poly_view *x, const obk_trunc *t, uint32_t result_mem,
                                     obk_poly_result *out, obk_stats *stats)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_FORWARD_MULTI(e, obk_poly_truncate_degree(e->subs[0], x, t, result_mem, out, stats));
+
     if (!e || !out || !x || !t) return OBK_ERR_INVALID_ARG;
     std::memset(out, 0, sizeof(*out));
     obk_stats st{};
@@ -2778,12 +3058,55 @@ void obk_result_free(obk_engine *e, obk_poly_result *r)
         if (own->pc >= 0) pinned_release(eng, own->pc);
     }
     std::free(own->seg_offsets);
+    std::free(own->hk);
+    std::free(own->hc);
     delete own;
     std::memset(r, 0, sizeof(*r));
 }
 
+obk_status obk_microbench(obk_engine *e, const char *name, double *value)
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_FORWARD_MULTI(e, obk_microbench(e->subs[0], name, value));
+
+    if (!e || !name || !value) return OBK_ERR_INVALID_ARG;
+    *value = 0;
+    if (std::string(name) != "int_mac") {
+        e->err = "unknown micro-benchmark (known: int_mac)";
+        return OBK_ERR_INVALID_ARG;
+    }
+    try {
+        CU_CHECK(e, cudaSetDevice(e->device));
+        Scratch sc(e);
+        cudaStream_t s = e->stream;
+        const unsigned grid = (unsigned)e->sm_count * 8u, threads = 256;
+        const uint32_t iters = 1u << 15;
+        uint64_t *in = sc.alloc<uint64_t>(256), *out = sc.alloc<uint64_t>((size_t)grid * threads);
+        std::vector<uint64_t> h(256);
+        for (size_t i = 0; i < h.size(); ++i) h[i] = 0x9E3779B97F4A7C15ULL * (i + 1) >> 3; // 61-bit unsigned operands
+        CU_CHECK(e, cudaMemcpyAsync(in, h.data(), 256 * 8, cudaMemcpyHostToDevice, s));
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep) { // first repetition warms up
+            CU_CHECK(e, cudaEventRecord(e->ev[0], s));
+            k_bench_int_mac<<<grid, threads, 0, s>>>(in, iters, out);
+            CU_CHECK(e, cudaEventRecord(e->ev[1], s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+            const double rate = (double)grid * threads * iters * 4.0 / (ms * 1e-3);
+            if (rep > 0) best = std::max(best, rate);
+        }
+        CU_CHECK(e, cudaGetLastError());
+        *value = best;
+        return OBK_OK;
+    } catch (const obk_fail &f) {
+        return f.st;
+    }
+}
+
 obk_status obk_overflow_check(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int *ok)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_FORWARD_MULTI(e, obk_overflow_check(e->subs[0], x, y, ok));
+
     if (!e || !x || !y || !ok) return OBK_ERR_INVALID_ARG;
     // Same statistics pass as the product; report the verdict only.
     *ok = 1;
@@ -2827,7 +3150,9 @@ obk_status obk_overflow_check(obk_engine *e, const obk_poly_view *x, const obk_p
 }
 
 obk_status obk_key_degrees(obk_engine *e, const obk_poly_view *x, const obk_trunc *which, int64_t *out_host)
-{
+{    if (!e) return OBK_ERR_INVALID_ARG;
+    OBK_FORWARD_MULTI(e, obk_key_degrees(e->subs[0], x, which, out_host));
+
     if (!e || !x || !out_host) return OBK_ERR_INVALID_ARG;
     if (x->nterms == 0) return OBK_OK;
     try {

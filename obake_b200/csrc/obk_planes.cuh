@@ -685,4 +685,32 @@ __global__ void __launch_bounds__(256) k_plane_expand(const uint64_t *__restrict
     }
 }
 
+// ---- micro-benchmark: the exact multiply-accumulate rate of the chip -------------------------------------------------
+// Register-resident z += x * y (64 x 64 -> carry-save 160 bits, the plane kernel's accumulator) with four independent
+// accumulators per thread and nothing else in the loop: the compute roofline the dense kernels are reported against
+// (bench.py, roofline.int_mac).  out[thread] keeps the result alive.
+__global__ void __launch_bounds__(256) k_bench_int_mac(const uint64_t *__restrict__ in, uint32_t iters, uint64_t *__restrict__ out)
+{
+    PlaneAcc<3, false, true> a0, a1, a2, a3;
+    a0.clear();
+    a1.clear();
+    a2.clear();
+    a3.clear();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t x0 = in[t & 255u], x1 = in[(t + 1u) & 255u], y0 = in[(t + 2u) & 255u], y1 = in[(t + 3u) & 255u];
+#pragma unroll 4
+    for (uint32_t i = 0; i < iters; ++i) {
+        a0.mac(x0, y0);
+        a1.mac(x1, y0);
+        a2.mac(x0, y1);
+        a3.mac(x1, y1);
+    }
+    uint64_t l0[3], l1[3], l2[3], l3[3];
+    a0.limbs(l0);
+    a1.limbs(l1);
+    a2.limbs(l2);
+    a3.limbs(l3);
+    out[t] = l0[0] ^ l1[1] ^ l2[2] ^ l3[0] ^ l0[2] ^ l1[0] ^ l2[1] ^ l3[2];
+}
+
 } // namespace obk

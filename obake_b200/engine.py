@@ -370,6 +370,14 @@ class Engine:
             _raise(rc, self.last_error())
         return Product(self, res, st)
 
+    def microbench(self, name: str = "int_mac") -> float:
+        """Measured ceiling of this GPU for the named primitive (include/obk_b200.h, obk_microbench)."""
+        v = C.c_double(0.0)
+        rc = _capi.lib().obk_microbench(self._h, name.encode(), C.byref(v))
+        if rc != 0:
+            _raise(rc, self.last_error())
+        return float(v.value)
+
     def overflow_check(self, x, y) -> bool:
         hx, hy = HostOperand(x, 1 if not x.is_f64 else None), HostOperand(y, 1 if not y.is_f64 else None)
         ok = C.c_int(1)
