@@ -20,6 +20,7 @@
 #include "../include/obake/kpack.hpp"
 #include "obk_kernels.cuh"
 #include "obk_planes.cuh"
+#include "obk_tiles.cuh"
 
 using namespace obk;
 
@@ -1274,6 +1275,242 @@ RowsResult run_planes(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t 
     return R;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile-blocked dense path (obk_tiles.cuh, "kernel 3")
+// ------------------------------------------------------------------------------------------------
+struct TileCfg {
+    uint32_t nw, t, ctas;
+};
+TileCfg tile_cfg(const obk_engine *e)
+{
+    switch (e->opt_plane_cfg) {
+        case 1: return {8, 2, 3};
+        case 2: return {8, 1, 3};
+        case 3: return {16, 2, 1};
+        default: return {8, 2, 2};
+    }
+}
+
+template <int LACC, bool F64, bool UNS, int NW, int T, int MINB>
+void launch_tiles_c(obk_engine *e, const TileParams &P, unsigned grid)
+{
+    auto fn = k_tileconv<LACC, F64, UNS, NW, T, MINB>;
+    const size_t smem = (size_t)P.nstage * tl_stage(P.rcap, P.P).bytes;
+    CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<grid, (NW + 1) * 32, smem, e->stream>>>(P);
+    e->launches += 1;
+    CU_CHECK(e, cudaGetLastError());
+}
+
+template <int LACC, bool F64, bool UNS>
+void launch_tiles_t(obk_engine *e, const TileParams &P, unsigned grid)
+{
+    switch (e->opt_plane_cfg) {
+        case 1: launch_tiles_c<LACC, F64, UNS, 8, 2, 3>(e, P, grid); break;
+        case 2: launch_tiles_c<LACC, F64, UNS, 8, 1, 3>(e, P, grid); break;
+        case 3: launch_tiles_c<LACC, F64, UNS, 16, 2, 1>(e, P, grid); break;
+        default: launch_tiles_c<LACC, F64, UNS, 8, 2, 2>(e, P, grid); break;
+    }
+}
+
+void launch_tiles(obk_engine *e, int mode, bool uns, const TileParams &P, unsigned grid)
+{
+    switch (mode) {
+        case CF_I1A1: launch_tiles_t<1, false, false>(e, P, grid); break;
+        case CF_I1A2: uns ? launch_tiles_t<2, false, true>(e, P, grid) : launch_tiles_t<2, false, false>(e, P, grid); break;
+        case CF_I1A3: uns ? launch_tiles_t<3, false, true>(e, P, grid) : launch_tiles_t<3, false, false>(e, P, grid); break;
+        case CF_F64: launch_tiles_t<1, true, false>(e, P, grid); break;
+        default: e->err = "internal: coefficient mode not supported by the tile path"; throw obk_fail{OBK_ERR_INVALID_ARG};
+    }
+}
+
+struct TileDims {
+    uint32_t wx, wy, rx, ry; // row width (first symbol's largest exponent + 1) and rows (second symbol's) of each operand
+    // truncation as an output filter: on, weights of the two low symbols, limit, the symbols it counts
+    bool trunc = false;
+    uint32_t w0 = 0, w1 = 0;
+    int64_t limit = 0;
+    uint64_t var_mask = 0;
+};
+
+// dense enough for the plane / tile paths?  (a plane costs KBs of HBM and a staged pair is only worth its copy with
+// enough terms in it)
+bool planes_dense(const PlanePre &pre, uint64_t nx, uint64_t ny)
+{
+    const uint32_t hx = pre.h[0], hy = pre.same ? pre.h[0] : pre.h[1];
+    return (double)nx >= 8.0 * hx && (double)ny >= 8.0 * hy && (uint64_t)hx * hy <= (1ull << 21);
+}
+
+// Returns done=false when the operands do not qualify (the caller then tries the other paths).
+RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx,
+                     const uint64_t *dyk, const uint64_t *dyc, uint64_t ny, const Layout &L, int mode, int accw, bool forced, bool uns,
+                     uint32_t rank, uint32_t nranks, bool owner, const TileDims &D, bool need_total, obk_stats &st)
+{
+    RowsResult R;
+    cudaStream_t s = e->stream;
+    const uint64_t delta = L.delta;
+    if (delta >= (1ull << 32)) return R; // delta^2 must fit 64 bits
+    if (D.wx > (uint32_t)TL_MAX_DIM || D.wy > (uint32_t)TL_MAX_DIM || D.rx > (uint32_t)TL_MAX_DIM || D.ry > (uint32_t)TL_MAX_DIM) return R;
+    TileCfg cfg = tile_cfg(e);
+    const uint32_t P = tl_pitch(std::max(D.wx, D.wy)), rcap = std::max(D.rx, D.ry);
+    const uint32_t blob_words = tl_blob_words(rcap, P);
+    const TileStage G = tl_stage(rcap, P);
+    // shared memory of one SM (228 KB) shared by cfg.ctas resident CTAs, 1 KB reserved per CTA; at least 2 stages
+    while (cfg.ctas > 1 && ((228u << 10) / cfg.ctas - 1024u - 512u) / G.bytes < 3u) --cfg.ctas;
+    const uint32_t nstage = (uint32_t)std::min<size_t>(TL_MAX_STAGES, (std::min<size_t>(e->smem_optin, (228u << 10) / cfg.ctas - 1024) - 512) / G.bytes);
+    if (nstage < 2) return R;
+    if (!pre.launched) {
+        planes_prepare(e, sc, dxk, nx, dyk, ny, delta, pre);
+        CU_CHECK(e, cudaStreamSynchronize(s));
+    }
+    PlaneSide &X = pre.X, &Y = pre.Y;
+    const uint32_t hx = pre.h[0], hy = pre.same ? pre.h[0] : pre.h[1];
+    const uint64_t plane_pairs = (uint64_t)hx * hy;
+    if (plane_pairs > (1ull << 21) || hx >= (1u << 24) || hy >= (1u << 24) || (!forced && !planes_dense(pre, nx, ny))) return R;
+    auto build = [&](const uint64_t *keys, const uint64_t *cfs, uint64_t n, PlaneSide &p) {
+        p.mat = sc.alloc<uint64_t>((size_t)p.nplanes * blob_words);
+        p.pinfo = sc.alloc<uint32_t>((size_t)p.nplanes * 4);
+        uint32_t *rowlen = sc.alloc<uint32_t>((size_t)p.nplanes * rcap);
+        CU_CHECK(e, cudaMemsetAsync(p.mat, 0, (size_t)p.nplanes * blob_words * 8, s));
+        CU_CHECK(e, cudaMemsetAsync(p.pinfo, 0, (size_t)p.nplanes * 16, s));
+        CU_CHECK(e, cudaMemsetAsync(rowlen, 0, (size_t)p.nplanes * rcap * 4, s));
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
+        k_tile_fill<<<grid, 256, 0, s>>>(keys, cfs, n, delta, p.tab, p.log2_cap, p.slot_id, p.mat, blob_words, P, rcap, rowlen, p.pinfo);
+        k_tile_finish<<<(p.nplanes + 127) / 128, 128, 0, s>>>(p.nplanes, rcap, rowlen, p.mat, blob_words, p.pinfo);
+        e->launches += 2;
+    };
+    X.nplanes = hx;
+    build(dxk, dxc, nx, X);
+    if (pre.same) {
+        Y = X;
+    } else {
+        Y.nplanes = hy;
+        build(dyk, dyc, ny, Y);
+    }
+    // multi-GPU partial product (left operand sharded): this rank forms the pairs of the left planes it owns
+    const uint32_t part_nranks = (nranks > 1 && !owner) ? nranks : 1u;
+    const uint64_t npairs = plane_pairs;
+    // ---- symbolic plane product ------------------------------------------------------------------------------
+    uint32_t l2 = 4;
+    while ((1ull << l2) < 2 * npairs) ++l2;
+    const uint32_t cap = 1u << l2;
+    uint64_t *tab = sc.alloc<uint64_t>(cap);
+    // one zeroed block: per-slot records, diagonal bounds and work, per-plane fill cursors, counters
+    const size_t zero_words = (size_t)cap * 4 + (size_t)cap * 2 + cap + npairs + 8;
+    uint32_t *zero = sc.alloc<uint32_t>(zero_words);
+    uint4 *rec = reinterpret_cast<uint4 *>(zero);
+    unsigned long long *work = reinterpret_cast<unsigned long long *>(zero + (size_t)cap * 4);
+    uint32_t *dmax = zero + (size_t)cap * 6;
+    uint32_t *fill = dmax + cap;
+    uint32_t *counters = fill + npairs; // [0] output planes, [1] product-kernel unit cursor
+    CU_CHECK(e, cudaMemsetAsync(tab, 0xFF, (size_t)cap * 8, s));
+    CU_CHECK(e, cudaMemsetAsync(zero, 0, zero_words * 4, s));
+    uint64_t *okey = sc.alloc<uint64_t>(npairs);
+    uint32_t *ocnt = sc.alloc<uint32_t>(npairs + 1), *oshape = sc.alloc<uint32_t>(npairs + 1);
+    unsigned long long *owork = sc.alloc<unsigned long long>(npairs);
+    uint32_t *pair_off = sc.alloc<uint32_t>(npairs + 2), *row_base = sc.alloc<uint32_t>(npairs + 2);
+    uint2 *pairs = sc.alloc<uint2>(npairs);
+    uint32_t *totals = sc.alloc<uint32_t>(4);
+    const uint32_t tpu = cfg.nw * cfg.t; // tiles per unit
+    const uint32_t wo_raw = D.wx + D.wy - 1u, ro_raw = D.rx + D.ry - 1u;
+    const uint32_t groups_max = (tl_ntiles(ro_raw, wo_raw, ro_raw + wo_raw) + tpu - 1) / tpu;
+    uint32_t *units = sc.alloc<uint32_t>(std::max<uint64_t>(npairs * groups_max, 1));
+    const unsigned gp = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 2048);
+    k_tile_sym_insert<<<gp, 256, 0, s>>>(X.plane_key, X.pinfo, X.nplanes, Y.plane_key, Y.pinfo, Y.nplanes, rank, part_nranks, tab, l2, rec,
+                                         dmax, work, okey, counters);
+    k_tile_sym_compact<<<(cap + 255) / 256, 256, 0, s>>>(tab, cap, rec, dmax, work, ocnt, owork, oshape);
+    TileTrunc tr{};
+    if (D.trunc) {
+        int64_t *dhi = sc.alloc<int64_t>(npairs);
+        k_tile_plane_degrees<<<gp, 256, 0, s>>>(okey, counters, delta, L.nvars, D.var_mask, dhi);
+        e->launches += 1;
+        tr.on = 1;
+        tr.w0 = D.w0;
+        tr.w1 = D.w1;
+        tr.limit = D.limit;
+        tr.dhi = dhi;
+    }
+    k_tile_units<<<1, 1024, 0, s>>>(owork, oshape, ocnt, okey, counters, tpu, rank, owner ? nranks : 1u, tr, row_base, pair_off, units, totals);
+    k_plane_sym_fill<<<gp, 256, 0, s>>>(X.plane_key, X.nplanes, Y.plane_key, Y.nplanes, rank, part_nranks, tab, l2, rec, pair_off, fill, pairs);
+    e->launches += 4;
+    uint32_t htot[3] = {0, 0, 0};
+    CU_CHECK(e, cudaMemcpyAsync(htot, totals, 12, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(e, cudaStreamSynchronize(s));
+    const uint32_t nunits = htot[0], nro = htot[1], nout = htot[2];
+    // ---- the product ----------------------------------------------------------------------------------------
+    const uint32_t wo = (wo_raw + 31u) & ~31u, nch = wo / 32u;
+    const size_t omat_words = (size_t)std::max<uint32_t>(nro, 1) * wo * accw;
+    uint64_t *omat = sc.alloc<uint64_t>(omat_words);
+    uint64_t *or_hi = sc.alloc<uint64_t>(std::max<uint32_t>(nro, 1));
+    const uint64_t nitems = (uint64_t)nro * nch;
+    uint32_t *or_cnt = sc.alloc<uint32_t>(nitems + 1);
+    uint32_t *roffs = sc.alloc<uint32_t>(nitems + 2);
+    CU_CHECK(e, cudaMemsetAsync(omat, 0, omat_words * 8, s)); // tiles outside an output plane's support are never written
+    CU_CHECK(e, cudaMemsetAsync(or_cnt, 0, (nitems + 1) * 4, s));
+    TileParams Pm{};
+    Pm.xmat = X.mat;
+    Pm.ymat = Y.mat;
+    Pm.xinfo = X.pinfo;
+    Pm.yinfo = Y.pinfo;
+    Pm.pairs = pairs;
+    Pm.pair_off = pair_off;
+    Pm.okey = okey;
+    Pm.oshape = oshape;
+    Pm.row_base = row_base;
+    Pm.units = units;
+    Pm.nunits = nunits;
+    Pm.cursor = counters + 1;
+    Pm.delta = delta;
+    Pm.or_hi = or_hi;
+    Pm.omat = omat;
+    Pm.or_cnt = or_cnt;
+    Pm.P = P;
+    Pm.rcap = rcap;
+    Pm.blob_words = blob_words;
+    Pm.nstage = nstage;
+    Pm.wo = wo;
+    Pm.tr = tr;
+    const unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(nunits, (uint32_t)e->sm_count * cfg.ctas));
+    CU_CHECK(e, cudaEventRecord(e->ev[5], s));
+    if (nunits) launch_tiles(e, mode, uns, Pm, grid);
+    CU_CHECK(e, cudaEventRecord(e->ev[6], s));
+    st.mul_launches += 1;
+    uint64_t total = 0;
+    if (nro) {
+        device_scan(e, sc, or_cnt, roffs, nitems);
+        if (need_total) {
+            uint32_t ht = 0;
+            CU_CHECK(e, cudaMemcpyAsync(&ht, roffs + nitems, 4, cudaMemcpyDeviceToHost, s));
+            CU_CHECK(e, cudaStreamSynchronize(s));
+            total = ht;
+        } else {
+            total = (uint64_t)nro * wo; // bound: the arrays are sized for it, the count is read with the call's last sync
+            R.total_dev = roffs + nitems;
+        }
+    }
+    R.rk = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1));
+    R.rc = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1) * accw);
+    if (total) {
+        const unsigned ge = (unsigned)std::min<uint64_t>((nitems + 7) / 8, 8192);
+        switch (mode) {
+            case CF_I1A1: k_tile_expand<1, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
+            case CF_I1A2: k_tile_expand<2, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
+            case CF_I1A3: k_tile_expand<3, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
+            default: k_tile_expand<1, true><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
+        }
+        e->launches += 1;
+        CU_CHECK(e, cudaGetLastError());
+    }
+    R.total = total;
+    R.nro = nro;
+    R.m = nout;
+    R.est_rows = nro;
+    R.done = true;
+    st.table_slots = 32;
+    st.group_lanes = 32;
+    return R;
+}
+
 void set_empty_result(obk_poly_result *out, const obk_poly_view *x, int cf_limbs, uint32_t mem)
 {
     std::memset(out, 0, sizeof(*out));
@@ -1549,8 +1786,12 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         bool rows_ok = false; // every exponent >= 0 and the first symbol's exponents < 32 in both operands
         bool planes_ok = false; // ... and the second symbol's exponents < 32 as well (plane-blocked path)
         uint32_t plane_rows[2] = {PL_ROWS, PL_ROWS}; // largest second-symbol exponent + 1 of each operand
+        bool tiles_ok = false; // every exponent >= 0 and the two lowest symbols' exponents < 64 (tile-blocked path)
+        bool tiles_take = false; // a truncated product that the tile path will take (no two-sided plan needed)
+        TileDims tile_dims;
         PlanePre plane_pre;
         uint64_t tot_mults = 0;
+        uint64_t var_mask_t = 0; // symbols a truncation counts
         if (!rq.merge) {
             trunc = rq.t != nullptr;
             uint64_t var_mask = 0;
@@ -1566,6 +1807,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 } else {
                     var_mask = L.nvars >= 64 ? ~0ull : ((1ull << L.nvars) - 1);
                 }
+                var_mask_t = var_mask;
                 xdeg = sc.alloc<int64_t>(nx_full);
                 ydeg = (x == y) ? xdeg : sc.alloc<int64_t>(ny);
             } else {
@@ -1584,8 +1826,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             e->launches += 3;
             // dense candidates: number the planes of both operands now, so that their counts come back with the
             // statistics (one host round trip instead of two)
-            if (!trunc && W == 1 && L.nvars >= 3 && L.delta < (1ull << 32) && (e->opt_kernel == -1 || e->opt_kernel == 2)
-                && (e->opt_kernel == 2 || (double)nx_full * (double)ny >= (double)(1ull << 22)))
+            if (!trunc && W == 1 && L.nvars >= 3 && L.delta < (1ull << 32) && (e->opt_kernel == -1 || e->opt_kernel == 2 || e->opt_kernel == 3)
+                && (e->opt_kernel >= 2 || (double)nx_full * (double)ny >= (double)(1ull << 22)))
                 planes_prepare(e, sc, dxk, nx_full, dyk, ny, L.delta, plane_pre);
             StatsOut hs[2];
             CU_CHECK(e, cudaMemcpyAsync(hs, dstats, sizeof(StatsOut) * (x == y ? 1 : 2), cudaMemcpyDeviceToHost, s));
@@ -1680,6 +1922,18 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     plane_rows[0] = (uint32_t)unord(hs[0].emax[1], L.is_signed) + 1u;
                     plane_rows[1] = (uint32_t)unord(hs[1].emax[1], L.is_signed) + 1u;
                 }
+                tiles_ok = L.nvars >= 3 && hs[0].nonfinite == 0 && hs[1].nonfinite == 0;
+                for (uint32_t v = 0; v < L.nvars; ++v)
+                    if (unord(hs[0].emin[v], L.is_signed) < 0 || unord(hs[1].emin[v], L.is_signed) < 0) tiles_ok = false;
+                for (int o = 0; o < 2 && tiles_ok; ++o)
+                    for (uint32_t v = 0; v < 2; ++v)
+                        if (unord(hs[o].emax[v], L.is_signed) >= TL_MAX_DIM) tiles_ok = false;
+                if (tiles_ok) {
+                    tile_dims.wx = (uint32_t)unord(hs[0].emax[0], L.is_signed) + 1u;
+                    tile_dims.wy = (uint32_t)unord(hs[1].emax[0], L.is_signed) + 1u;
+                    tile_dims.rx = (uint32_t)unord(hs[0].emax[1], L.is_signed) + 1u;
+                    tile_dims.ry = (uint32_t)unord(hs[1].emax[1], L.is_signed) + 1u;
+                }
             }
             // a-priori accumulator width: |sum| <= min(nx,ny) * max|c1| * max|c2|
             if (f64) {
@@ -1761,6 +2015,12 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 e->launches += 1;
                 unsigned long long htot = 0;
                 CU_CHECK(e, cudaMemcpyAsync(&htot, dtot, 8, cudaMemcpyDeviceToHost, s));
+                // A truncated product of DENSE operands goes to the tile path, where the truncation is a filter on the
+                // output position: number the planes now so that their counts arrive with the next synchronisation.
+                const bool tile_cand = W == 1 && tiles_ok && CWx == 1 && L.delta < (1ull << 32) && (e->opt_kernel == -1 || e->opt_kernel == 3)
+                                       && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64)
+                                       && (e->opt_kernel == 3 || (double)nx_full * (double)ny >= (double)(1ull << 22));
+                if (tile_cand) planes_prepare(e, sc, dxk, nx_full, dyk, ny, L.delta, plane_pre);
                 // two-sided plan: degree histograms of both operands on the host
                 const i128 rangex = dmaxx - dminx + 1;
                 std::vector<uint32_t> hpy, hpx;
@@ -1780,7 +2040,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 }
                 CU_CHECK(e, cudaStreamSynchronize(s));
                 tot_mults = htot;
-                if (!hpx.empty() && tot_mults > 0) {
+                tiles_take = tile_cand && (e->opt_kernel == 3 || planes_dense(plane_pre, nx_full, ny));
+                if (!hpx.empty() && tot_mults > 0 && !tiles_take) {
                     // choose the left-degree threshold H that minimises the number of left terms visited
                     const uint32_t ndx = (uint32_t)rangex;
                     uint64_t best = ~0ull;
@@ -1868,7 +2129,22 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
         // ---- dense operands: row-blocked path (register accumulation, no table) --------------------------------
         RowsResult rows;
         int dense_kernel = 1;
-        if (!rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 3 && CWx == 1 && (e->opt_kernel == -1 || e->opt_kernel == 2)
+        if (!rq.merge && (!trunc || tiles_take) && snx > 0 && W == 1 && L.nvars >= 3 && CWx == 1 && (e->opt_kernel == -1 || e->opt_kernel == 3)
+            && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && tiles_ok
+            && (e->opt_kernel == 3 || tot_mults >= (1ull << 22) || tiles_take)) {
+            const bool need_total = rq.push != nullptr || (rq.nranks > 1 && !owner) || rq.result_mem != OBK_MEM_DEVICE || e->opt_regroup == 2;
+            if (trunc) {
+                tile_dims.trunc = true;
+                tile_dims.limit = rq.t->limit;
+                tile_dims.var_mask = var_mask_t;
+                tile_dims.w0 = (uint32_t)(var_mask_t & 1ull);
+                tile_dims.w1 = (uint32_t)((var_mask_t >> 1) & 1ull);
+            }
+            rows = run_tiles(e, sc, plane_pre, dxk, dxc, nx_full, dyk, dyc, ny, L, mode, accw, e->opt_kernel == 3, !f64 && hs_anyneg == 0,
+                             rq.rank, rq.nranks, owner, tile_dims, need_total, st);
+            if (rows.done) dense_kernel = 3;
+        }
+        if (!rows.done && !rq.merge && !trunc && snx > 0 && W == 1 && L.nvars >= 3 && CWx == 1 && (e->opt_kernel == -1 || e->opt_kernel == 2)
             && (mode == CF_I1A1 || mode == CF_I1A2 || mode == CF_I1A3 || mode == CF_F64) && rows_ok && planes_ok
             && (e->opt_kernel == 2 || tot_mults >= (1ull << 22))) {
             // the term count may stay on the device until the end of the call when the product is left in HBM as it is

@@ -402,6 +402,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint4 lds_u32x4(uint32_t a)
 {
     uint4 v;

@@ -1,0 +1,584 @@
+// obk_tiles.cuh -- tile-blocked dense path ("kernel 3") of the B200 series-product engine (sm_100a).
+//
+// Same algebra as the plane path (obk_planes.cuh): key = lo0 + delta * lo1 + delta^2 * hi2 (kpack.hpp:262-267), the terms
+// sharing hi2 form a PLANE indexed [lo1][lo0], and the product of two planes is a 2-D convolution that lands in the
+// single output plane hi2 + hi2' (digit-wise sums never carry once the exponent-overflow check of
+// polynomial.hpp:839-851 has passed).  What changes is how the convolution is mapped onto a warp:
+//   * a warp owns a TILE of 4 output rows x 8 output columns of the output plane (lane = (r, c)), not one output row.
+//     For a scalar S[b][i] of one plane the 32 lanes read the 4 x 8 window V[j0 + r - b][c0 + c - i] of the other one:
+//     a window of a simplex-shaped plane is far better filled than a 32-wide row of it (Fateman n=30: 1.26e8 warp
+//     steps for 2.15e9 term products instead of 1.48e8), and there is ONE code path -- no half / quarter-warp cases,
+//     no high / low halves of long rows, no choice of the shorter row per row pair;
+//   * because x sits at  S0 + (b P + i) 8  and y at  V0 + ((j0 + r - b) P + c0 + c - i) 8, the two addresses add up to
+//     a constant of the (plane pair, tile, lane): y = C - x.  The row loop is two byte loads (row length of S, widest
+//     row of the 4-row window of V), four integer operations for the scalar range and the multiply-accumulate steps;
+//   * planes may be up to 64 x 64 (exponents of the two lowest symbols up to 63), rows at pitch P = W16 + 8 words
+//     (P / 8 odd: the four rows of a tile fall into different banks); the zero tail of every row is the left / right
+//     padding of the windows, three zero rows above and below the plane are their top / bottom padding;
+//   * a total- or partial-degree truncation (polynomial.hpp:1337-1347) is a filter on the OUTPUT position: the degree
+//     of a product term is linear in its exponents, so every term of an output plane beyond the limit is simply never
+//     formed (tiles beyond the limit are not enumerated, the rest is masked when the rows are expanded to terms).
+// Staging (TMA bulk copies into a shared-memory ring, one producer warp), the symbolic plane product, exact
+// carry-save accumulators and the multi-GPU ownership rules are those of the plane path.
+#pragma once
+#include "obk_planes.cuh"
+
+namespace obk
+{
+
+constexpr int TL_R = 4, TL_C = 8;         // tile: 4 output rows x 8 output columns
+constexpr int TL_MAX_DIM = 64;            // rows / row width of an operand plane
+constexpr int TL_HDR_BYTES = 144;         // len[64] u8 (row lengths), wm[72] u8 (widest row of the window k-3 .. k), pad
+constexpr int TL_HDR = TL_HDR_BYTES / 8;  // words
+constexpr int TL_PAD_ROWS = TL_R - 1;     // zero rows above / below a plane in its vector role
+constexpr int TL_LEAD_BYTES = 64;         // zero words in front of the first zero row (left padding of its windows)
+constexpr int TL_MAX_STAGES = 8;
+
+// Row pitch in words: the widest row rounded to 16 plus 8 zero words; P / 8 is odd.
+__host__ __device__ inline uint32_t tl_pitch(uint32_t wmax)
+{
+    return ((wmax + 15u) & ~15u) + 8u;
+}
+// A plane in HBM: header, rows [0, rcap) at pitch P, TL_PAD_ROWS zero rows.
+__host__ __device__ inline uint32_t tl_blob_words(uint32_t rcap, uint32_t P)
+{
+    return TL_HDR + (rcap + TL_PAD_ROWS) * P;
+}
+// Shared-memory ring stage:  [S: header | rows]  [V: header | 64 B zeros | 3 zero rows | rows + 3 zero rows]  [descriptor]
+struct TileStage {
+    uint32_t s_rows, v_hdr, v_rows, desc, bytes;
+};
+__host__ __device__ inline TileStage tl_stage(uint32_t rcap, uint32_t P)
+{
+    TileStage g;
+    const uint32_t P8 = P * 8u;
+    g.s_rows = TL_HDR_BYTES;
+    g.v_hdr = g.s_rows + rcap * P8;
+    g.v_rows = g.v_hdr + TL_HDR_BYTES + TL_LEAD_BYTES + TL_PAD_ROWS * P8;
+    g.desc = g.v_rows + (rcap + TL_PAD_ROWS) * P8;
+    g.bytes = (g.desc + 32u + 127u) & ~127u;
+    return g;
+}
+// Tiles of an output plane with `rows` rows, rows at most `w` wide and lo1 + lo0 < d: row-major over the tile rows;
+// tile row tr holds ceil(min(w, d - 4 tr) / 8) tiles.
+__host__ __device__ inline uint32_t tl_ntiles(uint32_t rows, uint32_t w, uint32_t d)
+{
+    uint32_t n = 0;
+    const uint32_t jend = rows < d ? rows : d;
+    for (uint32_t j0 = 0; j0 < jend; j0 += TL_R) {
+        const uint32_t ww = w < d - j0 ? w : d - j0;
+        n += (ww + TL_C - 1u) / TL_C;
+    }
+    return n;
+}
+// tile number -> origin (j0, c0); false: no such tile
+__host__ __device__ inline bool tl_locate(uint32_t idx, uint32_t rows, uint32_t w, uint32_t d, uint32_t &j0, uint32_t &c0)
+{
+    const uint32_t jend = rows < d ? rows : d;
+    for (uint32_t j = 0; j < jend; j += TL_R) {
+        const uint32_t ww = w < d - j ? w : d - j;
+        const uint32_t n = (ww + TL_C - 1u) / TL_C;
+        if (idx < n) {
+            j0 = j;
+            c0 = idx * TL_C;
+            return true;
+        }
+        idx -= n;
+    }
+    return false;
+}
+// shape of an output plane: rows | widest row << 8 | (largest lo1 + lo0) + 1 << 16
+__host__ __device__ inline uint32_t tl_shape(uint32_t rows, uint32_t w, uint32_t d)
+{
+    return rows | (w << 8) | (d << 16);
+}
+
+// ---- plane building ------------------------------------------------------------------------------------------------
+// Scatter every term's coefficient into its plane's blob; row lengths and term counts by atomics.
+__global__ void __launch_bounds__(256) k_tile_fill(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ cfs, uint64_t n,
+                                                   uint64_t delta, const uint64_t *__restrict__ tab, uint32_t log2_cap,
+                                                   const uint32_t *__restrict__ slot_id, uint64_t *__restrict__ mat, uint32_t blob_words,
+                                                   uint32_t P, uint32_t rcap, uint32_t *__restrict__ rowlen, uint32_t *__restrict__ pinfo)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mask = (1u << log2_cap) - 1u;
+    const uint64_t d2 = delta * delta;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = keys[i];
+        const uint64_t hi = key / d2;
+        const uint64_t rem = key - hi * d2;
+        const uint32_t lo1 = (uint32_t)(rem / delta);
+        const uint32_t lo0 = (uint32_t)(rem - (uint64_t)lo1 * delta);
+        uint32_t h = plane_hash(hi, log2_cap);
+        while (tab[h] != hi) h = (h + 1u) & mask;
+        const uint32_t p = slot_id[h];
+        mat[(size_t)p * blob_words + TL_HDR + lo1 * P + lo0] = cfs[i];
+        atomicMax(&rowlen[(size_t)p * rcap + lo1], lo0 + 1u);
+        atomicAdd(&pinfo[4 * (size_t)p + 1], 1u);
+    }
+}
+
+// One thread per plane: rows, widest row, largest lo1 + lo0 (+1), and the header bytes of the blob.
+//   pinfo[4 p + 0] rows, [1] terms, [2] widest row, [3] max(b + len[b])
+__global__ void __launch_bounds__(128) k_tile_finish(uint32_t nplanes, uint32_t rcap, const uint32_t *__restrict__ rowlen,
+                                                     uint64_t *__restrict__ mat, uint32_t blob_words, uint32_t *__restrict__ pinfo)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nplanes) return;
+    const uint32_t *len = rowlen + (size_t)p * rcap;
+    uint8_t *hdr = reinterpret_cast<uint8_t *>(mat + (size_t)p * blob_words);
+    uint32_t rows = 0, w = 0, d = 0;
+    for (uint32_t b = 0; b < rcap; ++b) {
+        const uint32_t l = len[b];
+        hdr[b] = (uint8_t)l;
+        if (l) {
+            rows = b + 1u;
+            w = max(w, l);
+            d = max(d, b + l);
+        }
+    }
+    for (uint32_t b = rcap; b < (uint32_t)TL_MAX_DIM; ++b) hdr[b] = 0;
+    // wm[k] = widest of the rows k-3 .. k (rows outside the plane count as empty), k = 0 .. rcap + 2
+    for (uint32_t k = 0; k < 72u; ++k) {
+        uint32_t m = 0;
+        for (uint32_t q = 0; q < (uint32_t)TL_R; ++q) {
+            const uint32_t b = k - q; // wraps for k < q
+            if (b < rcap) m = max(m, len[b]);
+        }
+        hdr[64 + k] = (uint8_t)m;
+    }
+    pinfo[4 * (size_t)p] = rows;
+    pinfo[4 * (size_t)p + 2] = w;
+    pinfo[4 * (size_t)p + 3] = d;
+}
+
+// ---- symbolic plane product ----------------------------------------------------------------------------------------
+// Per-slot records of the output-plane set: rec = {pairs, rows, widest row, output plane number}, dmax, work.
+__global__ void __launch_bounds__(256) k_tile_sym_insert(const uint64_t *__restrict__ xh, const uint32_t *__restrict__ xinfo, uint32_t nx,
+                                                         const uint64_t *__restrict__ yh, const uint32_t *__restrict__ yinfo, uint32_t ny,
+                                                         uint32_t part_rank, uint32_t part_nranks, uint64_t *__restrict__ tab,
+                                                         uint32_t log2_cap, uint4 *__restrict__ rec, uint32_t *__restrict__ dmax,
+                                                         unsigned long long *__restrict__ work, uint64_t *__restrict__ okey,
+                                                         uint32_t *__restrict__ counters)
+{
+    const uint64_t total = (uint64_t)nx * ny, stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mask = (1u << log2_cap) - 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t a = (uint32_t)(i / ny), b = (uint32_t)(i - (uint64_t)a * ny);
+        const uint64_t ka = xh[a];
+        if (part_nranks > 1u && plane_owner(ka, part_nranks) != part_rank) continue;
+        const uint64_t key = ka + yh[b];
+        uint32_t h = plane_hash(key, log2_cap);
+        for (;;) {
+            const unsigned long long old = atomicCAS((unsigned long long *)&tab[h], (unsigned long long)ROW_EMPTY, (unsigned long long)key);
+            if (old == ROW_EMPTY) {
+                const uint32_t o = atomicAdd(&counters[0], 1u);
+                rec[h].w = o;
+                okey[o] = key;
+                break;
+            }
+            if (old == key) break;
+            h = (h + 1u) & mask;
+        }
+        const uint4 ia = *reinterpret_cast<const uint4 *>(xinfo + 4 * (size_t)a), ib = *reinterpret_cast<const uint4 *>(yinfo + 4 * (size_t)b);
+        uint32_t *r = reinterpret_cast<uint32_t *>(&rec[h]);
+        atomicAdd(&r[0], 1u);
+        atomicAdd(&work[h], (unsigned long long)ia.y * ib.y);
+        atomicMax(&r[1], ia.x + ib.x - 1u);
+        atomicMax(&r[2], ia.z + ib.z - 1u);
+        atomicMax(&dmax[h], ia.w + ib.w - 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tile_sym_compact(const uint64_t *__restrict__ tab, uint32_t cap, const uint4 *__restrict__ rec,
+                                                          const uint32_t *__restrict__ dmax, const unsigned long long *__restrict__ work,
+                                                          uint32_t *__restrict__ ocnt, unsigned long long *__restrict__ owork,
+                                                          uint32_t *__restrict__ oshape)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap || tab[i] == ROW_EMPTY) return;
+    const uint4 r = rec[i];
+    ocnt[r.w] = r.x;
+    owork[r.w] = work[i];
+    oshape[r.w] = tl_shape(r.y, r.z, dmax[i]);
+}
+
+// Truncation of a dense product (see the file header): the degree of the term at (lo1, lo0) of output plane o is
+// dhi[o] + w1 lo1 + w0 lo0 with w0, w1 in {0, 1}; terms with degree > limit are never formed.  `on` = 0: no truncation.
+struct TileTrunc {
+    uint32_t on, w0, w1;
+    int64_t limit;
+    const int64_t *dhi; // [output planes] degree of the hi2 part (over the truncation's symbols)
+};
+// largest admissible value of w1 lo1 + w0 lo0 on a plane, clamped to [-1, 2^20]
+__device__ __forceinline__ int32_t tl_budget(const TileTrunc &t, uint32_t o)
+{
+    if (!t.on) return 1 << 20;
+    const int64_t v = t.limit - t.dhi[o];
+    return (int32_t)(v < -1 ? -1 : (v > (1 << 20) ? (1 << 20) : v));
+}
+// the shape of an output plane cut by the truncation: only rows / columns / diagonals that hold admissible terms
+__device__ __forceinline__ uint32_t tl_cut_shape(uint32_t shape, const TileTrunc &t, int32_t budget)
+{
+    if (!t.on) return shape;
+    uint32_t rows = shape & 0xffu, w = (shape >> 8) & 0xffu, d = shape >> 16;
+    if (budget < 0) return 0u;
+    if (t.w1 && !t.w0) rows = min(rows, (uint32_t)budget + 1u);
+    if (t.w0 && !t.w1) w = min(w, (uint32_t)budget + 1u);
+    if (t.w0 && t.w1) {
+        d = min(d, (uint32_t)budget + 1u);
+        rows = min(rows, d);
+        w = min(w, d);
+    }
+    return tl_shape(rows, w, d);
+}
+
+// One CTA: pair_off = exclusive scan of the pairs per plane, row_base = exclusive scan of the rows per plane, and the
+// work units = (output plane, group of `tpu` tiles), heaviest planes first (counting sort by the bit length of the
+// work).  own_nranks > 1: only the units this rank owns (multi-GPU owner mode).  The shapes are cut by the truncation.
+//   units[u] = plane | group << 24;  totals[0] = units, [1] = output rows, [2] = output planes
+__global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *__restrict__ owork, uint32_t *__restrict__ oshape,
+                                                     const uint32_t *__restrict__ ocnt, const uint64_t *__restrict__ okey,
+                                                     const uint32_t *__restrict__ counters, uint32_t tpu, uint32_t own_rank,
+                                                     uint32_t own_nranks, TileTrunc tr, uint32_t *__restrict__ row_base,
+                                                     uint32_t *__restrict__ pair_off, uint32_t *__restrict__ units,
+                                                     uint32_t *__restrict__ totals)
+{
+    __shared__ uint32_t s_cls[65], s_tot, s_carry;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nout = counters[0];
+    auto owned = [&](uint32_t o, uint32_t b) { return own_nranks <= 1u || (plane_owner(okey[o], own_nranks) + b) % own_nranks == own_rank; };
+    if (tid < 65) s_cls[tid] = 0;
+    if (tid == 0) s_carry = 0;
+    for (uint32_t o = tid; o < nout; o += blockDim.x) oshape[o] = tl_cut_shape(oshape[o], tr, tl_budget(tr, o));
+    __syncthreads();
+    auto groups = [&](uint32_t o) {
+        const uint32_t sh = oshape[o];
+        return (tl_ntiles(sh & 0xffu, (sh >> 8) & 0xffu, sh >> 16) + tpu - 1u) / tpu;
+    };
+    for (uint32_t o = tid; o < nout; o += blockDim.x) {
+        const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
+        const uint32_t nb = groups(o);
+        uint32_t mine = 0;
+        for (uint32_t b = 0; b < nb; ++b) mine += owned(o, b) ? 1u : 0u;
+        if (mine) atomicAdd(&s_cls[64u - c], mine); // class 0 = heaviest
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int c = 0; c < 65; ++c) {
+            const uint32_t v = s_cls[c];
+            s_cls[c] = acc;
+            acc += v;
+        }
+        totals[0] = acc;
+        totals[2] = nout;
+    }
+    __syncthreads();
+    for (uint32_t o = tid; o < nout; o += blockDim.x) {
+        const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
+        const uint32_t nb = groups(o);
+        uint32_t mine = 0;
+        for (uint32_t b = 0; b < nb; ++b) mine += owned(o, b) ? 1u : 0u;
+        if (mine == 0u) continue;
+        uint32_t at = atomicAdd(&s_cls[64u - c], mine);
+        for (uint32_t b = 0; b < nb; ++b)
+            if (owned(o, b)) units[at++] = o | (b << 24);
+    }
+    for (int which = 0; which < 2; ++which) {
+        uint32_t *out = which == 0 ? row_base : pair_off;
+        __syncthreads();
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (uint32_t base0 = 0; base0 < nout; base0 += SCAN_BLOCK) {
+            const uint32_t base = base0 + tid * SCAN_ITEMS;
+            uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                v[j] = base + j < nout ? (which == 0 ? (oshape[base + j] & 0xffu) : ocnt[base + j]) : 0;
+                sum += v[j];
+            }
+            uint32_t ex = block_exclusive_scan(sum, &s_tot) + s_carry;
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                if (base + j < nout) out[base + j] = ex;
+                ex += v[j];
+            }
+            __syncthreads();
+            if (tid == 0) s_carry += s_tot;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            out[nout] = s_carry;
+            if (which == 0) totals[1] = s_carry;
+        }
+    }
+}
+
+// degree of the hi2 part of every output plane over the truncation's symbols (var_mask, symbols 2 .. nvars-1)
+__global__ void __launch_bounds__(256) k_tile_plane_degrees(const uint64_t *__restrict__ okey, const uint32_t *__restrict__ counters,
+                                                            uint64_t delta, uint32_t nvars, uint64_t var_mask, int64_t *__restrict__ dhi)
+{
+    const uint32_t nout = counters[0];
+    for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < nout; o += gridDim.x * blockDim.x) {
+        uint64_t k = okey[o];
+        int64_t d = 0;
+        for (uint32_t v = 2; v < nvars; ++v) {
+            const uint64_t q = k / delta;
+            if ((var_mask >> v) & 1ull) d += (int64_t)(k - q * delta);
+            k = q;
+        }
+        dhi[o] = d;
+    }
+}
+
+struct TileParams {
+    const uint64_t *xmat, *ymat;   // [planes][blob_words]
+    const uint32_t *xinfo, *yinfo; // [planes][4]: rows, terms, widest row, max(b + len[b])
+    const uint2 *pairs;            // plane pairs grouped by output plane
+    const uint32_t *pair_off;      // [nout + 1]
+    const uint64_t *okey;          // [nout] output plane keys (hi2 sums)
+    const uint32_t *oshape;        // [nout] tl_shape(), already cut by the truncation
+    const uint32_t *row_base;      // [nout + 1]
+    const uint32_t *units;         // plane | group << 24, heaviest first
+    uint32_t nunits;
+    uint32_t *cursor;
+    uint64_t delta;
+    uint64_t *or_hi;  // [rows] row key = okey * delta + j
+    uint64_t *omat;   // [rows][LACC][wo]
+    uint32_t *or_cnt; // [rows][wo / 32] non-zero entries per 32-column chunk
+    uint32_t P, rcap, blob_words, nstage, wo;
+    TileTrunc tr;
+};
+
+// NW consumer warps x T tiles each + one producer warp.
+template <int LACC, bool F64, bool UNS, int NW, int T, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TileParams P)
+{
+    using Acc = PlaneAcc<LACC, F64, UNS>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[TL_MAX_STAGES], s_empty[TL_MAX_STAGES];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t nstage = P.nstage;
+    const uint32_t Pw = P.P, P8 = Pw * 8u;
+    const TileStage G = tl_stage(P.rcap, Pw);
+    // zero everything once: the padding above a vector plane is never written again
+    for (uint32_t i = tid; i < nstage * G.bytes / 16u; i += blockDim.x) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy zeros before the bulk copies land
+    if (tid == 0) {
+        for (uint32_t s = 0; s < nstage; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], NW);
+        }
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ================= producer =================
+        uint32_t s = 0, ph = 0;
+        for (;;) {
+            uint32_t u = 0;
+            if (lane == 0) u = atomicAdd(P.cursor, 1u);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            const bool quit = u >= P.nunits;
+            uint32_t o = 0, g = 0, p0 = 0, p1 = 1, shape = 0, jmin = 0;
+            int32_t budget = 0;
+            if (!quit) {
+                const uint32_t ud = __ldg(P.units + u);
+                o = ud & 0x00ffffffu;
+                g = ud >> 24;
+                p0 = __ldg(P.pair_off + o);
+                p1 = __ldg(P.pair_off + o + 1);
+                shape = __ldg(P.oshape + o);
+                uint32_t c0;
+                tl_locate(g * (uint32_t)(NW * T), shape & 0xffu, (shape >> 8) & 0xffu, shape >> 16, jmin, c0);
+                budget = tl_budget(P.tr, o);
+            }
+            bool first = true;
+            for (uint32_t pb = p0; pb < p1; pb += 32u) {
+                uint2 pr = make_uint2(0, 0);
+                uint4 ia = make_uint4(0, 0, 0, 0), ib = ia;
+                if (!quit && pb + lane < p1) {
+                    pr = __ldg(P.pairs + pb + lane);
+                    ia = __ldg(reinterpret_cast<const uint4 *>(P.xinfo) + pr.x);
+                    ib = __ldg(reinterpret_cast<const uint4 *>(P.yinfo) + pr.y);
+                }
+                // what the stage needs: rows of both planes, which one supplies the scalars, the diagonal bound
+                const bool a_is_s = ia.y <= ib.y; // fewer terms
+                const uint32_t meta = (a_is_s ? ia.x : ib.x) | ((a_is_s ? ib.x : ia.x) << 8) | (a_is_s ? 0u : 1u << 16);
+                const uint32_t dsum = ia.w + ib.w - 1u, rsum = ia.x + ib.x - 1u;
+                const uint32_t cntp = quit ? 1u : min(32u, p1 - pb);
+                for (uint32_t q = 0; q < cntp; ++q) {
+                    const uint32_t px = __shfl_sync(0xffffffffu, pr.x, (int)q), py = __shfl_sync(0xffffffffu, pr.y, (int)q);
+                    const uint32_t mt = __shfl_sync(0xffffffffu, meta, (int)q), ds = __shfl_sync(0xffffffffu, dsum, (int)q);
+                    const uint32_t rs = __shfl_sync(0xffffffffu, rsum, (int)q);
+                    const bool last = pb + q + 1u == p1;
+                    // a pair that cannot reach this group of tiles is not staged (unless it carries the end-of-unit flag)
+                    if (!quit && !last && (jmin >= rs || jmin >= ds)) continue;
+                    mbar_wait(&s_empty[s], ph ^ 1u);
+                    if (lane == 0) {
+                        unsigned char *st = smem_raw + (size_t)s * G.bytes;
+                        uint32_t *d = reinterpret_cast<uint32_t *>(st + G.desc);
+                        const uint32_t nS = mt & 0xffu, nV = (mt >> 8) & 0xffu;
+                        d[0] = o;
+                        d[1] = g;
+                        d[2] = quit ? 2u : ((last ? 1u : 0u) | (first ? 4u : 0u));
+                        d[3] = shape;
+                        d[4] = mt;
+                        d[5] = ds;
+                        d[6] = (uint32_t)budget;
+                        const uint32_t bS = TL_HDR_BYTES + nS * P8, bV = (nV + TL_PAD_ROWS) * P8;
+                        mbar_expect_tx(&s_full[s], quit ? 0u : bS + TL_HDR_BYTES + bV);
+                        if (!quit) {
+                            const uint64_t *A = P.xmat + (size_t)px * P.blob_words, *B = P.ymat + (size_t)py * P.blob_words;
+                            const uint64_t *S = (mt >> 16) ? B : A, *V = (mt >> 16) ? A : B;
+                            tma_bulk_g2s(st, S, bS, &s_full[s]);
+                            tma_bulk_g2s(st + G.v_hdr, V, TL_HDR_BYTES, &s_full[s]);
+                            tma_bulk_g2s(st + G.v_rows, V + TL_HDR, bV, &s_full[s]);
+                        }
+                    }
+                    first = false;
+                    if (++s == nstage) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+            if (quit) break;
+        }
+        return;
+    }
+
+    // ================= consumers: warp w owns tiles  g * NW * T + t * NW + w,  t = 0 .. T-1,  of the unit's plane ==========
+    Acc z[T];
+    uint32_t tj[T], tc[T]; // tile origins; tj = 0x7fffffff: no tile
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        z[t].clear();
+        tj[t] = 0x7fffffffu;
+        tc[t] = 0;
+    }
+    const uint32_t r = lane >> 3, c = lane & 7u;
+    const uint32_t smem0 = smem_u32(smem_raw);
+    uint32_t s = 0, ph = 0;
+    for (;;) {
+        mbar_wait(&s_full[s], ph);
+        const uint32_t base = smem0 + s * G.bytes;
+        const uint4 d0 = lds_u32x4(base + G.desc);
+        if (d0.z & 2u) break;
+        const uint4 d1 = lds_u32x4(base + G.desc + 16u);
+        const uint32_t meta = d1.x, dsum = d1.y;
+        const uint32_t orows = d0.w & 0xffu;
+        if (d0.z & 4u) {
+            // a new unit: where are my tiles
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                uint32_t j0 = 0, c0 = 0;
+                const bool ok = tl_locate(d0.y * (uint32_t)(NW * T) + (uint32_t)t * NW + warp, orows, (d0.w >> 8) & 0xffu, d0.w >> 16, j0, c0);
+                tj[t] = ok ? j0 : 0x7fffffffu;
+                tc[t] = c0;
+            }
+        }
+        const uint32_t nS = meta & 0xffu, nV = (meta >> 8) & 0xffu;
+        const uint32_t aS = base + G.s_rows, aV = base + G.v_rows; // shared addresses of S[0][0] and V[0][0]
+        const uint32_t aWm = base + G.v_hdr + 64u + (uint32_t)TL_PAD_ROWS;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const uint32_t j0 = tj[t], c0 = tc[t];
+            if (j0 < nS + nV - 1u && j0 + c0 < dsum) {
+                const uint32_t blo = j0 + 1u > nV ? j0 + 1u - nV : 0u, bhi = min(nS - 1u, j0 + (uint32_t)TL_PAD_ROWS);
+                // x at aS + (b P + i) 8, y at aV + ((j0 + r - b) P + c0 + c - i) 8:  y = Cl - x
+                const uint32_t Cl = aS + aV + ((j0 + r) * Pw + c0 + c) * 8u;
+                // the row lengths of the next row are requested before the current row is convolved
+                uint32_t la = lds_u8(base + blo), wv = lds_u8(aWm + j0 - blo);
+                for (uint32_t b = blo; b <= bhi; ++b) {
+                    const uint32_t ilo = (c0 + 1u > wv ? c0 + 1u - wv : 0u) & ~1u, ihi = min(la, c0 + (uint32_t)TL_C);
+                    const uint32_t bn = min(b + 1u, bhi);
+                    la = lds_u8(base + bn);
+                    wv = lds_u8(aWm + j0 - bn);
+                    if (ilo < ihi) {
+                        const uint32_t ax = aS + b * P8 + ilo * 8u;
+                        conv_steps(z[t], ax, Cl - ax, 0u, ihi - ilo);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[s]);
+        if (++s == nstage) {
+            s = 0;
+            ph ^= 1u;
+        }
+        if (d0.z & 1u) {
+            // ---- the unit is complete: write my tiles, count their non-zero entries per 32-column chunk ----
+            const uint32_t nch = P.wo >> 5;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const uint32_t j = tj[t] + r;
+                if (tj[t] != 0x7fffffffu) {
+                    const bool inside = j < orows;
+                    const uint32_t row = __ldg(P.row_base + d0.x) + j, col = tc[t] + c;
+                    uint64_t o[LACC];
+                    z[t].limbs(o);
+                    bool nz = false;
+                    // a term beyond the truncation limit is not part of the product: it is stored as zero
+                    if (P.tr.on && (int32_t)(P.tr.w1 * j + P.tr.w0 * col) > (int32_t)d1.z) {
+#pragma unroll
+                        for (int l = 0; l < LACC; ++l) o[l] = 0;
+                    }
+                    if (inside) {
+                        uint64_t *om = P.omat + (size_t)row * LACC * P.wo + col;
+#pragma unroll
+                        for (int l = 0; l < LACC; ++l) {
+                            om[(size_t)l * P.wo] = o[l];
+                            nz |= o[l] != 0;
+                        }
+                        if constexpr (F64) nz = __longlong_as_double((long long)o[0]) != 0.0;
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+                    if (inside && c == 0u) {
+                        const uint32_t cnt = __popc((bal >> (8u * r)) & 0xffu);
+                        if (cnt) atomicAdd(P.or_cnt + (size_t)row * nch + (tc[t] >> 5), cnt);
+                        P.or_hi[row] = __ldg(P.okey + d0.x) * P.delta + j;
+                    }
+                }
+                z[t].clear();
+            }
+        }
+    }
+}
+
+// Expand the output rows into terms: key = hi * delta + lo, zero coefficients dropped (terms beyond a truncation limit
+// were stored as zeros); off[row * nch + chunk] is the exclusive scan of the per-chunk counts.
+template <int LACC, bool F64>
+__global__ void __launch_bounds__(256) k_tile_expand(const uint64_t *__restrict__ or_hi, const uint64_t *__restrict__ omat,
+                                                     const uint32_t *__restrict__ off, uint32_t nitems, uint32_t nch, uint32_t wo,
+                                                     uint64_t delta, uint64_t *__restrict__ okeys,
+                                                     uint64_t *__restrict__ ocfs)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb) {
+        const uint32_t base = off[it], cnt = off[it + 1] - base;
+        if (cnt == 0u) continue;
+        const uint32_t row = it / nch, col = (it - row * nch) * 32u + lane;
+        const uint64_t *o = omat + (size_t)row * LACC * wo + col;
+        uint64_t v[LACC];
+        bool nz = false;
+#pragma unroll
+        for (int l = 0; l < LACC; ++l) {
+            v[l] = o[(size_t)l * wo];
+            nz |= v[l] != 0;
+        }
+        if constexpr (F64) nz = __longlong_as_double((long long)v[0]) != 0.0;
+        const uint32_t b = __ballot_sync(0xffffffffu, nz);
+        if (nz) {
+            const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+            okeys[pos] = or_hi[row] * delta + (uint64_t)col;
+#pragma unroll
+            for (int l = 0; l < LACC; ++l) ocfs[(size_t)pos * LACC + l] = v[l];
+        }
+    }
+}
+
+} // namespace obk

@@ -441,10 +441,111 @@ def test_plane_path_forced(engine):
         engine.set_option("kernel", -1)
 
 
+def dense_poly2(rng, nvars, max0, max1, maxrest, fill, bits, tname="u64", f64=False, signed_cfs=True, simplex=False):
+    """Random polynomial that is dense in the two lowest symbols (planes of (max1 + 1) x (max0 + 1) entries, or the
+    simplex e0 + e1 <= max0 when `simplex`)."""
+    import itertools
+    terms = {}
+    for rest in itertools.product(range(maxrest + 1), repeat=nvars - 2):
+        if rng.random() < 0.75:
+            for e1 in range(max1 + 1):
+                for e0 in range(max0 + 1):
+                    if simplex and e0 + e1 > max0:
+                        continue
+                    if rng.random() < fill:
+                        if f64:
+                            terms[(e0, e1) + rest] = float(rng.standard_normal())
+                        else:
+                            v = int(rng.integers(1, 1 << bits))
+                            terms[(e0, e1) + rest] = -v if (signed_cfs and rng.integers(0, 2)) else v
+    return wl.from_dict(tuple(f"v{i}" for i in range(nvars)), terms, tname, 0, f64)
+
+
+def test_tile_path_forced(engine):
+    """The tile-blocked dense kernel (4 x 8 output tiles per warp, operand planes up to 64 x 64 staged by TMA) against
+    the oracle: unsigned / signed coefficients, 1-3 limb accumulators, fp64, holes, squares, planes wider and taller
+    than 32, simplex- and box-shaped planes, every tile geometry."""
+    rng = np.random.default_rng(37)
+    engine.set_option("kernel", 3)
+    try:
+        cases = ((3, 9, 5, 5, 0.9, 20, "u64", True, False), (4, 31, 12, 3, 0.6, 61, "u64", False, False),
+                 (3, 15, 31, 6, 1.0, 30, "i64", True, False), (3, 31, 6, 6, 0.3, 8, "i64", False, False),
+                 (5, 4, 2, 2, 1.0, 40, "u64", False, False), (4, 3, 3, 3, 0.8, 62, "u64", False, False),
+                 (3, 31, 31, 3, 0.5, 45, "u64", True, False), (4, 7, 7, 7, 1.0, 12, "u64", False, False),
+                 (3, 63, 20, 3, 0.7, 33, "u64", False, False), (3, 40, 63, 2, 0.5, 60, "i64", True, False),
+                 (3, 45, 45, 4, 1.0, 50, "u64", False, True), (4, 17, 17, 4, 1.0, 25, "u64", True, True))
+        for nvars, max0, max1, maxrest, fill, bits, tn, sgn, simplex in cases:
+            x = dense_poly2(rng, nvars, max0, max1, maxrest, fill, bits, tn, signed_cfs=sgn, simplex=simplex)
+            y = dense_poly2(rng, nvars, max0 // 2 + 1, max1, maxrest, fill, bits, tn, signed_cfs=sgn, simplex=simplex)
+            p = check_exact(engine, x, y)
+            assert p.stats["kernel"] == 3, "tile path was not taken"
+            p = check_exact(engine, y, x)
+            assert p.stats["kernel"] == 3
+            p = check_exact(engine, x, x)
+            assert p.stats["kernel"] == 3
+        for cfg in (1, 2, 3):
+            engine.set_option("plane_cfg", cfg)
+            x = dense_poly2(rng, 3, 33, 21, 5, 0.8, 40, "u64")
+            y = dense_poly2(rng, 3, 12, 40, 5, 0.8, 40, "u64")
+            p = check_exact(engine, x, y)
+            assert p.stats["kernel"] == 3
+        engine.set_option("plane_cfg", 0)
+        sy = ("a", "b", "c")
+        u = wl.from_dict(sy, {(1, 0, 0): 1, (0, 1, 0): 1, (0, 0, 1): 3}, "i64")
+        v = wl.from_dict(sy, {(1, 0, 0): 1, (0, 1, 0): -1, (0, 0, 1): 3}, "i64")
+        p = check_exact(engine, u, v)
+        assert p.stats["kernel"] == 3
+        x = dense_poly2(rng, 3, 12, 9, 6, 0.8, 0, "u64", f64=True)
+        y = dense_poly2(rng, 3, 40, 5, 6, 0.8, 0, "u64", f64=True)
+        p = check_f64(engine, x, y)
+        assert p.stats["kernel"] == 3
+        f, g = wl.fateman(14, 4, "u64")
+        p = engine.mul(f, g)
+        assert p.stats["kernel"] == 3
+        assert p.as_dict() == {kpack.pack(k, "u64"): v for k, v in wl.fateman_expected(14).items()}
+        f, g = wl.fateman(6, 5, "u64")
+        p = check_exact(engine, f, g)
+        assert p.stats["kernel"] == 3 and p.stats["acc_limbs"] == 1
+    finally:
+        engine.set_option("kernel", -1)
+        engine.set_option("plane_cfg", 0)
+
+
+def test_tile_path_truncated(engine):
+    """A total- or partial-degree truncation of a dense product is a filter on the output position in the tile path
+    (polynomial.hpp:1337-1347 forms exactly the pairs whose degree sum passes: same terms, same coefficients)."""
+    rng = np.random.default_rng(41)
+    engine.set_option("kernel", 3)
+    try:
+        x = dense_poly2(rng, 4, 12, 12, 4, 0.9, 30, "i64", simplex=True)
+        y = dense_poly2(rng, 4, 10, 10, 4, 0.9, 30, "i64", simplex=True)
+        for lim in (30, 14, 9, 3, 0, -1):
+            p = check_exact(engine, x, y, limit=lim)
+            assert p.stats["kernel"] == 3 or p.nterms == 0
+        for idx in ([0], [1], [0, 1], [2, 3], [0, 3], [1, 2, 3]):
+            for lim in (11, 4, 0):
+                p = check_exact(engine, x, y, limit=lim, idx=idx)
+        xf = dense_poly2(rng, 3, 20, 9, 7, 0.8, 0, "u64", f64=True)
+        yf = dense_poly2(rng, 3, 9, 20, 7, 0.8, 0, "u64", f64=True)
+        p = check_f64(engine, xf, yf, limit=17)
+        assert p.stats["kernel"] == 3
+    finally:
+        engine.set_option("kernel", -1)
+
+
+def test_tile_path_fateman_beyond_32(engine):
+    """Fateman with exponents >= 32 (benchmark/dense_4_vars.cpp with --power 34 here: one-limb coefficients) stays on the dense path."""
+    f, g = wl.fateman(34, 3, "u64")
+    p = engine.mul(f, g)
+    assert p.stats["kernel"] == 3
+    r = orc.poly_mul(f, g, nthreads=NT)
+    assert p.as_dict() == as_key_dict(r["keys"], r["cfs"])
+
+
 def test_row_path_auto_selection(engine):
     f, g = wl.fateman(16, 4, "u64")
     p = check_exact(engine, f, g)
-    assert p.stats["kernel"] in (1, 2)     # dense: rows or planes
+    assert p.stats["kernel"] in (1, 2, 3)  # dense: rows, planes or tiles
     fs, gs = wl.sparse_mp(9, "u64")
     p = engine.mul(fs, gs)
     assert p.stats["kernel"] == 0          # sparse: segment-owner scatter
