@@ -1279,47 +1279,44 @@ RowsResult run_planes(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t 
 // Tile-blocked dense path (obk_tiles.cuh, "kernel 3")
 // ------------------------------------------------------------------------------------------------
 struct TileCfg {
-    uint32_t nw, t, ctas;
+    uint32_t nw, ctas; // consumer warps per CTA, CTAs per SM
 };
-TileCfg tile_cfg(const obk_engine *e)
+TileCfg tile_cfg(const obk_engine *e, uint32_t tiles_max)
 {
     switch (e->opt_plane_cfg) {
-        case 1: return {8, 2, 3};
-        case 2: return {8, 1, 3};
-        case 3: return {16, 2, 1};
-        default: return {8, 2, 2};
+        case 1: return {10, 2};
+        case 2: return {16, 1};
+        case 3: return {7, 3};
+        case 4: return {12, 1};
+        case 5: return {15, 2};
+        case 6: return {31, 1};
+        case 7: return {20, 1};
+        // Measured (F30, F20: output planes of up to 121 / 66 tiles in the bounding box; D5: 32): large planes want the deeper ring and the
+        // larger accumulator area of 2 CTAs per SM, small ones the cheaper end-of-unit barrier of 3 small CTAs.
+        default: return tiles_max <= 32u ? TileCfg{7, 3} : TileCfg{10, 2};
     }
 }
 
-template <int LACC, bool F64, bool UNS, int NW, int T, int MINB>
-void launch_tiles_c(obk_engine *e, const TileParams &P, unsigned grid)
+template <int LACC, bool F64, bool UNS>
+void launch_tiles_t(obk_engine *e, const TileParams &P, unsigned grid, unsigned threads, unsigned ctas, size_t smem)
 {
-    auto fn = k_tileconv<LACC, F64, UNS, NW, T, MINB>;
-    const size_t smem = (size_t)P.nstage * tl_stage(P.rcap, P.P).bytes;
+    // register budget by geometry: <= 64 registers when more than 704 threads share an SM's register file with 80
+    auto fn = threads > (unsigned)TL_MAX_THREADS ? k_tileconv<LACC, F64, UNS, 1024, 1>
+                                                 : (threads * ctas * 80u > 65536u ? k_tileconv<LACC, F64, UNS, 512, 2>
+                                                                                   : k_tileconv<LACC, F64, UNS, TL_MAX_THREADS, 1>);
     CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fn<<<grid, (NW + 1) * 32, smem, e->stream>>>(P);
+    fn<<<grid, threads, smem, e->stream>>>(P);
     e->launches += 1;
     CU_CHECK(e, cudaGetLastError());
 }
 
-template <int LACC, bool F64, bool UNS>
-void launch_tiles_t(obk_engine *e, const TileParams &P, unsigned grid)
-{
-    switch (e->opt_plane_cfg) {
-        case 1: launch_tiles_c<LACC, F64, UNS, 8, 2, 3>(e, P, grid); break;
-        case 2: launch_tiles_c<LACC, F64, UNS, 8, 1, 3>(e, P, grid); break;
-        case 3: launch_tiles_c<LACC, F64, UNS, 16, 2, 1>(e, P, grid); break;
-        default: launch_tiles_c<LACC, F64, UNS, 8, 2, 2>(e, P, grid); break;
-    }
-}
-
-void launch_tiles(obk_engine *e, int mode, bool uns, const TileParams &P, unsigned grid)
+void launch_tiles(obk_engine *e, int mode, bool uns, const TileParams &P, unsigned grid, unsigned threads, unsigned ctas, size_t smem)
 {
     switch (mode) {
-        case CF_I1A1: launch_tiles_t<1, false, false>(e, P, grid); break;
-        case CF_I1A2: uns ? launch_tiles_t<2, false, true>(e, P, grid) : launch_tiles_t<2, false, false>(e, P, grid); break;
-        case CF_I1A3: uns ? launch_tiles_t<3, false, true>(e, P, grid) : launch_tiles_t<3, false, false>(e, P, grid); break;
-        case CF_F64: launch_tiles_t<1, true, false>(e, P, grid); break;
+        case CF_I1A1: launch_tiles_t<1, false, false>(e, P, grid, threads, ctas, smem); break;
+        case CF_I1A2: uns ? launch_tiles_t<2, false, true>(e, P, grid, threads, ctas, smem) : launch_tiles_t<2, false, false>(e, P, grid, threads, ctas, smem); break;
+        case CF_I1A3: uns ? launch_tiles_t<3, false, true>(e, P, grid, threads, ctas, smem) : launch_tiles_t<3, false, false>(e, P, grid, threads, ctas, smem); break;
+        case CF_F64: launch_tiles_t<1, true, false>(e, P, grid, threads, ctas, smem); break;
         default: e->err = "internal: coefficient mode not supported by the tile path"; throw obk_fail{OBK_ERR_INVALID_ARG};
     }
 }
@@ -1340,6 +1337,14 @@ bool planes_dense(const PlanePre &pre, uint64_t nx, uint64_t ny)
     const uint32_t hx = pre.h[0], hy = pre.same ? pre.h[0] : pre.h[1];
     return (double)nx >= 8.0 * hx && (double)ny >= 8.0 * hy && (uint64_t)hx * hy <= (1ull << 21);
 }
+// The tile path pays a fixed cost per staged plane pair (measured: ~2-9 ns chip-wide) against ~15 ps per term product
+// saved over the scatter kernel: it wins from a few hundred term products per plane pair on (D5: 292 -> 1.0 ms vs
+// 2.3 ms; S12: 185, where most pairs feed an output plane of their own -> 1.9 ms vs 0.64 ms).
+bool tiles_dense(const PlanePre &pre, uint64_t nx, uint64_t ny)
+{
+    const uint32_t hx = pre.h[0], hy = pre.same ? pre.h[0] : pre.h[1];
+    return planes_dense(pre, nx, ny) && (double)nx * (double)ny >= 256.0 * (double)hx * (double)hy;
+}
 
 // Returns done=false when the operands do not qualify (the caller then tries the other paths).
 RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *dxk, const uint64_t *dxc, uint64_t nx,
@@ -1351,13 +1356,24 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     const uint64_t delta = L.delta;
     if (delta >= (1ull << 32)) return R; // delta^2 must fit 64 bits
     if (D.wx > (uint32_t)TL_MAX_DIM || D.wy > (uint32_t)TL_MAX_DIM || D.rx > (uint32_t)TL_MAX_DIM || D.ry > (uint32_t)TL_MAX_DIM) return R;
-    TileCfg cfg = tile_cfg(e);
     const uint32_t P = tl_pitch(std::max(D.wx, D.wy)), rcap = std::max(D.rx, D.ry);
     const uint32_t blob_words = tl_blob_words(rcap, P);
     const TileStage G = tl_stage(rcap, P);
-    // shared memory of one SM (228 KB) shared by cfg.ctas resident CTAs, 1 KB reserved per CTA; at least 2 stages
-    while (cfg.ctas > 1 && ((228u << 10) / cfg.ctas - 1024u - 512u) / G.bytes < 3u) --cfg.ctas;
-    const uint32_t nstage = (uint32_t)std::min<size_t>(TL_MAX_STAGES, (std::min<size_t>(e->smem_optin, (228u << 10) / cfg.ctas - 1024) - 512) / G.bytes);
+    // Shared memory of one SM (228 KB) shared by cfg.ctas resident CTAs, 1 KB reserved per CTA: the tile accumulators of
+    // a unit (all tiles of the largest output plane if they fit) and a ring of at least 3 staged plane pairs.
+    const uint32_t wo_raw = D.wx + D.wy - 1u, ro_raw = D.rx + D.ry - 1u;
+    const uint32_t shape_max = tl_shape(ro_raw, wo_raw, std::min(ro_raw + wo_raw - 1u, 255u));
+    const uint32_t tiles_max = tl_ntiles(ro_raw, wo_raw, std::min(ro_raw + wo_raw - 1u, 255u));
+    TileCfg cfg = tile_cfg(e, tiles_max);
+    uint32_t slots = 0, nstage = 0;
+    for (;; --cfg.ctas) {
+        const size_t per_cta = std::min<size_t>(e->smem_optin, (228u << 10) / cfg.ctas - 1024) - 512;
+        slots = std::max<uint32_t>(16u, tiles_max);
+        while (slots > 16u && tl_acc_bytes(slots, accw) + 3u * (size_t)G.bytes > per_cta) --slots;
+        const size_t accb = tl_acc_bytes(slots, accw);
+        nstage = accb < per_cta ? (uint32_t)std::min<size_t>(TL_MAX_STAGES, (per_cta - accb) / G.bytes) : 0;
+        if (nstage >= 3 || cfg.ctas == 1) break;
+    }
     if (nstage < 2) return R;
     if (!pre.launched) {
         planes_prepare(e, sc, dxk, nx, dyk, ny, delta, pre);
@@ -1366,7 +1382,7 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     PlaneSide &X = pre.X, &Y = pre.Y;
     const uint32_t hx = pre.h[0], hy = pre.same ? pre.h[0] : pre.h[1];
     const uint64_t plane_pairs = (uint64_t)hx * hy;
-    if (plane_pairs > (1ull << 21) || hx >= (1u << 24) || hy >= (1u << 24) || (!forced && !planes_dense(pre, nx, ny))) return R;
+    if (plane_pairs > (1ull << 21) || hx >= (1u << 24) || hy >= (1u << 24) || (!forced && !tiles_dense(pre, nx, ny))) return R;
     auto build = [&](const uint64_t *keys, const uint64_t *cfs, uint64_t n, PlaneSide &p) {
         p.mat = sc.alloc<uint64_t>((size_t)p.nplanes * blob_words);
         p.pinfo = sc.alloc<uint32_t>((size_t)p.nplanes * 4);
@@ -1411,9 +1427,7 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     uint32_t *pair_off = sc.alloc<uint32_t>(npairs + 2), *row_base = sc.alloc<uint32_t>(npairs + 2);
     uint2 *pairs = sc.alloc<uint2>(npairs);
     uint32_t *totals = sc.alloc<uint32_t>(4);
-    const uint32_t tpu = cfg.nw * cfg.t; // tiles per unit
-    const uint32_t wo_raw = D.wx + D.wy - 1u, ro_raw = D.rx + D.ry - 1u;
-    const uint32_t groups_max = (tl_ntiles(ro_raw, wo_raw, ro_raw + wo_raw) + tpu - 1) / tpu;
+    const uint32_t groups_max = tl_ngroups(shape_max, slots);
     uint32_t *units = sc.alloc<uint32_t>(std::max<uint64_t>(npairs * groups_max, 1));
     const unsigned gp = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 2048);
     k_tile_sym_insert<<<gp, 256, 0, s>>>(X.plane_key, X.pinfo, X.nplanes, Y.plane_key, Y.pinfo, Y.nplanes, rank, part_nranks, tab, l2, rec,
@@ -1430,7 +1444,7 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
         tr.limit = D.limit;
         tr.dhi = dhi;
     }
-    k_tile_units<<<1, 1024, 0, s>>>(owork, oshape, ocnt, okey, counters, tpu, rank, owner ? nranks : 1u, tr, row_base, pair_off, units, totals);
+    k_tile_units<<<1, 1024, 0, s>>>(owork, oshape, ocnt, okey, counters, slots, rank, owner ? nranks : 1u, tr, row_base, pair_off, units, totals);
     k_plane_sym_fill<<<gp, 256, 0, s>>>(X.plane_key, X.nplanes, Y.plane_key, Y.nplanes, rank, part_nranks, tab, l2, rec, pair_off, fill, pairs);
     e->launches += 4;
     uint32_t htot[3] = {0, 0, 0};
@@ -1469,10 +1483,11 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     Pm.blob_words = blob_words;
     Pm.nstage = nstage;
     Pm.wo = wo;
+    Pm.slots = slots;
     Pm.tr = tr;
     const unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(nunits, (uint32_t)e->sm_count * cfg.ctas));
     CU_CHECK(e, cudaEventRecord(e->ev[5], s));
-    if (nunits) launch_tiles(e, mode, uns, Pm, grid);
+    if (nunits) launch_tiles(e, mode, uns, Pm, grid, (cfg.nw + 1) * 32, cfg.ctas, tl_acc_bytes(slots, accw) + (size_t)nstage * G.bytes);
     CU_CHECK(e, cudaEventRecord(e->ev[6], s));
     st.mul_launches += 1;
     uint64_t total = 0;
@@ -2040,7 +2055,7 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 }
                 CU_CHECK(e, cudaStreamSynchronize(s));
                 tot_mults = htot;
-                tiles_take = tile_cand && (e->opt_kernel == 3 || planes_dense(plane_pre, nx_full, ny));
+                tiles_take = tile_cand && (e->opt_kernel == 3 || tiles_dense(plane_pre, nx_full, ny));
                 if (!hpx.empty() && tot_mults > 0 && !tiles_take) {
                     // choose the left-degree threshold H that minimises the number of left terms visited
                     const uint32_t ndx = (uint32_t)rangex;

@@ -280,14 +280,14 @@ __global__ void __launch_bounds__(256) k_plane_sym_fill(const uint64_t *__restri
 template <int LACC, bool F64, bool UNS>
 struct PlaneAcc {
     static constexpr int KIND = F64 ? 3 : (LACC == 1 ? 2 : (UNS ? 0 : 1));
-    uint64_t A, B, C;    // KIND 0: column accumulators, weights 2^0, 2^32, 2^64
-    uint32_t ca, cb, cc; // KIND 0: carry-outs of the three columns (weights 2^64, 2^96, 2^128)
-    uint64_t z[3];       // KIND 1, 2
-    double d;            // KIND 3
+    uint64_t A, B, B2, C; // KIND 0: column accumulators, weights 2^0, 2^32 (x0 y1), 2^32 (x1 y0), 2^64
+    uint32_t ca, cb, cc;  // KIND 0: carry-outs of the columns (weights 2^64, 2^96, 2^128)
+    uint64_t z[3];        // KIND 1, 2
+    double d;             // KIND 3
 
     __device__ __forceinline__ void clear()
     {
-        A = B = C = 0;
+        A = B = B2 = C = 0;
         ca = cb = cc = 0;
         z[0] = z[1] = z[2] = 0;
         d = 0.0;
@@ -297,21 +297,24 @@ struct PlaneAcc {
         if constexpr (KIND == 0) {
             // ptxas fuses every mad.lo.cc / madc.hi.cc pair into ONE IMAD.WIDE.U32 with a carry-out predicate and
             // the four addc into two IADD3.X with two carry-in predicates each: 4 FMA-pipe + 2 ALU-pipe instructions
-            // per product (profiles/r02_sass_planeconv.txt).  The accumulators travel as 64-bit operands so that they
-            // sit in aligned register pairs and no MOV is needed around the IMAD.WIDE.
+            // per product.  The accumulators travel as 64-bit operands so that they sit in aligned register pairs and
+            // no MOV is needed around the IMAD.WIDE.  The two middle products have a column each (B, B2): the four
+            // IMAD.WIDE of a product are independent, and the dependent chain through a column is one per product.
             asm("{\n\t.reg .u32 x0, x1, y0, y1, l, h;\n\t"
-                "mov.b64 {x0, x1}, %6;\n\tmov.b64 {y0, y1}, %7;\n\t"
+                "mov.b64 {x0, x1}, %7;\n\tmov.b64 {y0, y1}, %8;\n\t"
                 "mov.b64 {l, h}, %0;\n\t"
-                "mad.lo.cc.u32  l, x0, y0, l;\n\tmadc.hi.cc.u32 h, x0, y0, h;\n\taddc.u32 %3, %3, 0;\n\t"
+                "mad.lo.cc.u32  l, x0, y0, l;\n\tmadc.hi.cc.u32 h, x0, y0, h;\n\taddc.u32 %4, %4, 0;\n\t"
                 "mov.b64 %0, {l, h};\n\t"
                 "mov.b64 {l, h}, %1;\n\t"
-                "mad.lo.cc.u32  l, x0, y1, l;\n\tmadc.hi.cc.u32 h, x0, y1, h;\n\taddc.u32 %4, %4, 0;\n\t"
-                "mad.lo.cc.u32  l, x1, y0, l;\n\tmadc.hi.cc.u32 h, x1, y0, h;\n\taddc.u32 %4, %4, 0;\n\t"
+                "mad.lo.cc.u32  l, x0, y1, l;\n\tmadc.hi.cc.u32 h, x0, y1, h;\n\taddc.u32 %5, %5, 0;\n\t"
                 "mov.b64 %1, {l, h};\n\t"
                 "mov.b64 {l, h}, %2;\n\t"
-                "mad.lo.cc.u32  l, x1, y1, l;\n\tmadc.hi.cc.u32 h, x1, y1, h;\n\taddc.u32 %5, %5, 0;\n\t"
-                "mov.b64 %2, {l, h};\n\t}"
-                : "+l"(A), "+l"(B), "+l"(C), "+r"(ca), "+r"(cb), "+r"(cc)
+                "mad.lo.cc.u32  l, x1, y0, l;\n\tmadc.hi.cc.u32 h, x1, y0, h;\n\taddc.u32 %5, %5, 0;\n\t"
+                "mov.b64 %2, {l, h};\n\t"
+                "mov.b64 {l, h}, %3;\n\t"
+                "mad.lo.cc.u32  l, x1, y1, l;\n\tmadc.hi.cc.u32 h, x1, y1, h;\n\taddc.u32 %6, %6, 0;\n\t"
+                "mov.b64 %3, {l, h};\n\t}"
+                : "+l"(A), "+l"(B), "+l"(B2), "+l"(C), "+r"(ca), "+r"(cb), "+r"(cc)
                 : "l"(x), "l"(y));
         } else if constexpr (KIND == 1) {
             uint64_t(&zz)[LACC] = reinterpret_cast<uint64_t(&)[LACC]>(z);
@@ -326,7 +329,7 @@ struct PlaneAcc {
     __device__ __forceinline__ void limbs(uint64_t (&o)[LACC]) const
     {
         if constexpr (KIND == 0) {
-            const unsigned __int128 lo = (unsigned __int128)A + ((unsigned __int128)B << 32);
+            const unsigned __int128 lo = (unsigned __int128)A + ((unsigned __int128)B << 32) + ((unsigned __int128)B2 << 32);
             const unsigned __int128 mid = (lo >> 64) + (unsigned __int128)C + ca + ((unsigned __int128)cb << 32);
             o[0] = (uint64_t)lo;
             o[1] = (uint64_t)mid;
@@ -406,6 +409,12 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a)
 {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint4 lds_u32x4(uint32_t a)

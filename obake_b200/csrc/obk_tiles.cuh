@@ -33,6 +33,8 @@ constexpr int TL_HDR = TL_HDR_BYTES / 8;  // words
 constexpr int TL_PAD_ROWS = TL_R - 1;     // zero rows above / below a plane in its vector role
 constexpr int TL_LEAD_BYTES = 64;         // zero words in front of the first zero row (left padding of its windows)
 constexpr int TL_MAX_STAGES = 8;
+constexpr int TL_DESC_BYTES = 128;        // descriptor of a staged pair: 16 words + the tile-row prefix table u16[32]
+constexpr int TL_MAX_THREADS = 704;
 
 // Row pitch in words: the widest row rounded to 16 plus 8 zero words; P / 8 is odd.
 __host__ __device__ inline uint32_t tl_pitch(uint32_t wmax)
@@ -56,7 +58,7 @@ __host__ __device__ inline TileStage tl_stage(uint32_t rcap, uint32_t P)
     g.v_hdr = g.s_rows + rcap * P8;
     g.v_rows = g.v_hdr + TL_HDR_BYTES + TL_LEAD_BYTES + TL_PAD_ROWS * P8;
     g.desc = g.v_rows + (rcap + TL_PAD_ROWS) * P8;
-    g.bytes = (g.desc + 32u + 127u) & ~127u;
+    g.bytes = (g.desc + (uint32_t)TL_DESC_BYTES + 127u) & ~127u;
     return g;
 }
 // Tiles of an output plane with `rows` rows, rows at most `w` wide and lo1 + lo0 < d: row-major over the tile rows;
@@ -91,6 +93,62 @@ __host__ __device__ inline bool tl_locate(uint32_t idx, uint32_t rows, uint32_t 
 __host__ __device__ inline uint32_t tl_shape(uint32_t rows, uint32_t w, uint32_t d)
 {
     return rows | (w << 8) | (d << 16);
+}
+
+// Groups of an output plane: whole tile rows, packed greedily into at most `slots` tiles (slots >= tiles of one tile row).
+// Returns the tile-row range [tr_lo, tr_hi) of group g and its tile count; tr_lo == tr_hi: no such group.
+__host__ __device__ inline uint32_t tl_group(uint32_t shape, uint32_t slots, uint32_t g, uint32_t &tr_lo, uint32_t &tr_hi)
+{
+    const uint32_t rows = shape & 0xffu, w = (shape >> 8) & 0xffu, d = shape >> 16;
+    const uint32_t jend = rows < d ? rows : d;
+    uint32_t cur = 0, n = 0, lo = 0, tr = 0;
+    for (uint32_t j = 0; j < jend; j += TL_R, ++tr) {
+        const uint32_t ww = w < d - j ? w : d - j;
+        const uint32_t c = (ww + TL_C - 1u) / TL_C;
+        if (n + c > slots) {
+            if (cur == g) {
+                tr_lo = lo;
+                tr_hi = tr;
+                return n;
+            }
+            ++cur;
+            lo = tr;
+            n = 0;
+        }
+        n += c;
+    }
+    if (cur == g && n) {
+        tr_lo = lo;
+        tr_hi = tr;
+        return n;
+    }
+    tr_lo = tr_hi = 0;
+    return 0;
+}
+__host__ __device__ inline uint32_t tl_ngroups(uint32_t shape, uint32_t slots)
+{
+    const uint32_t rows = shape & 0xffu, w = (shape >> 8) & 0xffu, d = shape >> 16;
+    const uint32_t jend = rows < d ? rows : d;
+    uint32_t cur = 0, n = 0;
+    for (uint32_t j = 0; j < jend; j += TL_R) {
+        const uint32_t ww = w < d - j ? w : d - j;
+        const uint32_t c = (ww + TL_C - 1u) / TL_C;
+        if (n + c > slots) {
+            ++cur;
+            n = 0;
+        }
+        n += c;
+    }
+    return cur + (n ? 1u : 0u);
+}
+// tiles of tile row tr of a shape
+__host__ __device__ inline uint32_t tl_row_tiles(uint32_t shape, uint32_t tr)
+{
+    const uint32_t rows = shape & 0xffu, w = (shape >> 8) & 0xffu, d = shape >> 16;
+    const uint32_t jend = rows < d ? rows : d, j = tr * TL_R;
+    if (j >= jend) return 0u;
+    const uint32_t ww = w < d - j ? w : d - j;
+    return (ww + TL_C - 1u) / TL_C;
 }
 
 // ---- plane building ------------------------------------------------------------------------------------------------
@@ -234,7 +292,7 @@ __device__ __forceinline__ uint32_t tl_cut_shape(uint32_t shape, const TileTrunc
 }
 
 // One CTA: pair_off = exclusive scan of the pairs per plane, row_base = exclusive scan of the rows per plane, and the
-// work units = (output plane, group of `tpu` tiles), heaviest planes first (counting sort by the bit length of the
+// work units = (output plane, group of tile rows holding at most `tpu` tiles), heaviest planes first (counting sort by the bit length of the
 // work).  own_nranks > 1: only the units this rank owns (multi-GPU owner mode).  The shapes are cut by the truncation.
 //   units[u] = plane | group << 24;  totals[0] = units, [1] = output rows, [2] = output planes
 __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *__restrict__ owork, uint32_t *__restrict__ oshape,
@@ -252,10 +310,7 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
     if (tid == 0) s_carry = 0;
     for (uint32_t o = tid; o < nout; o += blockDim.x) oshape[o] = tl_cut_shape(oshape[o], tr, tl_budget(tr, o));
     __syncthreads();
-    auto groups = [&](uint32_t o) {
-        const uint32_t sh = oshape[o];
-        return (tl_ntiles(sh & 0xffu, (sh >> 8) & 0xffu, sh >> 16) + tpu - 1u) / tpu;
-    };
+    auto groups = [&](uint32_t o) { return tl_ngroups(oshape[o], tpu); };
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
         const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
         const uint32_t nb = groups(o);
@@ -332,6 +387,32 @@ __global__ void __launch_bounds__(256) k_tile_plane_degrees(const uint64_t *__re
     }
 }
 
+// `np` pairs of steps of one row pair: z[lane] += x[i] y[-i]; px / py are the shared addresses of x[0] and of y[0].
+// Running pointers (two additions per four steps), every load at an immediate offset.
+template <class Acc>
+__device__ __forceinline__ void conv_run(Acc &z, uint32_t px, uint32_t py, uint32_t np)
+{
+    for (; np >= 2u; np -= 2u) {
+        uint64_t x0, x1, x2, x3;
+        lds_2u64(px, x0, x1);
+        lds_2u64(px + 16u, x2, x3);
+        const uint64_t y0 = lds_u64(py), y1 = lds_u64(py - 8u), y2 = lds_u64(py - 16u), y3 = lds_u64(py - 24u);
+        z.mac(x0, y0);
+        z.mac(x1, y1);
+        z.mac(x2, y2);
+        z.mac(x3, y3);
+        px += 32u;
+        py -= 32u;
+    }
+    if (np) {
+        uint64_t x0, x1;
+        lds_2u64(px, x0, x1);
+        const uint64_t y0 = lds_u64(py), y1 = lds_u64(py - 8u);
+        z.mac(x0, y0);
+        z.mac(x1, y1);
+    }
+}
+
 struct TileParams {
     const uint64_t *xmat, *ymat;   // [planes][blob_words]
     const uint32_t *xinfo, *yinfo; // [planes][4]: rows, terms, widest row, max(b + len[b])
@@ -348,22 +429,42 @@ struct TileParams {
     uint64_t *omat;   // [rows][LACC][wo]
     uint32_t *or_cnt; // [rows][wo / 32] non-zero entries per 32-column chunk
     uint32_t P, rcap, blob_words, nstage, wo;
+    uint32_t slots; // accumulator tiles in shared memory = most tiles of a unit
     TileTrunc tr;
 };
 
-// NW consumer warps x T tiles each + one producer warp.
-template <int LACC, bool F64, bool UNS, int NW, int T, int MINB>
-__global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TileParams P)
+
+// Shared memory of the product kernel:  accumulators [slots][LACC][32] u64 | locks [slots] u32 | item counters
+// [TL_MAX_STAGES] u32 | ring stages.
+__host__ __device__ inline uint32_t tl_acc_bytes(uint32_t slots, uint32_t lacc)
+{
+    return (slots * lacc * 256u + slots * 4u + TL_MAX_STAGES * 4u + 127u) & ~127u;
+}
+
+// nw consumer warps (blockDim / 32 - 1) + one producer warp.  The unit of work of a consumer warp is an ITEM = (staged
+// plane pair, output tile): items are handed out by a shared-memory counter per ring stage, so a warp never waits for
+// a slower one -- tiles in the middle of a simplex-shaped plane carry 1.6x the work of the average tile, which is what
+// a static tile-per-warp assignment loses.  An item is accumulated in registers and added to the tile's accumulator
+// in shared memory under a per-tile lock; when the unit's last pair has been consumed the tiles are written out.
+template <int LACC, bool F64, bool UNS, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB) k_tileconv(const TileParams P)
 {
     using Acc = PlaneAcc<LACC, F64, UNS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_full[TL_MAX_STAGES], s_empty[TL_MAX_STAGES];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t NW = (blockDim.x >> 5) - 1u;
     const uint32_t nstage = P.nstage;
     const uint32_t Pw = P.P, P8 = Pw * 8u;
     const TileStage G = tl_stage(P.rcap, Pw);
-    // zero everything once: the padding above a vector plane is never written again
-    for (uint32_t i = tid; i < nstage * G.bytes / 16u; i += blockDim.x) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+    const uint32_t acc_bytes = tl_acc_bytes(P.slots, LACC);
+    uint64_t *s_acc = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_lock = reinterpret_cast<uint32_t *>(smem_raw + (size_t)P.slots * LACC * 256u);
+    uint32_t *s_next = s_lock + P.slots;
+    unsigned char *ring = smem_raw + acc_bytes;
+    // zero everything once: accumulators, locks, and the padding above a vector plane that is never written again
+    for (uint32_t i = tid; i < (acc_bytes + nstage * G.bytes) / 16u; i += blockDim.x)
+        reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy zeros before the bulk copies land
     if (tid == 0) {
         for (uint32_t s = 0; s < nstage; ++s) {
@@ -381,7 +482,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TilePara
             if (lane == 0) u = atomicAdd(P.cursor, 1u);
             u = __shfl_sync(0xffffffffu, u, 0);
             const bool quit = u >= P.nunits;
-            uint32_t o = 0, g = 0, p0 = 0, p1 = 1, shape = 0, jmin = 0;
+            uint32_t o = 0, g = 0, p0 = 0, p1 = 1, shape = 0, tr_lo = 0, tr_hi = 0;
             int32_t budget = 0;
             if (!quit) {
                 const uint32_t ud = __ldg(P.units + u);
@@ -390,8 +491,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TilePara
                 p0 = __ldg(P.pair_off + o);
                 p1 = __ldg(P.pair_off + o + 1);
                 shape = __ldg(P.oshape + o);
-                uint32_t c0;
-                tl_locate(g * (uint32_t)(NW * T), shape & 0xffu, (shape >> 8) & 0xffu, shape >> 16, jmin, c0);
+                tl_group(shape, P.slots, g, tr_lo, tr_hi);
                 budget = tl_budget(P.tr, o);
             }
             bool first = true;
@@ -403,21 +503,32 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TilePara
                     ia = __ldg(reinterpret_cast<const uint4 *>(P.xinfo) + pr.x);
                     ib = __ldg(reinterpret_cast<const uint4 *>(P.yinfo) + pr.y);
                 }
-                // what the stage needs: rows of both planes, which one supplies the scalars, the diagonal bound
+                // what the stage needs: rows of both planes, which one supplies the scalars, the pair's output shape
                 const bool a_is_s = ia.y <= ib.y; // fewer terms
                 const uint32_t meta = (a_is_s ? ia.x : ib.x) | ((a_is_s ? ib.x : ia.x) << 8) | (a_is_s ? 0u : 1u << 16);
-                const uint32_t dsum = ia.w + ib.w - 1u, rsum = ia.x + ib.x - 1u;
+                const uint32_t pshape = tl_shape(min(ia.x + ib.x - 1u, shape & 0xffu), min(ia.z + ib.z - 1u, (shape >> 8) & 0xffu),
+                                                 min(ia.w + ib.w - 1u, shape >> 16));
                 const uint32_t cntp = quit ? 1u : min(32u, p1 - pb);
                 for (uint32_t q = 0; q < cntp; ++q) {
                     const uint32_t px = __shfl_sync(0xffffffffu, pr.x, (int)q), py = __shfl_sync(0xffffffffu, pr.y, (int)q);
-                    const uint32_t mt = __shfl_sync(0xffffffffu, meta, (int)q), ds = __shfl_sync(0xffffffffu, dsum, (int)q);
-                    const uint32_t rs = __shfl_sync(0xffffffffu, rsum, (int)q);
+                    const uint32_t mt = __shfl_sync(0xffffffffu, meta, (int)q), psh = __shfl_sync(0xffffffffu, pshape, (int)q);
                     const bool last = pb + q + 1u == p1;
+                    // items of this pair in this group: lane i looks at tile row tr_lo + i
+                    const uint32_t mine = tr_lo + lane < tr_hi ? tl_row_tiles(psh, tr_lo + lane) : 0u;
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if ((int)lane >= d) incl += v;
+                    }
+                    const uint32_t nitems = __shfl_sync(0xffffffffu, incl, 31);
                     // a pair that cannot reach this group of tiles is not staged (unless it carries the end-of-unit flag)
-                    if (!quit && !last && (jmin >= rs || jmin >= ds)) continue;
+                    if (!quit && !last && nitems == 0u) continue;
                     mbar_wait(&s_empty[s], ph ^ 1u);
+                    unsigned char *st = ring + (size_t)s * G.bytes;
+                    reinterpret_cast<uint16_t *>(st + G.desc + 64)[lane] = (uint16_t)incl;
+                    __syncwarp();
                     if (lane == 0) {
-                        unsigned char *st = smem_raw + (size_t)s * G.bytes;
                         uint32_t *d = reinterpret_cast<uint32_t *>(st + G.desc);
                         const uint32_t nS = mt & 0xffu, nV = (mt >> 8) & 0xffu;
                         d[0] = o;
@@ -425,8 +536,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TilePara
                         d[2] = quit ? 2u : ((last ? 1u : 0u) | (first ? 4u : 0u));
                         d[3] = shape;
                         d[4] = mt;
-                        d[5] = ds;
+                        d[5] = psh;
                         d[6] = (uint32_t)budget;
+                        d[7] = quit ? 0u : nitems;
+                        d[8] = tr_lo | (tr_hi << 8);
+                        s_next[s] = 0;
                         const uint32_t bS = TL_HDR_BYTES + nS * P8, bV = (nV + TL_PAD_ROWS) * P8;
                         mbar_expect_tx(&s_full[s], quit ? 0u : bS + TL_HDR_BYTES + bV);
                         if (!quit) {
@@ -449,57 +563,94 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TilePara
         return;
     }
 
-    // ================= consumers: warp w owns tiles  g * NW * T + t * NW + w,  t = 0 .. T-1,  of the unit's plane ==========
-    Acc z[T];
-    uint32_t tj[T], tc[T]; // tile origins; tj = 0x7fffffff: no tile
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        z[t].clear();
-        tj[t] = 0x7fffffffu;
-        tc[t] = 0;
-    }
+    // ================= consumers =================
     const uint32_t r = lane >> 3, c = lane & 7u;
-    const uint32_t smem0 = smem_u32(smem_raw);
+    const uint32_t smem0 = smem_u32(ring);
     uint32_t s = 0, ph = 0;
+    uint32_t gp_excl = 0; // tiles of the unit's group in front of tile row tr_lo + lane (the slot of its first tile)
+    uint32_t gtiles = 0;  // tiles of the unit's group
     for (;;) {
         mbar_wait(&s_full[s], ph);
         const uint32_t base = smem0 + s * G.bytes;
         const uint4 d0 = lds_u32x4(base + G.desc);
         if (d0.z & 2u) break;
         const uint4 d1 = lds_u32x4(base + G.desc + 16u);
-        const uint32_t meta = d1.x, dsum = d1.y;
-        const uint32_t orows = d0.w & 0xffu;
+        const uint32_t trr = lds_u32(base + G.desc + 32u), tr_lo = trr & 0xffu, tr_hi = trr >> 8;
         if (d0.z & 4u) {
-            // a new unit: where are my tiles
+            // a new unit: slots of the tile rows of its group
+            const uint32_t mine = tr_lo + lane < tr_hi ? tl_row_tiles(d0.w, tr_lo + lane) : 0u;
+            uint32_t incl = mine;
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-                uint32_t j0 = 0, c0 = 0;
-                const bool ok = tl_locate(d0.y * (uint32_t)(NW * T) + (uint32_t)t * NW + warp, orows, (d0.w >> 8) & 0xffu, d0.w >> 16, j0, c0);
-                tj[t] = ok ? j0 : 0x7fffffffu;
-                tc[t] = c0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += v;
             }
+            gp_excl = incl - mine;
+            gtiles = __shfl_sync(0xffffffffu, incl, 31);
         }
+        const uint32_t meta = d1.x, nitems = d1.w;
         const uint32_t nS = meta & 0xffu, nV = (meta >> 8) & 0xffu;
+        const uint32_t prow = d1.y & 0xffu, pd = d1.y >> 16; // the pair's output rows / diagonal bound (clipped to the plane's)
         const uint32_t aS = base + G.s_rows, aV = base + G.v_rows; // shared addresses of S[0][0] and V[0][0]
         const uint32_t aWm = base + G.v_hdr + 64u + (uint32_t)TL_PAD_ROWS;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const uint32_t j0 = tj[t], c0 = tc[t];
-            if (j0 < nS + nV - 1u && j0 + c0 < dsum) {
+        const uint32_t pin = lds_u16(base + G.desc + 64u + 2u * lane); // inclusive tile count up to tile row tr_lo + lane
+        for (;;) {
+            uint32_t idx = 0;
+            if (lane == 0) idx = atomicAdd(&s_next[s], 1u);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= nitems) break;
+            const uint32_t trel = __popc(__ballot_sync(0xffffffffu, idx >= pin));
+            const uint32_t prev = __shfl_sync(0xffffffffu, pin, (int)((trel + 31u) & 31u));
+            const uint32_t tcn = idx - (trel ? prev : 0u);
+            const uint32_t j0 = (tr_lo + trel) * (uint32_t)TL_R, c0 = tcn * (uint32_t)TL_C;
+            const uint32_t slot = __shfl_sync(0xffffffffu, gp_excl, (int)trel) + tcn;
+            Acc z;
+            z.clear();
+            bool any = false;
+            if (j0 < prow && j0 + c0 < pd) {
                 const uint32_t blo = j0 + 1u > nV ? j0 + 1u - nV : 0u, bhi = min(nS - 1u, j0 + (uint32_t)TL_PAD_ROWS);
                 // x at aS + (b P + i) 8, y at aV + ((j0 + r - b) P + c0 + c - i) 8:  y = Cl - x
                 const uint32_t Cl = aS + aV + ((j0 + r) * Pw + c0 + c) * 8u;
-                // the row lengths of the next row are requested before the current row is convolved
-                uint32_t la = lds_u8(base + blo), wv = lds_u8(aWm + j0 - blo);
-                for (uint32_t b = blo; b <= bhi; ++b) {
-                    const uint32_t ilo = (c0 + 1u > wv ? c0 + 1u - wv : 0u) & ~1u, ihi = min(la, c0 + (uint32_t)TL_C);
-                    const uint32_t bn = min(b + 1u, bhi);
-                    la = lds_u8(base + bn);
-                    wv = lds_u8(aWm + j0 - bn);
-                    if (ilo < ihi) {
-                        const uint32_t ax = aS + b * P8 + ilo * 8u;
-                        conv_steps(z[t], ax, Cl - ax, 0u, ihi - ilo);
+                // the scalar ranges of up to 32 rows at a time, one row per lane; then the non-empty rows one by one
+                for (uint32_t bb = blo; bb <= bhi; bb += 32u) {
+                    const uint32_t bl = bb + lane;
+                    uint32_t pk = 0;
+                    if (bl <= bhi) {
+                        const uint32_t la = lds_u8(base + bl), wv = lds_u8(aWm + j0 - bl);
+                        const uint32_t ilo = (c0 + 1u > wv ? c0 + 1u - wv : 0u) & ~1u, ihi = min(la, c0 + (uint32_t)TL_C);
+                        if (ilo < ihi) pk = (aS + bl * P8 + ilo * 8u) | ((ihi - ilo + 1u) >> 1) << 24; // x address | step pairs
                     }
+                    uint32_t m = __ballot_sync(0xffffffffu, pk != 0u);
+                    any |= m != 0u;
+                    while (m) {
+                        const uint32_t q = (uint32_t)__ffs(m) - 1u;
+                        m &= m - 1u;
+                        const uint32_t v = __shfl_sync(0xffffffffu, pk, (int)q);
+                        const uint32_t ax = v & 0x00ffffffu;
+                        conv_run(z, ax, Cl - ax, v >> 24);
+                    }
+                }
+            }
+            if (any) {
+                // add the item to the tile's accumulator under the tile's lock
+                uint64_t o[LACC];
+                z.limbs(o);
+                uint64_t *ac = s_acc + (size_t)slot * LACC * 32u + lane;
+                if (lane == 0) {
+                    while (atomicCAS(&s_lock[slot], 0u, 1u) != 0u) __nanosleep(32);
+                    __threadfence_block();
+                }
+                __syncwarp();
+                uint64_t v[LACC];
+#pragma unroll
+                for (int l = 0; l < LACC; ++l) v[l] = ac[l * 32];
+                cf_add<LACC, F64>(v, o);
+#pragma unroll
+                for (int l = 0; l < LACC; ++l) ac[l * 32] = v[l];
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    atomicExch(&s_lock[slot], 0u);
                 }
             }
         }
@@ -510,40 +661,48 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) k_tileconv(const TilePara
             ph ^= 1u;
         }
         if (d0.z & 1u) {
-            // ---- the unit is complete: write my tiles, count their non-zero entries per 32-column chunk ----
-            const uint32_t nch = P.wo >> 5;
+            // ---- the unit's last pair: when every warp has left it, write the tiles and clear the accumulators ----
+            asm volatile("bar.sync 1, %0;" ::"r"(NW * 32u) : "memory");
+            const uint32_t nch = P.wo >> 5, orows = d0.w & 0xffu;
+            const uint32_t rb = __ldg(P.row_base + d0.x);
+            const uint64_t okd = __ldg(P.okey + d0.x) * P.delta;
+            const uint32_t gin = gp_excl + (tr_lo + lane < tr_hi ? tl_row_tiles(d0.w, tr_lo + lane) : 0u); // inclusive
+            for (uint32_t slot = warp; slot < gtiles; slot += NW) {
+                const uint32_t trel = __popc(__ballot_sync(0xffffffffu, slot >= gin));
+                const uint32_t j = (tr_lo + trel) * (uint32_t)TL_R + r;
+                const uint32_t c0 = (slot - __shfl_sync(0xffffffffu, gp_excl, (int)trel)) * (uint32_t)TL_C, col = c0 + c;
+                uint64_t *ac = s_acc + (size_t)slot * LACC * 32u + lane;
+                uint64_t o[LACC];
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const uint32_t j = tj[t] + r;
-                if (tj[t] != 0x7fffffffu) {
-                    const bool inside = j < orows;
-                    const uint32_t row = __ldg(P.row_base + d0.x) + j, col = tc[t] + c;
-                    uint64_t o[LACC];
-                    z[t].limbs(o);
-                    bool nz = false;
-                    // a term beyond the truncation limit is not part of the product: it is stored as zero
-                    if (P.tr.on && (int32_t)(P.tr.w1 * j + P.tr.w0 * col) > (int32_t)d1.z) {
-#pragma unroll
-                        for (int l = 0; l < LACC; ++l) o[l] = 0;
-                    }
-                    if (inside) {
-                        uint64_t *om = P.omat + (size_t)row * LACC * P.wo + col;
-#pragma unroll
-                        for (int l = 0; l < LACC; ++l) {
-                            om[(size_t)l * P.wo] = o[l];
-                            nz |= o[l] != 0;
-                        }
-                        if constexpr (F64) nz = __longlong_as_double((long long)o[0]) != 0.0;
-                    }
-                    const uint32_t bal = __ballot_sync(0xffffffffu, nz);
-                    if (inside && c == 0u) {
-                        const uint32_t cnt = __popc((bal >> (8u * r)) & 0xffu);
-                        if (cnt) atomicAdd(P.or_cnt + (size_t)row * nch + (tc[t] >> 5), cnt);
-                        P.or_hi[row] = __ldg(P.okey + d0.x) * P.delta + j;
-                    }
+                for (int l = 0; l < LACC; ++l) {
+                    o[l] = ac[l * 32];
+                    ac[l * 32] = 0;
                 }
-                z[t].clear();
+                // a term beyond the truncation limit is not part of the product: it is stored as zero
+                if (P.tr.on && (int32_t)(P.tr.w1 * j + P.tr.w0 * col) > (int32_t)d1.z) {
+#pragma unroll
+                    for (int l = 0; l < LACC; ++l) o[l] = 0;
+                }
+                const bool inside = j < orows;
+                const uint32_t row = rb + j;
+                bool nz = false;
+                if (inside) {
+                    uint64_t *om = P.omat + (size_t)row * LACC * P.wo + col;
+#pragma unroll
+                    for (int l = 0; l < LACC; ++l) {
+                        om[(size_t)l * P.wo] = o[l];
+                        nz |= o[l] != 0;
+                    }
+                    if constexpr (F64) nz = __longlong_as_double((long long)o[0]) != 0.0;
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+                if (inside && c == 0u) {
+                    const uint32_t cnt = __popc((bal >> (8u * r)) & 0xffu);
+                    if (cnt) atomicAdd(P.or_cnt + (size_t)row * nch + (c0 >> 5), cnt);
+                    P.or_hi[row] = okd + j;
+                }
             }
+            asm volatile("bar.sync 1, %0;" ::"r"(NW * 32u) : "memory");
         }
     }
 }

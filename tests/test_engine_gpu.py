@@ -483,7 +483,7 @@ def test_tile_path_forced(engine):
             assert p.stats["kernel"] == 3
             p = check_exact(engine, x, x)
             assert p.stats["kernel"] == 3
-        for cfg in (1, 2, 3):
+        for cfg in (1, 2, 3, 4, 5, 6, 7):
             engine.set_option("plane_cfg", cfg)
             x = dense_poly2(rng, 3, 33, 21, 5, 0.8, 40, "u64")
             y = dense_poly2(rng, 3, 12, 40, 5, 0.8, 40, "u64")
