@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--also", default="S12,S16T,AUDI,AUDID,F20,D5,RECT", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
-    ap.add_argument("--mgpu-mode", default="push", choices=["all", "both", "exchange", "push", "owner"],
+    ap.add_argument("--mgpu-mode", default="all", choices=["all", "both", "exchange", "push", "owner"],
                     help="N>1: left-operand sharding + NCCL all-to-all + merge (the contract design), the same with "
                          "the exchange fused into the producer as P2P stores into NVLink peer windows (push), "
                          "owner-computes (zero exchange), or all (value = the fastest, all reported; modes measured later in "
@@ -338,7 +338,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
     # resident 64x64->160-bit carry-save MACs, 4 IMAD.WIDE + 2 IADD3.X each).  For fp64 coefficients the same figure
     # is reported against that integer rate only as an indication (DMUL + DADD issue at a similar rate).
     int_mac = None
-    if stats_last.get("kernel") in (1, 2):
+    if stats_last.get("kernel") in (1, 2, 3):
         if INT_MAC[0] is None:
             INT_MAC[0] = eng.microbench("int_mac")
         ach = per_launch_products / (kernel_mean * 1e-3)
@@ -357,7 +357,7 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": frac, "note": note,
                      "int_mac": int_mac,
                      "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, profiles/traffic.json)",
-                     "kernel": {1: "k_rowconv", 2: "k_planeconv"}.get(stats_last.get("kernel"), "k_mul"),
+                     "kernel": {1: "k_rowconv", 2: "k_planeconv", 3: "k_tileconv"}.get(stats_last.get("kernel"), "k_mul"),
                      "algorithmic_bytes_per_launch": B * per_launch_products, "algorithmic_bytes_per_product": B,
                      "peak_source": peak_src, "kernel_ms": kernel_mean,
                      "kernel_share_of_step": kernel_mean / ms,

@@ -56,7 +56,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1, opt_plane_cfg = 0,
+    int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1, opt_plane_cfg = 0, opt_tile_split = 1,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
     uint32_t last_rslices = 1;
@@ -1366,8 +1366,9 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     const uint32_t tiles_max = tl_ntiles(ro_raw, wo_raw, std::min(ro_raw + wo_raw - 1u, 255u));
     TileCfg cfg = tile_cfg(e, tiles_max);
     uint32_t slots = 0, nstage = 0;
+    size_t per_cta = 0;
     for (;; --cfg.ctas) {
-        const size_t per_cta = std::min<size_t>(e->smem_optin, (228u << 10) / cfg.ctas - 1024) - 512;
+        per_cta = std::min<size_t>(e->smem_optin, (228u << 10) / cfg.ctas - 1024) - 512;
         slots = std::max<uint32_t>(16u, tiles_max);
         while (slots > 16u && tl_acc_bytes(slots, accw) + 3u * (size_t)G.bytes > per_cta) --slots;
         const size_t accb = tl_acc_bytes(slots, accw);
@@ -1392,7 +1393,7 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
         CU_CHECK(e, cudaMemsetAsync(rowlen, 0, (size_t)p.nplanes * rcap * 4, s));
         const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
         k_tile_fill<<<grid, 256, 0, s>>>(keys, cfs, n, delta, p.tab, p.log2_cap, p.slot_id, p.mat, blob_words, P, rcap, rowlen, p.pinfo);
-        k_tile_finish<<<(p.nplanes + 127) / 128, 128, 0, s>>>(p.nplanes, rcap, rowlen, p.mat, blob_words, p.pinfo);
+        k_tile_finish<<<(p.nplanes + 7) / 8, 256, 0, s>>>(p.nplanes, rcap, rowlen, p.mat, blob_words, p.pinfo);
         e->launches += 2;
     };
     X.nplanes = hx;
@@ -1426,9 +1427,10 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     unsigned long long *owork = sc.alloc<unsigned long long>(npairs);
     uint32_t *pair_off = sc.alloc<uint32_t>(npairs + 2), *row_base = sc.alloc<uint32_t>(npairs + 2);
     uint2 *pairs = sc.alloc<uint2>(npairs);
-    uint32_t *totals = sc.alloc<uint32_t>(4);
-    const uint32_t groups_max = tl_ngroups(shape_max, slots);
-    uint32_t *units = sc.alloc<uint32_t>(std::max<uint64_t>(npairs * groups_max, 1));
+    uint32_t *totals = sc.alloc<uint32_t>(8);
+    const uint32_t groups_max = tl_ngroups(shape_max, 16u);
+    // a plane yields at most groups x chunks units, and chunks hold at least 4 pairs each: <= groups_max * (1 + pairs / 4)
+    uint2 *units = sc.alloc<uint2>(std::max<uint64_t>(npairs * groups_max + (npairs / 4 + 1) * groups_max, 1));
     const unsigned gp = (unsigned)std::min<uint64_t>((npairs + 255) / 256, 2048);
     k_tile_sym_insert<<<gp, 256, 0, s>>>(X.plane_key, X.pinfo, X.nplanes, Y.plane_key, Y.pinfo, Y.nplanes, rank, part_nranks, tab, l2, rec,
                                          dmax, work, okey, counters);
@@ -1444,16 +1446,27 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
         tr.limit = D.limit;
         tr.dhi = dhi;
     }
-    k_tile_units<<<1, 1024, 0, s>>>(owork, oshape, ocnt, okey, counters, slots, rank, owner ? nranks : 1u, tr, row_base, pair_off, units, totals);
+    {
+        uint32_t *qbase = sc.alloc<uint32_t>(npairs + 1);
+        const size_t sort_bytes = owner && nranks > 1 ? (size_t)TL_SORT_MAX * 20 : 0;
+        if (sort_bytes) CU_CHECK(e, cudaFuncSetAttribute(k_tile_units, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_bytes));
+        k_tile_units<<<1, 1024, sort_bytes, s>>>(owork, oshape, ocnt, okey, counters, slots, 4u * (uint32_t)e->sm_count * cfg.ctas, rank,
+                                                 owner ? nranks : 1u, e->opt_tile_split != 0 ? 1u : 0u, tr, qbase, row_base, pair_off, units, totals);
+    }
     k_plane_sym_fill<<<gp, 256, 0, s>>>(X.plane_key, X.nplanes, Y.plane_key, Y.nplanes, rank, part_nranks, tab, l2, rec, pair_off, fill, pairs);
     e->launches += 4;
-    uint32_t htot[3] = {0, 0, 0};
-    CU_CHECK(e, cudaMemcpyAsync(htot, totals, 12, cudaMemcpyDeviceToHost, s));
+    uint32_t htot[5] = {0, 0, 0, 0, 0};
+    CU_CHECK(e, cudaMemcpyAsync(htot, totals, 20, cudaMemcpyDeviceToHost, s));
     CU_CHECK(e, cudaStreamSynchronize(s));
     const uint32_t nunits = htot[0], nro = htot[1], nout = htot[2];
+    slots = htot[3]; // tiles per unit chosen on the device (<= the accumulator area); the ring takes what it leaves
+    nstage = (uint32_t)std::min<size_t>(TL_MAX_STAGES, (per_cta - tl_acc_bytes(slots, accw)) / G.bytes);
     // ---- the product ----------------------------------------------------------------------------------------
+    const bool split = htot[4] != 0;
+    const bool is_f64 = mode == CF_F64;
+    const uint32_t ls = split && !is_f64 ? 2u * (uint32_t)accw : (uint32_t)accw; // words per output entry
     const uint32_t wo = (wo_raw + 31u) & ~31u, nch = wo / 32u;
-    const size_t omat_words = (size_t)std::max<uint32_t>(nro, 1) * wo * accw;
+    const size_t omat_words = (size_t)std::max<uint32_t>(nro, 1) * wo * ls;
     uint64_t *omat = sc.alloc<uint64_t>(omat_words);
     uint64_t *or_hi = sc.alloc<uint64_t>(std::max<uint32_t>(nro, 1));
     const uint64_t nitems = (uint64_t)nro * nch;
@@ -1484,6 +1497,7 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     Pm.nstage = nstage;
     Pm.wo = wo;
     Pm.slots = slots;
+    Pm.split = split ? 1u : 0u;
     Pm.tr = tr;
     const unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(nunits, (uint32_t)e->sm_count * cfg.ctas));
     CU_CHECK(e, cudaEventRecord(e->ev[5], s));
@@ -1491,7 +1505,17 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     CU_CHECK(e, cudaEventRecord(e->ev[6], s));
     st.mul_launches += 1;
     uint64_t total = 0;
+    const unsigned ge = (unsigned)std::min<uint64_t>((nitems + 7) / 8, 8192);
     if (nro) {
+        if (split) {
+            switch (mode) {
+                case CF_I1A1: k_tile_norm<1, false><<<ge, 256, 0, s>>>(omat, (uint32_t)nitems, nch, wo, or_cnt); break;
+                case CF_I1A2: k_tile_norm<2, false><<<ge, 256, 0, s>>>(omat, (uint32_t)nitems, nch, wo, or_cnt); break;
+                case CF_I1A3: k_tile_norm<3, false><<<ge, 256, 0, s>>>(omat, (uint32_t)nitems, nch, wo, or_cnt); break;
+                default: k_tile_norm<1, true><<<ge, 256, 0, s>>>(omat, (uint32_t)nitems, nch, wo, or_cnt); break;
+            }
+            e->launches += 1;
+        }
         device_scan(e, sc, or_cnt, roffs, nitems);
         if (need_total) {
             uint32_t ht = 0;
@@ -1506,12 +1530,11 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     R.rk = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1));
     R.rc = sc.alloc_out<uint64_t>(std::max<uint64_t>(total, 1) * accw);
     if (total) {
-        const unsigned ge = (unsigned)std::min<uint64_t>((nitems + 7) / 8, 8192);
         switch (mode) {
-            case CF_I1A1: k_tile_expand<1, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
-            case CF_I1A2: k_tile_expand<2, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
-            case CF_I1A3: k_tile_expand<3, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
-            default: k_tile_expand<1, true><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, delta, R.rk, R.rc); break;
+            case CF_I1A1: k_tile_expand<1, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, ls, delta, R.rk, R.rc); break;
+            case CF_I1A2: k_tile_expand<2, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, ls, delta, R.rk, R.rc); break;
+            case CF_I1A3: k_tile_expand<3, false><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, ls, delta, R.rk, R.rc); break;
+            default: k_tile_expand<1, true><<<ge, 256, 0, s>>>(or_hi, omat, roffs, (uint32_t)nitems, nch, wo, ls, delta, R.rk, R.rc); break;
         }
         e->launches += 1;
         CU_CHECK(e, cudaGetLastError());
@@ -1521,8 +1544,9 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     R.m = nout;
     R.est_rows = nro;
     R.done = true;
-    st.table_slots = 32;
-    st.group_lanes = 32;
+    st.table_slots = slots;  // tiles per unit
+    st.group_lanes = nstage; // ring depth
+    st.reserved = nunits;
     return R;
 }
 
@@ -2632,6 +2656,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "threads") e->opt_threads = value;
     else if (n == "kernel") e->opt_kernel = value;
     else if (n == "plane_cfg") e->opt_plane_cfg = value;
+    else if (n == "tile_split") e->opt_tile_split = value;
     else if (n == "max_retries") e->opt_max_retries = value;
     else if (n == "fill_pct") e->opt_fill_pct = value;
     else {

@@ -176,28 +176,29 @@ __global__ void __launch_bounds__(256) k_tile_fill(const uint64_t *__restrict__ 
     }
 }
 
-// One thread per plane: rows, widest row, largest lo1 + lo0 (+1), and the header bytes of the blob.
+// One warp per plane: rows, widest row, largest lo1 + lo0 (+1), and the header bytes of the blob.
 //   pinfo[4 p + 0] rows, [1] terms, [2] widest row, [3] max(b + len[b])
-__global__ void __launch_bounds__(128) k_tile_finish(uint32_t nplanes, uint32_t rcap, const uint32_t *__restrict__ rowlen,
+__global__ void __launch_bounds__(256) k_tile_finish(uint32_t nplanes, uint32_t rcap, const uint32_t *__restrict__ rowlen,
                                                      uint64_t *__restrict__ mat, uint32_t blob_words, uint32_t *__restrict__ pinfo)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= nplanes) return;
     const uint32_t *len = rowlen + (size_t)p * rcap;
     uint8_t *hdr = reinterpret_cast<uint8_t *>(mat + (size_t)p * blob_words);
     uint32_t rows = 0, w = 0, d = 0;
-    for (uint32_t b = 0; b < rcap; ++b) {
-        const uint32_t l = len[b];
+    // row lengths: lanes over the rows (at most 64)
+    for (uint32_t b = lane; b < (uint32_t)TL_MAX_DIM; b += 32u) {
+        const uint32_t l = b < rcap ? len[b] : 0u;
         hdr[b] = (uint8_t)l;
         if (l) {
-            rows = b + 1u;
+            rows = max(rows, b + 1u);
             w = max(w, l);
             d = max(d, b + l);
         }
     }
-    for (uint32_t b = rcap; b < (uint32_t)TL_MAX_DIM; ++b) hdr[b] = 0;
-    // wm[k] = widest of the rows k-3 .. k (rows outside the plane count as empty), k = 0 .. rcap + 2
-    for (uint32_t k = 0; k < 72u; ++k) {
+    // wm[k] = widest of the rows k-3 .. k (rows outside the plane count as empty), k = 0 .. 71
+    for (uint32_t k = lane; k < 72u; k += 32u) {
         uint32_t m = 0;
         for (uint32_t q = 0; q < (uint32_t)TL_R; ++q) {
             const uint32_t b = k - q; // wraps for k < q
@@ -205,9 +206,14 @@ __global__ void __launch_bounds__(128) k_tile_finish(uint32_t nplanes, uint32_t 
         }
         hdr[64 + k] = (uint8_t)m;
     }
-    pinfo[4 * (size_t)p] = rows;
-    pinfo[4 * (size_t)p + 2] = w;
-    pinfo[4 * (size_t)p + 3] = d;
+    rows = __reduce_max_sync(0xffffffffu, rows);
+    w = __reduce_max_sync(0xffffffffu, w);
+    d = __reduce_max_sync(0xffffffffu, d);
+    if (lane == 0) {
+        pinfo[4 * (size_t)p] = rows;
+        pinfo[4 * (size_t)p + 2] = w;
+        pinfo[4 * (size_t)p + 3] = d;
+    }
 }
 
 // ---- symbolic plane product ----------------------------------------------------------------------------------------
@@ -294,29 +300,137 @@ __device__ __forceinline__ uint32_t tl_cut_shape(uint32_t shape, const TileTrunc
 // One CTA: pair_off = exclusive scan of the pairs per plane, row_base = exclusive scan of the rows per plane, and the
 // work units = (output plane, group of tile rows holding at most `tpu` tiles), heaviest planes first (counting sort by the bit length of the
 // work).  own_nranks > 1: only the units this rank owns (multi-GPU owner mode).  The shapes are cut by the truncation.
-//   units[u] = plane | group << 24;  totals[0] = units, [1] = output rows, [2] = output planes
+//   units[u] = {plane | group << 24, chunk | chunks << 16};  totals[0] = units, [1] = output rows, [2] = output planes,
+//   [3] = tiles per unit, [4] = 1 if some plane is cut into chunks of pairs (split mode)
+constexpr uint32_t TL_SORT_MAX = 4096; // output planes the owner-mode assignment sorts (dynamic shared memory: 20 B each)
+
+// rank of position q of the canonical unit sequence: 0 1 .. n-1 n-1 .. 1 0 0 1 ..
+__device__ __forceinline__ uint32_t tl_snake(uint32_t q, uint32_t n)
+{
+    const uint32_t m = q % (2u * n);
+    return m < n ? m : 2u * n - 1u - m;
+}
+
 __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *__restrict__ owork, uint32_t *__restrict__ oshape,
                                                      const uint32_t *__restrict__ ocnt, const uint64_t *__restrict__ okey,
-                                                     const uint32_t *__restrict__ counters, uint32_t tpu, uint32_t own_rank,
-                                                     uint32_t own_nranks, TileTrunc tr, uint32_t *__restrict__ row_base,
-                                                     uint32_t *__restrict__ pair_off, uint32_t *__restrict__ units,
+                                                     const uint32_t *__restrict__ counters, uint32_t tpu_max, uint32_t want_units,
+                                                     uint32_t own_rank, uint32_t own_nranks, uint32_t allow_split, TileTrunc tr,
+                                                     uint32_t *__restrict__ qbase, uint32_t *__restrict__ row_base,
+                                                     uint32_t *__restrict__ pair_off, uint2 *__restrict__ units,
                                                      uint32_t *__restrict__ totals)
 {
-    __shared__ uint32_t s_cls[65], s_tot, s_carry;
+    extern __shared__ __align__(16) unsigned char sort_raw[];
+    __shared__ uint32_t s_cls[65], s_tot, s_carry, s_cand[4];
     const uint32_t tid = threadIdx.x;
     const uint32_t nout = counters[0];
-    auto owned = [&](uint32_t o, uint32_t b) { return own_nranks <= 1u || (plane_owner(okey[o], own_nranks) + b) % own_nranks == own_rank; };
     if (tid < 65) s_cls[tid] = 0;
     if (tid == 0) s_carry = 0;
+    if (tid < 4) s_cand[tid] = 0;
     for (uint32_t o = tid; o < nout; o += blockDim.x) oshape[o] = tl_cut_shape(oshape[o], tr, tl_budget(tr, o));
     __syncthreads();
+    // Tiles per unit: as many as the accumulator area holds (every pair of a plane is then staged once), unless that
+    // leaves fewer than `want_units` units for the resident CTAs of this GPU -- a small product, or one rank's share of
+    // a product spread over several GPUs: then the planes are cut into groups of a half, a quarter, an eighth of that.
+    {
+        uint32_t all[4] = {0, 0, 0, 0};
+        for (uint32_t o = tid; o < nout; o += blockDim.x) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) all[k] += tl_ngroups(oshape[o], max(16u, tpu_max >> k));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (all[k]) atomicAdd(&s_cand[k], all[k]);
+    }
+    __syncthreads();
+    uint32_t tpu = tpu_max;
+    for (int k = 0; k < 4 && !allow_split; ++k) { // with pair chunks (below) the planes need not be cut into tile groups
+        tpu = max(16u, tpu_max >> k);
+        if (s_cand[k] >= want_units * max(own_nranks, 1u) || tpu == 16u) break;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        totals[3] = tpu;
+        s_cand[0] = 0;
+    }
     auto groups = [&](uint32_t o) { return tl_ngroups(oshape[o], tpu); };
+    // Multi-GPU owner mode: who forms unit (o, b).  Every rank runs the same symbolic product but numbers the planes in
+    // the order its own atomics resolved, so the rule must be a function of the plane KEYS and works alone: the planes
+    // are sorted by (work descending, key), and dealt to the ranks back and forth along that order
+    // (a longest-processing-time deal of whole planes: every output term is complete on one rank).  Beyond TL_SORT_MAX
+    // planes a hash of the key decides (the law of large numbers does the balancing there).
+    const bool sorted = own_nranks > 1u && nout <= TL_SORT_MAX;
+    if (own_nranks > 1u) {
+        if (sorted) {
+            uint32_t n2 = 1;
+            while (n2 < nout) n2 <<= 1;
+            uint64_t *ka = reinterpret_cast<uint64_t *>(sort_raw), *kb = ka + n2;
+            uint32_t *id = reinterpret_cast<uint32_t *>(kb + n2);
+            for (uint32_t i = tid; i < n2; i += blockDim.x) {
+                ka[i] = i < nout ? ~(uint64_t)owork[i] : ~0ull;
+                kb[i] = i < nout ? okey[i] : ~0ull;
+                id[i] = i < nout ? i : 0xffffffffu;
+            }
+            __syncthreads();
+            for (uint32_t k = 2; k <= n2; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = tid; i < n2; i += blockDim.x) {
+                        const uint32_t l = i ^ j;
+                        if (l > i) {
+                            const bool up = (i & k) == 0u;
+                            const bool gt = ka[i] > ka[l] || (ka[i] == ka[l] && kb[i] > kb[l]);
+                            if (gt == up) {
+                                const uint64_t ta = ka[i], tb = kb[i];
+                                const uint32_t ti = id[i];
+                                ka[i] = ka[l];
+                                kb[i] = kb[l];
+                                id[i] = id[l];
+                                ka[l] = ta;
+                                kb[l] = tb;
+                                id[l] = ti;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (uint32_t i = tid; i < n2; i += blockDim.x)
+                if (id[i] != 0xffffffffu) qbase[id[i]] = i; // position in the canonical order
+        } else {
+            for (uint32_t o = tid; o < nout; o += blockDim.x) qbase[o] = plane_owner(okey[o], own_nranks);
+        }
+        __syncthreads();
+    }
+    auto owned = [&](uint32_t o) {
+        if (own_nranks <= 1u) return true;
+        return (sorted ? tl_snake(qbase[o], own_nranks) : qbase[o]) == own_rank;
+    };
+    // Pair chunks: a unit stages the pairs of its plane one after the other (a few us each), so a plane with hundreds
+    // of pairs would occupy one CTA for milliseconds while the others run dry.  Heavy planes are cut into K chunks of
+    // pairs that different CTAs accumulate independently and add to the output rows with 64-bit atomics on 32-bit
+    // digits (k_tileconv, split mode); the target is want_units units of equal work on this GPU.
+    __shared__ unsigned long long s_work;
+    if (tid == 0) s_work = 0;
+    __syncthreads();
+    {
+        unsigned long long w = 0;
+        for (uint32_t o = tid; o < nout; o += blockDim.x)
+            if (owned(o)) w += owork[o];
+        if (w) atomicAdd(&s_work, w);
+    }
+    __syncthreads();
+    const unsigned long long w_unit = s_work / max(want_units, 1u) + 1ull;
+    auto chunks = [&](uint32_t o, uint32_t nb) {
+        if (!allow_split || nb == 0u) return 1u;
+        const unsigned long long k = (owork[o] / nb + w_unit / 2ull) / w_unit;
+        const uint32_t kmax = min(64u, max(1u, ocnt[o] / 4u));
+        return (uint32_t)min((unsigned long long)kmax, max(1ull, k));
+    };
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
+        if (!owned(o)) continue;
         const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
-        const uint32_t nb = groups(o);
-        uint32_t mine = 0;
-        for (uint32_t b = 0; b < nb; ++b) mine += owned(o, b) ? 1u : 0u;
-        if (mine) atomicAdd(&s_cls[64u - c], mine); // class 0 = heaviest
+        const uint32_t nb = groups(o), K = chunks(o, nb);
+        if (nb) atomicAdd(&s_cls[64u - c], nb * K); // class 0 = heaviest
+        if (K > 1u) s_cand[0] = 1u;                  // (re-used as the split flag: same value from every writer)
     }
     __syncthreads();
     if (tid == 0) {
@@ -328,17 +442,17 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
         }
         totals[0] = acc;
         totals[2] = nout;
+        totals[4] = s_cand[0];
     }
     __syncthreads();
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
+        if (!owned(o)) continue;
         const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
-        const uint32_t nb = groups(o);
-        uint32_t mine = 0;
-        for (uint32_t b = 0; b < nb; ++b) mine += owned(o, b) ? 1u : 0u;
-        if (mine == 0u) continue;
-        uint32_t at = atomicAdd(&s_cls[64u - c], mine);
+        const uint32_t nb = groups(o), K = chunks(o, nb);
+        if (nb == 0u) continue;
+        uint32_t at = atomicAdd(&s_cls[64u - c], nb * K);
         for (uint32_t b = 0; b < nb; ++b)
-            if (owned(o, b)) units[at++] = o | (b << 24);
+            for (uint32_t k = 0; k < K; ++k, ++at) units[at] = make_uint2(o | (b << 24), k | (K << 16));
     }
     for (int which = 0; which < 2; ++which) {
         uint32_t *out = which == 0 ? row_base : pair_off;
@@ -421,15 +535,16 @@ struct TileParams {
     const uint64_t *okey;          // [nout] output plane keys (hi2 sums)
     const uint32_t *oshape;        // [nout] tl_shape(), already cut by the truncation
     const uint32_t *row_base;      // [nout + 1]
-    const uint32_t *units;         // plane | group << 24, heaviest first
+    const uint2 *units;            // {plane | group << 24, chunk | chunks << 16}, heaviest first
     uint32_t nunits;
     uint32_t *cursor;
     uint64_t delta;
     uint64_t *or_hi;  // [rows] row key = okey * delta + j
-    uint64_t *omat;   // [rows][LACC][wo]
+    uint64_t *omat;   // [rows][LACC][wo]  (split mode: [rows][2 LACC][wo] digits; fp64: [rows][1][wo])
     uint32_t *or_cnt; // [rows][wo / 32] non-zero entries per 32-column chunk
     uint32_t P, rcap, blob_words, nstage, wo;
     uint32_t slots; // accumulator tiles in shared memory = most tiles of a unit
+    uint32_t split; // 1: units add 32-bit digits to omat[rows][2 LACC][wo] with atomics (k_tile_norm finishes the rows)
     TileTrunc tr;
 };
 
@@ -485,11 +600,13 @@ __global__ void __launch_bounds__(BT, MINB) k_tileconv(const TileParams P)
             uint32_t o = 0, g = 0, p0 = 0, p1 = 1, shape = 0, tr_lo = 0, tr_hi = 0;
             int32_t budget = 0;
             if (!quit) {
-                const uint32_t ud = __ldg(P.units + u);
-                o = ud & 0x00ffffffu;
-                g = ud >> 24;
-                p0 = __ldg(P.pair_off + o);
-                p1 = __ldg(P.pair_off + o + 1);
+                const uint2 ud = __ldg(P.units + u);
+                o = ud.x & 0x00ffffffu;
+                g = ud.x >> 24;
+                const uint32_t q0 = __ldg(P.pair_off + o), cnt = __ldg(P.pair_off + o + 1) - q0;
+                const uint32_t ch = ud.y & 0xffffu, K = ud.y >> 16;
+                p0 = q0 + (uint32_t)(((uint64_t)cnt * ch) / K);
+                p1 = q0 + (uint32_t)(((uint64_t)cnt * (ch + 1u)) / K);
                 shape = __ldg(P.oshape + o);
                 tl_group(shape, P.slots, g, tr_lo, tr_hi);
                 budget = tl_budget(P.tr, o);
@@ -686,7 +803,21 @@ __global__ void __launch_bounds__(BT, MINB) k_tileconv(const TileParams P)
                 const bool inside = j < orows;
                 const uint32_t row = rb + j;
                 bool nz = false;
-                if (inside) {
+                if (inside && P.split) {
+                    // another unit may hold the other pairs of this plane: add, 32 bits per 64-bit word
+                    if constexpr (F64) {
+                        if (__longlong_as_double((long long)o[0]) != 0.0)
+                            atomicAdd(reinterpret_cast<double *>(P.omat + (size_t)row * P.wo + col), __longlong_as_double((long long)o[0]));
+                    } else {
+                        unsigned long long *om = reinterpret_cast<unsigned long long *>(P.omat + (size_t)row * (2 * LACC) * P.wo + col);
+#pragma unroll
+                        for (int l = 0; l < LACC; ++l) {
+                            if (o[l] & 0xffffffffull) atomicAdd(om + (size_t)(2 * l) * P.wo, o[l] & 0xffffffffull);
+                            if (o[l] >> 32) atomicAdd(om + (size_t)(2 * l + 1) * P.wo, o[l] >> 32);
+                        }
+                    }
+                    if (c == 0u) P.or_hi[row] = okd + j;
+                } else if (inside) {
                     uint64_t *om = P.omat + (size_t)row * LACC * P.wo + col;
 #pragma unroll
                     for (int l = 0; l < LACC; ++l) {
@@ -696,7 +827,7 @@ __global__ void __launch_bounds__(BT, MINB) k_tileconv(const TileParams P)
                     if constexpr (F64) nz = __longlong_as_double((long long)o[0]) != 0.0;
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, nz);
-                if (inside && c == 0u) {
+                if (inside && c == 0u && !P.split) {
                     const uint32_t cnt = __popc((bal >> (8u * r)) & 0xffu);
                     if (cnt) atomicAdd(P.or_cnt + (size_t)row * nch + (c0 >> 5), cnt);
                     P.or_hi[row] = okd + j;
@@ -707,12 +838,53 @@ __global__ void __launch_bounds__(BT, MINB) k_tileconv(const TileParams P)
     }
 }
 
+// Split mode: the 32-bit digits of every output entry -> limbs (in place, words 0 .. LACC-1 of the entry), and the
+// non-zero count of every (row, 32-column chunk).  Two's-complement contributions add up modulo 2^(64 LACC).
+template <int LACC, bool F64>
+__global__ void __launch_bounds__(256) k_tile_norm(uint64_t *__restrict__ omat, uint32_t nitems, uint32_t nch, uint32_t wo,
+                                                   uint32_t *__restrict__ or_cnt)
+{
+    constexpr int LS = F64 ? 1 : 2 * LACC;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb) {
+        const uint32_t row = it / nch, col = (it - row * nch) * 32u + lane;
+        uint64_t *o = omat + (size_t)row * LS * wo + col;
+        bool nz = false;
+        if constexpr (F64) {
+            nz = __longlong_as_double((long long)o[0]) != 0.0;
+        } else {
+            uint64_t dg[LS], carry = 0, any = 0;
+#pragma unroll
+            for (int d = 0; d < LS; ++d) {
+                dg[d] = o[(size_t)d * wo];
+                any |= dg[d];
+            }
+            if (any) {
+                uint64_t v[LACC];
+#pragma unroll
+                for (int l = 0; l < LACC; ++l) {
+                    const uint64_t t0 = dg[2 * l] + carry;                // < 2^64: digits are sums of < 2^32 values
+                    const uint64_t t1 = dg[2 * l + 1] + (t0 >> 32);
+                    v[l] = (t0 & 0xffffffffull) | (t1 << 32);
+                    carry = t1 >> 32;
+                    nz |= v[l] != 0;
+                }
+#pragma unroll
+                for (int l = 0; l < LACC; ++l) o[(size_t)l * wo] = v[l];
+            }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) or_cnt[it] = __popc(b);
+    }
+}
+
 // Expand the output rows into terms: key = hi * delta + lo, zero coefficients dropped (terms beyond a truncation limit
-// were stored as zeros); off[row * nch + chunk] is the exclusive scan of the per-chunk counts.
+// were stored as zeros); off[row * nch + chunk] is the exclusive scan of the per-chunk counts; `ls` = words per entry.
 template <int LACC, bool F64>
 __global__ void __launch_bounds__(256) k_tile_expand(const uint64_t *__restrict__ or_hi, const uint64_t *__restrict__ omat,
                                                      const uint32_t *__restrict__ off, uint32_t nitems, uint32_t nch, uint32_t wo,
-                                                     uint64_t delta, uint64_t *__restrict__ okeys,
+                                                     uint32_t ls, uint64_t delta, uint64_t *__restrict__ okeys,
                                                      uint64_t *__restrict__ ocfs)
 {
     const uint32_t lane = threadIdx.x & 31u;
@@ -721,7 +893,7 @@ __global__ void __launch_bounds__(256) k_tile_expand(const uint64_t *__restrict_
         const uint32_t base = off[it], cnt = off[it + 1] - base;
         if (cnt == 0u) continue;
         const uint32_t row = it / nch, col = (it - row * nch) * 32u + lane;
-        const uint64_t *o = omat + (size_t)row * LACC * wo + col;
+        const uint64_t *o = omat + (size_t)row * ls * wo + col;
         uint64_t v[LACC];
         bool nz = false;
 #pragma unroll

@@ -75,9 +75,13 @@ def owner_mul(engine: Engine, vx, vy, limit=None, idx=None, group=None):
                 if "segment table" not in str(ex):
                     raise
                 failed = 1
-            flag = torch.tensor([failed], dtype=torch.int64, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-            if int(flag.item()) == 0:
+            # The dense kernels have no table to overflow, and every rank takes the same kernel decision (it depends on
+            # the statistics of the FULL operands): no verdict to agree on, no collective at all on that path.
+            dense = failed == 0 and part.stats["kernel"] in (1, 2, 3)
+            if not dense:
+                flag = torch.tensor([failed], dtype=torch.int64, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if dense or int(flag.item()) == 0:
                 return part, {"mode": "owner", "partial_stats": part.stats, "attempts": attempt + 1,
                               "sent_rows": 0, "recv_rows": 0, "bytes_sent": 0, "partial_terms": part.nterms,
                               "nsegs": part.stats["nsegs"]}
