@@ -46,9 +46,9 @@ def parse_args():
     ap.add_argument("--mgpu-mode", default="all", choices=["all", "both", "exchange", "push", "owner"],
                     help="N>1: left-operand sharding + NCCL all-to-all + merge (the contract design), the same with "
                          "the exchange fused into the producer as P2P stores into NVLink peer windows (push), "
-                         "owner-computes (zero exchange), or all (value = the fastest, all reported; modes measured later in "
-                         "one process run a few percent slower, so the default measures the push design alone and "
-                         "falls back to exchange when CUDA IPC is unavailable)")
+                         "owner-computes (zero exchange), or all (default: value = the fastest, all reported; owner-computes "
+                         "is measured first -- modes measured later in one process run a few percent slower; push is "
+                         "dropped when CUDA IPC is unavailable)")
     return ap.parse_args()
 
 
@@ -510,7 +510,7 @@ def main():
                           "config": {"workload": "RECT", "description": "rectangular_01: 70 chained 13-term products, fp64, device-resident chain", **r}}))
         eng.close()
         return 0
-    modes = ["exchange"] if world == 1 else {"all": ["exchange", "push", "owner"], "both": ["exchange", "owner"]}.get(
+    modes = ["exchange"] if world == 1 else {"all": ["owner", "push", "exchange"], "both": ["owner", "exchange"]}.get(
         args.mgpu_mode, [args.mgpu_mode])
     if world > 1 and "push" in modes:
         from obake_b200 import dist as obd

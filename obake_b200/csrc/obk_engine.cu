@@ -336,7 +336,7 @@ void validate_view(obk_engine *e, const obk_poly_view *v, const char *name)
         throw obk_fail{OBK_ERR_UNSUPPORTED};
     }
     if (v->cf_kind != OBK_CF_INT && v->cf_kind != OBK_CF_F64) bad("cf_kind");
-    if (v->cf_kind == OBK_CF_INT && (v->cf_limbs < 1 || v->cf_limbs > 3)) bad("cf_limbs must be in [1,3]");
+    if (v->cf_kind == OBK_CF_INT && (v->cf_limbs < 1 || v->cf_limbs > (uint32_t)MAX_CF_LIMBS)) bad("cf_limbs must be in [1,5]");
     if (v->mem != OBK_MEM_HOST && v->mem != OBK_MEM_DEVICE) bad("mem");
     if (v->nterms && (!v->keys || !v->cfs)) bad("null keys/cfs");
     if (v->key_bits != 0 && v->key_bits != 32 && v->key_bits != 64) bad("key_bits must be 32 or 64");
@@ -448,7 +448,7 @@ void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, un
 #define OBK_CASE(M)                                                                                                    \
     case M: {                                                                                                          \
         if (P.npass > 1) {                                                                                             \
-            if constexpr (M == CF_ADD1 || M == CF_ADD2 || M == CF_ADD3 || M == CF_ADDF) {                              \
+            if constexpr (M == CF_ADD1 || M == CF_ADD2 || M == CF_ADD3 || M == CF_ADDF || M == CF_ADD5) {                              \
                 e->err = "internal: two-sided pass in merge mode";                                                     \
                 throw obk_fail{OBK_ERR_INVALID_ARG};                                                                   \
             } else {                                                                                                   \
@@ -474,6 +474,9 @@ void launch_mul_w(obk_engine *e, int mode, const MulParams &P, unsigned grid, un
         OBK_CASE(CF_ADD2)
         OBK_CASE(CF_ADD3)
         OBK_CASE(CF_ADDF)
+        OBK_CASE(CF_I2A5)
+        OBK_CASE(CF_I3A5)
+        OBK_CASE(CF_ADD5)
         default:
             e->err = "internal: bad coefficient mode";
             throw obk_fail{OBK_ERR_INVALID_ARG};
@@ -523,6 +526,7 @@ int acc_words_of(int mode)
         case CF_SYM: return 0;
         case CF_I1A1: case CF_F64: case CF_ADD1: case CF_ADDF: return 1;
         case CF_I1A2: case CF_ADD2: return 2;
+        case CF_I2A5: case CF_I3A5: case CF_ADD5: return 5;
         default: return 3;
     }
 }
@@ -1874,14 +1878,14 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             if (x == y) hs[1] = hs[0];
             st.d2h_bytes += sizeof(StatsOut) * 2;
             if (!f64) {
-                // Input limbs are whatever the VALUES need (1 or 2), not what the caller's arrays carry: a product
-                // left in HBM with a 3-limb accumulator is a valid operand of the next product as long as its
-                // coefficients fit two limbs, and operands of different widths are brought to a common one.
+                // Input limbs are whatever the VALUES need (1, 2 or 3), not what the caller's arrays carry: a product
+                // left in HBM with a wide accumulator is a valid operand of the next product as long as its
+                // coefficients fit three limbs, and operands of different widths are brought to a common one.
                 const unsigned bits_in = std::max(hs[0].cfbits, hs[1].cfbits) + 1;
                 const int need = (int)std::max(1u, (bits_in + 63) / 64);
-                if (need > 2) {
-                    e->err = "3-limb input coefficients are not supported (inputs are 1 or 2 limbs): the operands need "
-                             + std::to_string(bits_in) + " bits";
+                if (need > 3) {
+                    e->err = "input coefficients beyond 3 limbs are not supported: the operands need " + std::to_string(bits_in)
+                             + " bits";
                     return OBK_ERR_UNSUPPORTED;
                 }
                 auto renorm = [&](const uint64_t *&dc, uint64_t n, int cw) {
@@ -1981,8 +1985,8 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             } else {
                 const unsigned bits = hs[0].cfbits + hs[1].cfbits + bitlen64(std::min(nx_full, ny)) + 1;
                 const unsigned lacc = (bits + 63) / 64;
-                if (lacc > 3) {
-                    e->err = "coefficient overflow beyond 3 limbs: the exact product needs " + std::to_string(bits)
+                if (lacc > (unsigned)MAX_CF_LIMBS) {
+                    e->err = "coefficient overflow beyond 5 limbs: the exact product needs " + std::to_string(bits)
                              + " bits";
                     return OBK_ERR_CF_OVERFLOW;
                 }
@@ -1994,11 +1998,11 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                     mode = lacc == 1 ? CF_I1A1 : (lacc == 2 ? CF_I1A2 : CF_I1A3);
                     st.acc_limbs = lacc;
                 } else if (CWx == 2) {
-                    mode = CF_I2A3;
-                    st.acc_limbs = 3;
+                    mode = lacc <= 3 ? CF_I2A3 : CF_I2A5;
+                    st.acc_limbs = lacc <= 3 ? 3 : 5;
                 } else {
-                    e->err = "3-limb input coefficients are not supported (inputs are 1 or 2 limbs)";
-                    return OBK_ERR_UNSUPPORTED;
+                    mode = CF_I3A5;
+                    st.acc_limbs = 5;
                 }
             }
             if (snx == 0) {
@@ -2143,7 +2147,11 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
             }
         } else {
             // merge mode: sum acc-limb coefficients by key
-            mode = f64 ? CF_ADDF : (y->cf_limbs == 1 ? CF_ADD1 : (y->cf_limbs == 2 ? CF_ADD2 : CF_ADD3));
+            mode = f64 ? CF_ADDF : (y->cf_limbs == 1 ? CF_ADD1 : (y->cf_limbs == 2 ? CF_ADD2 : (y->cf_limbs == 3 ? CF_ADD3 : CF_ADD5)));
+            if (!f64 && y->cf_limbs == 4) {
+                e->err = "internal: merge input must carry 1, 2, 3 or 5 limbs";
+                return OBK_ERR_INVALID_ARG;
+            }
             st.acc_limbs = f64 ? 1 : y->cf_limbs;
             tot_mults = ny;
         }
@@ -2838,8 +2846,8 @@ obk_status obk_peer_merge(obk_engine *e, const obk_peer_windows *w, const obk_po
         CU_CHECK(e, cudaStreamSynchronize(e->stream));
         const bool f64 = like->cf_kind == OBK_CF_F64;
         const uint32_t L = f64 ? 1u : acc_limbs;
-        if (L < 1 || L > 3) {
-            e->err = "acc_limbs must be in [1,3]";
+        if (L < 1 || L > (uint32_t)MAX_CF_LIMBS || L == 4) {
+            e->err = "acc_limbs must be 1, 2, 3 or 5";
             return OBK_ERR_INVALID_ARG;
         }
         const uint64_t cap = (w->window_bytes - PUSH_HEADER) / ((uint64_t)8 * (like->key_words + L));
@@ -2931,8 +2939,9 @@ obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly
                 CU_CHECK(e, cudaStreamSynchronize(s));
                 const unsigned bits = std::max(hs[0].cfbits, hs[1].cfbits) + 2;
                 lout = (int)((bits + 63) / 64);
-                if (lout > 3) {
-                    e->err = "coefficient overflow beyond 3 limbs: the exact sum needs " + std::to_string(bits) + " bits";
+                if (lout == 4) lout = 5; // the merge kernel carries 1, 2, 3 or 5 limbs
+                if (lout > MAX_CF_LIMBS) {
+                    e->err = "coefficient overflow beyond 5 limbs: the exact sum needs " + std::to_string(bits) + " bits";
                     return OBK_ERR_CF_OVERFLOW;
                 }
             }

@@ -467,12 +467,12 @@ __global__ void __launch_bounds__(256) k_widen_cfs(const uint64_t *__restrict__ 
             out[i] = negate ? in[i] ^ 0x8000000000000000ULL : in[i];
             continue;
         }
-        uint64_t v[3];
+        uint64_t v[5]; // MAX_CF_LIMBS
         const uint64_t ext = (uint64_t)((long long)in[i * lin + lin - 1] >> 63);
-        for (int l = 0; l < 3; ++l) v[l] = l < lin ? in[i * lin + l] : ext;
+        for (int l = 0; l < 5; ++l) v[l] = l < lin ? in[i * lin + l] : ext;
         if (negate) {
             uint64_t c = 1;
-            for (int l = 0; l < 3; ++l) {
+            for (int l = 0; l < 5; ++l) {
                 const uint64_t t = ~v[l] + c;
                 c = (c && t == 0) ? 1 : 0;
                 v[l] = t;
@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(256) k_count_mults(const int64_t *__restrict__
 // Coefficient arithmetic (polynomial.hpp:1368-1384; fma3.hpp:84-88 mppp::addmul; :65-72 double)
 // ------------------------------------------------------------------------------------------------
 enum CfMode { CF_SYM = 0, CF_I1A1 = 1, CF_I1A2 = 2, CF_I1A3 = 3, CF_F64 = 4, CF_I2A3 = 5, CF_ADD1 = 6, CF_ADD2 = 7,
-              CF_ADD3 = 8, CF_ADDF = 9 };
+              CF_ADD3 = 8, CF_ADDF = 9, CF_I2A5 = 10, CF_I3A5 = 11, CF_ADD5 = 12 };
+constexpr int MAX_CF_LIMBS = 5; // widest coefficient the engine carries (320 bits): inputs up to 3 limbs, sums up to 5
 
 template <int MODE>
 struct CfTraits;
@@ -600,6 +601,11 @@ OBK_TRAITS(CF_ADD1, 1, 1, false, false, true)
 OBK_TRAITS(CF_ADD2, 2, 2, false, false, true)
 OBK_TRAITS(CF_ADD3, 3, 3, false, false, true)
 OBK_TRAITS(CF_ADDF, 1, 1, true, false, true)
+// coefficient growth along chains of products (the reference's integer<N> grows without bound, fma3.hpp:84-88): two- and
+// three-limb operands with a five-limb accumulator
+OBK_TRAITS(CF_I2A5, 2, 5, false, false, false)
+OBK_TRAITS(CF_I3A5, 3, 5, false, false, false)
+OBK_TRAITS(CF_ADD5, 5, 5, false, false, true)
 #undef OBK_TRAITS
 
 // p (LACC limbs, two's complement) = a * b for LIN-limb two's-complement inputs.
@@ -623,7 +629,7 @@ __device__ __forceinline__ void cf_mul(const uint64_t *a, const uint64_t *b, uin
             p[1] = (uint64_t)hi;
             if constexpr (LACC >= 3) p[2] = (uint64_t)(hi >> 63);
         }
-    } else {
+    } else if constexpr (LIN == 2 && LACC <= 3) {
         // 128 x 128 -> low 192 bits of the signed product (the a-priori bound guarantees it fits).
         // Signed product mod 2^192 = unsigned schoolbook on the sign-extended operands, truncated.
         const uint64_t a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
@@ -641,6 +647,29 @@ __device__ __forceinline__ void cf_mul(const uint64_t *a, const uint64_t *b, uin
         p[0] = r0;
         p[1] = r1;
         if constexpr (LACC >= 3) p[2] = r2;
+    } else {
+        // General case: the signed product modulo 2^(64 LACC) is the unsigned schoolbook product of the operands
+        // sign-extended to LACC limbs, truncated.  Column k sums a_i b_(k-i) into a three-word carry-save window.
+        uint64_t ax[LACC], bx[LACC];
+        const uint64_t ea = (uint64_t)((long long)a[LIN - 1] >> 63), eb = (uint64_t)((long long)b[LIN - 1] >> 63);
+#pragma unroll
+        for (int l = 0; l < LACC; ++l) {
+            ax[l] = l < LIN ? a[l] : ea;
+            bx[l] = l < LIN ? b[l] : eb;
+        }
+        uint64_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int k = 0; k < LACC; ++k) {
+#pragma unroll
+            for (int i = 0; i <= k; ++i) {
+                const uint64_t lo = ax[i] * bx[k - i], hi = __umul64hi(ax[i], bx[k - i]);
+                asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, 0;" : "+l"(c0), "+l"(c1), "+l"(c2) : "l"(lo), "l"(hi));
+            }
+            p[k] = c0;
+            c0 = c1;
+            c1 = c2;
+            c2 = 0;
+        }
     }
 }
 
@@ -651,10 +680,20 @@ __device__ __forceinline__ void limbs_add(uint64_t *acc, const uint64_t *p)
         acc[0] += p[0];
     } else if constexpr (LACC == 2) {
         asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(acc[0]), "+l"(acc[1]) : "l"(p[0]), "l"(p[1]));
-    } else {
+    } else if constexpr (LACC == 3) {
         asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u64 %2, %2, %5;"
             : "+l"(acc[0]), "+l"(acc[1]), "+l"(acc[2])
             : "l"(p[0]), "l"(p[1]), "l"(p[2]));
+    } else {
+        uint64_t carry = 0;
+#pragma unroll
+        for (int l = 0; l < LACC; ++l) {
+            const uint64_t t = acc[l] + p[l];
+            const uint64_t c1 = t < p[l];
+            const uint64_t u = t + carry;
+            carry = c1 | (uint64_t)(u < t);
+            acc[l] = u;
+        }
     }
 }
 

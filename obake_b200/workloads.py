@@ -210,8 +210,15 @@ def random_poly(rng: np.random.Generator, nterms: int, nvars: int, max_expo: int
                 if f64:
                     seen[t] = float(rng.standard_normal())
                 else:
-                    mag = int(rng.integers(1, 1 << min(cf_bits, 62))) if cf_bits <= 62 else \
-                        int(rng.integers(1, 1 << 62)) << (cf_bits - 62) | int(rng.integers(0, 1 << (cf_bits - 62)))
+                    if cf_bits <= 62:
+                        mag = int(rng.integers(1, 1 << cf_bits))
+                    else:
+                        # 62 random leading bits, then the rest in chunks of at most 62 bits
+                        mag, left = int(rng.integers(1, 1 << 62)), cf_bits - 62
+                        while left > 0:
+                            c = min(left, 62)
+                            mag = mag << c | int(rng.integers(0, 1 << c))
+                            left -= c
                     sgn = -1 if (signed_cfs and rng.integers(0, 2)) else 1
                     seen[t] = sgn * mag
                 if len(seen) == nterms:

@@ -249,7 +249,7 @@ typedef struct {
     uint32_t nvars;
     uint32_t psize;    // 0: packed_monomial
     uint32_t cf_kind;  // 0: integer limbs, 1: f64
-    uint32_t cf_limbs; // L_in (1 or 2) for integer
+    uint32_t cf_limbs; // L_in (1, 2 or 3) for integer
     const uint64_t *keys;
     const void *cfs;
 } orc_poly;
@@ -454,20 +454,32 @@ inline void mul_to_limbs(const uint64_t *a, const uint64_t *b, uint64_t *p /* LA
         const uint64_t ext = pr < 0 ? ~(uint64_t)0 : 0;
         for (int i = 2; i < LACC; ++i) p[i] = ext;
     } else {
-        // 128 x 128 -> 256 signed, via magnitudes
-        i128 va = (i128)(((u128)a[1] << 64) | a[0]), vb = (i128)(((u128)b[1] << 64) | b[0]);
-        const bool neg = (va < 0) != (vb < 0);
-        u128 ma = va < 0 ? (u128)0 - (u128)va : (u128)va, mb = vb < 0 ? (u128)0 - (u128)vb : (u128)vb;
-        uint64_t x[2] = {(uint64_t)ma, (uint64_t)(ma >> 64)}, y[2] = {(uint64_t)mb, (uint64_t)(mb >> 64)};
+        // LIN x LIN limbs -> 2 LIN limbs signed, via magnitudes (mp++ integers are sign + magnitude as well)
+        uint64_t x[LIN], y[LIN];
+        const bool na = (int64_t)a[LIN - 1] < 0, nb = (int64_t)b[LIN - 1] < 0;
+        auto magnitude = [](const uint64_t *v, bool negv, uint64_t *m) {
+            uint64_t c = 1;
+            for (int i = 0; i < LIN; ++i) {
+                if (negv) {
+                    m[i] = ~v[i] + c;
+                    c = (c && m[i] == 0) ? 1 : 0;
+                } else {
+                    m[i] = v[i];
+                }
+            }
+        };
+        magnitude(a, na, x);
+        magnitude(b, nb, y);
+        const bool neg = na != nb;
         uint64_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < LIN; ++i) {
             uint64_t carry = 0;
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < LIN; ++j) {
                 u128 cur = (u128)x[i] * y[j] + r[i + j] + carry;
                 r[i + j] = (uint64_t)cur;
                 carry = (uint64_t)(cur >> 64);
             }
-            r[i + 2] += carry;
+            r[i + LIN] += carry;
         }
         if (neg) {
             // two's complement negate over 8 limbs
@@ -831,6 +843,8 @@ int dispatch_cf(const orc_poly *x, const orc_poly *y, const orc_trunc *tr, int n
             case 3: return mul_impl<W, 2, 3, false>(x, y, tr, nthreads, out);
             case 5: return mul_impl<W, 2, 5, false>(x, y, tr, nthreads, out);
         }
+    } else if (lin == 3) {
+        if (lacc == 5) return mul_impl<W, 3, 5, false>(x, y, tr, nthreads, out);
     }
     return ORC_BAD_ARG;
 }

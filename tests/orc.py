@@ -124,6 +124,8 @@ def poly_mul(x, y, limit=None, idx=None, nthreads=1, lacc=None):
         lacc = acc_limbs_bound(x, y)
         if lin == 2 and lacc < 3:
             lacc = 3
+        if lin == 3:
+            lacc = 5
     tr = None
     if limit is not None:
         ia = np.ascontiguousarray(sorted(idx), dtype=np.uint32) if idx is not None else None

@@ -142,10 +142,48 @@ def test_two_limb_inputs(engine):
 
 def test_coefficient_overflow_is_detected(engine):
     rng = np.random.default_rng(15)
-    x = wl.random_poly(rng, 50, 2, 9, 120, "u64")
-    y = wl.random_poly(rng, 50, 2, 9, 120, "u64")
-    with pytest.raises(OverflowError, match="coefficient overflow beyond 3 limbs"):
+    x = wl.random_poly(rng, 50, 2, 9, 185, "u64")
+    y = wl.random_poly(rng, 50, 2, 9, 185, "u64")
+    with pytest.raises(OverflowError, match="coefficient overflow beyond 5 limbs"):
         engine.mul(x, y)
+    z = wl.random_poly(rng, 50, 2, 9, 200, "u64")
+    with pytest.raises((OverflowError, RuntimeError, ValueError), match="beyond 3 limbs"):
+        engine.mul(z, z)
+
+
+def test_wide_coefficients(engine):
+    """Coefficient growth along chains (the reference's integer<N> grows without bound, fma3.hpp:84-88): two- and
+    three-limb operands, four- and five-limb exact sums -- scatter kernel, both signs, sparse and dense keys."""
+    rng = np.random.default_rng(16)
+    for bx, by, want in ((120, 120, 5), (90, 125, 5), (150, 20, 5), (185, 100, 5), (130, 130, 5), (100, 60, 3)):
+        x = wl.random_poly(rng, 300, 3, 7, bx, "i64")
+        y = wl.random_poly(rng, 250, 3, 7, by, "i64")
+        p = check_exact(engine, x, y)
+        assert p.cf_limbs == want, (bx, by, p.cf_limbs)
+    # all-positive sums that really fill the fifth limb
+    x = wl.random_poly(rng, 400, 2, 19, 128, "u64", signed_cfs=False)
+    y = wl.random_poly(rng, 400, 2, 19, 120, "u64", signed_cfs=False)
+    p = check_exact(engine, x, y)
+    assert p.cf_limbs == 5 and max(abs(c) for c in p.cfs) >= 1 << 250
+    # truncated, d_packed keys
+    x = wl.random_poly(rng, 500, 6, 5, 140, "u64").with_layout("u64", 3)
+    y = wl.random_poly(rng, 500, 6, 5, 70, "u64").with_layout("u64", 3)
+    check_exact(engine, x, y, limit=14)
+    # a chain f *= f past the old three-limb ceiling: (1 + x + y + z)^n, n = 16 -> 32 -> 64 -> 128 by repeated squaring,
+    # every step against the closed form; the last step multiplies two-limb operands into five-limb coefficients
+    def closed(n):
+        return {tuple(int(v) for v in e): wl._multinomial(n, tuple(int(v) for v in e)) for e in wl._compositions_le(3, n)}
+    sy = ("x", "y", "z")
+    cur = wl.from_dict(sy, closed(16), "u64")
+    for n in (32, 64, 128):
+        p = engine.mul(cur, cur)
+        want = closed(n)
+        got = {tuple(kpack.unpack(k, 3, "u64")): v for k, v in p.as_dict().items()}
+        assert got == want, n
+        cur = wl.from_dict(sy, want, "u64")
+    assert p.cf_limbs == 5 and max(want.values()).bit_length() > 192
+    with pytest.raises(Exception, match="beyond 3 limbs"):
+        engine.mul(cur, cur)          # (1+x+y+z)^128 has four-limb coefficients: refused, never wrapped
 
 
 def test_exponent_overflow_throws(engine):

@@ -228,3 +228,14 @@ def test_series_ops_golden():
         else:
             got = pyoracle.extend_symbols(unpack(c["x"]), c["new_nvars"], c["pos"])
         assert got == unpack(c["out"]), c["op"]
+
+
+def test_three_limb_inputs_against_python_bigints():
+    """Inputs beyond 128 bits (three limbs, five-limb sums): the C++ oracle against exact Python integers."""
+    rng = np.random.default_rng(77)
+    for bx, by in ((150, 30), (185, 100), (129, 129), (64, 190)):
+        x = wl.random_poly(rng, 120, 3, 6, bx, "i64")
+        y = wl.random_poly(rng, 100, 3, 6, by, "i64")
+        r = orc.poly_mul(x, y, nthreads=2)
+        assert r["status"] == 0
+        assert orc.result_to_dict(r, x) == pyoracle.poly_mul(x.to_dict(), y.to_dict())
