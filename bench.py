@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--also", default="S12,S16T,AUDI,AUDID,F20,D5,RECT", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-cpp", action="store_true", help="skip the C++ operator* end-to-end leg (tools/bench_cpp.cpp)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
     ap.add_argument("--mgpu-mode", default="all", choices=["all", "both", "exchange", "push", "owner"],
                     help="N>1: left-operand sharding + NCCL all-to-all + merge (the contract design), the same with "
@@ -192,6 +193,35 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------
+def e2e_cpp(names):
+    """True end to end (SURVEY 8d "incl. host series rebuild"): obake's own benchmark drivers (benchmark/dense.hpp:21-44,
+    sparse.hpp:21-50) against the C++ host mirror -- operands built with the library's arithmetic, ONE timed
+    `ret = f * g` through operator*: marshal + obk_poly_mul with host buffers + rebuild of the host container."""
+    import subprocess
+
+    from obake_b200 import build
+
+    known = {"F30": "F30", "F20": "F20", "S12": "S12"}
+    want = [known[n] for n in names if n in known]
+    if not want:
+        return None
+    try:
+        exe = build.build_bench_cpp()
+        r = subprocess.run([exe] + want + ["--reps", "3"], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        out = {}
+        for ln in r.stdout.strip().splitlines():
+            d = json.loads(ln)
+            out[d["workload"]] = {"value": d["value"], "unit": UNIT, "ms_per_product_call": d["e2e_cpp_ms"], "best_ms": d["e2e_cpp_best_ms"],
+                                  "terms_out": d["terms_out"], "products": d["products"], "build_operands_ms": d["build_operands_ms"]}
+        out["what"] = ("C++ obake::operator* of the host mirror (tools/bench_cpp.cpp): marshal the host containers + "
+                       "obk_poly_mul with host buffers + rebuild of the host container, wall clock, mean of 3 after 1 warm-up")
+        return out
+    except Exception as ex:  # noqa: BLE001
+        return {"error": str(ex)[-300:]}
+
+
 def check_parity(name, f, g, limit, p, info, torch, dev, rank, world, mgpu_mode):
     from obake_b200 import _capi, verify
 
@@ -576,6 +606,8 @@ def main():
         line["config"]["multi_gpu_mode_reported"] = best
     if also:
         line["also"] = also
+    if rank == 0 and world == 1 and not args.no_e2e_cpp:
+        line["e2e_cpp"] = e2e_cpp([args.workload.upper()] + (["S12"] if "S12" in also else []))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import orc
 

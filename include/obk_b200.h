@@ -38,7 +38,7 @@ typedef enum obk_status {
     OBK_ERR_KEY_OVERFLOW = 2,
     /* std::overflow_error, table larger than the series allows -- polynomial.hpp:1544-1550 */
     OBK_ERR_TABLE_OVERFLOW = 3,
-    /* the exact result needs more than 3 accumulator limbs (the reference would spill to GMP) */
+    /* the exact result needs more than 5 accumulator limbs = 320 bits (the reference would spill to GMP) */
     OBK_ERR_CF_OVERFLOW = 4,
     OBK_ERR_CUDA = 5,
     OBK_ERR_UNSUPPORTED = 6,
@@ -57,7 +57,7 @@ typedef struct obk_poly_view {
     uint32_t nvars;      /* size of the symbol set */
     uint32_t psize;      /* 0: packed_monomial (one word packs nvars exponents); k: d_packed_monomial<T,k> */
     uint32_t cf_kind;    /* OBK_CF_INT | OBK_CF_F64 */
-    uint32_t cf_limbs;   /* integer: 1 or 2 input limbs; f64: 1 */
+    uint32_t cf_limbs;   /* integer: 1..5 limbs carried, values of at most 3 limbs (192 bits) as product operands; f64: 1 */
     uint32_t mem;        /* OBK_MEM_HOST | OBK_MEM_DEVICE */
     uint32_t key_bits;   /* width of T: 64 (or 0) | 32.  Selects the Kronecker tables (delta, limits); 32-bit
                           * keys still travel widened to 64-bit words */
@@ -89,7 +89,7 @@ typedef struct obk_poly_result {
     uint64_t nterms;
     uint32_t key_words;
     uint32_t cf_kind;
-    uint32_t cf_limbs;    /* integer: accumulator limbs (1..3), two's complement */
+    uint32_t cf_limbs;    /* integer: accumulator limbs (1, 2, 3 or 5), two's complement */
     uint32_t log2_nsegs;
     uint32_t mem;         /* where keys/cfs live */
     uint32_t nsegs;       /* number of groups */
@@ -238,7 +238,7 @@ obk_status obk_poly_extend_symbols(obk_engine *e, const obk_poly_view *x, uint32
 
 /* Series addition / subtraction of two polynomials over the SAME symbol set (series.hpp:2195-2991, the
  * identical-symbol-set branch of series_default_addsub_impl): out = x + y or x - y, exact for integers (the result
- * uses as many limbs as the sum needs, at most 3), terms that cancel are erased. */
+ * uses as many limbs as the sum needs: 1, 2, 3 or 5), terms that cancel are erased. */
 obk_status obk_poly_addsub(obk_engine *e, const obk_poly_view *x, const obk_poly_view *y, int subtract, uint32_t result_mem,
                            obk_poly_result *out, obk_stats *stats);
 

@@ -54,5 +54,25 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+BENCH_CPP = os.path.join(ROOT, "tools", "_build", "bench_cpp")
+
+
+def build_bench_cpp(force: bool = False) -> str:
+    """tools/bench_cpp.cpp: obake's benchmark drivers (benchmark/dense.hpp, sparse.hpp) against the C++ host mirror --
+    the end-to-end timing of operator* that bench.py reports as e2e_cpp."""
+    src = os.path.join(ROOT, "tools", "bench_cpp.cpp")
+    inc = os.path.join(PKG, "include")
+    build_native()
+    newest = max(os.path.getmtime(os.path.join(dp, f)) for dp, _, fs in os.walk(inc) for f in fs)
+    newest = max(newest, os.path.getmtime(src), os.path.getmtime(os.path.join(ROOT, "include", "obk_b200.h")), os.path.getmtime(LIB))
+    if not force and os.path.exists(BENCH_CPP) and os.path.getmtime(BENCH_CPP) >= newest:
+        return BENCH_CPP
+    os.makedirs(os.path.dirname(BENCH_CPP), exist_ok=True)
+    cmd = ["g++", "-std=c++20", "-O2", "-Wall", "-I", inc, "-o", BENCH_CPP, src, "-L", os.path.join(PKG, "lib"), "-lobk_b200", "-pthread",
+           "-Wl,-rpath,$ORIGIN/../../obake_b200/lib"]
+    subprocess.check_call(cmd)
+    return BENCH_CPP
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))

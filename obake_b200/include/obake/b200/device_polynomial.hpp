@@ -317,6 +317,53 @@ public:
     }
 };
 
+// base^n with every intermediate power resident in HBM: one upload, n - 1 products, one download.  The reference's
+// series pow multiplies the previous power by the base (series.hpp:1628-1712, `v.back() * b`); its natural-power
+// cache (one host series per power) is replaced by keeping the running power on the device.
+template <typename K, typename C>
+inline device_polynomial<K, C> pow(const device_polynomial<K, C> &base, unsigned n)
+{
+    if (n == 0u) {
+        throw std::invalid_argument("pow(device_polynomial, 0): the unit polynomial has no device form -- use the host pow");
+    }
+    device_polynomial<K, C> acc = base * base; // n == 1 is handled by the callers that can copy
+    for (unsigned i = 2; i < n; ++i) {
+        acc = acc * base;
+    }
+    return acc;
+}
+// The truncated power loop of benchmark/audi_01.cpp:32-42 (f = truncated_mul(f, base, limit), n - 1 times).
+template <typename K, typename C, typename V>
+inline device_polynomial<K, C> truncated_pow(const device_polynomial<K, C> &base, unsigned n, const V &max_degree)
+{
+    if (n < 2u) {
+        throw std::invalid_argument("truncated_pow(device_polynomial, n): n must be at least 2");
+    }
+    device_polynomial<K, C> acc = truncated_mul(base, base, max_degree);
+    for (unsigned i = 2; i < n; ++i) {
+        acc = truncated_mul(acc, base, max_degree);
+    }
+    return acc;
+}
+
+// obake::pow of a host polynomial (declared in polynomials/polynomial.hpp) as a device-resident chain.
+template <typename K, typename C>
+inline polynomial<K, C> pow_device_chain(const polynomial<K, C> &b, unsigned n)
+{
+    if (n == 0u) {
+        return polynomial<K, C>(1);
+    }
+    if (n == 1u) {
+        return polynomial<K, C>(1) * b; // what the reference's cache holds as v[1] = v[0] * b
+    }
+    if (b.empty()) {
+        polynomial<K, C> r;
+        r.set_symbol_set(b.get_symbol_set());
+        return r;
+    }
+    return pow(device_polynomial<K, C>(b), n).to_host();
+}
+
 } // namespace obake::b200
 
 #endif

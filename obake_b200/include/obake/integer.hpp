@@ -21,10 +21,172 @@
 namespace obake
 {
 
+namespace detail
+{
+// Little-endian limbs with room for three of them inline (mppp::integer<N> keeps N limbs inline as well): the
+// coefficients of the benchmark products (at most 190 bits) never touch the heap, which is what the term-by-term
+// rebuild of a multi-million-term result pays for otherwise.
+class limb_vec
+{
+    static constexpr std::size_t N = 3;
+    std::uint64_t m_inl[N];
+    std::uint64_t *m_ptr = m_inl;
+    std::size_t m_size = 0, m_cap = N;
+
+    void grow(std::size_t cap)
+    {
+        if (cap <= m_cap) {
+            return;
+        }
+        cap = std::max(cap, m_cap * 2u);
+        auto *p = new std::uint64_t[cap];
+        std::copy(m_ptr, m_ptr + m_size, p);
+        if (m_ptr != m_inl) {
+            delete[] m_ptr;
+        }
+        m_ptr = p;
+        m_cap = cap;
+    }
+
+public:
+    limb_vec() = default;
+    explicit limb_vec(std::size_t n)
+    {
+        resize(n);
+    }
+    limb_vec(const limb_vec &o)
+    {
+        assign(o.m_ptr, o.m_ptr + o.m_size);
+    }
+    limb_vec(limb_vec &&o) noexcept
+    {
+        steal(o);
+    }
+    limb_vec &operator=(const limb_vec &o)
+    {
+        if (this != &o) {
+            assign(o.m_ptr, o.m_ptr + o.m_size);
+        }
+        return *this;
+    }
+    limb_vec &operator=(limb_vec &&o) noexcept
+    {
+        if (this != &o) {
+            if (m_ptr != m_inl) {
+                delete[] m_ptr;
+            }
+            m_ptr = m_inl;
+            m_cap = N;
+            steal(o);
+        }
+        return *this;
+    }
+    ~limb_vec()
+    {
+        if (m_ptr != m_inl) {
+            delete[] m_ptr;
+        }
+    }
+    void steal(limb_vec &o) noexcept
+    {
+        if (o.m_ptr == o.m_inl) {
+            std::copy(o.m_inl, o.m_inl + o.m_size, m_inl);
+            m_ptr = m_inl;
+            m_cap = N;
+        } else {
+            m_ptr = o.m_ptr;
+            m_cap = o.m_cap;
+            o.m_ptr = o.m_inl;
+            o.m_cap = N;
+        }
+        m_size = o.m_size;
+        o.m_size = 0;
+    }
+    std::size_t size() const
+    {
+        return m_size;
+    }
+    bool empty() const
+    {
+        return m_size == 0u;
+    }
+    std::uint64_t &operator[](std::size_t i)
+    {
+        return m_ptr[i];
+    }
+    const std::uint64_t &operator[](std::size_t i) const
+    {
+        return m_ptr[i];
+    }
+    std::uint64_t &back()
+    {
+        return m_ptr[m_size - 1u];
+    }
+    const std::uint64_t &back() const
+    {
+        return m_ptr[m_size - 1u];
+    }
+    void push_back(std::uint64_t v)
+    {
+        grow(m_size + 1u);
+        m_ptr[m_size++] = v;
+    }
+    void pop_back()
+    {
+        --m_size;
+    }
+    void clear()
+    {
+        m_size = 0;
+    }
+    void resize(std::size_t n)
+    {
+        grow(n);
+        for (std::size_t i = m_size; i < n; ++i) {
+            m_ptr[i] = 0u;
+        }
+        m_size = n;
+    }
+    template <typename It>
+    void assign(It first, It last)
+    {
+        const auto n = static_cast<std::size_t>(last - first);
+        m_size = 0;
+        grow(n);
+        std::copy(first, last, m_ptr);
+        m_size = n;
+    }
+    std::uint64_t *begin()
+    {
+        return m_ptr;
+    }
+    std::uint64_t *end()
+    {
+        return m_ptr + m_size;
+    }
+    const std::uint64_t *begin() const
+    {
+        return m_ptr;
+    }
+    const std::uint64_t *end() const
+    {
+        return m_ptr + m_size;
+    }
+    friend bool operator==(const limb_vec &a, const limb_vec &b)
+    {
+        return a.m_size == b.m_size && std::equal(a.m_ptr, a.m_ptr + a.m_size, b.m_ptr);
+    }
+    friend bool operator!=(const limb_vec &a, const limb_vec &b)
+    {
+        return !(a == b);
+    }
+};
+} // namespace detail
+
 class integer
 {
     // magnitude, little endian, no leading zero limbs; zero is the empty vector
-    std::vector<std::uint64_t> m_mag;
+    detail::limb_vec m_mag;
     bool m_neg = false;
     using u128 = unsigned __int128;
 
@@ -37,7 +199,7 @@ class integer
             m_neg = false;
         }
     }
-    static int cmp_mag(const std::vector<std::uint64_t> &a, const std::vector<std::uint64_t> &b)
+    static int cmp_mag(const detail::limb_vec &a, const detail::limb_vec &b)
     {
         if (a.size() != b.size()) {
             return a.size() < b.size() ? -1 : 1;
@@ -49,11 +211,11 @@ class integer
         }
         return 0;
     }
-    static std::vector<std::uint64_t> add_mag(const std::vector<std::uint64_t> &a, const std::vector<std::uint64_t> &b)
+    static detail::limb_vec add_mag(const detail::limb_vec &a, const detail::limb_vec &b)
     {
         const auto &l = a.size() >= b.size() ? a : b;
         const auto &s = a.size() >= b.size() ? b : a;
-        std::vector<std::uint64_t> r(l.size() + 1u);
+        detail::limb_vec r(l.size() + 1u);
         std::uint64_t c = 0;
         for (std::size_t i = 0; i < l.size(); ++i) {
             const u128 t = static_cast<u128>(l[i]) + (i < s.size() ? s[i] : 0u) + c;
@@ -64,9 +226,9 @@ class integer
         return r;
     }
     // a - b, |a| >= |b|
-    static std::vector<std::uint64_t> sub_mag(const std::vector<std::uint64_t> &a, const std::vector<std::uint64_t> &b)
+    static detail::limb_vec sub_mag(const detail::limb_vec &a, const detail::limb_vec &b)
     {
-        std::vector<std::uint64_t> r(a.size());
+        detail::limb_vec r(a.size());
         std::uint64_t brw = 0;
         for (std::size_t i = 0; i < a.size(); ++i) {
             const std::uint64_t bi = i < b.size() ? b[i] : 0u;
@@ -248,7 +410,7 @@ public:
             m_neg = false;
             return *this;
         }
-        std::vector<std::uint64_t> r(m_mag.size() + o.m_mag.size(), 0u);
+        detail::limb_vec r(m_mag.size() + o.m_mag.size());
         for (std::size_t i = 0; i < m_mag.size(); ++i) {
             std::uint64_t carry = 0;
             for (std::size_t j = 0; j < o.m_mag.size(); ++j) {

@@ -17,8 +17,10 @@
 #include <array>
 #include <cstdint>
 #include <limits>
+#include <iterator>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <unordered_map>
 #include <utility>
@@ -62,6 +64,288 @@ struct key_hasher {
 template <typename T, typename = void>
 struct is_poly : std::false_type {
 };
+
+// The term container of a series (series.hpp:396-400, `s_table`): 2^log2 open-addressing tables, a term lives in table
+// hash(key) & (2^log2 - 1).  The engine hands its results over grouped exactly that way (obk_poly_result::seg_offsets),
+// so a product is adopted table by table, in parallel, without rehashing anything (_adopt_grouped) -- the
+// reference's multiplication threads fill the same tables in place (polynomial.hpp:1441-1450).
+template <typename K, typename C>
+class seg_table
+{
+public:
+    using value_type = std::pair<K, C>;
+
+private:
+    struct tab {
+        std::vector<value_type> slots;
+        std::vector<unsigned char> full;
+        std::size_t n = 0;
+    };
+    std::vector<tab> m_tabs = std::vector<tab>(1);
+    unsigned m_log2 = 0;
+    std::size_t m_size = 0;
+
+    static std::size_t slot_of(std::size_t h, std::size_t cap, unsigned log2)
+    {
+        // the low bits chose the table; the rest is scrambled (packed keys are far from uniform)
+        const std::uint64_t x = (static_cast<std::uint64_t>(h) >> log2) * 0x9E3779B97F4A7C15ull;
+        return static_cast<std::size_t>(x >> 20) & (cap - 1u);
+    }
+    static void grow(tab &t, std::size_t want, unsigned log2)
+    {
+        std::size_t cap = t.slots.empty() ? 8u : t.slots.size();
+        while (want * 10u > cap * 7u) {
+            cap *= 2u;
+        }
+        if (cap == t.slots.size()) {
+            return;
+        }
+        std::vector<value_type> os(cap);
+        std::vector<unsigned char> of(cap, 0);
+        os.swap(t.slots);
+        of.swap(t.full);
+        for (std::size_t i = 0; i < os.size(); ++i) {
+            if (of[i]) {
+                std::size_t j = slot_of(key_hasher<K>{}(os[i].first), cap, log2);
+                while (t.full[j]) {
+                    j = (j + 1u) & (cap - 1u);
+                }
+                t.full[j] = 1;
+                t.slots[j] = std::move(os[i]);
+            }
+        }
+    }
+    template <bool Const>
+    class iter
+    {
+        friend class seg_table;
+        using owner_t = std::conditional_t<Const, const seg_table, seg_table>;
+        owner_t *m_o = nullptr;
+        std::size_t m_t = 0, m_i = 0;
+        void settle()
+        {
+            while (m_t < m_o->m_tabs.size()) {
+                const auto &t = m_o->m_tabs[m_t];
+                while (m_i < t.slots.size() && !t.full[m_i]) {
+                    ++m_i;
+                }
+                if (m_i < t.slots.size()) {
+                    return;
+                }
+                ++m_t;
+                m_i = 0;
+            }
+        }
+
+    public:
+        using iterator_category = std::forward_iterator_tag;
+        using value_type = typename seg_table::value_type;
+        using difference_type = std::ptrdiff_t;
+        using reference = std::conditional_t<Const, const value_type &, value_type &>;
+        using pointer = std::conditional_t<Const, const value_type *, value_type *>;
+        iter() = default;
+        iter(owner_t *o, std::size_t t, std::size_t i) : m_o(o), m_t(t), m_i(i) {}
+        template <bool B = Const, std::enable_if_t<B, int> = 0>
+        iter(const iter<false> &o) : m_o(o.m_o), m_t(o.m_t), m_i(o.m_i)
+        {
+        }
+        reference operator*() const
+        {
+            return m_o->m_tabs[m_t].slots[m_i];
+        }
+        pointer operator->() const
+        {
+            return &m_o->m_tabs[m_t].slots[m_i];
+        }
+        iter &operator++()
+        {
+            ++m_i;
+            settle();
+            return *this;
+        }
+        iter operator++(int)
+        {
+            iter c(*this);
+            ++*this;
+            return c;
+        }
+        friend bool operator==(const iter &a, const iter &b)
+        {
+            return a.m_t == b.m_t && a.m_i == b.m_i;
+        }
+        friend bool operator!=(const iter &a, const iter &b)
+        {
+            return !(a == b);
+        }
+    };
+
+public:
+    using iterator = iter<false>;
+    using const_iterator = iter<true>;
+    std::size_t size() const
+    {
+        return m_size;
+    }
+    bool empty() const
+    {
+        return m_size == 0u;
+    }
+    unsigned log2_tables() const
+    {
+        return m_log2;
+    }
+    const_iterator begin() const
+    {
+        const_iterator it(this, 0, 0);
+        it.settle();
+        return it;
+    }
+    const_iterator end() const
+    {
+        return const_iterator(this, m_tabs.size(), 0);
+    }
+    iterator begin()
+    {
+        iterator it(this, 0, 0);
+        it.settle();
+        return it;
+    }
+    iterator end()
+    {
+        return iterator(this, m_tabs.size(), 0);
+    }
+    void clear()
+    {
+        m_tabs.assign(1, tab{});
+        m_log2 = 0;
+        m_size = 0;
+    }
+    void reserve(std::size_t n)
+    {
+        if (m_log2 == 0u) {
+            grow(m_tabs[0], n, 0);
+        }
+    }
+
+private:
+    template <typename Self>
+    static auto find_impl(Self &self, const K &k)
+    {
+        using it_t = std::conditional_t<std::is_const_v<Self>, const_iterator, iterator>;
+        const std::size_t h = key_hasher<K>{}(k), ti = h & ((std::size_t(1) << self.m_log2) - 1u);
+        auto &t = self.m_tabs[ti];
+        if (!t.slots.empty()) {
+            const std::size_t cap = t.slots.size();
+            for (std::size_t j = slot_of(h, cap, self.m_log2); t.full[j]; j = (j + 1u) & (cap - 1u)) {
+                if (t.slots[j].first == k) {
+                    return it_t(&self, ti, j);
+                }
+            }
+        }
+        return it_t(&self, self.m_tabs.size(), 0);
+    }
+
+public:
+    const_iterator find(const K &k) const
+    {
+        return find_impl(*this, k);
+    }
+    iterator find(const K &k)
+    {
+        return find_impl(*this, k);
+    }
+    std::pair<iterator, bool> try_emplace(const K &k, const C &c)
+    {
+        const std::size_t h = key_hasher<K>{}(k), ti = h & ((std::size_t(1) << m_log2) - 1u);
+        auto &t = m_tabs[ti];
+        grow(t, t.n + 1u, m_log2);
+        const std::size_t cap = t.slots.size();
+        std::size_t j = slot_of(h, cap, m_log2);
+        for (; t.full[j]; j = (j + 1u) & (cap - 1u)) {
+            if (t.slots[j].first == k) {
+                return {iterator(this, ti, j), false};
+            }
+        }
+        t.full[j] = 1;
+        t.slots[j] = value_type(k, c);
+        ++t.n;
+        ++m_size;
+        return {iterator(this, ti, j), true};
+    }
+    void emplace(K k, C c)
+    {
+        try_emplace(k, c);
+    }
+    void erase(iterator it)
+    {
+        // backward-shift deletion: no tombstones
+        auto &t = m_tabs[it.m_t];
+        const std::size_t cap = t.slots.size();
+        std::size_t i = it.m_i, j = i;
+        for (;;) {
+            j = (j + 1u) & (cap - 1u);
+            if (!t.full[j]) {
+                break;
+            }
+            const std::size_t home = slot_of(key_hasher<K>{}(t.slots[j].first), cap, m_log2);
+            // can the entry at j move to the hole at i?  only if its home is not cyclically inside (i, j]
+            const bool between = i <= j ? (home > i && home <= j) : (home > i || home <= j);
+            if (!between) {
+                t.slots[i] = std::move(t.slots[j]);
+                i = j;
+            }
+        }
+        t.full[i] = 0;
+        t.slots[i] = value_type();
+        --t.n;
+        --m_size;
+    }
+    // Adopt `n` distinct, non-zero terms that arrive grouped by hash & (2^log2 - 1) (offs[2^log2 + 1]); make(i) builds
+    // term i.  The tables are filled by up to `nthreads` threads, each owning whole tables.
+    template <typename Make>
+    void adopt_grouped(std::size_t n, unsigned log2, const std::uint64_t *offs, const Make &make, unsigned nthreads)
+    {
+        const std::size_t nt = std::size_t(1) << log2;
+        m_tabs.assign(nt, tab{});
+        m_log2 = log2;
+        m_size = n;
+        auto work = [&](std::size_t first, std::size_t step) {
+            for (std::size_t ti = first; ti < nt; ti += step) {
+                auto &t = m_tabs[ti];
+                const std::size_t b = static_cast<std::size_t>(offs[ti]), e = static_cast<std::size_t>(offs[ti + 1u]);
+                if (b == e) {
+                    continue;
+                }
+                grow(t, e - b, log2);
+                const std::size_t cap = t.slots.size();
+                for (std::size_t i = b; i < e; ++i) {
+                    value_type v = make(i);
+                    std::size_t j = slot_of(key_hasher<K>{}(v.first), cap, log2);
+                    while (t.full[j]) {
+                        j = (j + 1u) & (cap - 1u);
+                    }
+                    t.full[j] = 1;
+                    t.slots[j] = std::move(v);
+                }
+                t.n = e - b;
+            }
+        };
+        const std::size_t th = std::max<std::size_t>(1, std::min<std::size_t>({nthreads, nt, n / 8192u + 1u}));
+        if (th == 1u) {
+            work(0, 1);
+            return;
+        }
+        std::vector<std::thread> pool;
+        pool.reserve(th - 1u);
+        for (std::size_t w = 1; w < th; ++w) {
+            pool.emplace_back(work, w, th);
+        }
+        work(0, th);
+        for (auto &p : pool) {
+            p.join();
+        }
+    }
+};
 } // namespace detail
 
 template <typename K, typename C>
@@ -70,7 +354,7 @@ class polynomial
 public:
     using key_type = K;
     using cf_type = C;
-    using table_type = std::unordered_map<K, C, detail::key_hasher<K>>;
+    using table_type = detail::seg_table<K, C>;
 
 private:
     symbol_set m_ss;
@@ -163,6 +447,20 @@ public:
     void _insert_unique(K k, C c)
     {
         m_terms.emplace(std::move(k), std::move(c));
+    }
+    // a whole product from the engine: terms grouped by hash & (2^log2 - 1), distinct and non-zero
+    template <typename Make>
+    void _adopt_grouped(std::size_t n, unsigned log2, const std::uint64_t *offs, const Make &make)
+    {
+        m_terms.adopt_grouped(n, log2, offs, make, std::max(1u, std::thread::hardware_concurrency()));
+    }
+    auto begin()
+    {
+        return m_terms.begin();
+    }
+    auto end()
+    {
+        return m_terms.end();
     }
 };
 
@@ -358,12 +656,21 @@ inline polynomial<K, R> poly_mul_impl_identical_ss(const polynomial<K, C0> &x, c
         std::lock_guard<std::mutex> g(eng.mutex());
         eng.check(::obk_poly_mul(eng.handle(), &vx, &vy, ta.on ? &tr : nullptr, OBK_MEM_HOST, &res, nullptr));
     }
-    // Rebuild the host container (terms arrive grouped by table, without zeros or duplicates).
+    // Rebuild the host container (terms arrive grouped by table, without zeros or duplicates): table by table, in
+    // parallel when the engine grouped them by hash & (2^k - 1) (it always does for host results).
     try {
-        ret.reserve(res.nterms);
         const auto *rc = static_cast<const std::uint64_t *>(res.cfs);
-        for (std::uint64_t i = 0; i < res.nterms; ++i) {
-            ret._insert_unique(K::from_words(res.keys + i * W, nvars), RT::load(rc + i * res.cf_limbs, res.cf_limbs));
+        auto make = [&](std::size_t i) {
+            return std::pair<K, R>(K::from_words(res.keys + i * W, nvars), RT::load(rc + i * res.cf_limbs, res.cf_limbs));
+        };
+        if (res.seg_kind == 0u && res.seg_offsets != nullptr && res.nsegs == (std::uint64_t(1) << res.log2_nsegs)) {
+            ret._adopt_grouped(static_cast<std::size_t>(res.nterms), res.log2_nsegs, res.seg_offsets, make);
+        } else {
+            ret.reserve(res.nterms);
+            for (std::uint64_t i = 0; i < res.nterms; ++i) {
+                auto t = make(i);
+                ret._insert_unique(std::move(t.first), std::move(t.second));
+            }
         }
     } catch (...) {
         ::obk_result_free(eng.handle(), &res);
@@ -626,15 +933,17 @@ inline polynomial<K, C> truncate_p_degree(const polynomial<K, C> &p, const V &li
     return r;
 }
 
-// obake::pow by repeated multiplication (series pow, series.hpp:1628-1712: v.back() * b)
+// obake::pow by repeated multiplication (series pow, series.hpp:1628-1712: v.back() * b), every intermediate power
+// resident in HBM (b200/device_polynomial.hpp, included at the end of this header)
+namespace b200
+{
+template <typename K, typename C>
+polynomial<K, C> pow_device_chain(const polynomial<K, C> &, unsigned);
+}
 template <typename K, typename C>
 inline polynomial<K, C> pow(const polynomial<K, C> &b, unsigned n)
 {
-    polynomial<K, C> r(1);
-    for (unsigned i = 0; i < n; ++i) {
-        r = r * b;
-    }
-    return r;
+    return b200::pow_device_chain(b, n);
 }
 
 // ---- make_polynomials (polynomial.hpp:97-227) --------------------------------------------------------------
@@ -671,5 +980,8 @@ inline std::array<P, sizeof...(Names)> make_polynomials(const Names &...names)
 }
 
 } // namespace obake
+
+// device-resident chains: the definition of b200::pow_device_chain (this header's guard is already set)
+#include "../b200/device_polynomial.hpp"
 
 #endif

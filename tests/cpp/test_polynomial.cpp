@@ -439,6 +439,36 @@ static void p_series_tests()
     }
 }
 
+// obake::pow (series pow, series.hpp:1628-1712: the previous power times the base) as a device-resident chain, and the
+// truncated power loop of benchmark/audi_01.cpp:32-42; both against the same chains through the host container.
+template <typename K, typename C>
+static void pow_test()
+{
+    using poly_t = polynomial<K, C>;
+    using dpoly_t = b200::device_polynomial<K, C>;
+    const symbol_set ss{"t", "x", "y", "z"};
+    auto [t, x, y, z] = make_polynomials<poly_t>(ss, "t", "x", "y", "z");
+    const poly_t base = x - y * 3 + z * 2 + t + 1;
+    REQUIRE(pow(base, 0) == poly_t(1));
+    REQUIRE(pow(base, 1) == base);
+    poly_t h = base;
+    for (unsigned n = 2; n <= 9; ++n) {
+        h = h * base;
+        REQUIRE(pow(base, n) == h);
+    }
+    poly_t empty;
+    empty.set_symbol_set(ss);
+    REQUIRE(pow(empty, 3).empty());
+    // truncated powers
+    const dpoly_t dbase(base);
+    poly_t ht = base;
+    for (unsigned n = 2; n <= 8; ++n) {
+        ht = truncated_mul(ht, base, 5);
+        REQUIRE(b200::truncated_pow(dbase, n, 5).to_host() == ht);
+    }
+    REQUIRE(b200::pow(dbase, 6).to_host() == pow(base, 6));
+}
+
 int main(int argc, char **argv)
 {
     const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
@@ -469,6 +499,9 @@ int main(int argc, char **argv)
         device_chain_test<packed_monomial<std::uint64_t>, integer>();
         device_chain_test<packed_monomial<std::int64_t>, double>();
         device_chain_test<d_packed_monomial<std::int64_t, 2>, integer>();
+        pow_test<packed_monomial<std::uint64_t>, integer>();
+        pow_test<packed_monomial<std::int64_t>, double>();
+        pow_test<d_packed_monomial<std::int64_t, 2>, integer>();
     }
     std::printf("%s: %d checks, %d failures%s\n", g_fail ? "FAILED" : "OK", g_checks, g_fail, cpu_only ? " (host-only subset)" : "");
     return g_fail ? 1 : 0;

@@ -21,7 +21,7 @@ def build_exe():
         return EXE
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     cmd = ["g++", "-std=c++20", "-O2", "-Wall", "-I", inc, "-o", EXE, SRC, "-L", os.path.join(ROOT, "obake_b200", "lib"),
-           "-lobk_b200", "-Wl,-rpath,$ORIGIN/../../obake_b200/lib"]
+           "-lobk_b200", "-pthread", "-Wl,-rpath,$ORIGIN/../../obake_b200/lib"]
     subprocess.check_call(cmd)
     return EXE
 
