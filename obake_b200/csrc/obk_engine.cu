@@ -1358,6 +1358,17 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     RowsResult R;
     cudaStream_t s = e->stream;
     const uint64_t delta = L.delta;
+    // OBK_TILE_TIMING=1: device time between the phases of this path (development aid)
+    static const bool timing = std::getenv("OBK_TILE_TIMING") != nullptr;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    auto mark = [&](const char *what) {
+        if (!timing) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, s);
+        marks.emplace_back(what, ev);
+    };
+    mark("start");
     if (delta >= (1ull << 32)) return R; // delta^2 must fit 64 bits
     if (D.wx > (uint32_t)TL_MAX_DIM || D.wy > (uint32_t)TL_MAX_DIM || D.rx > (uint32_t)TL_MAX_DIM || D.ry > (uint32_t)TL_MAX_DIM) return R;
     const uint32_t P = tl_pitch(std::max(D.wx, D.wy)), rcap = std::max(D.rx, D.ry);
@@ -1408,6 +1419,7 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
         Y.nplanes = hy;
         build(dyk, dyc, ny, Y);
     }
+    mark("planes built");
     // multi-GPU partial product (left operand sharded): this rank forms the pairs of the left planes it owns
     const uint32_t part_nranks = (nranks > 1 && !owner) ? nranks : 1u;
     const uint64_t npairs = plane_pairs;
@@ -1459,6 +1471,7 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     }
     k_plane_sym_fill<<<gp, 256, 0, s>>>(X.plane_key, X.nplanes, Y.plane_key, Y.nplanes, rank, part_nranks, tab, l2, rec, pair_off, fill, pairs);
     e->launches += 4;
+    mark("symbolic product");
     uint32_t htot[5] = {0, 0, 0, 0, 0};
     CU_CHECK(e, cudaMemcpyAsync(htot, totals, 20, cudaMemcpyDeviceToHost, s));
     CU_CHECK(e, cudaStreamSynchronize(s));
@@ -1504,9 +1517,11 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     Pm.split = split ? 1u : 0u;
     Pm.tr = tr;
     const unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>(nunits, (uint32_t)e->sm_count * cfg.ctas));
+    mark("sync + output set-up");
     CU_CHECK(e, cudaEventRecord(e->ev[5], s));
     if (nunits) launch_tiles(e, mode, uns, Pm, grid, (cfg.nw + 1) * 32, cfg.ctas, tl_acc_bytes(slots, accw) + (size_t)nstage * G.bytes);
     CU_CHECK(e, cudaEventRecord(e->ev[6], s));
+    mark("k_tileconv");
     st.mul_launches += 1;
     uint64_t total = 0;
     const unsigned ge = (unsigned)std::min<uint64_t>((nitems + 7) / 8, 8192);
@@ -1542,6 +1557,20 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
         }
         e->launches += 1;
         CU_CHECK(e, cudaGetLastError());
+    }
+    mark("normalise + scan + expand");
+    if (timing) {
+        cudaStreamSynchronize(s);
+        std::string line = "[obk tile timing]";
+        for (size_t k = 1; k < marks.size(); ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[k - 1].second, marks[k].second);
+            char buf[96];
+            std::snprintf(buf, sizeof(buf), " %s %.3f ms |", marks[k].first, ms);
+            line += buf;
+        }
+        std::fprintf(stderr, "%s units %u planes %u rows %u split %d\n", line.c_str(), nunits, nout, nro, (int)split);
+        for (auto &m : marks) cudaEventDestroy(m.second);
     }
     R.total = total;
     R.nro = nro;
