@@ -233,13 +233,23 @@ class Product:
 class Engine:
     """One CUDA device + stream + grow-only workspace (obk_engine)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """`device`: one CUDA device ordinal, or a list of ordinals for the single-process multi-device engine
+        (obk_engine_create_multi: host operands in, host result out, every device forms the output it owns)."""
         L = _capi.lib()
         h = C.c_void_p()
-        st = L.obk_engine_create(int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            st = L.obk_engine_create_multi(devs, len(device), C.byref(h))
+            what = "obk_engine_create_multi"
+            self.devices = [int(d) for d in device]
+            device = self.devices[0] if self.devices else 0
+        else:
+            st = L.obk_engine_create(int(device), C.byref(h))
+            what = "obk_engine_create"
+            self.devices = [int(device)]
         if st != 0:
-            raise ObkCudaError(
-                "obk_engine_create failed: " + L.obk_last_error(None).decode() + " (no CPU fallback exists)")
+            raise ObkCudaError(what + " failed: " + L.obk_last_error(None).decode() + " (no CPU fallback exists)")
         self._h = h
         self.device = device
 

@@ -361,6 +361,14 @@ inline polynomial<K, C> pow_device_chain(const polynomial<K, C> &b, unsigned n)
         r.set_symbol_set(b.get_symbol_set());
         return r;
     }
+    if (engine::instance().n_devices() > 1u) {
+        // the single-process multi-device engine takes host operands: the chain goes through the host container
+        polynomial<K, C> r = b * b;
+        for (unsigned i = 2; i < n; ++i) {
+            r = r * b;
+        }
+        return r;
+    }
     return pow(device_polynomial<K, C>(b), n).to_host();
 }
 

@@ -25,8 +25,23 @@ class engine
 {
     obk_engine *m_h = nullptr;
     std::mutex m_mtx; // calls are serialised per handle (SURVEY 8b "Threading")
+    unsigned m_ndev = 1;
 
 public:
+    // Single-process multi-device engine (obk_engine_create_multi): obake::operator* and truncated_mul spread over
+    // the devices; device-resident chains (device_polynomial) need a one-device engine.
+    explicit engine(const std::vector<int> &devices) : m_ndev(static_cast<unsigned>(devices.size()))
+    {
+        const auto st = ::obk_engine_create_multi(devices.data(), static_cast<int>(devices.size()), &m_h);
+        if (st != OBK_OK) {
+            throw std::runtime_error(std::string("obk_engine_create_multi failed: ") + ::obk_last_error(nullptr)
+                                     + " (the B200 engine has no CPU fallback)");
+        }
+    }
+    unsigned n_devices() const
+    {
+        return m_ndev;
+    }
     explicit engine(int device = 0)
     {
         const auto st = ::obk_engine_create(device, &m_h);
@@ -73,12 +88,33 @@ public:
                 throw std::runtime_error(msg);
         }
     }
-    // Process-wide default engine on device OBAKE_B200_DEVICE (default 0), created on first use.
+    // Process-wide default engine, created on first use: the devices listed in OBAKE_B200_DEVICES ("0,1,2,3": the
+    // single-process multi-device engine), else device OBAKE_B200_DEVICE (default 0).
     static engine &instance()
     {
         static std::unique_ptr<engine> inst;
         static std::once_flag flag;
         std::call_once(flag, [] {
+            if (const char *l = std::getenv("OBAKE_B200_DEVICES")) {
+                std::vector<int> devs;
+                for (const char *q = l; *q;) {
+                    char *end = nullptr;
+                    const long v = std::strtol(q, &end, 10);
+                    if (end == q) {
+                        break;
+                    }
+                    devs.push_back(static_cast<int>(v));
+                    q = *end == ',' ? end + 1 : end;
+                }
+                if (devs.size() > 1u) {
+                    inst = std::make_unique<engine>(devs);
+                    return;
+                }
+                if (devs.size() == 1u) {
+                    inst = std::make_unique<engine>(devs[0]);
+                    return;
+                }
+            }
             int dev = 0;
             if (const char *s = std::getenv("OBAKE_B200_DEVICE")) {
                 dev = std::atoi(s);

@@ -472,6 +472,21 @@ static void pow_test()
 int main(int argc, char **argv)
 {
     const bool cpu_only = argc > 1 && std::strcmp(argv[1], "--cpu") == 0;
+    if (argc > 1 && std::strcmp(argv[1], "--multi") == 0) {
+        // OBAKE_B200_DEVICES=0,1,...: the host-container paths through the single-process multi-device engine
+        const unsigned nd = b200::engine::instance().n_devices();
+        mul_mt_hm_test<packed_monomial<std::int64_t>, integer>();
+        mul_mt_hm_test<packed_monomial<std::int64_t>, double>();
+        mul_mt_hm_test<d_packed_monomial<std::int64_t, 8>, integer>();
+        mul_general_test<packed_monomial<std::int64_t>>();
+        truncated_tests<packed_monomial<std::int64_t>, integer>();
+        truncated_tests<d_packed_monomial<std::int64_t, 2>, integer>();
+        large_tests<packed_monomial<std::int64_t>, integer>();
+        fateman_test();
+        p_series_tests();
+        std::printf("%s: %d checks, %d failures (%u devices)\n", g_fail ? "FAILED" : "OK", g_checks, g_fail, nd);
+        return g_fail || nd < 2u ? 1 : 0;
+    }
     kpack_tests<std::int32_t>();
     kpack_tests<std::uint32_t>();
     kpack_tests<std::int64_t>();
