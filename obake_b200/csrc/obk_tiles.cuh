@@ -464,7 +464,8 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
             uint32_t v[SCAN_ITEMS], sum = 0;
 #pragma unroll
             for (int j = 0; j < SCAN_ITEMS; ++j) {
-                v[j] = base + j < nout ? (which == 0 ? (oshape[base + j] & 0xffu) : ocnt[base + j]) : 0;
+                // output rows exist only for the planes this rank forms (owner mode: 1 / nranks of them)
+                v[j] = base + j < nout ? (which == 0 ? (owned(base + j) ? (oshape[base + j] & 0xffu) : 0u) : ocnt[base + j]) : 0;
                 sum += v[j];
             }
             uint32_t ex = block_exclusive_scan(sum, &s_tot) + s_carry;
