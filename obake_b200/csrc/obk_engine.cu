@@ -1293,7 +1293,6 @@ TileCfg tile_cfg(const obk_engine *e, uint32_t tiles_max)
         case 3: return {7, 3};
         case 4: return {12, 1};
         case 5: return {15, 2};
-        case 6: return {31, 1};
         case 7: return {20, 1};
         // Measured (F30, F20: output planes of up to 121 / 66 tiles in the bounding box; D5: 32): large planes want the deeper ring and the
         // larger accumulator area of 2 CTAs per SM, small ones the cheaper end-of-unit barrier of 3 small CTAs.
@@ -1304,10 +1303,8 @@ TileCfg tile_cfg(const obk_engine *e, uint32_t tiles_max)
 template <int LACC, bool F64, bool UNS>
 void launch_tiles_t(obk_engine *e, const TileParams &P, unsigned grid, unsigned threads, unsigned ctas, size_t smem)
 {
-    // register budget by geometry: <= 64 registers when more than 704 threads share an SM's register file with 80
-    auto fn = threads > (unsigned)TL_MAX_THREADS ? k_tileconv<LACC, F64, UNS, 1024, 1>
-                                                 : (threads * ctas * 80u > 65536u ? k_tileconv<LACC, F64, UNS, 512, 2>
-                                                                                   : k_tileconv<LACC, F64, UNS, TL_MAX_THREADS, 1>);
+    // register budget by geometry: the <= 64-register build when the resident CTAs would not fit the register file at 80
+    auto fn = threads * ctas * 80u > 65536u ? k_tileconv<LACC, F64, UNS, 512, 2> : k_tileconv<LACC, F64, UNS, TL_MAX_THREADS, 1>;
     CU_CHECK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fn<<<grid, threads, smem, e->stream>>>(P);
     e->launches += 1;

@@ -521,7 +521,7 @@ def test_tile_path_forced(engine):
             assert p.stats["kernel"] == 3
             p = check_exact(engine, x, x)
             assert p.stats["kernel"] == 3
-        for cfg in (1, 2, 3, 4, 5, 6, 7):
+        for cfg in (1, 2, 3, 4, 5, 7):
             engine.set_option("plane_cfg", cfg)
             x = dense_poly2(rng, 3, 33, 21, 5, 0.8, 40, "u64")
             y = dense_poly2(rng, 3, 12, 40, 5, 0.8, 40, "u64")
@@ -563,6 +563,13 @@ def test_tile_path_truncated(engine):
         for idx in ([0], [1], [0, 1], [2, 3], [0, 3], [1, 2, 3]):
             for lim in (11, 4, 0):
                 p = check_exact(engine, x, y, limit=lim, idx=idx)
+        # automatic selection: a truncated dense product above the size threshold takes the tile path by itself
+        engine.set_option("kernel", -1)
+        f, g = wl.fateman(16, 4, "u64")
+        for lim, idx in ((20, None), (9, [0, 2]), (32, None)):
+            p = check_exact(engine, f, g, limit=lim, idx=idx)
+            assert p.stats["kernel"] == 3, (lim, idx, p.stats["kernel"])
+        engine.set_option("kernel", 3)
         xf = dense_poly2(rng, 3, 20, 9, 7, 0.8, 0, "u64", f64=True)
         yf = dense_poly2(rng, 3, 9, 20, 7, 0.8, 0, "u64", f64=True)
         p = check_f64(engine, xf, yf, limit=17)
