@@ -1358,10 +1358,12 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     // OBK_TILE_TIMING=1: device time between the phases of this path (development aid)
     static const bool timing = std::getenv("OBK_TILE_TIMING") != nullptr;
     std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    std::vector<std::chrono::steady_clock::time_point> hmarks; // host time when the mark was enqueued
     auto mark = [&](const char *what) {
         if (!timing) return;
         cudaEvent_t ev;
         cudaEventCreate(&ev);
+        hmarks.push_back(std::chrono::steady_clock::now());
         cudaEventRecord(ev, s);
         marks.emplace_back(what, ev);
     };
@@ -1397,12 +1399,12 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     const uint64_t plane_pairs = (uint64_t)hx * hy;
     if (plane_pairs > (1ull << 21) || hx >= (1u << 24) || hy >= (1u << 24) || (!forced && !tiles_dense(pre, nx, ny))) return R;
     auto build = [&](const uint64_t *keys, const uint64_t *cfs, uint64_t n, PlaneSide &p) {
-        p.mat = sc.alloc<uint64_t>((size_t)p.nplanes * blob_words);
-        p.pinfo = sc.alloc<uint32_t>((size_t)p.nplanes * 4);
-        uint32_t *rowlen = sc.alloc<uint32_t>((size_t)p.nplanes * rcap);
-        CU_CHECK(e, cudaMemsetAsync(p.mat, 0, (size_t)p.nplanes * blob_words * 8, s));
-        CU_CHECK(e, cudaMemsetAsync(p.pinfo, 0, (size_t)p.nplanes * 16, s));
-        CU_CHECK(e, cudaMemsetAsync(rowlen, 0, (size_t)p.nplanes * rcap * 4, s));
+        // one zeroed block: blobs, plane info, row lengths
+        const size_t mat_words = (size_t)p.nplanes * blob_words, info_words = ((size_t)p.nplanes * 4 + 1) / 2, len_words = ((size_t)p.nplanes * rcap + 1) / 2;
+        p.mat = sc.alloc<uint64_t>(mat_words + info_words + len_words);
+        p.pinfo = reinterpret_cast<uint32_t *>(p.mat + mat_words);
+        uint32_t *rowlen = reinterpret_cast<uint32_t *>(p.mat + mat_words + info_words);
+        CU_CHECK(e, cudaMemsetAsync(p.mat, 0, (mat_words + info_words + len_words) * 8, s));
         const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 4096);
         k_tile_fill<<<grid, 256, 0, s>>>(keys, cfs, n, delta, p.tab, p.log2_cap, p.slot_id, p.mat, blob_words, P, rcap, rowlen, p.pinfo);
         k_tile_finish<<<(p.nplanes + 7) / 8, 256, 0, s>>>(p.nplanes, rcap, rowlen, p.mat, blob_words, p.pinfo);
@@ -1484,6 +1486,10 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
     uint64_t *omat = sc.alloc<uint64_t>(omat_words);
     uint64_t *or_hi = sc.alloc<uint64_t>(std::max<uint32_t>(nro, 1));
     const uint64_t nitems = (uint64_t)nro * nch;
+    if (nitems >= (1ull << 31)) {
+        e->err = "dense product too large for the tile path's row index";
+        throw obk_fail{OBK_ERR_UNSUPPORTED};
+    }
     uint32_t *or_cnt = sc.alloc<uint32_t>(nitems + 1);
     uint32_t *roffs = sc.alloc<uint32_t>(nitems + 2);
     CU_CHECK(e, cudaMemsetAsync(omat, 0, omat_words * 8, s)); // tiles outside an output plane's support are never written
@@ -1563,7 +1569,8 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
             float ms = 0;
             cudaEventElapsedTime(&ms, marks[k - 1].second, marks[k].second);
             char buf[96];
-            std::snprintf(buf, sizeof(buf), " %s %.3f ms |", marks[k].first, ms);
+            std::snprintf(buf, sizeof(buf), " %s %.3f ms (host %.3f) |", marks[k].first, ms,
+                          std::chrono::duration<double, std::milli>(hmarks[k] - hmarks[k - 1]).count());
             line += buf;
         }
         std::fprintf(stderr, "%s units %u planes %u rows %u split %d\n", line.c_str(), nunits, nout, nro, (int)split);
