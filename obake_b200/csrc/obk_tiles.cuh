@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
     // Tiles per unit: as many as the accumulator area holds (every pair of a plane is then staged once), unless that
     // leaves fewer than `want_units` units for the resident CTAs of this GPU -- a small product, or one rank's share of
     // a product spread over several GPUs: then the planes are cut into groups of a half, a quarter, an eighth of that.
-    {
+    if (!allow_split) {
         uint32_t all[4] = {0, 0, 0, 0};
         for (uint32_t o = tid; o < nout; o += blockDim.x) {
 #pragma unroll
@@ -425,12 +425,18 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
         const uint32_t kmax = min(64u, max(1u, ocnt[o] / 4u));
         return (uint32_t)min((unsigned long long)kmax, max(1ull, k));
     };
+    // (row_base and pair_off are scratch until the scans at the end fill them: groups | chunks << 8 and the work class of
+    // every plane this rank forms are computed once)
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
-        if (!owned(o)) continue;
-        const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
-        const uint32_t nb = groups(o), K = chunks(o, nb);
-        if (nb) atomicAdd(&s_cls[64u - c], nb * K); // class 0 = heaviest
-        if (K > 1u) s_cand[0] = 1u;                  // (re-used as the split flag: same value from every writer)
+        uint32_t nb = 0, K = 1, c = 0;
+        if (owned(o)) {
+            c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
+            nb = groups(o);
+            K = chunks(o, nb);
+            if (nb) atomicAdd(&s_cls[64u - c], nb * K); // class 0 = heaviest
+            if (K > 1u) s_cand[0] = 1u;                  // (re-used as the split flag: same value from every writer)
+        }
+        row_base[o] = nb | (K << 8) | (c << 16);
     }
     __syncthreads();
     if (tid == 0) {
@@ -446,9 +452,7 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
     }
     __syncthreads();
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
-        if (!owned(o)) continue;
-        const uint32_t c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
-        const uint32_t nb = groups(o), K = chunks(o, nb);
+        const uint32_t pk = row_base[o], nb = pk & 0xffu, K = (pk >> 8) & 0xffu, c = pk >> 16;
         if (nb == 0u) continue;
         uint32_t at = atomicAdd(&s_cls[64u - c], nb * K);
         for (uint32_t b = 0; b < nb; ++b)
