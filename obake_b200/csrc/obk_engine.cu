@@ -56,7 +56,7 @@ struct obk_engine {
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
     // options
-    int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1, opt_plane_cfg = 0, opt_tile_split = 1,
+    int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1, opt_plane_cfg = 0, opt_tile_split = 1, opt_tile_units = 0,
             opt_max_retries = 6, opt_fill_pct = 62;
     unsigned launches = 0;
     uint32_t last_rslices = 1;
@@ -1465,7 +1465,8 @@ RowsResult run_tiles(obk_engine *e, Scratch &sc, PlanePre &pre, const uint64_t *
         uint32_t *qbase = sc.alloc<uint32_t>(npairs + 1);
         const size_t sort_bytes = owner && nranks > 1 ? (size_t)TL_SORT_MAX * 20 : 0;
         if (sort_bytes) CU_CHECK(e, cudaFuncSetAttribute(k_tile_units, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_bytes));
-        k_tile_units<<<1, 1024, sort_bytes, s>>>(owork, oshape, ocnt, okey, counters, slots, 4u * (uint32_t)e->sm_count * cfg.ctas, rank,
+        k_tile_units<<<1, 1024, sort_bytes, s>>>(owork, oshape, ocnt, okey, counters, slots, (uint32_t)std::max<int64_t>(1, e->opt_tile_units) * (uint32_t)e->sm_count * cfg.ctas,
+                                                 e->opt_tile_units <= 0 ? 1u : 0u, rank,
                                                  owner ? nranks : 1u, e->opt_tile_split != 0 ? 1u : 0u, tr, qbase, row_base, pair_off, units, totals);
     }
     k_plane_sym_fill<<<gp, 256, 0, s>>>(X.plane_key, X.nplanes, Y.plane_key, Y.nplanes, rank, part_nranks, tab, l2, rec, pair_off, fill, pairs);
@@ -2698,6 +2699,7 @@ obk_status obk_engine_set_option(obk_engine *e, const char *name, int64_t value)
     else if (n == "kernel") e->opt_kernel = value;
     else if (n == "plane_cfg") e->opt_plane_cfg = value;
     else if (n == "tile_split") e->opt_tile_split = value;
+    else if (n == "tile_units") e->opt_tile_units = value;
     else if (n == "max_retries") e->opt_max_retries = value;
     else if (n == "fill_pct") e->opt_fill_pct = value;
     else {

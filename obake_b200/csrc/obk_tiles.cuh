@@ -313,7 +313,7 @@ __device__ __forceinline__ uint32_t tl_snake(uint32_t q, uint32_t n)
 
 __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *__restrict__ owork, uint32_t *__restrict__ oshape,
                                                      const uint32_t *__restrict__ ocnt, const uint64_t *__restrict__ okey,
-                                                     const uint32_t *__restrict__ counters, uint32_t tpu_max, uint32_t want_units,
+                                                     const uint32_t *__restrict__ counters, uint32_t tpu_max, uint32_t want_units, uint32_t want_scale,
                                                      uint32_t own_rank, uint32_t own_nranks, uint32_t allow_split, TileTrunc tr,
                                                      uint32_t *__restrict__ qbase, uint32_t *__restrict__ row_base,
                                                      uint32_t *__restrict__ pair_off, uint2 *__restrict__ units,
@@ -418,6 +418,15 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
         if (w) atomicAdd(&s_work, w);
     }
     __syncthreads();
+    // `want_units` = units per resident CTA x resident CTAs.  The more work a CTA has, the coarser its units may be (every
+    // unit pays a ring fill and a flush); the less, the finer they must be for the last wave to stay short.  Measured
+    // on F30 (7.3 M term products per CTA) and on one rank's share of it at 8 GPUs (0.9 M): 4 units per CTA are best
+    // for the first (16: +1 %), 16 for the second (4: +14 %).
+    if (want_scale) {
+        const unsigned long long per_cta = s_work / max(want_units, 1u);
+        const unsigned long long f = per_cta ? (16ull << 20) / per_cta : 16ull;
+        want_units *= (uint32_t)min(16ull, max(4ull, f));
+    }
     const unsigned long long w_unit = s_work / max(want_units, 1u) + 1ull;
     auto chunks = [&](uint32_t o, uint32_t nb) {
         if (!allow_split || nb == 0u) return 1u;
