@@ -13,9 +13,11 @@
 //   k_mul          the product: one CTA owns one output segment's open-addressing table in shared memory; term
 //                  products are expanded warp-cooperatively and every segment is written straight to the final
 //                  arrays (also: symbolic key-only products, the owner-side merge of the multi-GPU path)
-//   k_rowconv      row-blocked dense path: one warp owns one output row, register accumulation
-//                  (k_row_insert / k_row_flags / k_row_keys / k_row_fill / k_row_pack build the rows,
-//                  k_compact orders the symbolic row product, k_row_expand turns rows back into terms)
+//   k_rowconv      row-blocked dense path of round 1 (option kernel=1): one warp owns one output row, register
+//                  accumulation (k_row_insert / k_row_flags / k_row_keys / k_row_fill / k_row_pack build the rows,
+//                  k_compact orders the symbolic row product, k_row_expand turns rows back into terms).  The dense
+//                  path in use is the tile-blocked kernel of obk_tiles.cuh (k_tileconv, kernel 3) on top of the plane
+//                  sets, exact accumulators and symbolic plane product of obk_planes.cuh (k_planeconv, kernel 2)
 //   k_push         multi-GPU: partial terms written straight into the owners' NVLink peer windows
 //   k_widen_cfs / k_flag_keep / k_select / k_extend_symbols   series add/sub, degree truncation, symbol extension
 #pragma once
