@@ -320,10 +320,12 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
                                                      uint32_t *__restrict__ totals)
 {
     extern __shared__ __align__(16) unsigned char sort_raw[];
-    __shared__ uint32_t s_cls[65], s_tot, s_carry, s_cand[4];
+    // unit counts per (work class, warp): the planes of a Fateman product fall into five or six classes, and 1 891
+    // atomics on the same shared word serialise (most of this kernel's time in its first version)
+    __shared__ uint32_t s_cls[65][33], s_tot, s_carry, s_cand[4];
     const uint32_t tid = threadIdx.x;
     const uint32_t nout = counters[0];
-    if (tid < 65) s_cls[tid] = 0;
+    for (uint32_t i = tid; i < 65u * 33u; i += blockDim.x) (&s_cls[0][0])[i] = 0;
     if (tid == 0) s_carry = 0;
     if (tid < 4) s_cand[tid] = 0;
     for (uint32_t o = tid; o < nout; o += blockDim.x) oshape[o] = tl_cut_shape(oshape[o], tr, tl_budget(tr, o));
@@ -373,9 +375,10 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
             __syncthreads();
             for (uint32_t k = 2; k <= n2; k <<= 1) {
                 for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t i = tid; i < n2; i += blockDim.x) {
-                        const uint32_t l = i ^ j;
-                        if (l > i) {
+                    // comparator c of this pass exchanges i = (c / j) 2j + c % j with i + j: every thread has one to do
+                    for (uint32_t cidx = tid; cidx < (n2 >> 1); cidx += blockDim.x) {
+                        const uint32_t i = ((cidx & ~(j - 1u)) << 1) | (cidx & (j - 1u)), l = i | j;
+                        {
                             const bool up = (i & k) == 0u;
                             const bool gt = ka[i] > ka[l] || (ka[i] == ka[l] && kb[i] > kb[l]);
                             if (gt == up) {
@@ -412,10 +415,13 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
     if (tid == 0) s_work = 0;
     __syncthreads();
     {
+        // (a 64-bit shared-memory atomicAdd is a compare-and-swap loop: 1 024 threads on one word took 50 us)
         unsigned long long w = 0;
         for (uint32_t o = tid; o < nout; o += blockDim.x)
             if (owned(o)) w += owork[o];
-        if (w) atomicAdd(&s_work, w);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
+        if ((tid & 31u) == 0u && w) atomicAdd(&s_work, w);
     }
     __syncthreads();
     // `want_units` = units per resident CTA x resident CTAs.  The more work a CTA has, the coarser its units may be (every
@@ -442,17 +448,28 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
             c = 64u - (uint32_t)__clzll((long long)(owork[o] | 1ull));
             nb = groups(o);
             K = chunks(o, nb);
-            if (nb) atomicAdd(&s_cls[64u - c], nb * K); // class 0 = heaviest
+            if (nb) atomicAdd(&s_cls[64u - c][tid >> 5], nb * K); // class 0 = heaviest
             if (K > 1u) s_cand[0] = 1u;                  // (re-used as the split flag: same value from every writer)
         }
         row_base[o] = nb | (K << 8) | (c << 16);
     }
     __syncthreads();
+    // exclusive offsets in (class, warp) order: every class row first (one thread each), then the class bases
+    if (tid < 65) {
+        uint32_t acc = 0;
+        for (int w = 0; w < 32; ++w) {
+            const uint32_t v = s_cls[tid][w];
+            s_cls[tid][w] = acc;
+            acc += v;
+        }
+        s_cls[tid][32] = acc; // class total
+    }
+    __syncthreads();
     if (tid == 0) {
         uint32_t acc = 0;
         for (int c = 0; c < 65; ++c) {
-            const uint32_t v = s_cls[c];
-            s_cls[c] = acc;
+            const uint32_t v = s_cls[c][32];
+            s_cls[c][32] = acc;
             acc += v;
         }
         totals[0] = acc;
@@ -463,7 +480,7 @@ __global__ void __launch_bounds__(1024) k_tile_units(const unsigned long long *_
     for (uint32_t o = tid; o < nout; o += blockDim.x) {
         const uint32_t pk = row_base[o], nb = pk & 0xffu, K = (pk >> 8) & 0xffu, c = pk >> 16;
         if (nb == 0u) continue;
-        uint32_t at = atomicAdd(&s_cls[64u - c], nb * K);
+        uint32_t at = s_cls[64u - c][32] + atomicAdd(&s_cls[64u - c][tid >> 5], nb * K);
         for (uint32_t b = 0; b < nb; ++b)
             for (uint32_t k = 0; k < K; ++k, ++at) units[at] = make_uint2(o | (b << 24), k | (K << 16));
     }
