@@ -4,7 +4,9 @@
 //   ./test_polynomial          all tests (needs a B200)
 //   ./test_polynomial --cpu    host-only tests (kpack, monomials, integer, symbol sets)
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <unordered_map>
 #include <iostream>
 #include <random>
 #include <sstream>
@@ -140,6 +142,93 @@ static void integer_tests()
     REQUIRE((integer(1) * integer(std::string("18446744073709551616"))).limbs_needed() == 2u);
     REQUIRE(integer(5) < integer(7) && integer(-7) < integer(-5) && integer(-1) < integer(1));
     REQUIRES_THROWS_CONTAINS(a.to_limbs(l, 1), std::overflow_error, "does not fit");
+    // across the inline-limb boundary (three limbs inline, the heap beyond): 13^60 has 223 bits, 13^120 has 445
+    const integer p60 = pow(integer(13), 60), p120 = pow(integer(13), 120);
+    REQUIRE(p60.to_string() == "6864377172744689378196133203444067624537070830997366604446306636401");
+    REQUIRE(p60 * p60 == p120);
+    REQUIRE((p120 - p60 * p60).is_zero() && (p120 - p60 * p60).limbs_needed() == 1u);
+    integer copy = p120; // heap storage copied, moved, shrunk back
+    integer moved = std::move(copy);
+    REQUIRE(moved == p120);
+    moved = moved - p120 + integer(7);
+    REQUIRE(moved == integer(7) && moved.limbs_needed() == 1u);
+    std::uint64_t l5[5];
+    (integer(0) - p60).to_limbs(l5, 5);
+    REQUIRE(integer::from_limbs(l5, 5) == integer(0) - p60);
+    REQUIRE(p60.limbs_needed() == 4u);
+}
+
+// The term container of the mirror (detail::seg_table, the reference's segmented tables series.hpp:396-400) against
+// std::unordered_map: insertion with growth, lookup, accumulate-to-zero erasure (backward-shift deletion), iteration,
+// and the parallel adoption of terms grouped by hash & (2^k - 1).
+static void seg_table_tests()
+{
+    using K = packed_monomial<std::uint64_t>;
+    using poly_t = polynomial<K, integer>;
+    std::uint64_t st = 88172645463325252ull;
+    auto rnd = [&st]() {
+        st ^= st << 13;
+        st ^= st >> 7;
+        st ^= st << 17;
+        return st;
+    };
+    const symbol_set ss{"a", "b", "c"};
+    poly_t p;
+    p.set_symbol_set(ss);
+    std::unordered_map<std::uint64_t, long long> ref;
+    for (int it = 0; it < 60000; ++it) {
+        const std::uint64_t e0 = rnd() % 40u, e1 = rnd() % 40u, e2 = rnd() % 40u;
+        const K k{e0, e1, e2};
+        std::uint64_t w;
+        k.to_words(&w, 3);
+        const long long c = static_cast<long long>(rnd() % 7u) - 3;
+        if (c == 0) {
+            continue;
+        }
+        p.add_term(k, integer(c));
+        auto [pos, fresh] = ref.try_emplace(w, c);
+        if (!fresh) {
+            pos->second += c;
+        }
+        if (pos->second == 0) {
+            ref.erase(pos);
+        }
+    }
+    REQUIRE(p.size() == ref.size());
+    std::size_t seen = 0;
+    bool same = true;
+    for (const auto &[k, c] : p) {
+        std::uint64_t w;
+        k.to_words(&w, 3);
+        const auto f = ref.find(w);
+        same = same && f != ref.end() && c == integer(f->second);
+        ++seen;
+    }
+    REQUIRE(same && seen == ref.size());
+    for (const auto &[w, c] : ref) {
+        const auto f = p.find(K::from_words(&w, 3));
+        same = same && f != p.end() && f->second == integer(c);
+    }
+    REQUIRE(same);
+    REQUIRE(p.find(K{std::uint64_t(41), std::uint64_t(0), std::uint64_t(0)}) == p.end());
+    // grouped adoption: the same terms sorted by hash & 63, adopted in parallel, must compare equal
+    std::vector<std::pair<std::uint64_t, long long>> terms(ref.begin(), ref.end());
+    std::sort(terms.begin(), terms.end(), [](const auto &x, const auto &y) { return (x.first & 63u) < (y.first & 63u); });
+    std::vector<std::uint64_t> offs(65, 0);
+    for (const auto &t : terms) {
+        ++offs[(t.first & 63u) + 1u];
+    }
+    for (int i = 0; i < 64; ++i) {
+        offs[i + 1] += offs[i];
+    }
+    poly_t q;
+    q.set_symbol_set(ss);
+    q._adopt_grouped(terms.size(), 6, offs.data(), [&](std::size_t i) {
+        return std::pair<K, integer>(K::from_words(&terms[i].first, 3), integer(terms[i].second));
+    });
+    REQUIRE(q.size() == p.size() && q == p);
+    q.add_term(K::from_words(&terms[0].first, 3), integer(-terms[0].second)); // erase inside a grouped table
+    REQUIRE(q.size() + 1u == p.size() && q.find(K::from_words(&terms[0].first, 3)) == q.end());
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -495,6 +584,7 @@ int main(int argc, char **argv)
     monomial_tests<std::uint64_t>();
     monomial_tests<std::int32_t>();
     integer_tests();
+    seg_table_tests();
     if (!cpu_only) {
         mul_mt_hm_test<packed_monomial<std::int64_t>, integer>();
         mul_mt_hm_test<packed_monomial<std::int64_t>, double>();

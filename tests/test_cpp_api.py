@@ -39,3 +39,19 @@ def test_cpp_full_suite_on_gpu():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=580)
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0 and "OK:" in r.stdout
+
+
+def test_tile_geometry_helpers_on_host():
+    """tests/cpp/test_tiles_host.cu: the tile path's geometry helpers (tile enumeration and its inverse, tile groups,
+    ring-stage layout) against brute force, compiled with nvcc and run on the CPU."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_tiles_host.cu")
+    exe = os.path.join(ROOT, "tests", "_build", "test_tiles_host")
+    dep = os.path.join(ROOT, "obake_b200", "csrc")
+    newest = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(dep, f)) for f in os.listdir(dep)])
+    if not (os.path.exists(exe) and os.path.getmtime(exe) >= newest):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
+        subprocess.check_call([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "OK:" in r.stdout
