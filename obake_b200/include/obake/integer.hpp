@@ -25,38 +25,73 @@ namespace detail
 {
 // Little-endian limbs with room for three of them inline (mppp::integer<N> keeps N limbs inline as well): the
 // coefficients of the benchmark products (at most 190 bits) never touch the heap, which is what the term-by-term
-// rebuild of a multi-million-term result pays for otherwise.
+// rebuild of a multi-million-term result pays for otherwise.  The object is 32 bytes, holds no pointer into
+// itself (the inline limbs and the heap pointer share storage) and its all-zero byte pattern is the empty vector,
+// so a table of terms can be allocated as zeroed pages without running a constructor per slot
+// (detail::zero_init_ok, polynomial.hpp).  One spare bit is kept for the owner: integer stores its sign there.
 class limb_vec
 {
-    static constexpr std::size_t N = 3;
-    std::uint64_t m_inl[N];
-    std::uint64_t *m_ptr = m_inl;
-    std::size_t m_size = 0, m_cap = N;
+    static constexpr std::uint32_t N = 3;
+    union {
+        std::uint64_t m_inl[N];
+        struct {
+            std::uint64_t *ptr;
+            std::uint64_t cap;
+        } m_heap;
+    };
+    std::uint32_t m_size = 0;
+    std::uint16_t m_on_heap = 0;
+    std::uint16_t m_flag = 0;
 
+    std::size_t capacity() const
+    {
+        return m_on_heap ? static_cast<std::size_t>(m_heap.cap) : N;
+    }
     void grow(std::size_t cap)
     {
-        if (cap <= m_cap) {
+        const std::size_t cur = capacity();
+        if (cap <= cur) {
             return;
         }
-        cap = std::max(cap, m_cap * 2u);
+        cap = std::max(cap, cur * 2u);
         auto *p = new std::uint64_t[cap];
-        std::copy(m_ptr, m_ptr + m_size, p);
-        if (m_ptr != m_inl) {
-            delete[] m_ptr;
+        std::copy(data(), data() + m_size, p);
+        release();
+        m_heap.ptr = p;
+        m_heap.cap = cap;
+        m_on_heap = 1;
+    }
+    void release() noexcept
+    {
+        if (m_on_heap) {
+            delete[] m_heap.ptr;
+            m_on_heap = 0;
         }
-        m_ptr = p;
-        m_cap = cap;
+    }
+    void steal(limb_vec &o) noexcept
+    {
+        // bitwise hand-over: whatever o held (inline limbs or the heap block) is now ours
+        m_inl[0] = o.m_inl[0];
+        m_inl[1] = o.m_inl[1];
+        m_inl[2] = o.m_inl[2];
+        m_size = o.m_size;
+        m_on_heap = o.m_on_heap;
+        m_flag = o.m_flag;
+        o.m_size = 0;
+        o.m_on_heap = 0;
+        o.m_flag = 0;
     }
 
 public:
-    limb_vec() = default;
-    explicit limb_vec(std::size_t n)
+    limb_vec() : m_inl{0, 0, 0} {}
+    explicit limb_vec(std::size_t n) : m_inl{0, 0, 0}
     {
         resize(n);
     }
-    limb_vec(const limb_vec &o)
+    limb_vec(const limb_vec &o) : m_inl{0, 0, 0}
     {
-        assign(o.m_ptr, o.m_ptr + o.m_size);
+        assign(o.data(), o.data() + o.m_size);
+        m_flag = o.m_flag;
     }
     limb_vec(limb_vec &&o) noexcept
     {
@@ -65,42 +100,44 @@ public:
     limb_vec &operator=(const limb_vec &o)
     {
         if (this != &o) {
-            assign(o.m_ptr, o.m_ptr + o.m_size);
+            assign(o.data(), o.data() + o.m_size);
+            m_flag = o.m_flag;
         }
         return *this;
     }
     limb_vec &operator=(limb_vec &&o) noexcept
     {
         if (this != &o) {
-            if (m_ptr != m_inl) {
-                delete[] m_ptr;
-            }
-            m_ptr = m_inl;
-            m_cap = N;
+            release();
             steal(o);
         }
         return *this;
     }
     ~limb_vec()
     {
-        if (m_ptr != m_inl) {
-            delete[] m_ptr;
-        }
+        release();
     }
-    void steal(limb_vec &o) noexcept
+    // true when the limbs live in a heap block (destroying or relocating the object then needs more than a memcpy)
+    bool on_heap() const
     {
-        if (o.m_ptr == o.m_inl) {
-            std::copy(o.m_inl, o.m_inl + o.m_size, m_inl);
-            m_ptr = m_inl;
-            m_cap = N;
-        } else {
-            m_ptr = o.m_ptr;
-            m_cap = o.m_cap;
-            o.m_ptr = o.m_inl;
-            o.m_cap = N;
-        }
-        m_size = o.m_size;
-        o.m_size = 0;
+        return m_on_heap != 0;
+    }
+    // the owner's spare bit (not interpreted here; copied and moved with the value)
+    bool flag() const
+    {
+        return m_flag != 0;
+    }
+    void set_flag(bool f)
+    {
+        m_flag = f ? 1 : 0;
+    }
+    std::uint64_t *data()
+    {
+        return m_on_heap ? m_heap.ptr : m_inl;
+    }
+    const std::uint64_t *data() const
+    {
+        return m_on_heap ? m_heap.ptr : m_inl;
     }
     std::size_t size() const
     {
@@ -112,24 +149,24 @@ public:
     }
     std::uint64_t &operator[](std::size_t i)
     {
-        return m_ptr[i];
+        return data()[i];
     }
     const std::uint64_t &operator[](std::size_t i) const
     {
-        return m_ptr[i];
+        return data()[i];
     }
     std::uint64_t &back()
     {
-        return m_ptr[m_size - 1u];
+        return data()[m_size - 1u];
     }
     const std::uint64_t &back() const
     {
-        return m_ptr[m_size - 1u];
+        return data()[m_size - 1u];
     }
     void push_back(std::uint64_t v)
     {
         grow(m_size + 1u);
-        m_ptr[m_size++] = v;
+        data()[m_size++] = v;
     }
     void pop_back()
     {
@@ -142,10 +179,11 @@ public:
     void resize(std::size_t n)
     {
         grow(n);
+        std::uint64_t *p = data();
         for (std::size_t i = m_size; i < n; ++i) {
-            m_ptr[i] = 0u;
+            p[i] = 0u;
         }
-        m_size = n;
+        m_size = static_cast<std::uint32_t>(n);
     }
     template <typename It>
     void assign(It first, It last)
@@ -153,41 +191,58 @@ public:
         const auto n = static_cast<std::size_t>(last - first);
         m_size = 0;
         grow(n);
-        std::copy(first, last, m_ptr);
-        m_size = n;
+        std::copy(first, last, data());
+        m_size = static_cast<std::uint32_t>(n);
     }
     std::uint64_t *begin()
     {
-        return m_ptr;
+        return data();
     }
     std::uint64_t *end()
     {
-        return m_ptr + m_size;
+        return data() + m_size;
     }
     const std::uint64_t *begin() const
     {
-        return m_ptr;
+        return data();
     }
     const std::uint64_t *end() const
     {
-        return m_ptr + m_size;
+        return data() + m_size;
     }
+    // value comparison of the limbs (the owner's bit is the owner's business)
     friend bool operator==(const limb_vec &a, const limb_vec &b)
     {
-        return a.m_size == b.m_size && std::equal(a.m_ptr, a.m_ptr + a.m_size, b.m_ptr);
+        return a.m_size == b.m_size && std::equal(a.data(), a.data() + a.m_size, b.data());
     }
     friend bool operator!=(const limb_vec &a, const limb_vec &b)
     {
         return !(a == b);
     }
 };
+static_assert(sizeof(limb_vec) == 32, "limb_vec is meant to be 32 bytes");
 } // namespace detail
 
 class integer
 {
     // magnitude, little endian, no leading zero limbs; zero is the empty vector
+    // (the sign lives in the limb vector's spare bit: sizeof(integer) == 32, all-zero bytes == 0)
     detail::limb_vec m_mag;
-    bool m_neg = false;
+    bool neg() const
+    {
+        return m_mag.flag();
+    }
+    void set_neg(bool n)
+    {
+        m_mag.set_flag(n);
+    }
+    // replace the magnitude, keep the sign
+    void set_mag(detail::limb_vec &&r)
+    {
+        const bool n = neg();
+        m_mag = std::move(r);
+        set_neg(n);
+    }
     using u128 = unsigned __int128;
 
     void trim()
@@ -196,7 +251,7 @@ class integer
             m_mag.pop_back();
         }
         if (m_mag.empty()) {
-            m_neg = false;
+            set_neg(false);
         }
     }
     static int cmp_mag(const detail::limb_vec &a, const detail::limb_vec &b)
@@ -246,9 +301,9 @@ public:
     {
         if (v != 0) {
             if constexpr (std::is_signed_v<I>) {
-                m_neg = v < 0;
+                set_neg(v < 0);
                 const auto u = static_cast<std::uint64_t>(static_cast<std::int64_t>(v));
-                m_mag.push_back(m_neg ? std::uint64_t(0) - u : u);
+                m_mag.push_back(neg() ? std::uint64_t(0) - u : u);
             } else {
                 m_mag.push_back(static_cast<std::uint64_t>(v));
             }
@@ -279,7 +334,7 @@ public:
             *this *= integer(10);
             *this += integer(s[i] - '0');
         }
-        m_neg = neg && !m_mag.empty();
+        set_neg(neg && !m_mag.empty());
     }
 
     // Two's-complement view on `n` little-endian limbs; throws if the value does not fit.
@@ -287,14 +342,14 @@ public:
     {
         if (nbits() + 1u > 64u * n) {
             // exactly -2^(64n-1) also fits; keep the simple, slightly conservative rule
-            if (!(m_neg && nbits() == 64u * n && is_pow2())) {
+            if (!(neg() && nbits() == 64u * n && is_pow2())) {
                 throw std::overflow_error("integer does not fit in the requested number of limbs");
             }
         }
         for (unsigned i = 0; i < n; ++i) {
             out[i] = i < m_mag.size() ? m_mag[i] : 0u;
         }
-        if (m_neg) {
+        if (neg()) {
             std::uint64_t c = 1;
             for (unsigned i = 0; i < n; ++i) {
                 out[i] = ~out[i] + c;
@@ -314,7 +369,7 @@ public:
                 c = (c != 0u && l == 0u) ? 1u : 0u;
             }
         }
-        r.m_neg = neg;
+        r.set_neg(neg);
         r.trim();
         return r;
     }
@@ -325,6 +380,12 @@ public:
         return std::max(1u, (b + 63u) / 64u);
     }
 
+    // true when the limbs live in a heap block (more than three limbs): the term containers use it to skip the
+    // destructor walk over tables whose coefficients are all inline
+    bool _on_heap() const
+    {
+        return m_mag.on_heap();
+    }
     bool is_zero() const
     {
         return m_mag.empty();
@@ -343,7 +404,7 @@ public:
     }
     int sgn() const
     {
-        return m_mag.empty() ? 0 : (m_neg ? -1 : 1);
+        return m_mag.empty() ? 0 : (neg() ? -1 : 1);
     }
     unsigned nbits() const
     {
@@ -362,38 +423,38 @@ public:
         for (std::size_t i = m_mag.size(); i-- > 0;) {
             r = r * 18446744073709551616.0L + static_cast<long double>(m_mag[i]);
         }
-        return static_cast<double>(m_neg ? -r : r);
+        return static_cast<double>(neg() ? -r : r);
     }
     explicit operator std::int64_t() const
     {
-        if (nbits() > 63u && !(m_neg && nbits() == 64u && is_pow2())) {
+        if (nbits() > 63u && !(neg() && nbits() == 64u && is_pow2())) {
             throw std::overflow_error("integer does not fit in int64_t");
         }
         const std::uint64_t u = m_mag.empty() ? 0u : m_mag[0];
-        return static_cast<std::int64_t>(m_neg ? std::uint64_t(0) - u : u);
+        return static_cast<std::int64_t>(neg() ? std::uint64_t(0) - u : u);
     }
 
     integer operator-() const
     {
         integer r(*this);
         if (!r.m_mag.empty()) {
-            r.m_neg = !r.m_neg;
+            r.set_neg(!r.neg());
         }
         return r;
     }
     integer &operator+=(const integer &o)
     {
-        if (m_neg == o.m_neg) {
-            m_mag = add_mag(m_mag, o.m_mag);
+        if (neg() == o.neg()) {
+            set_mag(add_mag(m_mag, o.m_mag));
         } else {
             const int c = cmp_mag(m_mag, o.m_mag);
             if (c == 0) {
                 m_mag.clear();
             } else if (c > 0) {
-                m_mag = sub_mag(m_mag, o.m_mag);
+                set_mag(sub_mag(m_mag, o.m_mag));
             } else {
                 m_mag = sub_mag(o.m_mag, m_mag);
-                m_neg = o.m_neg;
+                set_neg(o.neg());
             }
         }
         trim();
@@ -407,7 +468,7 @@ public:
     {
         if (m_mag.empty() || o.m_mag.empty()) {
             m_mag.clear();
-            m_neg = false;
+            set_neg(false);
             return *this;
         }
         detail::limb_vec r(m_mag.size() + o.m_mag.size());
@@ -420,8 +481,9 @@ public:
             }
             r[i + o.m_mag.size()] += carry;
         }
-        m_neg = m_neg != o.m_neg;
+        const bool n = neg() != o.neg();
         m_mag = std::move(r);
+        set_neg(n);
         trim();
         return *this;
     }
@@ -439,7 +501,7 @@ public:
     }
     friend bool operator==(const integer &a, const integer &b)
     {
-        return a.m_neg == b.m_neg && a.m_mag == b.m_mag;
+        return a.neg() == b.neg() && a.m_mag == b.m_mag;
     }
     friend bool operator!=(const integer &a, const integer &b)
     {
@@ -447,11 +509,11 @@ public:
     }
     friend bool operator<(const integer &a, const integer &b)
     {
-        if (a.m_neg != b.m_neg) {
-            return a.m_neg;
+        if (a.neg() != b.neg()) {
+            return a.neg();
         }
         const int c = cmp_mag(a.m_mag, b.m_mag);
-        return a.m_neg ? c > 0 : c < 0;
+        return a.neg() ? c > 0 : c < 0;
     }
     friend bool operator>(const integer &a, const integer &b)
     {
@@ -484,8 +546,8 @@ public:
             return "0";
         }
         integer t(*this);
-        const bool neg = t.m_neg;
-        t.m_neg = false;
+        const bool neg = t.neg();
+        t.set_neg(false);
         std::string s;
         while (!t.m_mag.empty()) {
             std::uint64_t r = t.div_small(10000000000000000000ull);
@@ -508,6 +570,8 @@ public:
         return os << n.to_string();
     }
 };
+
+static_assert(sizeof(integer) == 32, "integer is meant to be 32 bytes (three inline limbs, size, sign)");
 
 inline integer pow(const integer &b, unsigned n)
 {

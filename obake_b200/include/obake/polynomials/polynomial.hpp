@@ -14,8 +14,13 @@
 #ifndef OBAKE_B200_POLYNOMIAL_HPP
 #define OBAKE_B200_POLYNOMIAL_HPP
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
 #include <limits>
 #include <iterator>
 #include <stdexcept>
@@ -25,6 +30,10 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include "../b200/engine.hpp"
 #include "../integer.hpp"
@@ -65,10 +74,169 @@ template <typename T, typename = void>
 struct is_poly : std::false_type {
 };
 
+// ---- storage traits of the term container --------------------------------------------------------------------
+// zero_init_ok<T>: a T whose bytes are all zero is a valid default-constructed T, so a table of them can be handed
+// out as zeroed pages (calloc / a fresh anonymous mapping) without running a constructor per slot.
+template <typename T>
+struct zero_init_ok : std::bool_constant<std::is_arithmetic_v<T>> {
+};
+template <typename T>
+struct zero_init_ok<packed_monomial<T>> : std::true_type {
+};
+template <>
+struct zero_init_ok<integer> : std::true_type {
+};
+// holds_no_resource(v): destroying v is a no-op (nothing on the heap).  A table whose terms were all adopted in that
+// state is released without a destructor walk over millions of slots.
+template <typename T>
+inline bool holds_no_resource(const T &)
+{
+    return std::is_trivially_destructible_v<T>;
+}
+inline bool holds_no_resource(const integer &n)
+{
+    return !n._on_heap();
+}
+
+// Storage of a table group.  Large blocks come straight from the kernel as an anonymous mapping (transparent huge
+// pages requested: a 340 MB result is 170 page faults instead of 83 000), small ones from malloc.  The contents are
+// NOT defined: a table clears its own part right before it is filled (seg_table::bind), which is sequential, runs on
+// the thread that fills the table and leaves the table in that core's cache for the random insertions that follow.
+//
+// The last large block that was released is kept for the next product (one block, at most
+// OBAKE_B200_SLAB_CACHE_MB megabytes, default 1024; 0 disables): a chain of products, or a benchmark loop, then
+// reuses the pages instead of having the kernel unmap, remap and zero a few hundred MB per product -- measured on
+// the sparse benchmark's 5.8 M-term result, fresh pages cost 145 ms of system time per product, more than filling
+// the tables.
+struct raw_block {
+    void *ptr = nullptr;
+    std::size_t bytes = 0;
+    bool mapped = false;
+    static constexpr std::size_t map_threshold = std::size_t(1) << 21;
+
+    struct cache_t {
+        std::mutex mtx;
+        void *ptr = nullptr;
+        std::size_t bytes = 0, limit = std::size_t(1024) << 20;
+        cache_t()
+        {
+            if (const char *e = std::getenv("OBAKE_B200_SLAB_CACHE_MB")) {
+                limit = static_cast<std::size_t>(std::strtoull(e, nullptr, 10)) << 20;
+            }
+        }
+    };
+    static cache_t &cache()
+    {
+        // never destroyed: a polynomial with static storage duration may be released after any other static
+        static cache_t *c = new cache_t;
+        return *c;
+    }
+
+    raw_block() = default;
+    explicit raw_block(std::size_t n) : bytes(n)
+    {
+        if (n == 0u) {
+            return;
+        }
+#if defined(__linux__)
+        if (n >= map_threshold) {
+            {
+                // a cached block that is large enough, and not absurdly larger than the request
+                auto &c = cache();
+                std::lock_guard<std::mutex> g(c.mtx);
+                if (c.ptr != nullptr && c.bytes >= n && c.bytes / 4u <= n) {
+                    ptr = c.ptr;
+                    bytes = c.bytes;
+                    mapped = true;
+                    c.ptr = nullptr;
+                    c.bytes = 0;
+                    return;
+                }
+            }
+            void *p = ::mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+            if (p != MAP_FAILED) {
+#if defined(MADV_HUGEPAGE)
+                ::madvise(p, n, MADV_HUGEPAGE);
+#endif
+                ptr = p;
+                mapped = true;
+                return;
+            }
+        }
+#endif
+        ptr = std::malloc(n);
+        if (ptr == nullptr) {
+            throw std::bad_alloc();
+        }
+    }
+    raw_block(const raw_block &) = delete;
+    raw_block &operator=(const raw_block &) = delete;
+    raw_block(raw_block &&o) noexcept : ptr(o.ptr), bytes(o.bytes), mapped(o.mapped)
+    {
+        o.ptr = nullptr;
+        o.bytes = 0;
+        o.mapped = false;
+    }
+    raw_block &operator=(raw_block &&o) noexcept
+    {
+        if (this != &o) {
+            reset();
+            ptr = o.ptr;
+            bytes = o.bytes;
+            mapped = o.mapped;
+            o.ptr = nullptr;
+            o.bytes = 0;
+            o.mapped = false;
+        }
+        return *this;
+    }
+    ~raw_block()
+    {
+        reset();
+    }
+    void reset() noexcept
+    {
+        if (ptr != nullptr) {
+#if defined(__linux__)
+            if (mapped) {
+                void *drop = ptr;
+                std::size_t drop_bytes = bytes;
+                {
+                    // keep the larger of this block and the cached one
+                    auto &c = cache();
+                    std::lock_guard<std::mutex> g(c.mtx);
+                    if (bytes <= c.limit && bytes > c.bytes) {
+                        drop = c.ptr;
+                        drop_bytes = c.bytes;
+                        c.ptr = ptr;
+                        c.bytes = bytes;
+                    }
+                }
+                if (drop != nullptr) {
+                    ::munmap(drop, drop_bytes);
+                }
+            } else
+#endif
+                std::free(ptr);
+        }
+        ptr = nullptr;
+        bytes = 0;
+        mapped = false;
+    }
+};
+
 // The term container of a series (series.hpp:396-400, `s_table`): 2^log2 open-addressing tables, a term lives in table
 // hash(key) & (2^log2 - 1).  The engine hands its results over grouped exactly that way (obk_poly_result::seg_offsets),
 // so a product is adopted table by table, in parallel, without rehashing anything (_adopt_grouped) -- the
 // reference's multiplication threads fill the same tables in place (polynomial.hpp:1441-1450).
+//
+// Storage.  A table is an array of `cap` slots (any size, not a power of two: the home slot is the high half of
+// hash * cap, so a table holds n / 0.7 slots, not up to twice that) plus one occupancy byte per slot.  The tables of
+// an adopted product share ONE block (`m_slab`): one allocation and one release per product instead of two per
+// table, and no constructor pass when the term type allows zeroed storage.  A table that has to grow later gets a
+// block of its own.  (The first version kept two std::vectors per table and 64-byte slots: rebuilding the
+// 5.8 M-term result of the sparse benchmark took 70 ms on 8 cores and destroying it 80 ms, against 0.9 ms for the
+// product itself on the GPU; tools/bench_adopt.cpp measures this part alone.)
 template <typename K, typename C>
 class seg_table
 {
@@ -76,43 +244,132 @@ public:
     using value_type = std::pair<K, C>;
 
 private:
+    static constexpr bool zero_ok = zero_init_ok<K>::value && zero_init_ok<C>::value;
+    static constexpr bool trivial_dtor = std::is_trivially_destructible_v<value_type>;
     struct tab {
-        std::vector<value_type> slots;
-        std::vector<unsigned char> full;
-        std::size_t n = 0;
+        value_type *slots = nullptr;
+        unsigned char *full = nullptr;
+        std::size_t cap = 0, n = 0;
+        raw_block own; // storage of a table that is not (or no longer) part of the slab
     };
     std::vector<tab> m_tabs = std::vector<tab>(1);
+    raw_block m_slab;
     unsigned m_log2 = 0;
     std::size_t m_size = 0;
+    // false: every stored term satisfied holds_no_resource when it was adopted and nothing has been handed out for
+    // modification since, so the slots need no destructor calls
+    bool m_walk = !trivial_dtor;
 
+    static std::size_t slot_bytes(std::size_t cap)
+    {
+        // slots first (alignment of value_type), occupancy bytes behind them, rounded to 64 bytes
+        return (cap * sizeof(value_type) + cap + 63u) & ~std::size_t(63);
+    }
+    static void bind(tab &t, void *base, std::size_t cap)
+    {
+        t.slots = static_cast<value_type *>(base);
+        t.full = reinterpret_cast<unsigned char *>(t.slots + cap);
+        t.cap = cap;
+        // clear slots and occupancy bytes (the block's contents are undefined, see raw_block)
+        std::memset(base, 0, cap * sizeof(value_type) + cap);
+        if constexpr (!zero_ok) {
+            for (std::size_t i = 0; i < cap; ++i) {
+                ::new (static_cast<void *>(t.slots + i)) value_type();
+            }
+        }
+    }
+    static std::size_t cap_for(std::size_t n)
+    {
+        // load factor 0.7
+        return std::max<std::size_t>(8u, n + (n * 3u + 6u) / 7u + 1u);
+    }
     static std::size_t slot_of(std::size_t h, std::size_t cap, unsigned log2)
     {
-        // the low bits chose the table; the rest is scrambled (packed keys are far from uniform)
+        // the low bits chose the table; the rest is scrambled (packed keys are far from uniform) and mapped to
+        // [0, cap) by the high half of the product with cap
         const std::uint64_t x = (static_cast<std::uint64_t>(h) >> log2) * 0x9E3779B97F4A7C15ull;
-        return static_cast<std::size_t>(x >> 20) & (cap - 1u);
+        return static_cast<std::size_t>((static_cast<unsigned __int128>(x ^ (x >> 29)) * cap) >> 64);
     }
-    static void grow(tab &t, std::size_t want, unsigned log2)
+    static std::size_t next(std::size_t j, std::size_t cap)
     {
-        std::size_t cap = t.slots.empty() ? 8u : t.slots.size();
-        while (want * 10u > cap * 7u) {
-            cap *= 2u;
+        return j + 1u == cap ? 0u : j + 1u;
+    }
+    void destroy_slots(tab &t) noexcept
+    {
+        if constexpr (!trivial_dtor) {
+            if (t.slots != nullptr && (m_walk || !zero_ok)) {
+                for (std::size_t i = 0; i < t.cap; ++i) {
+                    if (!zero_ok || t.full[i]) {
+                        t.slots[i].~value_type();
+                    }
+                }
+            }
         }
-        if (cap == t.slots.size()) {
+    }
+    // move table t into a block of its own with room for `want` terms
+    void grow(tab &t, std::size_t want)
+    {
+        if (t.cap != 0u && want * 10u <= t.cap * 7u) {
             return;
         }
-        std::vector<value_type> os(cap);
-        std::vector<unsigned char> of(cap, 0);
-        os.swap(t.slots);
-        of.swap(t.full);
-        for (std::size_t i = 0; i < os.size(); ++i) {
-            if (of[i]) {
-                std::size_t j = slot_of(key_hasher<K>{}(os[i].first), cap, log2);
-                while (t.full[j]) {
-                    j = (j + 1u) & (cap - 1u);
+        std::size_t cap = std::max(cap_for(want), t.cap * 2u);
+        tab nt;
+        nt.own = raw_block(slot_bytes(cap));
+        bind(nt, nt.own.ptr, cap);
+        for (std::size_t i = 0; i < t.cap; ++i) {
+            if (t.full[i]) {
+                std::size_t j = slot_of(key_hasher<K>{}(t.slots[i].first), cap, m_log2);
+                while (nt.full[j]) {
+                    j = next(j, cap);
                 }
-                t.full[j] = 1;
-                t.slots[j] = std::move(os[i]);
+                nt.full[j] = 1;
+                nt.slots[j] = std::move(t.slots[i]);
             }
+        }
+        nt.n = t.n;
+        // the old slots: run the destructors unless zeroed storage made them unnecessary (moved-from terms hold
+        // nothing), then drop the block (a slab part simply stays unused until the slab goes)
+        if constexpr (!zero_ok) {
+            for (std::size_t i = 0; i < t.cap; ++i) {
+                t.slots[i].~value_type();
+            }
+        }
+        t = std::move(nt);
+    }
+    void release() noexcept
+    {
+        for (auto &t : m_tabs) {
+            destroy_slots(t);
+        }
+        m_tabs.clear();
+        m_slab.reset();
+    }
+    void copy_from(const seg_table &o)
+    {
+        // same geometry, every term at the same slot
+        m_tabs = std::vector<tab>(o.m_tabs.size());
+        m_log2 = o.m_log2;
+        m_size = o.m_size;
+        m_walk = !trivial_dtor;
+        std::vector<std::size_t> off(o.m_tabs.size() + 1u, 0);
+        for (std::size_t i = 0; i < o.m_tabs.size(); ++i) {
+            off[i + 1u] = off[i] + (o.m_tabs[i].cap ? slot_bytes(o.m_tabs[i].cap) : 0u);
+        }
+        m_slab = raw_block(off.back());
+        for (std::size_t i = 0; i < o.m_tabs.size(); ++i) {
+            const tab &s = o.m_tabs[i];
+            if (s.cap == 0u) {
+                continue;
+            }
+            tab &t = m_tabs[i];
+            bind(t, static_cast<unsigned char *>(m_slab.ptr) + off[i], s.cap);
+            for (std::size_t j = 0; j < s.cap; ++j) {
+                if (s.full[j]) {
+                    t.full[j] = 1;
+                    t.slots[j] = s.slots[j];
+                }
+            }
+            t.n = s.n;
         }
     }
     template <bool Const>
@@ -126,10 +383,10 @@ private:
         {
             while (m_t < m_o->m_tabs.size()) {
                 const auto &t = m_o->m_tabs[m_t];
-                while (m_i < t.slots.size() && !t.full[m_i]) {
+                while (m_i < t.cap && !t.full[m_i]) {
                     ++m_i;
                 }
-                if (m_i < t.slots.size()) {
+                if (m_i < t.cap) {
                     return;
                 }
                 ++m_t;
@@ -182,6 +439,47 @@ private:
 public:
     using iterator = iter<false>;
     using const_iterator = iter<true>;
+    seg_table() = default;
+    seg_table(const seg_table &o)
+    {
+        copy_from(o);
+    }
+    seg_table(seg_table &&o) noexcept
+        : m_tabs(std::move(o.m_tabs)), m_slab(std::move(o.m_slab)), m_log2(o.m_log2), m_size(o.m_size), m_walk(o.m_walk)
+    {
+        o.m_tabs = std::vector<tab>(1);
+        o.m_log2 = 0;
+        o.m_size = 0;
+        o.m_walk = !trivial_dtor;
+    }
+    seg_table &operator=(const seg_table &o)
+    {
+        if (this != &o) {
+            seg_table tmp(o);
+            *this = std::move(tmp);
+        }
+        return *this;
+    }
+    seg_table &operator=(seg_table &&o) noexcept
+    {
+        if (this != &o) {
+            release();
+            m_tabs = std::move(o.m_tabs);
+            m_slab = std::move(o.m_slab);
+            m_log2 = o.m_log2;
+            m_size = o.m_size;
+            m_walk = o.m_walk;
+            o.m_tabs = std::vector<tab>(1);
+            o.m_log2 = 0;
+            o.m_size = 0;
+            o.m_walk = !trivial_dtor;
+        }
+        return *this;
+    }
+    ~seg_table()
+    {
+        release();
+    }
     std::size_t size() const
     {
         return m_size;
@@ -193,6 +491,15 @@ public:
     unsigned log2_tables() const
     {
         return m_log2;
+    }
+    // slots allocated over all tables (table_stats-style diagnostics and tests)
+    std::size_t capacity() const
+    {
+        std::size_t c = 0;
+        for (const auto &t : m_tabs) {
+            c += t.cap;
+        }
+        return c;
     }
     const_iterator begin() const
     {
@@ -206,6 +513,7 @@ public:
     }
     iterator begin()
     {
+        m_walk = !trivial_dtor; // the caller may store anything through a mutable iterator
         iterator it(this, 0, 0);
         it.settle();
         return it;
@@ -216,14 +524,16 @@ public:
     }
     void clear()
     {
-        m_tabs.assign(1, tab{});
+        release();
+        m_tabs = std::vector<tab>(1);
         m_log2 = 0;
         m_size = 0;
+        m_walk = !trivial_dtor;
     }
     void reserve(std::size_t n)
     {
         if (m_log2 == 0u) {
-            grow(m_tabs[0], n, 0);
+            grow(m_tabs[0], n);
         }
     }
 
@@ -234,9 +544,8 @@ private:
         using it_t = std::conditional_t<std::is_const_v<Self>, const_iterator, iterator>;
         const std::size_t h = key_hasher<K>{}(k), ti = h & ((std::size_t(1) << self.m_log2) - 1u);
         auto &t = self.m_tabs[ti];
-        if (!t.slots.empty()) {
-            const std::size_t cap = t.slots.size();
-            for (std::size_t j = slot_of(h, cap, self.m_log2); t.full[j]; j = (j + 1u) & (cap - 1u)) {
+        if (t.cap != 0u) {
+            for (std::size_t j = slot_of(h, t.cap, self.m_log2); t.full[j]; j = next(j, t.cap)) {
                 if (t.slots[j].first == k) {
                     return it_t(&self, ti, j);
                 }
@@ -252,16 +561,18 @@ public:
     }
     iterator find(const K &k)
     {
+        m_walk = !trivial_dtor;
         return find_impl(*this, k);
     }
     std::pair<iterator, bool> try_emplace(const K &k, const C &c)
     {
+        m_walk = !trivial_dtor;
         const std::size_t h = key_hasher<K>{}(k), ti = h & ((std::size_t(1) << m_log2) - 1u);
         auto &t = m_tabs[ti];
-        grow(t, t.n + 1u, m_log2);
-        const std::size_t cap = t.slots.size();
+        grow(t, t.n + 1u);
+        const std::size_t cap = t.cap;
         std::size_t j = slot_of(h, cap, m_log2);
-        for (; t.full[j]; j = (j + 1u) & (cap - 1u)) {
+        for (; t.full[j]; j = next(j, cap)) {
             if (t.slots[j].first == k) {
                 return {iterator(this, ti, j), false};
             }
@@ -280,10 +591,10 @@ public:
     {
         // backward-shift deletion: no tombstones
         auto &t = m_tabs[it.m_t];
-        const std::size_t cap = t.slots.size();
+        const std::size_t cap = t.cap;
         std::size_t i = it.m_i, j = i;
         for (;;) {
-            j = (j + 1u) & (cap - 1u);
+            j = next(j, cap);
             if (!t.full[j]) {
                 break;
             }
@@ -301,48 +612,75 @@ public:
         --m_size;
     }
     // Adopt `n` distinct, non-zero terms that arrive grouped by hash & (2^log2 - 1) (offs[2^log2 + 1]); make(i) builds
-    // term i.  The tables are filled by up to `nthreads` threads, each owning whole tables.
+    // term i.  One block holds every table; up to `nthreads` threads fill them, each a contiguous range of tables
+    // with about the same number of terms (so a thread also faults in a contiguous part of the block).
     template <typename Make>
     void adopt_grouped(std::size_t n, unsigned log2, const std::uint64_t *offs, const Make &make, unsigned nthreads)
     {
         const std::size_t nt = std::size_t(1) << log2;
-        m_tabs.assign(nt, tab{});
+        release();
+        m_tabs = std::vector<tab>(nt);
         m_log2 = log2;
         m_size = n;
-        auto work = [&](std::size_t first, std::size_t step) {
-            for (std::size_t ti = first; ti < nt; ti += step) {
+        std::vector<std::size_t> boff(nt + 1u, 0);
+        for (std::size_t ti = 0; ti < nt; ++ti) {
+            const std::size_t cnt = static_cast<std::size_t>(offs[ti + 1u] - offs[ti]);
+            boff[ti + 1u] = boff[ti] + (cnt ? slot_bytes(cap_for(cnt)) : 0u);
+        }
+        m_slab = raw_block(boff[nt]);
+        const std::size_t th = std::max<std::size_t>(1, std::min<std::size_t>({nthreads, nt, n / 8192u + 1u}));
+        std::vector<unsigned char> resource(th, 0);
+        auto work = [&](std::size_t w) {
+            // tables [t0, t1): the w-th share of the terms
+            const std::uint64_t lo = static_cast<std::uint64_t>(n) * w / th, hi = static_cast<std::uint64_t>(n) * (w + 1u) / th;
+            const std::size_t t0 = w == 0u ? 0u : static_cast<std::size_t>(std::lower_bound(offs, offs + nt, lo) - offs);
+            const std::size_t t1 = w + 1u == th ? nt : static_cast<std::size_t>(std::lower_bound(offs, offs + nt, hi) - offs);
+            bool res = false;
+            for (std::size_t ti = t0; ti < t1; ++ti) {
                 auto &t = m_tabs[ti];
                 const std::size_t b = static_cast<std::size_t>(offs[ti]), e = static_cast<std::size_t>(offs[ti + 1u]);
                 if (b == e) {
                     continue;
                 }
-                grow(t, e - b, log2);
-                const std::size_t cap = t.slots.size();
+                const std::size_t cap = cap_for(e - b);
+                bind(t, static_cast<unsigned char *>(m_slab.ptr) + boff[ti], cap);
                 for (std::size_t i = b; i < e; ++i) {
                     value_type v = make(i);
+                    res = res || !holds_no_resource(v.first) || !holds_no_resource(v.second);
                     std::size_t j = slot_of(key_hasher<K>{}(v.first), cap, log2);
                     while (t.full[j]) {
-                        j = (j + 1u) & (cap - 1u);
+                        j = next(j, cap);
                     }
                     t.full[j] = 1;
-                    t.slots[j] = std::move(v);
+                    if constexpr (zero_ok && std::is_trivially_copyable_v<K>) {
+                        ::new (static_cast<void *>(t.slots + j)) value_type(std::move(v));
+                    } else {
+                        t.slots[j] = std::move(v);
+                    }
                 }
                 t.n = e - b;
             }
+            resource[w] = res ? 1 : 0;
         };
-        const std::size_t th = std::max<std::size_t>(1, std::min<std::size_t>({nthreads, nt, n / 8192u + 1u}));
         if (th == 1u) {
-            work(0, 1);
-            return;
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            pool.reserve(th - 1u);
+            for (std::size_t w = 1; w < th; ++w) {
+                pool.emplace_back(work, w);
+            }
+            work(0);
+            for (auto &p : pool) {
+                p.join();
+            }
         }
-        std::vector<std::thread> pool;
-        pool.reserve(th - 1u);
-        for (std::size_t w = 1; w < th; ++w) {
-            pool.emplace_back(work, w, th);
+        m_walk = false;
+        for (auto r : resource) {
+            m_walk = m_walk || r != 0;
         }
-        work(0, th);
-        for (auto &p : pool) {
-            p.join();
+        if constexpr (!zero_ok) {
+            m_walk = !trivial_dtor;
         }
     }
 };
@@ -450,9 +788,9 @@ public:
     }
     // a whole product from the engine: terms grouped by hash & (2^log2 - 1), distinct and non-zero
     template <typename Make>
-    void _adopt_grouped(std::size_t n, unsigned log2, const std::uint64_t *offs, const Make &make)
+    void _adopt_grouped(std::size_t n, unsigned log2, const std::uint64_t *offs, const Make &make, unsigned nthreads = 0)
     {
-        m_terms.adopt_grouped(n, log2, offs, make, std::max(1u, std::thread::hardware_concurrency()));
+        m_terms.adopt_grouped(n, log2, offs, make, nthreads ? nthreads : std::max(1u, std::thread::hardware_concurrency()));
     }
     auto begin()
     {

@@ -229,6 +229,80 @@ static void seg_table_tests()
     REQUIRE(q.size() == p.size() && q == p);
     q.add_term(K::from_words(&terms[0].first, 3), integer(-terms[0].second)); // erase inside a grouped table
     REQUIRE(q.size() + 1u == p.size() && q.find(K::from_words(&terms[0].first, 3)) == q.end());
+    // value semantics of the slab-backed container: copies are deep, moves leave an empty polynomial behind
+    {
+        poly_t c(p);
+        REQUIRE(c == p);
+        c.add_term(K{std::uint64_t(50), std::uint64_t(50), std::uint64_t(50)}, integer(7));
+        REQUIRE(c.size() == p.size() + 1u && !(c == p));
+        poly_t m(std::move(c));
+        REQUIRE(c.empty() && m.size() == p.size() + 1u);
+        c = m;
+        REQUIRE(c == m);
+        m = poly_t{};
+        REQUIRE(m.empty() && c.size() == p.size() + 1u);
+        c.clear();
+        REQUIRE(c.empty() && c.begin() == c.end());
+        c.add_term(K{std::uint64_t(1), std::uint64_t(2), std::uint64_t(3)}, integer(5)); // usable after clear()
+        REQUIRE(c.size() == 1u);
+    }
+    // a product-sized adoption (the block comes from the kernel, is recycled by the next adoption, and grows table by
+    // table afterwards), with coefficients that spill to the heap in one of every 1000 terms
+    {
+        const std::size_t n = 300000;
+        const unsigned k = 5;
+        std::vector<std::uint64_t> keys(n);
+        for (std::size_t i = 0; i < n; ++i) {
+            const K key{static_cast<std::uint64_t>(i % 100u), static_cast<std::uint64_t>((i / 100u) % 100u),
+                        static_cast<std::uint64_t>(i / 10000u)};
+            key.to_words(&keys[i], 3);
+        }
+        std::sort(keys.begin(), keys.end(), [](auto x, auto y) { return (x & 31u) < (y & 31u); });
+        std::vector<std::uint64_t> off(33, 0);
+        for (auto v : keys) {
+            ++off[(v & 31u) + 1u];
+        }
+        for (int i = 0; i < 32; ++i) {
+            off[i + 1] += off[i];
+        }
+        auto cf = [](std::size_t i) {
+            integer c(static_cast<long long>(i % 977u) + 1);
+            if (i % 1000u == 0u) {
+                c = c * pow(integer(2), 300); // five limbs: heap
+            }
+            return (i & 1u) ? integer(0) - c : c;
+        };
+        for (int round = 0; round < 3; ++round) {
+            poly_t big;
+            big.set_symbol_set(ss);
+            big._adopt_grouped(n, k, off.data(),
+                               [&](std::size_t i) { return std::pair<K, integer>(K::from_words(&keys[i], 3), cf(i)); },
+                               round == 0 ? 1u : 0u);
+            REQUIRE(big.size() == n);
+            bool good = true;
+            for (std::size_t i = 0; i < n; i += 7) {
+                const auto f = big.find(K::from_words(&keys[i], 3));
+                good = good && f != big.end() && f->second == cf(i);
+            }
+            REQUIRE(good);
+            std::size_t cnt = 0;
+            for (const auto &t : big) {
+                cnt += t.second.is_zero() ? 0u : 1u;
+            }
+            REQUIRE(cnt == n);
+            // cancel every third term, then add new ones: erasure and growth inside slab-backed tables
+            for (std::size_t i = 0; i < n; i += 3) {
+                big.add_term<false>(K::from_words(&keys[i], 3), cf(i));
+            }
+            REQUIRE(big.size() == n - (n + 2u) / 3u);
+            for (std::size_t i = 0; i < n; i += 3) {
+                big.add_term(K::from_words(&keys[i], 3), integer(1));
+            }
+            REQUIRE(big.size() == n);
+            const poly_t copy(big);
+            REQUIRE(copy == big);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
