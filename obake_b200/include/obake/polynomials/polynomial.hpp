@@ -75,17 +75,6 @@ struct is_poly : std::false_type {
 };
 
 // ---- storage traits of the term container --------------------------------------------------------------------
-// zero_init_ok<T>: a T whose bytes are all zero is a valid default-constructed T, so a table of them can be handed
-// out as zeroed pages (calloc / a fresh anonymous mapping) without running a constructor per slot.
-template <typename T>
-struct zero_init_ok : std::bool_constant<std::is_arithmetic_v<T>> {
-};
-template <typename T>
-struct zero_init_ok<packed_monomial<T>> : std::true_type {
-};
-template <>
-struct zero_init_ok<integer> : std::true_type {
-};
 // holds_no_resource(v): destroying v is a no-op (nothing on the heap).  A table whose terms were all adopted in that
 // state is released without a destructor walk over millions of slots.
 template <typename T>
@@ -100,8 +89,8 @@ inline bool holds_no_resource(const integer &n)
 
 // Storage of a table group.  Large blocks come straight from the kernel as an anonymous mapping (transparent huge
 // pages requested: a 340 MB result is 170 page faults instead of 83 000), small ones from malloc.  The contents are
-// NOT defined: a table clears its own part right before it is filled (seg_table::bind), which is sequential, runs on
-// the thread that fills the table and leaves the table in that core's cache for the random insertions that follow.
+// NOT defined: slots are raw storage (a term is constructed in place when it is inserted); a table clears its part
+// of the block right before it is filled (seg_table::bind).
 //
 // The last large block that was released is kept for the next product (one block, at most
 // OBAKE_B200_SLAB_CACHE_MB megabytes, default 1024; 0 disables): a chain of products, or a benchmark loop, then
@@ -230,11 +219,11 @@ struct raw_block {
 // so a product is adopted table by table, in parallel, without rehashing anything (_adopt_grouped) -- the
 // reference's multiplication threads fill the same tables in place (polynomial.hpp:1441-1450).
 //
-// Storage.  A table is an array of `cap` slots (any size, not a power of two: the home slot is the high half of
-// hash * cap, so a table holds n / 0.7 slots, not up to twice that) plus one occupancy byte per slot.  The tables of
-// an adopted product share ONE block (`m_slab`): one allocation and one release per product instead of two per
-// table, and no constructor pass when the term type allows zeroed storage.  A table that has to grow later gets a
-// block of its own.  (The first version kept two std::vectors per table and 64-byte slots: rebuilding the
+// Storage.  A table is an array of `cap` RAW slots (any size, not a power of two: the home slot is the high half of
+// hash * cap, so a table holds n / 0.7 slots, not up to twice that) plus one occupancy byte per slot; a term object
+// exists in a slot exactly while its occupancy byte is set.  The tables of an adopted product share ONE block
+// (`m_slab`): one allocation and one release per product instead of two per table, nothing to construct or clear
+// but the occupancy bytes.  A table that has to grow later gets a block of its own.  (The first version kept two std::vectors per table and 64-byte slots: rebuilding the
 // 5.8 M-term result of the sparse benchmark took 70 ms on 8 cores and destroying it 80 ms, against 0.9 ms for the
 // product itself on the GPU; tools/bench_adopt.cpp measures this part alone.)
 template <typename K, typename C>
@@ -244,7 +233,6 @@ public:
     using value_type = std::pair<K, C>;
 
 private:
-    static constexpr bool zero_ok = zero_init_ok<K>::value && zero_init_ok<C>::value;
     static constexpr bool trivial_dtor = std::is_trivially_destructible_v<value_type>;
     struct tab {
         value_type *slots = nullptr;
@@ -270,13 +258,11 @@ private:
         t.slots = static_cast<value_type *>(base);
         t.full = reinterpret_cast<unsigned char *>(t.slots + cap);
         t.cap = cap;
-        // clear slots and occupancy bytes (the block's contents are undefined, see raw_block)
+        // Only the occupancy bytes NEED clearing (the slots are raw storage), but the whole table is cleared: the
+        // sequential pass pulls the table into this core's cache, and the random insertions that follow then hit
+        // it instead of missing to DRAM one line at a time (measured: filling 5.8 M terms single-threaded takes
+        // 130 ms this way and 266 ms when only the bytes are cleared).
         std::memset(base, 0, cap * sizeof(value_type) + cap);
-        if constexpr (!zero_ok) {
-            for (std::size_t i = 0; i < cap; ++i) {
-                ::new (static_cast<void *>(t.slots + i)) value_type();
-            }
-        }
     }
     static std::size_t cap_for(std::size_t n)
     {
@@ -297,9 +283,9 @@ private:
     void destroy_slots(tab &t) noexcept
     {
         if constexpr (!trivial_dtor) {
-            if (t.slots != nullptr && (m_walk || !zero_ok)) {
+            if (t.slots != nullptr && m_walk) {
                 for (std::size_t i = 0; i < t.cap; ++i) {
-                    if (!zero_ok || t.full[i]) {
+                    if (t.full[i]) {
                         t.slots[i].~value_type();
                     }
                 }
@@ -323,17 +309,13 @@ private:
                     j = next(j, cap);
                 }
                 nt.full[j] = 1;
-                nt.slots[j] = std::move(t.slots[i]);
+                ::new (static_cast<void *>(nt.slots + j)) value_type(std::move(t.slots[i]));
+                t.slots[i].~value_type();
+                t.full[i] = 0;
             }
         }
         nt.n = t.n;
-        // the old slots: run the destructors unless zeroed storage made them unnecessary (moved-from terms hold
-        // nothing), then drop the block (a slab part simply stays unused until the slab goes)
-        if constexpr (!zero_ok) {
-            for (std::size_t i = 0; i < t.cap; ++i) {
-                t.slots[i].~value_type();
-            }
-        }
+        // the old block goes (a slab part simply stays unused until the slab does)
         t = std::move(nt);
     }
     void release() noexcept
@@ -365,8 +347,8 @@ private:
             bind(t, static_cast<unsigned char *>(m_slab.ptr) + off[i], s.cap);
             for (std::size_t j = 0; j < s.cap; ++j) {
                 if (s.full[j]) {
+                    ::new (static_cast<void *>(t.slots + j)) value_type(s.slots[j]);
                     t.full[j] = 1;
-                    t.slots[j] = s.slots[j];
                 }
             }
             t.n = s.n;
@@ -577,8 +559,8 @@ public:
                 return {iterator(this, ti, j), false};
             }
         }
+        ::new (static_cast<void *>(t.slots + j)) value_type(k, c);
         t.full[j] = 1;
-        t.slots[j] = value_type(k, c);
         ++t.n;
         ++m_size;
         return {iterator(this, ti, j), true};
@@ -606,8 +588,8 @@ public:
                 i = j;
             }
         }
+        t.slots[i].~value_type(); // the erased term, or the moved-from husk the last shift left behind
         t.full[i] = 0;
-        t.slots[i] = value_type();
         --t.n;
         --m_size;
     }
@@ -651,12 +633,8 @@ public:
                     while (t.full[j]) {
                         j = next(j, cap);
                     }
+                    ::new (static_cast<void *>(t.slots + j)) value_type(std::move(v));
                     t.full[j] = 1;
-                    if constexpr (zero_ok && std::is_trivially_copyable_v<K>) {
-                        ::new (static_cast<void *>(t.slots + j)) value_type(std::move(v));
-                    } else {
-                        t.slots[j] = std::move(v);
-                    }
                 }
                 t.n = e - b;
             }
@@ -678,9 +656,6 @@ public:
         m_walk = false;
         for (auto r : resource) {
             m_walk = m_walk || r != 0;
-        }
-        if constexpr (!zero_ok) {
-            m_walk = !trivial_dtor;
         }
     }
 };
