@@ -40,7 +40,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="F30")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--also", default="S12,S16T,AUDI,AUDID,F20,D5,RECT", help="comma list of extra workloads to report in 'also' (N=1 only); '' = none")
+    ap.add_argument("--also", default="S12,S16T,AUDI,AUDID,F20,D5,RECT",
+                    help="comma list of extra workloads to report in 'also'; '' = none.  N>1: the same list minus RECT "
+                         "(a chain: replicas only), each in owner and exchange mode, bounded by --also-deadline")
+    ap.add_argument("--also-deadline", type=float, default=150.0,
+                    help="N>1: seconds the 'also' workloads may take in total; when it passes, the headline line is "
+                         "printed without them (a hung collective must not take the headline number with it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-cpp", action="store_true", help="skip the C++ operator* end-to-end leg (tools/bench_cpp.cpp)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value")
@@ -503,6 +508,58 @@ def bench_rect(args, eng, torch, dev, steps, warmup):
             "expected_final_terms": 1284816, "parity": parity}
 
 
+def also_multi_gpu(args, eng, torch, dev, rank, world, line):
+    """N > 1: the other named workloads (BASELINE configs 2, 4, 5 next to the headline config 3), each in owner mode
+    (zero exchange) and in exchange mode (left operand sharded, NCCL all-to-all, owner merge -- the contract's
+    design), parity-checked on every rank's share like the headline.  A deadline guards the headline: if these runs
+    hang or overrun (a rank failing alone leaves its peers in a collective), rank 0 prints the line it already has,
+    with the reason, and every process exits."""
+    names = [s.upper() for s in args.also.split(",") if s and s.upper() not in (args.workload.upper(), "RECT")]
+    also, state = {}, {"done": False}
+
+    def bail():
+        if state["done"]:
+            return
+        if rank == 0:
+            out = dict(line)
+            out["also"] = dict(also, error=f"deadline of {args.also_deadline:.0f} s passed; workloads above completed")
+            print(json.dumps(out), flush=True)
+        os._exit(0)
+
+    timer = threading.Timer(args.also_deadline, bail)
+    timer.daemon = True
+    timer.start()
+    steps = max(3, args.steps // 2)
+    try:
+        for nm in names:
+            per_mode = {}
+            for mode in ("owner", "exchange"):
+                r = bench_workload(nm, args, eng, torch, dev, rank, world, steps, 3, with_e2e=False, mgpu_mode=mode)
+                r.pop("_operands")
+                per_mode[mode] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"],
+                                  "kernel": r["roofline"]["kernel"], "roofline_frac": r["roofline"]["frac"],
+                                  "terms_out": r["terms_out"], "products": r["products"],
+                                  "parity_ok": r["parity"].get("ok"), "parity": r["parity"],
+                                  "exchange": r.get("exchange")}
+            best = max(per_mode, key=lambda m: per_mode[m]["value"])
+            also[nm] = dict(per_mode[best], mode=best, n_gpus=world, steps=steps,
+                            modes={m: {k: v[k] for k in ("value", "ms_per_step", "kernel_ms", "parity_ok")}
+                                   for m, v in per_mode.items()})
+    except Exception as ex:  # noqa: BLE001 -- keep the headline; the peers run into the deadline
+        also["error"] = f"{type(ex).__name__}: {str(ex)[-200:]}"
+        if rank == 0:
+            # this rank cannot join the collectives its peers are in any more: print and leave
+            state["done"] = True
+            out = dict(line)
+            out["also"] = also
+            print(json.dumps(out), flush=True)
+            os._exit(0)
+        os._exit(0)
+    state["done"] = True
+    timer.cancel()
+    return also
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -604,6 +661,8 @@ def main():
                                                  "timing_ms": (r.get("exchange") or {}).get("timing_ms")}
                                              for m, r in results.items()}
         line["config"]["multi_gpu_mode_reported"] = best
+    if world > 1 and args.also:
+        also = also_multi_gpu(args, eng, torch, dev, rank, world, line)
     if also:
         line["also"] = also
     if rank == 0 and world == 1 and not args.no_e2e_cpp:

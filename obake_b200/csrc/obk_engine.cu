@@ -36,6 +36,7 @@ struct PinnedBlock {
     void *ptr;
     size_t size;
     bool in_use;
+    uint64_t stamp = 0; // release order (the idle block released longest ago is the one evicted)
 };
 
 struct ArenaChunk {
@@ -55,6 +56,7 @@ struct obk_engine {
     cudaEvent_t ev[16];
     std::mutex mtx;
     std::vector<PinnedBlock> pinned;
+    uint64_t pinned_clock = 0;
     // options
     int64_t opt_nsegs = -1, opt_fence = 1, opt_regroup = 1, opt_row_threads = 1024, opt_two_sided = 1, opt_ctas_per_sm = 1, opt_refill_min = 16, opt_mgpu_owner = 0, opt_table_slots = 0, opt_threads = 1024, opt_kernel = -1, opt_plane_cfg = 0, opt_tile_split = 1, opt_tile_units = 0,
             opt_max_retries = 6, opt_fill_pct = 62;
@@ -226,10 +228,10 @@ int pinned_acquire(obk_engine *e, size_t bytes)
     // reuse a dead slot if any
     for (size_t i = 0; i < e->pinned.size(); ++i)
         if (e->pinned[i].ptr == nullptr) {
-            e->pinned[i] = {p, bytes, true};
+            e->pinned[i] = {p, bytes, true, 0};
             return (int)i;
         }
-    e->pinned.push_back({p, bytes, true});
+    e->pinned.push_back({p, bytes, true, 0});
     return (int)e->pinned.size() - 1;
 }
 
@@ -238,12 +240,22 @@ void pinned_release(obk_engine *e, int idx)
     std::lock_guard<std::mutex> g(e->mtx);
     if (idx < 0 || idx >= (int)e->pinned.size()) return;
     e->pinned[idx].in_use = false;
-    // keep at most ~8 cached blocks
+    e->pinned[idx].stamp = ++e->pinned_clock;
+    // Keep at most 8 idle blocks; evict the one released longest ago.  (Evicting the block that has just been
+    // released -- the first version -- meant that once eight blocks of other sizes sat idle, every call paid a
+    // cudaMallocHost and a cudaFreeHost: D5 measured 6.2 ms end to end against a 1.35 ms product when it ran after
+    // the sparse workloads.)
     size_t idle = 0;
-    for (auto &b : e->pinned) idle += (!b.in_use && b.ptr) ? 1 : 0;
-    if (idle > 8) {
-        cudaFreeHost(e->pinned[idx].ptr);
-        e->pinned[idx] = {nullptr, 0, false};
+    int oldest = -1;
+    for (size_t i = 0; i < e->pinned.size(); ++i) {
+        const auto &b = e->pinned[i];
+        if (b.in_use || !b.ptr) continue;
+        ++idle;
+        if (oldest < 0 || b.stamp < e->pinned[oldest].stamp) oldest = (int)i;
+    }
+    if (idle > 8 && oldest >= 0) {
+        cudaFreeHost(e->pinned[oldest].ptr);
+        e->pinned[oldest] = {nullptr, 0, false, 0};
     }
 }
 
