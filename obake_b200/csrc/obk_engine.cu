@@ -2281,7 +2281,9 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                                tot_mults, threads};
                 ein.ts = &ts;
                 est = estimate_terms(e, sc, ein);
-                nsegs = pick_nsegs(est, (double)cap * (double)e->opt_fill_pct / 100.0, tot_mults, wave);
+                // owner-computes over several GPUs: a wave is the resident CTAs of ALL ranks (a small product cut into one
+                // wave of one GPU leaves every rank with 1/nranks of its SMs busy: audi_01 has 139 segments)
+                nsegs = pick_nsegs(est, (double)cap * (double)e->opt_fill_pct / 100.0, tot_mults, owner ? wave * rq.nranks : wave);
             }
             st.est_nterms = est;
             CU_CHECK(e, cudaEventRecord(e->ev[3], s));
@@ -2372,16 +2374,11 @@ obk_status run_mul(obk_engine *e, MulRequest rq, obk_poly_result *out, obk_stats
                 P.lim_base = lim_base;
                 P.seg_list = nullptr;
                 P.nseg_list = nsegs;
-                uint32_t *own_list = nullptr;
                 if (owner) {
+                    // owner-computes: this rank forms the contiguous range [a, b) of the output segments
                     const uint32_t a = (uint32_t)((uint64_t)nsegs * rq.rank / rq.nranks);
                     const uint32_t b = (uint32_t)((uint64_t)nsegs * (rq.rank + 1) / rq.nranks);
-                    std::vector<uint32_t> hl(b - a);
-                    for (uint32_t i = a; i < b; ++i) hl[i - a] = i;
-                    own_list = sc.alloc<uint32_t>(std::max<uint32_t>(b - a, 1));
-                    if (b > a) CU_CHECK(e, cudaMemcpyAsync(own_list, hl.data(), (size_t)(b - a) * 4, cudaMemcpyHostToDevice, s));
-                    CU_CHECK(e, cudaStreamSynchronize(s)); // hl goes out of scope
-                    P.seg_list = own_list;
+                    P.seg_base = a;
                     P.nseg_list = b - a;
                 }
                 P.cursor = dflags + 1;

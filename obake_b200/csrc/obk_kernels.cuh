@@ -738,6 +738,7 @@ struct MulParams {
     // work list: segment ids to process (NULL = all nsegs) and the dynamic cursor
     const uint32_t *seg_list;
     uint32_t nseg_list;
+    uint32_t seg_base; // seg_list == NULL: the segments processed are seg_base .. seg_base + nseg_list - 1
     uint32_t *cursor;
     // shared-memory table geometry
     uint32_t log2_cap;
@@ -876,7 +877,7 @@ __global__ void __launch_bounds__(1024) k_mul(const MulParams P)
         __syncthreads();
         const uint32_t work = s_seg;
         if (work >= P.nseg_list) break;
-        const uint32_t seg = P.seg_list ? P.seg_list[work] : work;
+        const uint32_t seg = P.seg_list ? P.seg_list[work] : P.seg_base + work;
 
         // ---- warp state: the current unit -----------------------------------------------------------------
         uint32_t Tn = 0, next = 0; // products of the unit, next product index to hand out
