@@ -29,11 +29,11 @@ def _cases():
     return [
         ("fateman12 (tile path)", *wl.fateman(12, 4, "u64"), None, None),
         ("fateman8x5 (tile path, 5 symbols)", *wl.fateman(8, 5, "u64"), None, None),
-        ("sparse8 (scatter)", *wl.sparse_mp(8, "i64"), None, None),
-        ("sparse8 truncated 40", *wl.sparse_mp(8, "i64"), 40, None),
+        ("sparse7 (scatter)", *wl.sparse_mp(7, "i64"), None, None),
+        ("sparse7 truncated 30", *wl.sparse_mp(7, "i64"), 30, None),
         ("sparse7 partial degree", *wl.sparse_mp(7, "u64"), 9, [0, 3]),
         ("random signed", wl.random_poly(rng, 500, 3, 7, 120, "i64"), wl.random_poly(rng, 300, 3, 7, 100, "i64"), None, None),
-        ("short left operand", wl.random_poly(rng, 3, 3, 7, 50, "u64"), wl.random_poly(rng, 900, 3, 7, 50, "u64"), None, None),
+        ("short left operand", wl.random_poly(rng, 3, 4, 7, 50, "u64"), wl.random_poly(rng, 900, 4, 7, 50, "u64"), None, None),
         ("audi 6 vars fp64, two-sided", fa, ga, 6, None),
         ("audi d_packed fp64", fd, gd, 4, None),
     ]
