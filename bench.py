@@ -430,8 +430,13 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
             t0 = time.perf_counter()
             if mgpu_mode == "owner":
                 p, info = obd.owner_mul(eng, vfh, vgh, limit=limit)
-                hk_, hc_ = p.keys, p.cf_limb_array  # device -> host read of this rank's share
-                d2h = int(hk_.nbytes + hc_.nbytes)
+                # device -> host read of this rank's share through the engine's own download (obk_poly_copy: grouped
+                # into series tables, pinned host block) -- what the single-GPU arm's HOST result does.  (Reading the
+                # share with a plain pageable cudaMemcpy, as this leg first did, ran at 4 GB/s: 2.4 of the 5.2 ms at
+                # two GPUs.)
+                hp = eng.copy_view(eng.view_of(p, vfh), _capi.OBK_MEM_HOST)
+                d2h = int(hp.nterms) * 8 * (hp.key_words + hp.cf_limbs)
+                hp.free()
             elif mgpu_mode == "push":
                 p, info = PX[0].pushed_mul(vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
                 d2h = p.stats["d2h_bytes"]

@@ -324,6 +324,15 @@ class Engine:
                         OBK_MEM_DEVICE if prod.on_device else OBK_MEM_HOST, prod.keys_ptr, prod.cfs_ptr,
                         like.key_bits or 64)
 
+    def copy_view(self, vx: PolyView, result_mem=OBK_MEM_HOST) -> Product:
+        """obk_poly_copy: the terms of `vx` in engine-owned HOST (pinned, grouped the way a series stores its terms) or
+        DEVICE memory -- the upload that starts a device-resident chain and the download that ends it."""
+        res = PolyResult()
+        rc = _capi.lib().obk_poly_copy(self._h, C.byref(vx), int(result_mem), C.byref(res))
+        if rc != 0:
+            _raise(rc, self.last_error())
+        return Product(self, res, Stats())
+
     def addsub_views(self, vx: PolyView, vy: PolyView, subtract=False, result_mem=OBK_MEM_HOST) -> Product:
         """x + y / x - y over the same symbol set (series.hpp:2195-2991) on the engine's layout."""
         res, st = PolyResult(), Stats()

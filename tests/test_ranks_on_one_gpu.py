@@ -16,7 +16,7 @@ import pytest
 
 import orc
 from obake_b200 import _capi, engine as eng_mod, workloads as wl
-from test_engine_gpu import as_key_dict
+from test_engine_gpu import as_key_dict, check_segments
 
 pytestmark = pytest.mark.gpu
 NT = os.cpu_count() or 1
@@ -76,6 +76,12 @@ def test_owner_mode_shares_partition_the_product(engine, world):
                 if p.nterms:
                     kernels.add(p.stats["kernel"])
                 union.update(share)
+                if world == 2:
+                    # the download bench.py's multi-GPU e2e leg uses: obk_poly_copy of the share into host series tables
+                    hp = engine.copy_view(engine.view_of(p, hx.view), _capi.OBK_MEM_HOST)
+                    assert not hp.on_device and hp.as_dict() == share, name
+                    check_segments(hp)
+                    hp.free()
                 p.free()
             assert len(kernels) <= 1, (name, "the ranks must take the same kernel decision", kernels)
             assert nsum == len(union), (name, "two ranks hold the same key")
