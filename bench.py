@@ -424,16 +424,18 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
                       "result_terms": checksum}
     elif with_e2e:
         # N > 1: host operands on every rank, distributed result left on the owners' hosts
-        et = []
-        for _ in range(max(3, steps // 2)):
+        # (two untimed passes first, as in the single-GPU leg: the first call with host buffers allocates the pinned
+        # result blocks and grows the pools -- without them the mean of three steps was 5.2 ms at two GPUs for a
+        # 2.6 ms product)
+        et, n_warm = [], min(warmup, 2)
+        for it in range(n_warm + max(3, steps // 2)):
+            flush.zero_()
             barrier()
             t0 = time.perf_counter()
             if mgpu_mode == "owner":
                 p, info = obd.owner_mul(eng, vfh, vgh, limit=limit)
                 # device -> host read of this rank's share through the engine's own download (obk_poly_copy: grouped
-                # into series tables, pinned host block) -- what the single-GPU arm's HOST result does.  (Reading the
-                # share with a plain pageable cudaMemcpy, as this leg first did, ran at 4 GB/s: 2.4 of the 5.2 ms at
-                # two GPUs.)
+                # into series tables, pinned host block) -- what the single-GPU arm's HOST result does
                 hp = eng.copy_view(eng.view_of(p, vfh), _capi.OBK_MEM_HOST)
                 d2h = int(hp.nterms) * 8 * (hp.key_words + hp.cf_limbs)
                 hp.free()
@@ -444,7 +446,8 @@ def bench_workload(name, args, eng, torch, dev, rank, world, steps, warmup, with
                 p, info = obd.sharded_mul(eng, vfh, vgh, limit=limit, result_mem=_capi.OBK_MEM_HOST)
                 d2h = p.stats["d2h_bytes"]
             torch.cuda.synchronize(dev)
-            et.append(time.perf_counter() - t0)
+            if it >= n_warm:
+                et.append(time.perf_counter() - t0)
             h2d = info["partial_stats"]["h2d_bytes"]
             p.free()
         t = torch.tensor([float(np.mean(et))], dtype=torch.float64, device=dev)
