@@ -43,3 +43,47 @@ def test_algorithmic_bytes_model():
     assert bench.algorithmic_bytes(1, False, 1, 1) == 40   # dense_02
     assert bench.algorithmic_bytes(1, True, 1, 1) == 40    # fp64, one packed word
     assert bench.algorithmic_bytes(2, True, 1, 1) == 56    # fp64, d_packed with two words
+
+
+def test_multi_gpu_also_deadline_keeps_the_headline_line():
+    """bench.also_multi_gpu: if the extra workloads hang (a peer stuck in a collective), the deadline prints the
+    headline line that is already complete -- ONE JSON line, exit code 0 -- instead of losing it."""
+    code = r"""
+import json, sys, time, types
+sys.path.insert(0, %r)
+import bench
+def hang(*a, **k):
+    time.sleep(3600)
+bench.bench_workload = hang
+args = types.SimpleNamespace(also="S12,RECT", workload="F30", also_deadline=1.0, steps=4)
+line = {"metric": bench.METRIC, "value": 1.0, "n_gpus": 2}
+bench.also_multi_gpu(args, None, None, None, 0, 2, line)
+print("NOT REACHED")
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.strip()]
+    assert len(lines) == 1 and "NOT REACHED" not in r.stdout
+    d = json.loads(lines[0])
+    assert d["value"] == 1.0 and d["n_gpus"] == 2 and "deadline" in d["also"]["error"]
+    # a rank other than 0 leaves quietly
+    r = subprocess.run([sys.executable, "-c", code.replace("None, 0, 2, line", "None, 1, 2, line")], capture_output=True,
+                       text=True, timeout=60, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_multi_gpu_also_failure_on_one_rank_keeps_the_headline_line():
+    code = r"""
+import json, sys, types
+sys.path.insert(0, %r)
+import bench
+def boom(*a, **k):
+    raise RuntimeError("segment tables keep overflowing")
+bench.bench_workload = boom
+args = types.SimpleNamespace(also="S12", workload="F30", also_deadline=30.0, steps=4)
+bench.also_multi_gpu(args, None, None, None, 0, 2, {"metric": bench.METRIC, "value": 2.0})
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["value"] == 2.0 and "RuntimeError" in d["also"]["error"]
