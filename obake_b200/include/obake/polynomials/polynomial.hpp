@@ -9,8 +9,9 @@
 // Everything below the seam (overflow check, size estimate, segmentation, the multiply itself,
 // :797-1582) is the CUDA engine behind include/obk_b200.h; there is NO CPU multiplication here
 // (the reference's poly_mul_impl_simple small-input path, :1602-1874, is routed to the engine too).
-// The container is a plain hash map: the reference's segmented series table (series.hpp:637-639) is host
-// bookkeeping outside the path; the engine returns terms already grouped by hash & (2^k-1) for it.
+// The container (detail::seg_table) has the reference's shape -- 2^k open-addressing tables, a term in table
+// hash & (2^k-1) (series.hpp:396-400, 637-639) -- because the engine returns its terms grouped exactly that way and
+// the rebuild of the host container is part of what a caller of operator* waits for.
 #ifndef OBAKE_B200_POLYNOMIAL_HPP
 #define OBAKE_B200_POLYNOMIAL_HPP
 
