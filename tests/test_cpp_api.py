@@ -55,3 +55,21 @@ def test_tile_geometry_helpers_on_host():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "OK:" in r.stdout
+
+
+def test_container_rebuild_benchmark_builds_and_runs():
+    """tools/bench_adopt.cpp (the host container rebuild timed alone, no GPU): compiles against the mirror and adopts a
+    small synthetic grouped result, once with the block cache and once without."""
+    import json
+
+    src = os.path.join(ROOT, "tools", "bench_adopt.cpp")
+    exe = os.path.join(ROOT, "tests", "_build", "bench_adopt")
+    inc = os.path.join(ROOT, "obake_b200", "include")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-Wall", "-I", inc, "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+                           "-pthread"])
+    for env in (dict(os.environ), dict(os.environ, OBAKE_B200_SLAB_CACHE_MB="0")):
+        r = subprocess.run([exe, "200000", "6", "2", "2"], capture_output=True, text=True, timeout=120, env=env)
+        assert r.returncode == 0, r.stderr[-1000:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["terms"] == 200000 and d["slot_bytes"] == 40 and d["adopt_ms_mean"] > 0
