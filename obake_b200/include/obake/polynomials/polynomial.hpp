@@ -25,6 +25,7 @@
 #include <limits>
 #include <iterator>
 #include <stdexcept>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -475,6 +476,23 @@ public:
     {
         return m_log2;
     }
+    // terms in table i, number of tables, bytes held (series::table_stats, series.hpp:1383-1408)
+    std::size_t n_tables() const
+    {
+        return m_tabs.size();
+    }
+    std::size_t table_size(std::size_t i) const
+    {
+        return m_tabs[i].n;
+    }
+    std::size_t byte_size() const
+    {
+        std::size_t b = sizeof(*this) + m_tabs.capacity() * sizeof(tab) + m_slab.bytes;
+        for (const auto &t : m_tabs) {
+            b += t.own.bytes;
+        }
+        return b;
+    }
     // slots allocated over all tables (table_stats-style diagnostics and tests)
     std::size_t capacity() const
     {
@@ -728,6 +746,29 @@ public:
     const table_type &_terms() const
     {
         return m_terms;
+    }
+    // series::table_stats (series.hpp:1383-1408), the summary the reference's benchmark drivers print after the
+    // product (benchmark/dense.hpp:41, sparse.hpp:44): same lines, same labels.  "Total size in bytes" counts this
+    // container's storage (inline-limb coefficients included; heap limbs of coefficients beyond three limbs are not
+    // walked), where the reference reports its own byte_size().
+    std::string table_stats() const
+    {
+        std::ostringstream oss;
+        const auto s = m_terms.size();
+        const auto ntables = m_terms.n_tables();
+        oss << "Total number of terms             : " << s << '\n';
+        oss << "Total number of tables            : " << ntables << '\n';
+        if (s != 0u) {
+            oss << "Average terms per table           : " << static_cast<double>(s) / static_cast<double>(ntables) << '\n';
+            std::size_t mn = m_terms.table_size(0), mx = mn;
+            for (std::size_t i = 1; i < ntables; ++i) {
+                mn = std::min(mn, m_terms.table_size(i));
+                mx = std::max(mx, m_terms.table_size(i));
+            }
+            oss << "Min/max terms per table           : " << mn << '/' << mx << '\n';
+        }
+        oss << "Total size in bytes               : " << sizeof(*this) - sizeof(m_terms) + m_terms.byte_size() << '\n';
+        return oss.str();
     }
     auto find(const K &k) const
     {

@@ -227,6 +227,22 @@ static void seg_table_tests()
         return std::pair<K, integer>(K::from_words(&terms[i].first, 3), integer(terms[i].second));
     });
     REQUIRE(q.size() == p.size() && q == p);
+    // series::table_stats (series.hpp:1383-1408): the reference's labels, this container's numbers
+    {
+        const std::string ts = q.table_stats();
+        REQUIRE(ts.find("Total number of terms             : " + std::to_string(q.size()) + "\n") != std::string::npos);
+        REQUIRE(ts.find("Total number of tables            : 64\n") != std::string::npos);
+        std::size_t mn = ~std::size_t(0), mx = 0;
+        for (int i = 0; i < 64; ++i) {
+            mn = std::min<std::size_t>(mn, offs[i + 1] - offs[i]);
+            mx = std::max<std::size_t>(mx, offs[i + 1] - offs[i]);
+        }
+        REQUIRE(ts.find("Min/max terms per table           : " + std::to_string(mn) + "/" + std::to_string(mx) + "\n")
+                != std::string::npos);
+        REQUIRE(ts.find("Average terms per table           : ") != std::string::npos);
+        REQUIRE(ts.find("Total size in bytes               : ") != std::string::npos);
+        REQUIRE(poly_t{}.table_stats().find("Total number of terms             : 0\nTotal number of tables            : 1\nTotal size") == 0u);
+    }
     q.add_term(K::from_words(&terms[0].first, 3), integer(-terms[0].second)); // erase inside a grouped table
     REQUIRE(q.size() + 1u == p.size() && q.find(K::from_words(&terms[0].first, 3)) == q.end());
     // value semantics of the slab-backed container: copies are deep, moves leave an empty polynomial behind

@@ -89,6 +89,11 @@ int main(int argc, char **argv)
             best = ms < best ? ms : best;
             sum += ms;
         }
+        if (std::getenv("OBK_BENCH_TABLE_STATS")) {
+            // what the reference's drivers print after the product (benchmark/dense.hpp:41, sparse.hpp:44)
+            const poly_t ret = op.f * op.g;
+            std::fprintf(stderr, "%s", ret.table_stats().c_str());
+        }
         const double products = (double)op.f.size() * (double)op.g.size();
         std::printf("{\"workload\": \"%s\", \"e2e_cpp_ms\": %.4f, \"e2e_cpp_best_ms\": %.4f, \"reps\": %d, \"terms_f\": %zu, "
                     "\"terms_g\": %zu, \"terms_out\": %zu, \"products\": %.0f, \"value\": %.6g, \"build_operands_ms\": %.2f, "
