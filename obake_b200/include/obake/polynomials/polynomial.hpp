@@ -17,9 +17,12 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <barrier>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <limits>
@@ -75,6 +78,41 @@ struct key_hasher {
 template <typename T, typename = void>
 struct is_poly : std::false_type {
 };
+
+// f(w) for w in [0, th) on th threads (the caller's included); the first exception thrown by any of them is
+// rethrown here after all have finished.
+template <typename F>
+inline void parallel_for(std::size_t th, const F &f)
+{
+    if (th <= 1u) {
+        f(std::size_t(0));
+        return;
+    }
+    std::exception_ptr err;
+    std::mutex mtx;
+    auto guarded = [&](std::size_t w) {
+        try {
+            f(w);
+        } catch (...) {
+            std::lock_guard<std::mutex> g(mtx);
+            if (!err) {
+                err = std::current_exception();
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    pool.reserve(th - 1u);
+    for (std::size_t w = 1; w < th; ++w) {
+        pool.emplace_back(guarded, w);
+    }
+    guarded(0);
+    for (auto &p : pool) {
+        p.join();
+    }
+    if (err) {
+        std::rethrow_exception(err);
+    }
+}
 
 // ---- storage traits of the term container --------------------------------------------------------------------
 // holds_no_resource(v): destroying v is a no-op (nothing on the heap).  A table whose terms were all adopted in that
@@ -492,6 +530,65 @@ public:
             b += t.own.bytes;
         }
         return b;
+    }
+    // Indexed enumeration for the marshalling of an operand (polynomial.hpp:828-833 copies the terms into vectors
+    // before every product): the terms are numbered 0 .. size()-1 in (table, slot) order, and the numbering is known
+    // per CHUNK (a whole table, or a slot range of a large one) before any term is visited, so that several threads
+    // can each write their part of the SoA arrays.
+    struct enum_chunk {
+        std::size_t ti, b, e, first;
+    };
+    std::vector<enum_chunk> enum_plan() const
+    {
+        constexpr std::size_t CH = std::size_t(1) << 15;
+        std::vector<enum_chunk> ch;
+        std::size_t idx = 0;
+        for (std::size_t ti = 0; ti < m_tabs.size(); ++ti) {
+            const tab &t = m_tabs[ti];
+            if (t.n == 0u) {
+                continue;
+            }
+            if (t.cap <= CH) {
+                ch.push_back({ti, 0, t.cap, idx});
+                idx += t.n;
+                continue;
+            }
+            for (std::size_t b = 0; b < t.cap; b += CH) {
+                const std::size_t e = std::min(b + CH, t.cap);
+                std::size_t cnt = 0;
+                for (std::size_t j = b; j < e; ++j) {
+                    cnt += t.full[j];
+                }
+                if (cnt) {
+                    ch.push_back({ti, b, e, idx});
+                    idx += cnt;
+                }
+            }
+        }
+        return ch;
+    }
+    // share w of th of a plan: fn(index, term) for every term of the chunks whose first index falls in
+    // [size * w / th, size * (w + 1) / th)
+    template <typename Fn>
+    void enum_run(const std::vector<enum_chunk> &ch, std::size_t w, std::size_t th, const Fn &fn) const
+    {
+        const std::size_t lo = static_cast<std::size_t>(static_cast<unsigned __int128>(m_size) * w / th),
+                          hi = static_cast<std::size_t>(static_cast<unsigned __int128>(m_size) * (w + 1u) / th);
+        auto first_ge = [&](std::size_t v) {
+            return static_cast<std::size_t>(
+                std::lower_bound(ch.begin(), ch.end(), v, [](const enum_chunk &c, std::size_t x) { return c.first < x; })
+                - ch.begin());
+        };
+        const std::size_t c0 = w == 0u ? 0u : first_ge(lo), c1 = w + 1u == th ? ch.size() : first_ge(hi);
+        for (std::size_t c = c0; c < c1; ++c) {
+            const tab &t = m_tabs[ch[c].ti];
+            std::size_t i = ch[c].first;
+            for (std::size_t j = ch[c].b; j < ch[c].e; ++j) {
+                if (t.full[j]) {
+                    fn(i++, static_cast<const value_type &>(t.slots[j]));
+                }
+            }
+        }
     }
     // slots allocated over all tables (table_stats-style diagnostics and tests)
     std::size_t capacity() const
@@ -940,6 +1037,109 @@ inline void reduce_limit(trunc_args &ta, const V &lim)
     }
 }
 
+// The operands of a product as SoA arrays for the C ABI: keys[n][W], cfs[n][lin] (two's-complement limbs, or the bit
+// pattern of a double), lin = the widest coefficient of EITHER operand (the engine takes one limb count per call).
+// Returns lin.  What the reference does at polynomial.hpp:828-833 (copy the terms into vectors) -- here it is the
+// first thing a caller of operator* waits for, so large operands are marshalled by several threads in ONE round of
+// two phases with a barrier between them: every thread first finds the widest coefficient among its chunks of both
+// operands (seg_table::enum_plan), the barrier's completion step sizes the coefficient arrays for the limb count
+// now known, then every thread writes its chunks.  Small operands take the serial form of the same two passes.
+// `nthreads` = 0: all hardware threads.
+template <typename R, typename K, typename C0, typename C1>
+inline unsigned marshal_operands(const polynomial<K, C0> &x, const polynomial<K, C1> &y, unsigned W, std::size_t nvars,
+                                 std::vector<std::uint64_t> &kx, std::vector<std::uint64_t> &cx, std::vector<std::uint64_t> &ky,
+                                 std::vector<std::uint64_t> &cy, unsigned nthreads = 0)
+{
+    using RT = b200::cf_traits<R>;
+    constexpr bool is_int = RT::kind == OBK_CF_INT;
+    auto needed = [](const auto &c) -> unsigned {
+        using CP = std::decay_t<decltype(c)>;
+        if constexpr (is_int) {
+            return b200::cf_traits<CP>::limbs_needed(c);
+        } else {
+            return 1u;
+        }
+    };
+    auto store = [](const auto &c, std::uint64_t *out, unsigned n) {
+        using CP = std::decay_t<decltype(c)>;
+        if constexpr (std::is_same_v<CP, R>) {
+            RT::store(c, out, n);
+        } else {
+            RT::store(static_cast<R>(c), out, n); // mixed coefficient types: convert to the result type on the host
+        }
+    };
+    const std::size_t nx = x.size(), ny = y.size();
+    kx.resize(nx * W);
+    ky.resize(ny * W);
+    const std::size_t hw = nthreads ? nthreads : std::max(1u, std::thread::hardware_concurrency());
+    const std::size_t th = std::min<std::size_t>(hw, (nx + ny) / 16384u + 1u);
+    if (th > 1u) {
+        const auto px = x._terms().enum_plan(), py = y._terms().enum_plan();
+        std::atomic<unsigned> widest{1u};
+        unsigned lin = 1;
+        bool failed = false;
+        auto sized = [&]() noexcept {
+            try {
+                lin = widest.load();
+                cx.resize(nx * lin);
+                cy.resize(ny * lin);
+            } catch (...) {
+                failed = true;
+            }
+        };
+        std::barrier sync(static_cast<std::ptrdiff_t>(th), sized);
+        parallel_for(th, [&](std::size_t w) {
+            if constexpr (is_int) {
+                unsigned mine = 1;
+                auto scan = [&](std::size_t, const auto &term) { mine = std::max(mine, needed(term.second)); };
+                x._terms().enum_run(px, w, th, scan);
+                y._terms().enum_run(py, w, th, scan);
+                unsigned cur = widest.load(std::memory_order_relaxed);
+                while (mine > cur && !widest.compare_exchange_weak(cur, mine, std::memory_order_relaxed)) {
+                }
+            }
+            sync.arrive_and_wait(); // `sized` has run: lin, cx and cy are final
+            if (failed) {
+                return;
+            }
+            const unsigned l = lin;
+            auto put = [&](std::vector<std::uint64_t> &keys, std::vector<std::uint64_t> &cfs) {
+                return [&keys, &cfs, &store, W, nvars, l](std::size_t i, const auto &term) {
+                    term.first.to_words(&keys[i * W], nvars);
+                    store(term.second, &cfs[i * l], l);
+                };
+            };
+            x._terms().enum_run(px, w, th, put(kx, cx));
+            y._terms().enum_run(py, w, th, put(ky, cy));
+        });
+        if (failed) {
+            throw std::bad_alloc();
+        }
+        return lin;
+    }
+    unsigned lin = 1;
+    if constexpr (is_int) {
+        for (const auto &t : x) {
+            lin = std::max(lin, needed(t.second));
+        }
+        for (const auto &t : y) {
+            lin = std::max(lin, needed(t.second));
+        }
+    }
+    auto serial = [&](const auto &p, std::vector<std::uint64_t> &keys, std::vector<std::uint64_t> &cfs) {
+        cfs.resize(p.size() * lin);
+        std::size_t i = 0;
+        for (const auto &t : p) {
+            t.first.to_words(&keys[i * W], nvars);
+            store(t.second, &cfs[i * lin], lin);
+            ++i;
+        }
+    };
+    serial(x, kx, cx);
+    serial(y, ky, cy);
+    return lin;
+}
+
 // poly_mul_impl_identical_ss: both operands share the symbol set.
 template <typename K, typename C0, typename C1, typename R = decltype(std::declval<C0>() * std::declval<C1>())>
 inline polynomial<K, R> poly_mul_impl_identical_ss(const polynomial<K, C0> &x, const polynomial<K, C1> &y,
@@ -957,31 +1157,21 @@ inline polynomial<K, R> poly_mul_impl_identical_ss(const polynomial<K, C0> &x, c
     const unsigned W = K::n_words(nvars);
     using RT = b200::cf_traits<R>;
 
-    // Marshal the terms to SoA (what the reference copies into vectors at :828-833).
-    unsigned lin = 1;
-    if constexpr (RT::kind == OBK_CF_INT) {
-        for (const auto &[k, c] : x) lin = std::max(lin, b200::cf_traits<C0>::limbs_needed(c));
-        for (const auto &[k, c] : y) lin = std::max(lin, b200::cf_traits<C1>::limbs_needed(c));
-    }
-    auto marshal = [&](const auto &p, std::vector<std::uint64_t> &keys, std::vector<std::uint64_t> &cfs) {
-        using CP = typename std::decay_t<decltype(p)>::cf_type;
-        keys.resize(p.size() * W);
-        cfs.resize(p.size() * lin);
-        std::size_t i = 0;
-        for (const auto &[k, c] : p) {
-            k.to_words(&keys[i * W], nvars);
-            if constexpr (std::is_same_v<CP, R>) {
-                RT::store(c, &cfs[i * lin], lin);
-            } else {
-                // mixed coefficient types: convert to the result type once on the host
-                RT::store(static_cast<R>(c), &cfs[i * lin], lin);
+    // Marshal the terms to SoA (what the reference copies into vectors at :828-833).  The four arrays are kept per
+    // calling thread from one product to the next (fresh vectors of this size are fresh pages: faulting them in cost
+    // more than filling them); an array that grew beyond 64 MB is given back afterwards.
+    static thread_local std::vector<std::uint64_t> kx, cx, ky, cy;
+    struct scratch_guard {
+        ~scratch_guard()
+        {
+            for (auto *v : {&kx, &cx, &ky, &cy}) {
+                if (v->capacity() > (std::size_t(64) << 20) / 8u) {
+                    std::vector<std::uint64_t>().swap(*v);
+                }
             }
-            ++i;
         }
-    };
-    std::vector<std::uint64_t> kx, cx, ky, cy;
-    marshal(x, kx, cx);
-    marshal(y, ky, cy);
+    } guard;
+    const unsigned lin = marshal_operands<R>(x, y, W, nvars, kx, cx, ky, cy);
     auto view = [&](std::size_t n, const std::vector<std::uint64_t> &k, const std::vector<std::uint64_t> &c) {
         obk_poly_view v{};
         v.nterms = n;

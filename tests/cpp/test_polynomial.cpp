@@ -321,6 +321,173 @@ static void seg_table_tests()
     }
 }
 
+// The marshalling of the operands for the C ABI (detail::marshal_operands; what polynomial.hpp:828-833 does in the
+// reference): the multi-threaded one-round form must give the very arrays the serial two-pass form gives -- same
+// order, same limb count, same two's-complement limbs -- for one- to three-limb and wider coefficients of both
+// signs, doubles, mixed coefficient types, multi-word keys, single-table and multi-table containers.
+template <typename K, typename C>
+static polynomial<K, C> marshal_test_poly(const symbol_set &ss, std::size_t n, unsigned log2, std::uint64_t seed, int wide_every)
+{
+    std::uint64_t st = seed;
+    auto rnd = [&st]() {
+        st ^= st << 13;
+        st ^= st >> 7;
+        st ^= st << 17;
+        return st;
+    };
+    const std::size_t nv = ss.size();
+    polynomial<K, C> p;
+    p.set_symbol_set(ss);
+    auto cf = [&](std::size_t i) -> C {
+        if constexpr (std::is_same_v<C, integer>) {
+            integer c(static_cast<long long>(rnd() >> (24 + i % 30u)) | 1); // at most 40 bits
+            if (i % 7u == 3u) {
+                c = c * integer(static_cast<long long>(rnd() >> 24) | 1); // up to 80 bits: two limbs
+            }
+            if (i % 31u == 5u) {
+                c = c * pow(integer(2), 100); // up to 180 bits: three limbs
+            }
+            if (wide_every > 0 && i % static_cast<std::size_t>(wide_every) == 1u) {
+                c = c * pow(integer(2), 250); // beyond the three inline limbs: heap
+            }
+            return (i & 1u) ? integer(0) - c : c;
+        } else {
+            return static_cast<double>(static_cast<long long>(rnd() >> 12)) * ((i & 1u) ? -0.25 : 0.5) + 1.0;
+        }
+    };
+    std::vector<std::vector<std::uint64_t>> words; // distinct keys: mixed-radix digits of i
+    std::vector<std::size_t> order(n);
+    words.reserve(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        std::vector<typename K::value_type> e(nv);
+        std::size_t v = i;
+        for (std::size_t j = 0; j < nv; ++j) {
+            e[j] = static_cast<typename K::value_type>(v % 19u);
+            v /= 19u;
+        }
+        const K key(e);
+        std::vector<std::uint64_t> w(K::n_words(nv));
+        key.to_words(w.data(), nv);
+        words.push_back(std::move(w));
+        order[i] = i;
+    }
+    if (log2 == 0u) {
+        p.reserve(n / 3u); // grow a few times on the way
+        for (std::size_t i = 0; i < n; ++i) {
+            p._insert_unique(K::from_words(words[i].data(), nv), cf(i));
+        }
+        return p;
+    }
+    auto tab_of = [&](std::size_t i) {
+        std::uint64_t h = 0;
+        for (auto w : words[i]) {
+            h += w;
+        }
+        return h & ((std::uint64_t(1) << log2) - 1u);
+    };
+    std::stable_sort(order.begin(), order.end(), [&](std::size_t a, std::size_t b) { return tab_of(a) < tab_of(b); });
+    std::vector<std::uint64_t> offs((std::size_t(1) << log2) + 1u, 0);
+    for (std::size_t i = 0; i < n; ++i) {
+        ++offs[tab_of(i) + 1u];
+    }
+    for (std::size_t t = 0; t + 1u < offs.size(); ++t) {
+        offs[t + 1u] += offs[t];
+    }
+    std::vector<C> cfs(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        cfs[i] = cf(i);
+    }
+    p._adopt_grouped(n, log2, offs.data(), [&](std::size_t r) {
+        return std::pair<K, C>(K::from_words(words[order[r]].data(), nv), cfs[order[r]]);
+    });
+    return p;
+}
+
+template <typename R, typename K, typename C0, typename C1>
+static void marshal_case(const polynomial<K, C0> &x, const polynomial<K, C1> &y, unsigned want_lin)
+{
+    const std::size_t nv = x.get_symbol_set().size();
+    const unsigned W = K::n_words(nv);
+    std::vector<std::uint64_t> kx, cx, ky, cy, kx1, cx1, ky1, cy1;
+    const unsigned lin1 = obake::detail::marshal_operands<R>(x, y, W, nv, kx1, cx1, ky1, cy1, 1); // serial two-pass form
+    for (unsigned th : {0u, 2u, 5u}) {
+        const unsigned lin = obake::detail::marshal_operands<R>(x, y, W, nv, kx, cx, ky, cy, th);
+        REQUIRE(lin == lin1 && (want_lin == 0u || lin == want_lin));
+        REQUIRE(kx == kx1 && ky == ky1);
+        REQUIRE(cx == cx1 && cy == cy1);
+        REQUIRE(kx.size() == x.size() * W && cx.size() == x.size() * lin && cy.size() == y.size() * lin);
+    }
+    // and the serial form is what iteration gives
+    std::size_t i = 0;
+    bool same = true;
+    for (const auto &[k, c] : x) {
+        std::vector<std::uint64_t> w(W);
+        k.to_words(w.data(), nv);
+        same = same && std::equal(w.begin(), w.end(), kx1.begin() + static_cast<std::ptrdiff_t>(i * W));
+        if constexpr (std::is_same_v<C0, R>) {
+            same = same && obake::b200::cf_traits<R>::load(&cx1[i * lin1], lin1) == c;
+        }
+        ++i;
+    }
+    REQUIRE(same && i == x.size());
+}
+
+static void marshal_tests()
+{
+    using K1 = packed_monomial<std::uint64_t>;
+    using K2 = d_packed_monomial<std::int64_t, 2>;
+    const symbol_set s4{"a", "b", "c", "d"};
+    {
+        // integers of one to three limbs, multi-table x single-table
+        const auto x = marshal_test_poly<K1, integer>(s4, 60000, 6, 11, 0);
+        const auto y = marshal_test_poly<K1, integer>(s4, 45000, 0, 12, 0);
+        marshal_case<integer>(x, y, 3);
+        marshal_case<integer>(y, x, 3);
+        marshal_case<integer>(x, x, 3);
+    }
+    {
+        // one-limb coefficients only: the three-limb stride is narrowed to one
+        polynomial<K1, integer> x, y;
+        x.set_symbol_set(s4);
+        y.set_symbol_set(s4);
+        for (std::uint64_t i = 0; i < 40000; ++i) {
+            x._insert_unique(K1{i % 19u, (i / 19u) % 19u, (i / 361u) % 19u, i / 6859u}, integer(static_cast<long long>(i) - 20000ll) * integer(3) + integer(1));
+            y._insert_unique(K1{i % 17u, (i / 17u) % 17u, (i / 289u) % 17u, i / 4913u}, integer(static_cast<long long>(i % 1000u) + 1));
+        }
+        marshal_case<integer>(x, y, 1);
+    }
+    {
+        // a few coefficients beyond three limbs (heap-backed integers): the limb count follows the widest one
+        const auto x = marshal_test_poly<K1, integer>(s4, 50000, 5, 13, 977);
+        const auto y = marshal_test_poly<K1, integer>(s4, 30000, 4, 14, 0);
+        marshal_case<integer>(x, y, 0);
+        marshal_case<integer>(y, x, 0);
+    }
+    {
+        // doubles, and integer x double (converted to the result type on the host)
+        const auto x = marshal_test_poly<K1, double>(s4, 50000, 6, 15, 0);
+        const auto y = marshal_test_poly<K1, double>(s4, 50000, 0, 16, 0);
+        marshal_case<double>(x, y, 1);
+        const auto z = marshal_test_poly<K1, integer>(s4, 40000, 3, 17, 0);
+        marshal_case<double>(z, y, 1);
+        marshal_case<double>(x, z, 1);
+    }
+    {
+        // two-word keys
+        const auto x = marshal_test_poly<K2, integer>(s4, 40000, 5, 18, 0);
+        const auto y = marshal_test_poly<K2, integer>(s4, 40000, 0, 19, 0);
+        marshal_case<integer>(x, y, 3);
+    }
+    {
+        // small operands stay serial; empty operands
+        const auto x = marshal_test_poly<K1, integer>(s4, 100, 2, 20, 0);
+        polynomial<K1, integer> e;
+        e.set_symbol_set(s4);
+        marshal_case<integer>(x, x, 0);
+        marshal_case<integer>(x, e, 0);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 template <typename K, typename C>
 static void mul_mt_hm_test()
@@ -675,6 +842,7 @@ int main(int argc, char **argv)
     monomial_tests<std::int32_t>();
     integer_tests();
     seg_table_tests();
+    marshal_tests();
     if (!cpu_only) {
         mul_mt_hm_test<packed_monomial<std::int64_t>, integer>();
         mul_mt_hm_test<packed_monomial<std::int64_t>, double>();
